@@ -1,0 +1,169 @@
+/*
+ * plaac_cuda.h -- C ABI of libplaac_cuda.so: the B200 (sm_100a) implementation
+ * of PLAAC's per-protein scoring hot path.
+ *
+ * The reference (whitehead/plaac, cli/src/plaac.java; "plaac.java:N" below) has
+ * no FFI seam: the path is reached by plain Java calls from the two driver
+ * loops scoreallfastas (plaac.java:755-948) and plotsomefastas (:610-647).
+ * This header is the seam a host (Java via java.lang.foreign / JNI, C++, or
+ * Python ctypes) binds instead of those calls; INTEGRATION.md shows the stubs.
+ *
+ * Conventions
+ *  - plain C symbols, plain pointers and sizes; no C++/torch types;
+ *  - every function returns 0 on success or a negative PLAAC_E_* code and
+ *    never throws/aborts across the ABI; plaac_last_error() has the text;
+ *  - the caller owns every buffer it passes; the library owns device memory;
+ *  - a ctx is bound to ONE GPU and used by one host thread at a time
+ *    (multi-GPU = one ctx + one thread/process per GPU; proteins are
+ *    independent, no collective is needed);
+ *  - results are written in input order;
+ *  - positions are 0-based exactly as plaac.java holds them internally; the
+ *    host adds 1 when printing (plaac.java:899-945).
+ *  - the host computes every table with its own Math.log/exp (plaac.java:279-299,
+ *    :449-500, :968-1001, :2893-2935); the device only does IEEE double
+ *    + - * / floor compare (no FMA contraction), so reference-order results are
+ *    reproducible bit for bit where the algorithm is evaluated in reference order.
+ */
+#ifndef PLAAC_CUDA_H
+#define PLAAC_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLAAC_NAA 22        /* plaac.java:26  X A C D E F G H I K L M N P Q R S T V W Y *  */
+#define PLAAC_LUT_LEN 4001  /* plaac.java:34,282  loglut[0..4000] */
+
+#define PLAAC_OK 0
+#define PLAAC_E_INVALID (-1)     /* bad argument (NULL, negative size, offsets not monotone, code > 21) */
+#define PLAAC_E_CUDA (-2)        /* CUDA runtime error (text in plaac_last_error) */
+#define PLAAC_E_UNSUPPORTED (-3) /* parameter combination outside what the kernels implement */
+#define PLAAC_E_NOMEM (-4)       /* device or pinned-host allocation failed */
+#define PLAAC_E_NODEVICE (-5)    /* no CUDA device / not an sm_100 device */
+
+/* Everything scoreallfastas/plotsomefastas receive from main (plaac.java:526-528)
+ * plus the static tables of class plaac, already in log space. */
+typedef struct plaac_params {
+    int32_t core_len;        /* -c, plaac.java:317 (default 60) */
+    int32_t ww1;             /* -w FoldIndex window, :318 (41) */
+    int32_t ww2;             /* -W PAPA window, :319 (41) */
+    int32_t ww3;             /* PLAAC-LLR smoothing window, :320,:355 (= ww2) */
+    int32_t adjust_prolines; /* :328 (1) */
+    int32_t mw_window;       /* :767 (80) */
+    int32_t reserved[2];
+    /* hmm1 = prionhmm1(fg,bg), :968-981, after hmm.initialize :2893-2935 */
+    double lt[2][2];         /* ltprob[from][to] */
+    double li[2];            /* liprob */
+    double lf[2];            /* lfprob (0,0 for PLAAC's models) */
+    double le[2][PLAAC_NAA]; /* leprob[state][aa]; state 0 = background, 1 = PrD-like */
+    /* hmm0 = prionhmm0(bg), :988-1001: identity transitions, starts in state 0,
+     * so its Viterbi and marginal log-probabilities are both the sequential sum
+     * of le0[aa_t]. */
+    double le0[PLAAC_NAA];
+    double llr[PLAAC_NAA];      /* :497-500 */
+    double papa_lod[PLAAC_NAA]; /* lodpapa1, :285-291 */
+    double hydro2[PLAAC_NAA];   /* aahydro2, :90 */
+    double charge[PLAAC_NAA];   /* aacharge, :37-60 (must be small integers) */
+    double fi_cc[3];            /* {2.785, -1, -1.151}, :800 */
+    double big_neg;             /* -1e6, :817 */
+    double ln2;                 /* Math.log(2), :30 */
+    double loglut[PLAAC_LUT_LEN]; /* :282-283 */
+} plaac_params;
+
+/* One row of the summary table (plaac.java:899-945) before formatting:
+ * 14 x int32 + 13 x double = 160 bytes, no padding. */
+typedef struct plaac_summary {
+    int32_t mw_score, mw_start, mw_end;               /* hs1, :771 */
+    int32_t llr_start, llr_end;                       /* hs2, :783; -1/-2 when PROTlen < c */
+    int32_t vit_maxrun;                               /* longestrun(viterbipath), :814 */
+    int32_t core_start, core_end, prd_start, prd_end; /* :851-880; -1/-2 when no CORE */
+    int32_t prot_len;                                 /* 0 => the jar prints no row (:762) */
+    int32_t fi_numaa, fi_maxrun;                      /* numdisorderedstrict2, maxlen :5010-5060 */
+    int32_t papa_center;                              /* papamaxcenter (-1 if none), :4941-4948 */
+    double llr;          /* hs2[2]; -Inf when PROTlen < c (host prints NaN via inf2nan) */
+    double core_score;   /* hs3[2] or NaN */
+    double prd_score;    /* 0.0 when no CORE */
+    double hmm_all;      /* hmm1.lmarginalprob - hmm0.lmarginalprob, :797 */
+    double hmm_vit;      /* hmm1.lviterbiprob - hmm0.lviterbiprob, :798 */
+    double fi_meanhydro, fi_meancharge, fi_meancombo; /* :4876-4883 */
+    double papa_combo;   /* papamaxscore (-Inf if none), :4931 */
+    double papa_prop, papa_fi, papa_llr, papa_llr2;   /* :4990-4996 (NaN if none) */
+} plaac_summary;
+
+/* Per-residue table (plaac.java:603-605, :637-641), struct of arrays, each array
+ * as long as the total residue count of the call; element offsets[i]+t belongs to
+ * residue t of protein i.  82 bytes per residue. */
+typedef struct plaac_residue_out {
+    uint8_t *vit, *map;
+    double *charge, *hydro, *fi, *plaac, *papa, *fix2, *plaacx2, *papax2;
+    double *post_bg, *post_prd;
+} plaac_residue_out;
+
+typedef struct plaac_ctx plaac_ctx; /* opaque */
+
+int plaac_device_count(void);
+
+/* Validates params, uploads the tables, creates the stream.  Replaces the
+ * construction of hmm1/hmm0 + static tables for the device side. */
+int plaac_create(plaac_ctx **out, int device, const plaac_params *params);
+void plaac_destroy(plaac_ctx *ctx);
+
+/* Text of the last error on this ctx (ctx == NULL: last error of plaac_create /
+ * plaac_device_count on the calling thread).  Never NULL. */
+const char *plaac_last_error(const plaac_ctx *ctx);
+
+/* Summary mode and (per_res != NULL) per-residue mode with HOST buffers:
+ * replaces the bodies of plaac.java:755-948 / :610-647 for a batch.
+ *   codes    1 byte per residue, 0..21 (aatoint :1508-1534), terminal '*' already
+ *            stripped (:758); proteins concatenated;
+ *   offsets  nprot+1 monotone int64; protein i = codes[offsets[i] .. offsets[i+1])
+ *   summaries nprot records (may be NULL if per_res != NULL)
+ *   per_res  NULL, or host arrays offsets[nprot]-offsets[0] long.
+ * Input is processed in device-sized chunks, copies overlapped with compute;
+ * pinned host buffers make the copies asynchronous.  Blocks until done. */
+int plaac_score(plaac_ctx *ctx, const uint8_t *codes, const int64_t *offsets, int64_t nprot,
+                plaac_summary *summaries, const plaac_residue_out *per_res);
+
+/* Same with DEVICE buffers already resident on ctx's GPU (offsets[0] must be 0,
+ * ntotal = offsets[nprot]).  Work is enqueued on the ctx stream; call
+ * plaac_sync() (or synchronise plaac_stream()) before reading the outputs. */
+int plaac_score_device(plaac_ctx *ctx, const uint8_t *d_codes, const int64_t *d_offsets, int64_t nprot,
+                       int64_t ntotal, plaac_summary *d_summaries, const plaac_residue_out *d_per_res);
+int plaac_sync(plaac_ctx *ctx);
+void *plaac_stream(plaac_ctx *ctx); /* cudaStream_t of the ctx */
+
+/* Host-side parameter chain for hosts that do not have their own (the C++ CLI, Python tests): what
+ * plaac.java main computes between :310 and :518 -- bg/fg mixing with alpha (:449-458), the 1e-5
+ * pseudo-frequency for X and * (:490-496), llr (:497-500), prionhmm1/prionhmm0 (:968-1001) through
+ * hmm.initialize (:2893-2935), loglut and lodpapa1 (:279-299), aahydro2 (:90).  Uses the C library's
+ * log/exp.  bg_counts: the 22 numbers of `bgf` (:374-384) or NULL (all zero); fg_freq: 22 numbers or
+ * NULL for the built-in prd_freq_scer_28 (:269).  alpha outside [0,1] becomes 1 (:444-447).
+ * info (optional, 4 x 22 doubles): fg_used, bg_scer, bg_input, bg_used as printed at :506-509. */
+int plaac_params_init(plaac_params *out, double alpha, const double *bg_counts, const double *fg_freq,
+                      int core_len, int ww1, int ww2, int ww3, int adjust_prolines, double *info);
+
+/* residue encoding on the host side of the ABI (aatoint/string2aa, :1508-1534,
+ * :1764-1769): n chars -> n codes; does NOT strip the stop codon. */
+void plaac_encode_host(const char *chars, int64_t n, uint8_t *codes);
+
+/* Tuning/testing knob for plaac_score(): upper bounds of one device chunk (0 = keep default). */
+int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
+
+/* Accounting for benchmarks: kernels launched by this ctx so far, and the
+ * CUDA-event time (ms) the scoring kernel(s) of the LAST plaac_score_device
+ * call took on the ctx stream (valid after plaac_sync). */
+typedef struct plaac_stats {
+    int64_t kernel_launches;   /* all kernels of this library launched by the ctx */
+    int64_t score_launches;    /* launches of the dominant scoring kernel */
+    float last_total_ms;       /* whole pipeline of the last device call */
+    float last_score_ms;       /* dominant kernel of the last device call */
+    int64_t last_padded_slots; /* 16-byte lane slots in the bucketed stream of the last call */
+} plaac_stats;
+int plaac_get_stats(plaac_ctx *ctx, plaac_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

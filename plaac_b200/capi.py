@@ -1,0 +1,225 @@
+"""ctypes binding of include/plaac_cuda.h (+ include/plaac_bench.h).
+
+Mirrors the reference's per-protein interface at batch granularity:
+  Scorer.score(codes, offsets)          ~ the loop body of scoreallfastas (plaac.java:755-948)
+  Scorer.score(..., per_residue=True)   ~ the loop body of plotsomefastas (plaac.java:610-647)
+No CPU fallback: if libplaac_cuda.so is not built, importing `lib()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplaac_cuda.so")
+
+NAA = 22
+LUT_LEN = 4001
+AANAMES = "XACDEFGHIKLMNPQRSTVWY*"
+
+
+class PlaacError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libplaac_cuda error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("core_len", C.c_int32), ("ww1", C.c_int32), ("ww2", C.c_int32), ("ww3", C.c_int32),
+        ("adjust_prolines", C.c_int32), ("mw_window", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("lt", (C.c_double * 2) * 2), ("li", C.c_double * 2), ("lf", C.c_double * 2),
+        ("le", (C.c_double * NAA) * 2),
+        ("le0", C.c_double * NAA), ("llr", C.c_double * NAA), ("papa_lod", C.c_double * NAA),
+        ("hydro2", C.c_double * NAA), ("charge", C.c_double * NAA), ("fi_cc", C.c_double * 3),
+        ("big_neg", C.c_double), ("ln2", C.c_double), ("loglut", C.c_double * LUT_LEN),
+    ]
+
+
+class Summary(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "mw_score", "mw_start", "mw_end", "llr_start", "llr_end", "vit_maxrun", "core_start", "core_end",
+        "prd_start", "prd_end", "prot_len", "fi_numaa", "fi_maxrun", "papa_center")] + [(n, C.c_double) for n in (
+        "llr", "core_score", "prd_score", "hmm_all", "hmm_vit", "fi_meanhydro", "fi_meancharge", "fi_meancombo",
+        "papa_combo", "papa_prop", "papa_fi", "papa_llr", "papa_llr2")]
+
+
+assert C.sizeof(Summary) == 160
+SUMMARY_DTYPE = np.dtype([(n, "<i4" if t is C.c_int32 else "<f8") for n, t in Summary._fields_])
+assert SUMMARY_DTYPE.itemsize == 160
+
+RESIDUE_U8 = ("vit", "map")
+RESIDUE_F64 = ("charge", "hydro", "fi", "plaac", "papa", "fix2", "plaacx2", "papax2", "post_bg", "post_prd")
+
+
+class ResidueOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in RESIDUE_U8 + RESIDUE_F64]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("score_launches", C.c_int64), ("last_total_ms", C.c_float),
+                ("last_score_ms", C.c_float), ("last_padded_slots", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libplaac_cuda.so; raises (no fallback) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlaacError(-5, f"{LIB_PATH} is missing: run `python -m plaac_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        L.plaac_device_count.restype = C.c_int
+        L.plaac_create.restype = C.c_int
+        L.plaac_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params)]
+        L.plaac_destroy.restype = None
+        L.plaac_destroy.argtypes = [vp]
+        L.plaac_last_error.restype = C.c_char_p
+        L.plaac_last_error.argtypes = [vp]
+        L.plaac_score.restype = C.c_int
+        L.plaac_score.argtypes = [vp, vp, vp, i64, vp, C.POINTER(ResidueOut)]
+        L.plaac_score_device.restype = C.c_int
+        L.plaac_score_device.argtypes = [vp, vp, vp, i64, i64, vp, C.POINTER(ResidueOut)]
+        L.plaac_sync.restype = C.c_int
+        L.plaac_sync.argtypes = [vp]
+        L.plaac_stream.restype = vp
+        L.plaac_stream.argtypes = [vp]
+        L.plaac_params_init.restype = C.c_int
+        L.plaac_params_init.argtypes = [C.POINTER(Params), dbl, vp, vp, i32, i32, i32, i32, i32, vp]
+        L.plaac_encode_host.restype = None
+        L.plaac_encode_host.argtypes = [vp, i64, vp]
+        L.plaac_set_chunk.restype = C.c_int
+        L.plaac_set_chunk.argtypes = [vp, i64, i64]
+        L.plaac_get_stats.restype = C.c_int
+        L.plaac_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.plaac_bench_synth_lengths.restype = C.c_int
+        L.plaac_bench_synth_lengths.argtypes = [vp, C.c_uint64, i64, i64, dbl, dbl, i32, i32, vp]
+        L.plaac_bench_synth_residues.restype = C.c_int
+        L.plaac_bench_synth_residues.argtypes = [vp, C.c_uint64, i64, i64, vp, vp, vp, dbl, dbl, vp]
+        L.plaac_bench_fp64_peak.restype = C.c_int
+        L.plaac_bench_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(dbl), C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def default_params(alpha=1.0, bg_counts=None, fg_freq=None, core_len=60, ww1=41, ww2=41, ww3=None,
+                   adjust_prolines=True, return_info=False):
+    """plaac.java main :310-518 through plaac_params_init (host C++ code, not the oracle)."""
+    P = Params()
+    if ww3 is None:
+        ww3 = ww2  # plaac.java:355
+    bgp = fgp = None
+    if bg_counts is not None:
+        bg = np.ascontiguousarray(bg_counts, dtype=np.float64)
+        assert bg.shape == (NAA,)
+        bgp = bg.ctypes.data
+    if fg_freq is not None:
+        fg = np.ascontiguousarray(fg_freq, dtype=np.float64)
+        assert fg.shape == (NAA,)
+        fgp = fg.ctypes.data
+    info = np.zeros((4, NAA))
+    rc = lib().plaac_params_init(C.byref(P), float(alpha), bgp, fgp, core_len, ww1, ww2, ww3,
+                                 int(bool(adjust_prolines)), info.ctypes.data)
+    if rc != 0:
+        raise PlaacError(rc, "plaac_params_init failed")
+    return (P, info) if return_info else P
+
+
+def encode(seq, strip_stop=True) -> np.ndarray:
+    """string2aa (plaac.java:1764) after the terminal '*' strip of :758, via plaac_encode_host."""
+    if isinstance(seq, str):
+        seq = seq.encode("latin-1")
+    if strip_stop and seq[-1:] == b"*":
+        seq = seq[:-1]
+    src = np.frombuffer(seq, dtype=np.uint8)
+    out = np.empty(len(src), dtype=np.uint8)
+    if len(src):
+        lib().plaac_encode_host(src.ctypes.data, len(src), out.ctypes.data)
+    return out
+
+
+def pack(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    codes = np.concatenate(seqs).astype(np.uint8) if len(seqs) and offsets[-1] > 0 else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(codes), offsets
+
+
+class Scorer:
+    """One ctx on one GPU (plaac_create .. plaac_destroy)."""
+
+    def __init__(self, params: Params | None = None, device: int = 0):
+        self.params = params if params is not None else default_params()
+        self._h = C.c_void_p()
+        rc = lib().plaac_create(C.byref(self._h), device, C.byref(self.params))
+        if rc != 0:
+            raise PlaacError(rc, lib().plaac_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().plaac_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PlaacError(rc, lib().plaac_last_error(self._h).decode())
+
+    # ---- host buffers (numpy, or pinned torch tensors through .data_ptr()) ----
+    def score(self, codes: np.ndarray, offsets: np.ndarray, per_residue: bool = False, summaries: bool = True):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        nprot = len(offsets) - 1
+        out = np.zeros(nprot, dtype=SUMMARY_DTYPE) if summaries else None
+        res = None
+        ro = None
+        if per_residue:
+            ntot = int(offsets[-1] - offsets[0])
+            res = {n: np.zeros(ntot, dtype=np.uint8) for n in RESIDUE_U8}
+            res.update({n: np.zeros(ntot, dtype=np.float64) for n in RESIDUE_F64})
+            ro = C.byref(ResidueOut(**{n: a.ctypes.data for n, a in res.items()}))
+        self._check(lib().plaac_score(self._h, codes.ctypes.data, offsets.ctypes.data, nprot,
+                                      out.ctypes.data if out is not None else None, ro))
+        if per_residue:
+            return out, res
+        return out
+
+    def score_ptr(self, codes_ptr: int, offsets_ptr: int, nprot: int, summaries_ptr: int):
+        """Raw host pointers (e.g. pinned torch tensors)."""
+        self._check(lib().plaac_score(self._h, codes_ptr, offsets_ptr, nprot, summaries_ptr, None))
+
+    # ---- device buffers ----
+    def score_device(self, d_codes_ptr: int, d_offsets_ptr: int, nprot: int, ntotal: int, d_summaries_ptr: int,
+                     residue_ptrs: dict | None = None, sync: bool = True):
+        ro = None
+        if residue_ptrs is not None:
+            ro = C.byref(ResidueOut(**residue_ptrs))
+        self._check(lib().plaac_score_device(self._h, d_codes_ptr, d_offsets_ptr, nprot, ntotal, d_summaries_ptr, ro))
+        if sync:
+            self.sync()
+
+    def set_chunk(self, max_residues=0, max_proteins=0):
+        self._check(lib().plaac_set_chunk(self._h, max_residues, max_proteins))
+
+    def sync(self):
+        self._check(lib().plaac_sync(self._h))
+
+    def stream(self) -> int:
+        return int(lib().plaac_stream(self._h) or 0)
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(lib().plaac_get_stats(self._h, C.byref(s)))
+        return s

@@ -1,0 +1,42 @@
+// Shared device-side definitions for libplaac_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/plaac_cuda.h"
+
+namespace plaac {
+
+constexpr int kPad = 22;          // pad code: every table entry is 0 for it
+constexpr int kPapaMaskBit = 32;  // ext code bit: "proline not scored by PAPA" (plaac.java:2652-2655)
+constexpr int kTabN = 64;         // per-code tables are indexed by ext code 0..63
+constexpr int kChunk = 16;        // residues per 16-byte lane slot
+constexpr int kHistBins = 32768;  // exact-length bins; longer proteins share bin 0
+
+// Scalars of plaac_params the kernels read straight from the constant bank (kernel argument).
+struct KScalars {
+    int32_t core_len, w, h_fi, h_papa, mw_window, adjust_prolines;
+    uint32_t charge_plus, charge_minus, qn_mask;
+    double lt00, lt01, lt10, lt11, li0, li1, lf0, lf1;
+    double cc0, cc1, cc2, big_neg, ln2;
+};
+
+// Per-code tables + LUT as uploaded once per ctx (global memory; kernels stage them in shared memory).
+struct DeviceTables {
+    double le0[kTabN], le1[kTabN], lebg[kTabN], llr[kTabN], hyd[kTabN], pap[kTabN];
+    double lut[PLAAC_LUT_LEN + 3];
+};
+
+// Work description of one device batch after bucketing.
+struct BatchView {
+    const uint4* stream;      // [slot][lane] ext codes, 16 per slot; slot = chunk_base[b] + j
+    uint32_t* tbw;            // same indexing, one word per slot: traceback bits, later Viterbi bits
+    const int32_t* order;     // sorted rank -> protein index (descending length)
+    const int64_t* offsets;   // nprot+1
+    const int64_t* chunk_base;  // nbuckets+1, in slots-of-32-lanes
+    int64_t nprot;
+    int64_t nbuckets;
+    int64_t off_base;         // offsets[] are relative to this residue index
+};
+
+}  // namespace plaac

@@ -1,0 +1,538 @@
+// libplaac_cuda.so -- C ABI (include/plaac_cuda.h) over the sm_100a kernels.
+// No CPU fallback: every entry point either runs the CUDA path or returns an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "prep.cuh"
+#include "residue_kernel.cuh"
+#include "summary_kernel.cuh"
+
+using namespace plaac;
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// One set of device work buffers; plaac_score() uses two of them to overlap copies with compute.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, errflag;
+    DevBuf codes, offsets, summaries;  // staging for the host-buffer API
+    DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
+    int64_t* h_total = nullptr;        // pinned
+    int* h_err = nullptr;              // pinned
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    bool timing_valid = false;
+};
+
+}  // namespace
+
+struct plaac_ctx {
+    int device = 0;
+    plaac_params params;
+    KScalars ks;
+    DeviceTables* d_tabs = nullptr;
+    Slot slot[2];
+    int nwarps = 0, ring_words = 0;
+    size_t smem_bytes = 0;
+    int sm_count = 0;
+    plaac_stats stats;
+    int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
+    std::string err;
+    int last_slot = 0;
+};
+
+namespace {
+
+int fail(plaac_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_last_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? PLAAC_E_NOMEM : PLAAC_E_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                          \
+    } while (0)
+
+int ensure(plaac_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return PLAAC_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;  // a little slack so similar batches do not realloc
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes + 256);
+        want = bytes + 256;
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, PLAAC_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    b.cap = want;
+    return PLAAC_OK;
+}
+
+void release(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int next_pow2(int x)
+{
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+int setup_scalars(plaac_ctx* ctx)
+{
+    const plaac_params& P = ctx->params;
+    KScalars& k = ctx->ks;
+    if (P.core_len < 1) return fail(ctx, PLAAC_E_INVALID, "core_len must be >= 1 (got %d)", P.core_len);
+    if (P.ww1 < 1 || P.ww2 < 1 || P.ww3 < 1) return fail(ctx, PLAAC_E_INVALID, "window sizes must be >= 1");
+    if (P.mw_window < 1) return fail(ctx, PLAAC_E_INVALID, "mw_window must be >= 1");
+    if (P.ww1 / 2 != P.ww2 / 2 || P.ww1 / 2 != P.ww3 / 2 || (P.ww1 - 1) / 2 != (P.ww2 - 1) / 2)
+        return fail(ctx, PLAAC_E_UNSUPPORTED,
+                    "ww1=%d ww2=%d ww3=%d: the streaming kernels need equal half-widths (ww/2 and (ww-1)/2)", P.ww1,
+                    P.ww2, P.ww3);
+    k.core_len = P.core_len;
+    k.w = P.ww1 / 2;
+    k.h_fi = (P.ww1 - 1) / 2;
+    k.h_papa = (P.ww2 - 1) / 2;
+    k.mw_window = P.mw_window;
+    k.adjust_prolines = P.adjust_prolines ? 1 : 0;
+    k.charge_plus = k.charge_minus = 0;
+    for (int i = 0; i < PLAAC_NAA; i++) {
+        if (P.charge[i] == 1.0)
+            k.charge_plus |= 1u << i;
+        else if (P.charge[i] == -1.0)
+            k.charge_minus |= 1u << i;
+        else if (P.charge[i] != 0.0)
+            return fail(ctx, PLAAC_E_UNSUPPORTED, "charge[%d]=%g: only -1, 0, +1 are supported", i, P.charge[i]);
+    }
+    k.qn_mask = (1u << 12) | (1u << 14);  // N, Q  (qnmask, plaac.java:733)
+    k.lt00 = P.lt[0][0];
+    k.lt01 = P.lt[0][1];
+    k.lt10 = P.lt[1][0];
+    k.lt11 = P.lt[1][1];
+    k.li0 = P.li[0];
+    k.li1 = P.li[1];
+    k.lf0 = P.lf[0];
+    k.lf1 = P.lf[1];
+    k.cc0 = P.fi_cc[0];
+    k.cc1 = P.fi_cc[1];
+    k.cc2 = P.fi_cc[2];
+    k.big_neg = P.big_neg;
+    k.ln2 = P.ln2;
+
+    const int maxoff = std::max(std::max(4 * k.w + 2, k.core_len), k.mw_window);
+    ctx->ring_words = next_pow2((maxoff + 16 + 3) / 4 + 1);
+    const size_t per_warp = (size_t)ctx->ring_words * 32 * sizeof(uint32_t);
+    const size_t fixed = sizeof(SummarySmem);
+    const size_t limit = 227 * 1024;
+    if (fixed + per_warp > limit)
+        return fail(ctx, PLAAC_E_UNSUPPORTED, "core_len/window look-back of %d residues does not fit the shared-memory ring",
+                    maxoff);
+    ctx->nwarps = (int)std::min<size_t>(12, (limit - fixed) / per_warp);
+    ctx->smem_bytes = fixed + per_warp * ctx->nwarps;
+    return PLAAC_OK;
+}
+
+void fill_tables(const plaac_params& P, DeviceTables& T)
+{
+    memset(&T, 0, sizeof(T));
+    for (int e = 0; e < kTabN; e++) {
+        const int c = e & 31;
+        if (c >= PLAAC_NAA) continue;  // pad and unused codes: all zero
+        T.le0[e] = P.le[0][c];
+        T.le1[e] = P.le[1][c];
+        T.lebg[e] = P.le0[c];
+        T.llr[e] = P.llr[c];
+        T.hyd[e] = P.hydro2[c];
+        T.pap[e] = (e & kPapaMaskBit) ? 0.0 : P.papa_lod[c];
+    }
+    for (int i = 0; i < PLAAC_LUT_LEN; i++) T.lut[i] = P.loglut[i];
+}
+
+int slot_init(plaac_ctx* ctx, Slot& s)
+{
+    CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(ctx, cudaMallocHost((void**)&s.h_total, sizeof(int64_t)));
+    CU(ctx, cudaMallocHost((void**)&s.h_err, sizeof(int)));
+    CU(ctx, cudaEventCreate(&s.ev_a));
+    CU(ctx, cudaEventCreate(&s.ev_b));
+    CU(ctx, cudaEventCreate(&s.ev_c));
+    CU(ctx, cudaEventCreate(&s.ev_d));
+    int rc = ensure(ctx, s.errflag, sizeof(int));
+    if (rc) return rc;
+    CU(ctx, cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream));
+    return PLAAC_OK;
+}
+
+void slot_free(Slot& s)
+{
+    for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.errflag,
+                      &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64})
+        release(*b);
+    if (s.h_total) cudaFreeHost(s.h_total);
+    if (s.h_err) cudaFreeHost(s.h_err);
+    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d})
+        if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+// Enqueue the whole device pipeline for one batch on slot s.  d_offsets are absolute; off_base is
+// subtracted to index d_codes.  Contains ONE stream synchronisation (the padded stream size).
+int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_offsets, int64_t off_base,
+              int64_t nprot, int64_t ntotal, plaac_summary* d_summaries, const plaac_residue_out* d_res,
+              int64_t res_base)
+{
+    if (nprot == 0) return PLAAC_OK;
+    if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins in one device batch");
+    (void)ntotal;
+    cudaStream_t st = s.stream;
+    const int64_t nbuckets = (nprot + 31) / 32;
+    int rc;
+    if ((rc = ensure(ctx, s.hist, sizeof(int32_t) * (kHistBins + 1)))) return rc;
+    if ((rc = ensure(ctx, s.cursor, sizeof(int64_t) * (kHistBins + 2)))) return rc;
+    if ((rc = ensure(ctx, s.order, sizeof(int32_t) * nprot))) return rc;
+    if ((rc = ensure(ctx, s.nchunks, sizeof(int32_t) * nbuckets))) return rc;
+    if ((rc = ensure(ctx, s.chunk_base, sizeof(int64_t) * (nbuckets + 1)))) return rc;
+
+    CU(ctx, cudaEventRecord(s.ev_a, st));
+    CU(ctx, cudaMemsetAsync(s.hist.p, 0, sizeof(int32_t) * (kHistBins + 1), st));
+    const int tb = 256;
+    const unsigned gp = (unsigned)((nprot + tb - 1) / tb);
+    k_len_hist<<<gp, tb, 0, st>>>(d_offsets, nprot, (int32_t*)s.hist.p);
+    k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.hist.p, (int64_t*)s.cursor.p, kHistBins + 1);
+    k_scatter<<<gp, tb, 0, st>>>(d_offsets, nprot, (int64_t*)s.cursor.p, (int32_t*)s.order.p);
+    const unsigned gb = (unsigned)((nbuckets * 32 + tb - 1) / tb);
+    k_bucket_chunks<<<gb, tb, 0, st>>>(d_offsets, (const int32_t*)s.order.p, nprot, nbuckets, (int32_t*)s.nchunks.p);
+    k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.nchunks.p, (int64_t*)s.chunk_base.p, nbuckets);
+    ctx->stats.kernel_launches += 5;
+    CU(ctx, cudaMemcpyAsync(s.h_total, (int64_t*)s.chunk_base.p + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    const int64_t slots = *s.h_total;
+    ctx->stats.last_padded_slots = slots * 32;
+    if ((rc = ensure(ctx, s.stream_buf, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint4)))) return rc;
+    if ((rc = ensure(ctx, s.tbw, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint32_t)))) return rc;
+
+    const int pack_blocks = (int)std::min<int64_t>((nbuckets + 7) / 8, (int64_t)ctx->sm_count * 8);
+    k_pack<<<pack_blocks, 256, 0, st>>>(d_codes, d_offsets, off_base, (const int32_t*)s.order.p,
+                                        (const int64_t*)s.chunk_base.p, nprot, nbuckets, ctx->ks.adjust_prolines,
+                                        (uint4*)s.stream_buf.p, (int*)s.errflag.p);
+    ctx->stats.kernel_launches += 1;
+
+    BatchView bv;
+    bv.stream = (const uint4*)s.stream_buf.p;
+    bv.tbw = (uint32_t*)s.tbw.p;
+    bv.order = (const int32_t*)s.order.p;
+    bv.offsets = d_offsets;
+    bv.chunk_base = (const int64_t*)s.chunk_base.p;
+    bv.nprot = nprot;
+    bv.nbuckets = nbuckets;
+    bv.off_base = off_base;
+
+    CU(ctx, cudaEventRecord(s.ev_b, st));
+    if (d_summaries) {
+        const unsigned grid = (unsigned)((nbuckets + ctx->nwarps - 1) / ctx->nwarps);
+        k_score_summary<<<grid, ctx->nwarps * 32, ctx->smem_bytes, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries,
+                                                                         ctx->ring_words);
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.score_launches += 1;
+    }
+    CU(ctx, cudaEventRecord(s.ev_c, st));
+    if (d_res) {
+        rc = launch_residue(ctx->ks, ctx->d_tabs, bv, *d_res, res_base, ctx->sm_count, st, &ctx->stats.kernel_launches);
+        if (rc != PLAAC_OK) return fail(ctx, rc, "per-residue kernels failed to launch");
+    }
+    CU(ctx, cudaEventRecord(s.ev_d, st));
+    CU(ctx, cudaGetLastError());
+    s.timing_valid = true;
+    return PLAAC_OK;
+}
+
+int finish_slot(plaac_ctx* ctx, Slot& s)
+{
+    CU(ctx, cudaMemcpyAsync(s.h_err, s.errflag.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CU(ctx, cudaStreamSynchronize(s.stream));
+    if (*s.h_err) {
+        cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream);
+        return fail(ctx, PLAAC_E_INVALID, "input contains residue codes > 21 (treated as X)");
+    }
+    return PLAAC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plaac_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
+{
+    if (!out || !params) return fail(nullptr, PLAAC_E_INVALID, "plaac_create: NULL argument");
+    *out = nullptr;
+    int ndev = plaac_device_count();
+    if (ndev <= 0) return fail(nullptr, PLAAC_E_NODEVICE, "no CUDA device: %s", g_last_error.c_str());
+    if (device < 0 || device >= ndev) return fail(nullptr, PLAAC_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, PLAAC_E_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, PLAAC_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    plaac_ctx* ctx = new plaac_ctx();
+    ctx->device = device;
+    ctx->params = *params;
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    int rc = setup_scalars(ctx);
+    if (rc != PLAAC_OK) {
+        g_last_error = ctx->err;
+        delete ctx;
+        return rc;
+    }
+    auto bail = [&](int code) {
+        g_last_error = ctx->err;
+        plaac_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) {
+        ctx->err = "cudaSetDevice failed";
+        return bail(PLAAC_E_CUDA);
+    }
+    DeviceTables* h = new DeviceTables();
+    fill_tables(ctx->params, *h);
+    cudaError_t e = cudaMalloc((void**)&ctx->d_tabs, sizeof(DeviceTables));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tabs, h, sizeof(DeviceTables), cudaMemcpyHostToDevice);
+    delete h;
+    if (e != cudaSuccess) {
+        ctx->err = std::string("table upload: ") + cudaGetErrorString(e);
+        return bail(PLAAC_E_CUDA);
+    }
+    e = cudaFuncSetAttribute(k_score_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaFuncSetAttribute(k_score_summary): ") + cudaGetErrorString(e);
+        return bail(PLAAC_E_CUDA);
+    }
+    rc = residue_setup(ctx->ks, ctx->ring_words);
+    if (rc != PLAAC_OK) {
+        ctx->err = "cudaFuncSetAttribute(per-residue kernels) failed";
+        return bail(rc);
+    }
+    for (int i = 0; i < 2; i++) {
+        rc = slot_init(ctx, ctx->slot[i]);
+        if (rc != PLAAC_OK) return bail(rc);
+    }
+    *out = ctx;
+    return PLAAC_OK;
+}
+
+void plaac_destroy(plaac_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < 2; i++) slot_free(ctx->slot[i]);
+    if (ctx->d_tabs) cudaFree(ctx->d_tabs);
+    delete ctx;
+}
+
+const char* plaac_last_error(const plaac_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+int plaac_score_device(plaac_ctx* ctx, const uint8_t* d_codes, const int64_t* d_offsets, int64_t nprot, int64_t ntotal,
+                       plaac_summary* d_summaries, const plaac_residue_out* d_per_res)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_device: NULL ctx");
+    if (nprot < 0 || ntotal < 0) return fail(ctx, PLAAC_E_INVALID, "negative size");
+    if (nprot == 0) return PLAAC_OK;
+    if (!d_offsets || (!d_codes && ntotal > 0)) return fail(ctx, PLAAC_E_INVALID, "NULL codes/offsets");
+    if (!d_summaries && !d_per_res) return fail(ctx, PLAAC_E_INVALID, "no output requested");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->last_slot = 0;
+    return run_batch(ctx, ctx->slot[0], d_codes, d_offsets, 0, nprot, ntotal, d_summaries, d_per_res, 0);
+}
+
+int plaac_sync(plaac_ctx* ctx)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_sync: NULL ctx");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    int rc = finish_slot(ctx, s);
+    if (s.timing_valid) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.ev_a, s.ev_d) == cudaSuccess) ctx->stats.last_total_ms = ms;
+        if (cudaEventElapsedTime(&ms, s.ev_b, s.ev_c) == cudaSuccess) ctx->stats.last_score_ms = ms;
+    }
+    return rc;
+}
+
+void* plaac_stream(plaac_ctx* ctx)
+{
+    return ctx ? (void*)ctx->slot[0].stream : nullptr;
+}
+
+int plaac_set_chunk(plaac_ctx* ctx, int64_t max_residues, int64_t max_proteins)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_chunk: NULL ctx");
+    if (max_residues < 0 || max_proteins < 0) return fail(ctx, PLAAC_E_INVALID, "negative chunk size");
+    if (max_residues > 0) ctx->chunk_res = ctx->chunk_res_pr = max_residues;
+    if (max_proteins > 0) ctx->chunk_prot = std::min<int64_t>(max_proteins, 0x7fffffff);
+    return PLAAC_OK;
+}
+
+int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
+{
+    if (!ctx || !out) return fail(ctx, PLAAC_E_INVALID, "plaac_get_stats: NULL argument");
+    *out = ctx->stats;
+    return PLAAC_OK;
+}
+
+void plaac_encode_host(const char* chars, int64_t n, uint8_t* codes)
+{
+    // aatoint, plaac.java:1508-1534: upper or lower case, '*' -> 21, everything else (incl. X) -> 0
+    static const char names[] = "XACDEFGHIKLMNPQRSTVWY";
+    uint8_t lut[256];
+    memset(lut, 0, sizeof(lut));
+    for (int i = 1; i <= 20; i++) {
+        lut[(unsigned char)names[i]] = (uint8_t)i;
+        lut[(unsigned char)(names[i] + 32)] = (uint8_t)i;
+    }
+    lut[(unsigned char)'*'] = 21;
+    for (int64_t i = 0; i < n; i++) codes[i] = lut[(unsigned char)chars[i]];
+}
+
+int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int64_t nprot, plaac_summary* summaries,
+                const plaac_residue_out* per_res)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score: NULL ctx");
+    if (nprot < 0) return fail(ctx, PLAAC_E_INVALID, "negative nprot");
+    if (nprot == 0) return PLAAC_OK;
+    if (!offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
+    if (!summaries && !per_res) return fail(ctx, PLAAC_E_INVALID, "no output requested");
+    for (int64_t i = 0; i < nprot; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, PLAAC_E_INVALID, "offsets not monotone at protein %lld", (long long)i);
+        if (offsets[i + 1] - offsets[i] > 0x7fffff00LL) return fail(ctx, PLAAC_E_INVALID, "protein %lld longer than 2^31", (long long)i);
+    }
+    if (!codes && offsets[nprot] > offsets[0]) return fail(ctx, PLAAC_E_INVALID, "NULL codes");
+    CU(ctx, cudaSetDevice(ctx->device));
+
+    // Chunking: bounded device footprint, two slots so chunk i+1's H2D overlaps chunk i's kernels/D2H.
+    const int64_t max_res = per_res ? ctx->chunk_res_pr : ctx->chunk_res;
+    const int64_t max_prot = ctx->chunk_prot;
+    int64_t start = 0;
+    int which = 0;
+    bool pending[2] = {false, false};
+    int rc = PLAAC_OK;
+    auto drain = [&](int i) -> int {
+        if (!pending[i]) return PLAAC_OK;
+        pending[i] = false;
+        return finish_slot(ctx, ctx->slot[i]);
+    };
+    while (start < nprot && rc == PLAAC_OK) {
+        int64_t end = start;
+        const int64_t base = offsets[start];
+        while (end < nprot && end - start < max_prot && (end == start || offsets[end + 1] - base <= max_res)) end++;
+        const int64_t np = end - start;
+        const int64_t nres = offsets[end] - base;
+        Slot& s = ctx->slot[which];
+        if ((rc = drain(which))) break;
+        if ((rc = ensure(ctx, s.codes, (size_t)nres + 64))) break;
+        if ((rc = ensure(ctx, s.offsets, sizeof(int64_t) * (np + 1)))) break;
+        if (summaries && (rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * np))) break;
+        plaac_residue_out dres;
+        if (per_res) {
+            if ((rc = ensure(ctx, s.res_u8, (size_t)2 * (nres + 16)))) break;
+            if ((rc = ensure(ctx, s.res_f64, sizeof(double) * 10 * (size_t)(nres + 2)))) break;
+            uint8_t* u = (uint8_t*)s.res_u8.p;
+            double* d = (double*)s.res_f64.p;
+            const size_t N = (size_t)nres;
+            dres.vit = u;
+            dres.map = u + N;
+            dres.charge = d;
+            dres.hydro = d + N;
+            dres.fi = d + 2 * N;
+            dres.plaac = d + 3 * N;
+            dres.papa = d + 4 * N;
+            dres.fix2 = d + 5 * N;
+            dres.plaacx2 = d + 6 * N;
+            dres.papax2 = d + 7 * N;
+            dres.post_bg = d + 8 * N;
+            dres.post_prd = d + 9 * N;
+        }
+        if (nres > 0) CU(ctx, cudaMemcpyAsync(s.codes.p, codes + base, (size_t)nres, cudaMemcpyHostToDevice, s.stream));
+        CU(ctx, cudaMemcpyAsync(s.offsets.p, offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
+        rc = run_batch(ctx, s, (const uint8_t*)s.codes.p, (const int64_t*)s.offsets.p, base, np, nres,
+                       summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base);
+        if (rc) break;
+        if (summaries)
+            CU(ctx, cudaMemcpyAsync(summaries + start, s.summaries.p, sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));
+        if (per_res && nres > 0) {
+            const int64_t o = base - offsets[0];
+            const size_t N = (size_t)nres;
+            uint8_t* hu[2] = {per_res->vit, per_res->map};
+            const uint8_t* du[2] = {dres.vit, dres.map};
+            for (int k = 0; k < 2; k++)
+                if (hu[k]) CU(ctx, cudaMemcpyAsync(hu[k] + o, du[k], N, cudaMemcpyDeviceToHost, s.stream));
+            double* hd[10] = {per_res->charge, per_res->hydro,   per_res->fi,     per_res->plaac,   per_res->papa,
+                              per_res->fix2,   per_res->plaacx2, per_res->papax2, per_res->post_bg, per_res->post_prd};
+            const double* dd[10] = {dres.charge, dres.hydro,   dres.fi,     dres.plaac,   dres.papa,
+                                    dres.fix2,   dres.plaacx2, dres.papax2, dres.post_bg, dres.post_prd};
+            for (int k = 0; k < 10; k++)
+                if (hd[k]) CU(ctx, cudaMemcpyAsync(hd[k] + o, dd[k], N * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        }
+        pending[which] = true;
+        which ^= 1;
+        start = end;
+    }
+    int rc2 = drain(0);
+    int rc3 = drain(1);
+    if (rc == PLAAC_OK) rc = rc2 != PLAAC_OK ? rc2 : rc3;
+    return rc;
+}
+
+}  // extern "C"

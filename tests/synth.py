@@ -54,3 +54,25 @@ def edge_cases(seed=7):
     offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
     return np.concatenate(seqs).astype(np.uint8), offsets
+
+# web/bg_freqs/bg_freqs_HUMAN.txt of the reference (UniProt human proteome residue counts; data, X..*)
+BG_HUMAN_COUNTS = np.array([6721, 2428201, 765477, 1681675, 2518353, 1243278, 2277183, 901810, 1518152, 2016587,
+                            3445627, 764646, 1257376, 2211452, 1685966, 1984919, 2928531, 1884442, 2097434, 430493,
+                            910830, 0], dtype=np.float64)
+
+
+def long_proteins(seed=1005, lengths=(35000, 100000)):
+    """Config 5: titin-length and 100k-aa proteins, background composition with 150-aa PrD-like
+    segments at 10 %, 50 % and 86 % of the length (the late one exercises the -1e6 mask pollution)."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for n in lengths:
+        s = rng.choice(22, size=n, p=BG_SCER / BG_SCER.sum()).astype(np.uint8)
+        for frac in (0.10, 0.50, 0.86):
+            st = int(n * frac)
+            s[st:st + 150] = rng.choice(22, size=150, p=PRD_28 / PRD_28.sum())
+        seqs.append(s)
+    lens = np.array([len(x) for x in seqs], dtype=np.int64)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return np.concatenate(seqs), offsets

@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Integers bit-exact, doubles within 1e-9 relative (tests/parity.py states the exact rule)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import plaac_b200
+from oracle import orc
+from tests import parity, synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NT = max(1, min(32, os.cpu_count() or 1))
+
+
+@pytest.fixture(scope="module")
+def scorer():
+    s = plaac_b200.Scorer(device=0)
+    yield s
+    s.close()
+
+
+def _check(got, ref, what=""):
+    bad = parity.compare_summaries(got, ref, orc.INT_FIELDS, orc.DBL_FIELDS)
+    assert not bad, what + "\n" + "\n".join(bad[:40])
+    # columns evaluated in reference operation order must be (nearly) bit-exact, far inside the 1e-9 bar
+    for f in parity.REF_ORDER:
+        assert parity.max_rel(got, ref, f) <= 1e-13, (what, f, parity.max_rel(got, ref, f))
+
+
+def test_classic_prions_against_golden_fixture(scorer, golden):
+    seqs = [plaac_b200.encode(p["seq"]) for p in golden["proteins"]]
+    codes, offs = plaac_b200.pack(seqs)
+    got = scorer.score(codes, offs)
+    for i, prot in enumerate(golden["proteins"]):
+        for k, v in prot["summary"].items():
+            if isinstance(v, int):
+                assert int(got[i][k]) == v, (prot["name"], k)
+            elif math.isnan(v):
+                assert math.isnan(got[i][k])
+            else:
+                assert parity.close(got[i][k], v, parity.SCALE[k]), (prot["name"], k, got[i][k], v)
+    _check(got, orc.score_batch(orc.make_params(), codes, offs), "classic prions")
+
+
+def test_encode_matches_reference_alphabet():
+    s = "XACDEFGHIKLMNPQRSTVWY*acdefghiklmnpqrstvwyxBJOUZ -1\t"
+    assert list(plaac_b200.encode(s, strip_stop=False)) == list(orc.encode(s, strip_stop=False))
+    assert list(plaac_b200.encode("MKV*")) == [11, 9, 18]
+
+
+def test_edge_cases(scorer):
+    codes, offs = synth.edge_cases()
+    got = scorer.score(codes, offs)
+    ref = orc.score_batch(orc.make_params(), codes, offs)
+    _check(got, ref, "edge cases")
+    assert (got["prot_len"] == np.diff(offs)).all()
+
+
+def test_empty_and_zero_length_inputs(scorer):
+    assert len(scorer.score(np.zeros(0, np.uint8), np.zeros(1, np.int64))) == 0
+    codes, offs = plaac_b200.pack([np.array([12, 14, 12], np.uint8), np.zeros(0, np.uint8), np.array([1], np.uint8)])
+    got = scorer.score(codes, offs)
+    ref = orc.score_batch(orc.make_params(), codes, offs)
+    assert got["prot_len"].tolist() == [3, 0, 1]
+    _check(got[[0, 2]], ref[[0, 2]], "around an empty record")
+
+
+def test_yeast_sized_proteome(scorer):
+    """Config 2 size (about 6k proteins / 3M residues), default parameters."""
+    codes, offs = synth.proteome(6000, seed=1001)
+    got = scorer.score(codes, offs)
+    ref = orc.score_batch(orc.make_params(), codes, offs, nthreads=NT)
+    _check(got, ref, "yeast-sized")
+    assert (ref["core_start"] >= 0).sum() > 100  # the injected Q/N-rich segments are found
+
+
+def test_human_sized_blended_background(scorer):
+    """Config 3: human-like lengths, alpha = 0.5 blend of yeast and human backgrounds."""
+    kw = dict(alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS)
+    bg = synth.BG_HUMAN_COUNTS.copy()
+    bg[0] = 0
+    codes, offs = synth.proteome(20000, seed=1002, median=415.0, sigma=0.75, bg=bg)
+    sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    got = sc.score(codes, offs)
+    sc.close()
+    ref = orc.score_batch(orc.make_params(**kw), codes, offs, nthreads=NT)
+    _check(got, ref, "human-sized")
+
+
+def test_long_sequences(scorer):
+    """Config 5: 35k and 100k residues."""
+    codes, offs = synth.long_proteins()
+    got = scorer.score(codes, offs)
+    ref = orc.score_batch(orc.make_params(), codes, offs, nthreads=2)
+    _check(got, ref, "long sequences")
+    assert (got["core_start"] >= 0).all()
+
+
+@pytest.mark.parametrize("kw", [dict(core_len=30), dict(core_len=100, ww1=21, ww2=21), dict(ww1=40, ww2=40),
+                                dict(adjust_prolines=False), dict(core_len=7, ww1=5, ww2=5), dict(ww1=1, ww2=1)])
+def test_other_parameters(kw):
+    codes, offs = synth.proteome(1500, seed=11, median=200.0)
+    e, eo = synth.edge_cases()
+    codes, offs = np.concatenate([codes, e]), np.concatenate([offs, eo[1:] + offs[-1]])
+    sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    got = sc.score(codes, offs)
+    sc.close()
+    ref = orc.score_batch(orc.make_params(**kw), codes, offs, nthreads=NT)
+    _check(got, ref, str(kw))
+
+
+def test_real_yeast_proteome_if_staged(scorer):
+    """cli/example/Scer.fasta of the reference (staged into oracle/_ref by build(); not in git)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "Scer.fasta")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/Scer.fasta not staged")
+    seqs, cur = [], None
+    for line in open(path):
+        line = line.rstrip("\r\n")
+        if line.startswith(">"):
+            cur = []
+            seqs.append(cur)
+        elif not line:
+            cur = None
+        elif cur is not None:
+            cur.append(line)
+    seqs = [plaac_b200.encode("".join(s)) for s in seqs]
+    codes, offs = plaac_b200.pack(seqs)
+    got = scorer.score(codes, offs)
+    ref = orc.score_batch(orc.make_params(), codes, offs, nthreads=NT)
+    _check(got, ref, "Scer.fasta")
+    assert len(seqs) > 5000
+
+
+def test_chunked_host_path_and_permutation_invariance(scorer):
+    """Results are per-protein: independent of batch composition, order and chunking."""
+    codes, offs = synth.proteome(3000, seed=5, median=300.0)
+    full = scorer.score(codes, offs)
+    sc = plaac_b200.Scorer()
+    sc.set_chunk(max_residues=50_000, max_proteins=257)
+    chunked = sc.score(codes, offs)
+    sc.close()
+    assert full.tobytes() == chunked.tobytes()
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(offs) - 1)
+    pc, po = plaac_b200.pack([codes[offs[i]:offs[i + 1]] for i in perm])
+    shuffled = scorer.score(pc, po)
+    assert shuffled.tobytes() == full[perm].tobytes()
+
+
+def test_invalid_inputs_are_reported(scorer):
+    with pytest.raises(plaac_b200.PlaacError) as e:
+        scorer.score(np.array([1, 2, 40, 3], np.uint8), np.array([0, 4], np.int64))
+    assert e.value.code == -1
+    with pytest.raises(plaac_b200.PlaacError) as e:
+        scorer.score(np.array([1, 2, 3], np.uint8), np.array([0, 2, 1], np.int64))
+    assert e.value.code == -1
+    with pytest.raises(plaac_b200.PlaacError) as e:
+        plaac_b200.Scorer(plaac_b200.default_params(ww1=41, ww2=21))
+    assert e.value.code == -3
+    # the ctx still works afterwards
+    got = scorer.score(np.array([1, 2, 3], np.uint8), np.array([0, 3], np.int64))
+    assert got["prot_len"][0] == 3
+
+
+def test_device_resident_api_and_stats(scorer):
+    import torch
+
+    codes, offs = synth.proteome(2000, seed=9)
+    ref = scorer.score(codes, offs)
+    dc = torch.from_numpy(codes).cuda()
+    do = torch.from_numpy(offs).cuda()
+    out = torch.zeros(len(offs) - 1, 160, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    before = scorer.stats().kernel_launches
+    scorer.score_device(dc.data_ptr(), do.data_ptr(), len(offs) - 1, int(offs[-1]), out.data_ptr())
+    got = out.cpu().numpy().view(plaac_b200.SUMMARY_DTYPE).reshape(-1)
+    assert got.tobytes() == ref.tobytes()
+    st = scorer.stats()
+    assert st.kernel_launches - before == 7 and st.last_score_ms > 0 and st.last_total_ms >= st.last_score_ms
