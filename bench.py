@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- residues/s of full PLAAC summary scoring on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N ...             # the reference algorithm on the host CPUs
+
+Workload (config.workload): a UniProt-like synthetic proteome (SURVEY.md section 8(d), config 4:
+100M proteins / ~35G residues over 8 GPUs), 12.5M proteins per GPU, generated ON DEVICE with
+Philox keyed by (seed, global protein index): weak scaling, N=8 is the full config-4 set.
+A "step" scores the rank's whole shard once.
+
+  value  : whole-job residues/s with codes+offsets resident in HBM (device-timed, max over ranks)
+  e2e    : the same through plaac_score() with pinned HOST buffers (H2D of codes/offsets and D2H of the
+           160-byte records inside the timed region)
+  roofline: dominant kernel (k_score_summary), CUDA-event time measured inside the library on its stream
+  cpu_baseline: the CPU oracle (a line-faithful port of plaac.java; no JVM exists here) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "residues/s full PLAAC scoring"
+UNIT = "residues/s"
+F_PER_AA = 67.0      # algorithmic fp64 ops per residue, summary mode
+B_FIXED_PER_PROT = 168.0  # 160 B record + 8 B offset per protein; + 1 B per residue
+SEED = 1004          # config 4
+LN_MEDIAN, SIGMA, MIN_LEN, MAX_LEN = math.log(290.0), 0.62, 16, 40000
+PRD_RATE, X_RATE = 0.05, 1e-4
+
+BG_SCER = [0, 0.0550, 0.0126, 0.0586, 0.0655, 0.0441, 0.0498, 0.0217, 0.0655, 0.0735, 0.0950, 0.0207,
+           0.0615, 0.0438, 0.0396, 0.0444, 0.0899, 0.0592, 0.0556, 0.0104, 0.0337, 0]
+PRD_28 = [0, 0.04865, 0.00219, 0.01638, 0.00783, 0.02537, 0.07603, 0.0181, 0.02018, 0.01641, 0.02639,
+          0.02975, 0.25885, 0.05126, 0.15178, 0.025, 0.10988, 0.03841, 0.01972, 0.00157, 0.05624, 0]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--proteins-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--cpu-sample-proteins", type=int, default=0, help="0 = sized automatically")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(nprot, seed):
+    """Host-side sample of the same distribution (numpy) for the CPU baseline."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    lens = np.clip(np.rint(rng.lognormal(LN_MEDIAN, SIGMA, nprot)), MIN_LEN, MAX_LEN).astype(np.int64)
+    offsets = np.zeros(nprot + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    bg = np.array(BG_SCER) / sum(BG_SCER)
+    codes = rng.choice(22, size=int(offsets[-1]), p=bg).astype(np.uint8)
+    codes[rng.random(len(codes)) < X_RATE] = 0
+    prd = np.array(PRD_28) / sum(PRD_28)
+    for i in np.nonzero(rng.random(nprot) < PRD_RATE)[0]:
+        n = int(lens[i])
+        seg = int(min(n, rng.integers(60, 301)))
+        st = int(rng.integers(0, n - seg + 1))
+        codes[offsets[i] + st: offsets[i] + st + seg] = rng.choice(22, size=seg, p=prd)
+    return codes, offsets
+
+
+def time_oracle(nprot, nthreads, full_jar_work, repeats=1):
+    from oracle import orc
+
+    codes, offsets = cpu_sample(nprot, SEED)
+    P = orc.make_params()
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.score_batch(P, codes, offsets, full_jar_work=full_jar_work, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return int(offsets[-1]), best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm on the box's host cores.  plaac.jar cannot run
+    (no JVM in the image), so this is the oracle port with the jar's dead work switched on, OpenMP over
+    proteins on every host thread.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import orc
+
+    nthreads = orc.max_threads()
+    nprot = args.cpu_sample_proteins or 3000 * nthreads
+    codes, offsets = cpu_sample(nprot, SEED)
+    P = orc.make_params()
+    nres = int(offsets[-1])
+    for _ in range(max(1, min(args.warmup, 1))):
+        orc.score_batch(P, codes, offsets, full_jar_work=1, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.score_batch(P, codes, offsets, full_jar_work=1, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    value = nres * args.steps / dt
+    java = subprocess.run("java -version", shell=True, capture_output=True, text=True)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+                         "sample": f"{nprot} proteins / {nres} residues of the same synthetic distribution per step; "
+                                   "oracle port of plaac.java incl. the jar's dead posterior passes; "
+                                   f"JVM {'present' if java.returncode == 0 else 'absent'} (plaac.jar not runnable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "config4 UniProt-like synthetic proteome shard (lognormal lengths median 290 sigma 0.62, "
+                        "yeast background, 5% proteins with injected Q/N-rich segment, X 1e-4), summary mode -c 60 -a 1",
+            "proteins_per_gpu": args.proteins_per_gpu, "proteins_total": args.proteins_per_gpu * world,
+            "parallelism": f"shard{world} (independent proteins, no collective)",
+            "l2": "inputs larger than L2 (shard >> 126 MB); no flush needed"}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import plaac_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = plaac_b200.lib()
+    nprot = args.proteins_per_gpu
+    first = rank * nprot
+
+    # ---- synthetic shard, generated on device -------------------------------------------------
+    lens = torch.empty(nprot, dtype=torch.int64, device=dev)
+    rc = L.plaac_bench_synth_lengths(None, SEED, first, nprot, LN_MEDIAN, SIGMA, MIN_LEN, MAX_LEN, lens.data_ptr())
+    assert rc == 0
+    offsets = torch.zeros(nprot + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=offsets[1:])
+    ntotal = int(offsets[-1].item())
+    del lens
+    codes = torch.empty(ntotal + 64, dtype=torch.uint8, device=dev)
+    bg = np.array(BG_SCER, dtype=np.float64)
+    prd = np.array(PRD_28, dtype=np.float64)
+    rc = L.plaac_bench_synth_residues(None, SEED, first, nprot, offsets.data_ptr(), bg.ctypes.data, prd.ctypes.data,
+                                      PRD_RATE, X_RATE, codes.data_ptr())
+    assert rc == 0
+    summaries = torch.empty(nprot * 160, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    scorer = plaac_b200.Scorer(device=local_rank)
+    stream = torch.cuda.ExternalStream(scorer.stream(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        scorer.score_device(codes.data_ptr(), offsets.data_ptr(), nprot, ntotal, summaries.data_ptr(), sync=True)
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = scorer.stats().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    score_ms = []
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        score_ms.append(scorer.stats().last_score_ms)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = scorer.stats().kernel_launches - l0
+    dev_ms = ev0.elapsed_time(ev1)
+    t_rank = torch.tensor([dev_ms / 1e3, float(ntotal), wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t_rank.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t_rank.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_max, res_total = float(tmax[0]), float(tsum[1])
+    else:
+        t_max, res_total = float(t_rank[0]), float(ntotal)
+    value = res_total * args.steps / t_max
+
+    # ---- roofline of the dominant kernel (rank-local) ---------------------------------------------
+    kern_ms = sum(score_ms) / len(score_ms)
+    fp64_peak = C_double()
+    L.plaac_bench_fp64_peak(local_rank, 0, fp64_peak.ref(), None)
+    peak_ops = fp64_peak.value
+    fp64_fma = C_double()
+    L.plaac_bench_fp64_peak(local_rank, 1, fp64_fma.ref(), None)
+    achieved_ops = F_PER_AA * ntotal / (kern_ms * 1e-3)
+    alg_bytes = ntotal + B_FIXED_PER_PROT * nprot
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get("dram_bytes_per_residue") * ntotal if tr.get("dram_bytes_per_residue") else None
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp64", "kernel": "k_score_summary",
+        "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
+        "frac": achieved_ops / peak_ops, "traffic": traffic,
+        "note": "fp64 pipe binds (SURVEY 8d): achieved = 67 algorithmic fp64 ops/residue x residues per launch / "
+                "CUDA-event kernel time; peak = DADD issue rate measured by plaac_bench_fp64_peak in this run "
+                "(no FMA: the path may not contract a*b+c); DFMA rate for context: %.2f T instr/s" % (fp64_fma.value / 1e12),
+        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms * args.steps / dev_ms,
+        "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+
+    # ---- end to end through the public host-buffer call -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_codes = torch.empty(ntotal, dtype=torch.uint8).pin_memory()
+        h_offsets = torch.empty(nprot + 1, dtype=torch.int64).pin_memory()
+        h_sum = torch.empty(nprot * 160, dtype=torch.uint8).pin_memory()
+        h_codes.copy_(codes[:ntotal])
+        h_offsets.copy_(offsets)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            scorer.score_ptr(h_codes.data_ptr(), h_offsets.data_ptr(), nprot, h_sum.data_ptr())
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": res_total * args.steps / float(tt[0]), "unit": UNIT,
+               "h2d_bytes_per_step": int(ntotal + 8 * (nprot + 1)), "d2h_bytes_per_step": int(160 * nprot),
+               "ms_per_step": float(tt[0]) / args.steps * 1e3,
+               "note": "plaac_score() on pinned host buffers, per rank; wall clock between barriers, max over ranks"}
+        # sanity: both paths produce the same records
+        same = bool((h_sum.view(torch.int32)[:40] == summaries.cpu().view(torch.int32)[:40]).all())
+        e2e["matches_device_path"] = same
+        del h_codes, h_offsets, h_sum
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import orc
+
+        nthreads = orc.max_threads()
+        n1 = args.cpu_sample_proteins or 6000
+        nres1, dt1 = time_oracle(n1, 1, 1)
+        nall = args.cpu_sample_proteins or 3000 * nthreads
+        nresn, dtn = time_oracle(nall, nthreads, 1)
+        nresn2, dtn2 = time_oracle(nall, nthreads, 0)
+        cpu = {"value": nresn / dtn, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": f"{nall} proteins / {nresn} residues of the same synthetic distribution",
+               "single_thread_value": nres1 / dt1,
+               "needed_work_only_value": nresn2 / dtn2,
+               "note": "oracle/plaac_oracle.c (gcc -O2 -ffp-contract=off), a line-faithful port of plaac.java; "
+                       "value includes the posterior passes the jar computes but never prints; "
+                       "needed_work_only_value skips them; single_thread_value is the jar's execution model; "
+                       "no JVM in the image, plaac.jar itself cannot be timed"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "residues_per_gpu": ntotal, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "timing": "CUDA events on the library stream around K steps, max over ranks; wall %.3f s" % wall,
+        }
+        print(json.dumps(line), flush=True)
+    scorer.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class C_double:
+    def __init__(self):
+        import ctypes
+
+        self._c = ctypes.c_double(0.0)
+        self._ctypes = ctypes
+
+    def ref(self):
+        return self._ctypes.byref(self._c)
+
+    @property
+    def value(self):
+        return float(self._c.value)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,9 +169,32 @@ int setup_scalars(plaac_ctx* ctx)
     return PLAAC_OK;
 }
 
-void fill_tables(const plaac_params& P, DeviceTables& T)
+// The PAPA window sums are running sums (add the entering residue, subtract the leaving one).  To keep
+// them drift-free and, above all, to keep EXACT ties exact (PAPAcen is a first-strict-maximum search,
+// plaac.java:4941-4948), the PAPA log-odds are rounded to a grid 2^-k coarse enough that every partial sum
+// of up to (2w+1)^2 of them is exactly representable: all those double additions are then exact.
+// Grid error <= 2^-41 for the default windows (values ~0.1 => ~5e-12 relative).  Not applied when the
+// grid would be coarser than 2^-38 (huge windows) or a table entry is not finite.
+double papa_grid(const plaac_params& P, int w)
+{
+    double maxabs = 0;
+    for (int c = 0; c < PLAAC_NAA; c++) {
+        if (!std::isfinite(P.papa_lod[c])) return 0.0;
+        maxabs = std::max(maxabs, std::fabs(P.papa_lod[c]));
+    }
+    if (maxabs == 0) return 0.0;
+    const double taps = (2.0 * w + 2.0) * (2.0 * w + 2.0);
+    int e = 0;
+    std::frexp(taps * maxabs, &e);  // taps*maxabs < 2^e
+    const int k = e - 52;          // grid 2^k keeps sums below 2^52 grid units
+    if (k > -38) return 0.0;
+    return std::ldexp(1.0, k);
+}
+
+void fill_tables(const plaac_params& P, DeviceTables& T, int w)
 {
     memset(&T, 0, sizeof(T));
+    const double grid = papa_grid(P, w);
     for (int e = 0; e < kTabN; e++) {
         const int c = e & 31;
         if (c >= PLAAC_NAA) continue;  // pad and unused codes: all zero
@@ -180,7 +203,9 @@ void fill_tables(const plaac_params& P, DeviceTables& T)
         T.lebg[e] = P.le0[c];
         T.llr[e] = P.llr[c];
         T.hyd[e] = P.hydro2[c];
-        T.pap[e] = (e & kPapaMaskBit) ? 0.0 : P.papa_lod[c];
+        double pl = P.papa_lod[c];
+        if (grid > 0) pl = std::nearbyint(pl / grid) * grid;
+        T.pap[e] = (e & kPapaMaskBit) ? 0.0 : pl;
     }
     for (int i = 0; i < PLAAC_LUT_LEN; i++) T.lut[i] = P.loglut[i];
 }
@@ -344,7 +369,7 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         return bail(PLAAC_E_CUDA);
     }
     DeviceTables* h = new DeviceTables();
-    fill_tables(ctx->params, *h);
+    fill_tables(ctx->params, *h, ctx->ks.w);
     cudaError_t e = cudaMalloc((void**)&ctx->d_tabs, sizeof(DeviceTables));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tabs, h, sizeof(DeviceTables), cudaMemcpyHostToDevice);
     delete h;
