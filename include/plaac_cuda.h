@@ -151,6 +151,11 @@ void plaac_encode_host(const char *chars, int64_t n, uint8_t *codes);
 /* Tuning/testing knob for plaac_score(): upper bounds of one device chunk (0 = keep default). */
 int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
 
+/* Kernel selection for testing: 0 = automatic (default), 1 = the reference-order anchor kernel (one fused
+ * kernel, every recurrence in plaac.java's operation order, slower), 2 = the throughput kernel (needs
+ * loglut[0] == ln2 and le0 == le[0], true for tables built as plaac.java builds them). */
+int plaac_set_kernel_variant(plaac_ctx *ctx, int variant);
+
 /* Accounting for benchmarks: kernels launched by this ctx so far, and the
  * CUDA-event time (ms) the scoring kernel(s) of the LAST plaac_score_device
  * call took on the ctx stream (valid after plaac_sync). */

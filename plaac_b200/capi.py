@@ -95,6 +95,8 @@ def lib():
         L.plaac_encode_host.argtypes = [vp, i64, vp]
         L.plaac_set_chunk.restype = C.c_int
         L.plaac_set_chunk.argtypes = [vp, i64, i64]
+        L.plaac_set_kernel_variant.restype = C.c_int
+        L.plaac_set_kernel_variant.argtypes = [vp, C.c_int]
         L.plaac_get_stats.restype = C.c_int
         L.plaac_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.plaac_bench_synth_lengths.restype = C.c_int
@@ -212,6 +214,10 @@ class Scorer:
 
     def set_chunk(self, max_residues=0, max_proteins=0):
         self._check(lib().plaac_set_chunk(self._h, max_residues, max_proteins))
+
+    def set_kernel_variant(self, variant: int):
+        """0 auto, 1 reference-order anchor kernel, 2 throughput kernel."""
+        self._check(lib().plaac_set_kernel_variant(self._h, variant))
 
     def sync(self):
         self._check(lib().plaac_sync(self._h))

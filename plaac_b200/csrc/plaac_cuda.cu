@@ -15,6 +15,7 @@
 #include "prep.cuh"
 #include "residue_kernel.cuh"
 #include "summary_kernel.cuh"
+#include "summary_kernel_v2.cuh"
 
 using namespace plaac;
 
@@ -30,7 +31,7 @@ struct DevBuf {
 // One set of device work buffers; plaac_score() uses two of them to overlap copies with compute.
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, errflag;
+    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, errflag, core_list, core_count;
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
     int64_t* h_total = nullptr;        // pinned
@@ -49,6 +50,10 @@ struct plaac_ctx {
     Slot slot[2];
     int nwarps = 0, ring_words = 0;
     size_t smem_bytes = 0;
+    int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
+    size_t v2_smem_bytes = 0;
+    int variant = 0;           // 0 auto, 1 = v1 (reference-order anchor), 2 = v2
+    std::string v2_why;
     int sm_count = 0;
     plaac_stats stats;
     int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
@@ -166,6 +171,23 @@ int setup_scalars(plaac_ctx* ctx)
                     maxoff);
     ctx->nwarps = (int)std::min<size_t>(12, (limit - fixed) / per_warp);
     ctx->smem_bytes = fixed + per_warp * ctx->nwarps;
+
+    // v2 preconditions: loglut[0] == ln2 bit for bit (lets the a == b branch of logeapeb fold into the
+    // interpolation) and hmm0's emissions identical to hmm1's background state (as prionhmm0/1 build them).
+    ctx->v2_nwr = 0;
+    if (memcmp(&P.loglut[0], &P.ln2, sizeof(double)) != 0)
+        ctx->v2_why = "loglut[0] != ln2";
+    else if (memcmp(P.le0, P.le[0], sizeof(P.le0)) != 0)
+        ctx->v2_why = "hmm0 emissions differ from hmm1 state 0";
+    else {
+        const size_t fixed2 = sizeof(SmemV2);
+        if (fixed2 + 2 * per_warp <= limit) {
+            int nwr = (int)std::min<size_t>(kV2MaxThreads / 64, (limit - fixed2) / (2 * per_warp));
+            ctx->v2_nwr = nwr;
+            ctx->v2_smem_bytes = fixed2 + per_warp * 2 * nwr;
+        } else
+            ctx->v2_why = "ring does not fit beside the v2 tables";
+    }
     return PLAAC_OK;
 }
 
@@ -228,7 +250,7 @@ int slot_init(plaac_ctx* ctx, Slot& s)
 void slot_free(Slot& s)
 {
     for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.errflag,
-                      &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64})
+                      &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64})
         release(*b);
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
@@ -290,8 +312,29 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     bv.nbuckets = nbuckets;
     bv.off_base = off_base;
 
+    const bool use_v2 = ctx->variant == 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);
+    if (d_summaries && use_v2) {
+        if ((rc = ensure(ctx, s.core_list, sizeof(int32_t) * nprot))) return rc;
+        if ((rc = ensure(ctx, s.core_count, sizeof(int32_t)))) return rc;
+        CU(ctx, cudaMemsetAsync(s.core_count.p, 0, sizeof(int32_t), st));
+    }
     CU(ctx, cudaEventRecord(s.ev_b, st));
-    if (d_summaries) {
+    if (d_summaries && use_v2) {
+        V2Args g;
+        g.bv = bv;
+        g.ks = ctx->ks;
+        g.tabs = ctx->d_tabs;
+        g.out = d_summaries;
+        g.ring_words = ctx->ring_words;
+        g.nwr = ctx->v2_nwr;
+        g.core_list = (int32_t*)s.core_list.p;
+        g.core_count = (int32_t*)s.core_count.p;
+        const unsigned grid = (unsigned)((nbuckets + g.nwr - 1) / g.nwr);
+        k_score_summary_v2<<<grid, g.nwr * 64, ctx->v2_smem_bytes, st>>>(g);
+        k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
+        ctx->stats.kernel_launches += 2;
+        ctx->stats.score_launches += 1;
+    } else if (d_summaries) {
         const unsigned grid = (unsigned)((nbuckets + ctx->nwarps - 1) / ctx->nwarps);
         k_score_summary<<<grid, ctx->nwarps * 32, ctx->smem_bytes, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries,
                                                                          ctx->ring_words);
@@ -382,6 +425,13 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         ctx->err = std::string("cudaFuncSetAttribute(k_score_summary): ") + cudaGetErrorString(e);
         return bail(PLAAC_E_CUDA);
     }
+    if (ctx->v2_nwr > 0) {
+        e = cudaFuncSetAttribute(k_score_summary_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->v2_smem_bytes);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaFuncSetAttribute(k_score_summary_v2): ") + cudaGetErrorString(e);
+            return bail(PLAAC_E_CUDA);
+        }
+    }
     rc = residue_setup(ctx->ks, ctx->ring_words);
     if (rc != PLAAC_OK) {
         ctx->err = "cudaFuncSetAttribute(per-residue kernels) failed";
@@ -447,6 +497,16 @@ int plaac_set_chunk(plaac_ctx* ctx, int64_t max_residues, int64_t max_proteins)
     if (max_residues < 0 || max_proteins < 0) return fail(ctx, PLAAC_E_INVALID, "negative chunk size");
     if (max_residues > 0) ctx->chunk_res = ctx->chunk_res_pr = max_residues;
     if (max_proteins > 0) ctx->chunk_prot = std::min<int64_t>(max_proteins, 0x7fffffff);
+    return PLAAC_OK;
+}
+
+int plaac_set_kernel_variant(plaac_ctx* ctx, int variant)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_kernel_variant: NULL ctx");
+    if (variant < 0 || variant > 2) return fail(ctx, PLAAC_E_INVALID, "variant must be 0, 1 or 2");
+    if (variant == 2 && ctx->v2_nwr <= 0)
+        return fail(ctx, PLAAC_E_UNSUPPORTED, "v2 kernel unavailable for these parameters: %s", ctx->v2_why.c_str());
+    ctx->variant = variant;
     return PLAAC_OK;
 }
 

@@ -1,0 +1,531 @@
+// Summary-mode scoring, throughput version ("v2").
+//
+// One CTA = 2*NWR warps.  Warps 0..NWR-1 run role A, warps NWR..2*NWR-1 run role B, each on one length
+// bucket of 32 proteins (lane = protein), all lanes advancing the residue index t in lock step:
+//
+//   role A (the serial recurrences, REFERENCE OPERATION ORDER, bit-faithful to plaac.java):
+//     Viterbi max-plus recurrence + traceback bits   viterbidecodel :3077-3121
+//     LUT forward recurrence                          posteriorl :3349-3375, logeapeb :1024-1047
+//     hmm0's sequential log-emission sum              (= its Viterbi and marginal log-prob)
+//     sequential psum[] LLR window search             hss2 :1206-1257, call site :782-783
+//     MW Q/N window (exact integers)                  :764-771
+//     traceback -> Viterbi bits, longestrun           :3110-3113, :1787-1804
+//     proteins whose longest PrD run reaches the core length are appended to a list for k_core_search
+//   role B (sliding windows as running sums; |delta| ~1e-13, DESIGN.md "tolerances"):
+//     FoldIndex runs, means                           disorderreport :4866-5068
+//     PAPA centre search on the twice-smoothed tracks slidingaverage :2585-2662, :4941-4948
+//
+// Shared-memory traffic is the scarce resource (one 128-byte wavefront per cycle per SM), so every
+// per-code table is replicated per bank group (conflict-free for any code pattern) and the 4001-entry
+// log-sum-exp LUT is stored as {lut[d], lut[d+1]} pairs (one 16-byte load per lookup).  Integer <->
+// double conversions use the 2^52 bit trick on the FP64 pipe instead of the slow XU conversion unit.
+#pragma once
+#include "common.cuh"
+
+namespace plaac {
+
+constexpr int kV2MaxThreads = 768;
+
+struct SmemV2 {
+    double2 lut2[PLAAC_LUT_LEN + 1];  // {lut[d], lut[d+1]}
+    double2 lepair[32][8];            // [code][lane & 7]   {le0, le1}
+    double llrA[32][16];              // [code][lane & 15]
+    double hydB[kTabN][16];           // [ext code][lane & 15]
+    double llrB[kTabN][16];
+    double papB[kTabN][16];
+};
+
+__device__ __forceinline__ double u2d(uint32_t v)
+{
+    // exact uint32 -> double on the FP64 pipe: 2^52 + v, minus 2^52
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+// logeapeb :1024-1047 for finite-or-(-Inf) arguments, given loglut[0] == ln 2 bit for bit (checked at
+// plaac_create): the a == b branch (a + ln2) then equals the interpolation at c = 0, so one compare suffices.
+__device__ __forceinline__ double lse_lut2(double a, double b, const double2* __restrict__ lut2)
+{
+    const bool gt = a > b;
+    const double hi = gt ? a : b;
+    const double lo = gt ? b : a;
+    const double c = hi - lo;
+    const double x = 100.0 * c;
+    const bool in = c < 40.0;
+    int dex = __double2int_rd(x);
+    dex = min(dex, PLAAC_LUT_LEN - 1);
+    dex = max(dex, 0);
+    const double2 l = lut2[dex];
+    const double f1 = x - u2d((uint32_t)dex);  // 100*c - dex
+    const double f0 = 1.0 - f1;                // == (dex + 1) - 100*c exactly (both are exact differences)
+    const double r = hi + (f1 * l.y + f0 * l.x);
+    return in ? r : hi;
+}
+
+struct V2Args {
+    BatchView bv;
+    KScalars ks;
+    const DeviceTables* tabs;
+    plaac_summary* out;
+    int ring_words;       // per lane, power of two
+    int nwr;              // warps per role
+    int32_t* core_list;   // ranks needing the CORE search
+    int32_t* core_count;
+};
+
+// ------------------------------------------------------------------------------------------------ role A
+__device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_t* ring, int lane, int64_t b)
+{
+    const KScalars& ks = g.ks;
+    const BatchView& bv = g.bv;
+    const int rmask = g.ring_words - 1;
+    constexpr uint32_t kPadW = 0x01010101u * kPad;
+    const int64_t rank = b * 32 + lane;
+    int n = 0;
+    int32_t prot = -1;
+    if (rank < bv.nprot) {
+        prot = bv.order[rank];
+        n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
+    }
+    const int64_t cb = bv.chunk_base[b];
+    const int nch = (int)(bv.chunk_base[b + 1] - cb);
+    const uint4* sp = bv.stream + cb * 32 + lane;
+    uint32_t* tbp = bv.tbw + cb * 32 + lane;
+    const int c = ks.core_len, mw = ks.mw_window;
+
+    const char* lep = reinterpret_cast<const char*>(&S.lepair[0][lane & 7]);
+    const char* llp = reinterpret_cast<const char*>(&S.llrA[0][lane & 15]);
+
+    double s0 = 0, s1 = 0, a0 = 0, a1 = 0, sum0 = 0;
+    double ps = 0, psl = 0, llr_best = -INFINITY;
+    int llr_stop = -2;
+    int qn = 0, mw_best = 0, mw_stop = -1;
+    uint32_t tbacc = 0;
+
+    // lagged byte streams: position t - off, off = 4*a + b
+    const int ac = c >> 2, sc_ = 8 * (4 - (c & 3));
+    const int am = mw >> 2, sm_ = 8 * (4 - (mw & 3));
+    uint32_t lo_c = kPadW, lo_m = kPadW;
+
+    uint4 nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
+    if (nch > 0) nxt = sp[0];
+    const int nwords = nch * 4;  // nch*16 >= nmax
+#pragma unroll 1
+    for (int wv = 0; wv < nwords; wv++) {
+        if ((wv & 3) == 0) {
+            const int j = wv >> 2;
+            ring[((wv + 0) & rmask) * 32] = nxt.x;
+            ring[((wv + 1) & rmask) * 32] = nxt.y;
+            ring[((wv + 2) & rmask) * 32] = nxt.z;
+            ring[((wv + 3) & rmask) * 32] = nxt.w;
+            nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
+            if (j + 1 < nch) nxt = sp[(size_t)(j + 1) * 32];
+        }
+        const uint32_t w0 = ring[(wv & rmask) * 32];
+        const uint32_t hi_c = ring[((wv - ac) & rmask) * 32];
+        const uint32_t hi_m = ring[((wv - am) & rmask) * 32];
+        const uint32_t wc = __funnelshift_rc(lo_c, hi_c, sc_);
+        const uint32_t wm = __funnelshift_rc(lo_m, hi_m, sm_);
+        lo_c = hi_c;
+        lo_m = hi_m;
+        const int tbase = wv * 4;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int t = tbase + i;
+            const uint32_t c0 = (w0 >> (8 * i)) & 31u;
+            const uint32_t cc = (wc >> (8 * i)) & 31u;
+            const uint32_t cm = (wm >> (8 * i)) & 31u;
+            const double2 le = *reinterpret_cast<const double2*>(lep + c0 * 128u);
+            const double lr0 = *reinterpret_cast<const double*>(llp + c0 * 128u);
+            const double lrc = *reinterpret_cast<const double*>(llp + cc * 128u);
+            psl = psl + lrc;  // == psum[t-c+1]  (pad codes add +0.0)
+            qn += (int)((ks.qn_mask >> c0) & 1u) - (int)((ks.qn_mask >> cm) & 1u);
+            if (t < n) {
+                if (t == 0) {
+                    s0 = ks.li0 + le.x;
+                    s1 = ks.li1 + le.y;
+                    a0 = s0;
+                    a1 = s1;
+                    sum0 = le.x;
+                } else {
+                    const double v00 = ks.lt00 + s0, v10 = ks.lt10 + s1;
+                    const double v01 = ks.lt01 + s0, v11 = ks.lt11 + s1;
+                    const bool tb0 = v10 > v00, tb1 = v11 > v01;
+                    s0 = (tb0 ? v10 : v00) + le.x;
+                    s1 = (tb1 ? v11 : v01) + le.y;
+                    tbacc |= ((uint32_t)tb0 | ((uint32_t)tb1 << 1)) << ((t & 15) * 2);
+                    const double f0 = lse_lut2(ks.lt00 + a0, ks.lt10 + a1, S.lut2) + le.x;
+                    const double f1 = lse_lut2(ks.lt01 + a0, ks.lt11 + a1, S.lut2) + le.y;
+                    a0 = f0;
+                    a1 = f1;
+                    sum0 = sum0 + le.x;
+                }
+                ps = ps + lr0;
+                if (t >= c - 1) {
+                    const double d = ps - psl;
+                    if (t == c - 1 || d > llr_best) {
+                        llr_best = d;
+                        llr_stop = t;
+                    }
+                }
+                if (t >= mw - 1) {
+                    if (t == mw - 1 || qn > mw_best) {
+                        mw_best = qn;
+                        mw_stop = t;
+                    }
+                } else if (t == n - 1) {
+                    mw_best = qn;
+                    mw_stop = t;
+                }
+            }
+        }
+        if ((wv & 3) == 3) {
+            tbp[(size_t)(wv >> 2) * 32] = tbacc;
+            tbacc = 0;
+        }
+    }
+
+    if (prot < 0) return;
+    plaac_summary* r = g.out + prot;
+    r->prot_len = n;
+    if (n < 1) {
+        r->mw_score = r->mw_start = r->mw_end = r->llr_start = r->llr_end = r->vit_maxrun = 0;
+        r->core_start = r->core_end = r->prd_start = r->prd_end = 0;
+        r->llr = r->core_score = r->prd_score = r->hmm_all = r->hmm_vit = 0;
+        return;
+    }
+    r->mw_score = mw_best;
+    r->mw_start = (n < mw) ? 0 : mw_stop - mw + 1;
+    r->mw_end = mw_stop;
+    if (n < c) {
+        r->llr = -INFINITY;
+        r->llr_start = -1;
+        r->llr_end = -2;
+    } else {
+        r->llr = llr_best;
+        r->llr_start = llr_stop - c + 1;
+        r->llr_end = llr_stop;
+    }
+    const double e0v = s0 + ks.lf0, e1v = s1 + ks.lf1;
+    const int vlast = e1v > e0v ? 1 : 0;
+    const double lvit = vlast ? e1v : e0v;
+    const double lmarg = lse_lut2(a0 + ks.lf0, a1 + ks.lf1, S.lut2);
+    r->hmm_all = lmarg - sum0;
+    r->hmm_vit = lvit - sum0;
+
+    // traceback :3110-3113 + longestrun :1787-1804; the Viterbi bits replace the traceback words
+    int v = vlast, cur = 0, mx = 0;
+    for (int j = (n - 1) >> 4; j >= 0; j--) {
+        const uint32_t tw = tbp[(size_t)j * 32];
+        uint32_t vb = 0;
+        const int hi = (j == ((n - 1) >> 4)) ? ((n - 1) & 15) : 15;
+        for (int i = hi; i >= 0; i--) {
+            vb |= (uint32_t)v << i;
+            cur = v ? cur + 1 : 0;
+            mx = max(mx, cur);
+            v = (tw >> (2 * i + v)) & 1;
+        }
+        tbp[(size_t)j * 32] = vb;
+    }
+    r->vit_maxrun = mx;
+    r->core_start = -1;
+    r->core_end = -2;
+    r->prd_start = -1;
+    r->prd_end = -2;
+    r->core_score = nan("");
+    r->prd_score = 0.0;
+    if (mx >= c && n >= c) {
+        const int slot = atomicAdd(g.core_count, 1);
+        g.core_list[slot] = (int32_t)rank;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ role B
+__device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_t* ring, int lane, int64_t b)
+{
+    const KScalars& ks = g.ks;
+    const BatchView& bv = g.bv;
+    const int rmask = g.ring_words - 1;
+    constexpr uint32_t kPadW = 0x01010101u * kPad;
+    const int64_t rank = b * 32 + lane;
+    int n = 0;
+    int32_t prot = -1;
+    if (rank < bv.nprot) {
+        prot = bv.order[rank];
+        n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
+    }
+    const int64_t cb = bv.chunk_base[b];
+    const int nch = (int)(bv.chunk_base[b + 1] - cb);
+    const uint4* sp = bv.stream + cb * 32 + lane;
+    const int w = ks.w;
+    const int off1 = 2 * w + 1, off2 = 4 * w + 2;
+    const int a1o = off1 >> 2, s1o = 8 * (4 - (off1 & 3));
+    const int a2o = off2 >> 2, s2o = 8 * (4 - (off2 & 3));
+    const int full = 2 * w + 1;
+    const int Wfull = full * full;
+
+    const char* hp = reinterpret_cast<const char*>(&S.hydB[0][lane & 15]);
+    constexpr uint32_t kLl = sizeof(double) * kTabN * 16;  // hydB -> llrB -> papB are consecutive
+
+    int nmax = n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+    const int t_end = nmax + w;
+    const int nwords = (t_end + 3) >> 2;
+
+    double sh = 0;
+    int csum = 0;
+    double SLh = 0, SGh = 0, Th = 0, SLl = 0, SGl = 0, Tl = 0, Dp = 0, Tp = 0;
+    int SLc = 0, SGc = 0, Tac = 0;
+    double Tb = 0, Wb = 1, pfix = 0, pllr2 = 0;
+    int pcen = -1;
+    int halfw = ks.h_fi;
+    if (halfw > n / 2) halfw = n / 2;
+    int fi_run_start = -1, fi_numaa = 0, fi_maxrun = 0;
+    uint32_t lo1 = kPadW, lo2 = kPadW;
+
+    uint4 nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
+    if (nch > 0) nxt = sp[0];
+#pragma unroll 1
+    for (int wv = 0; wv < nwords; wv++) {
+        if ((wv & 3) == 0) {
+            const int j = wv >> 2;
+            ring[((wv + 0) & rmask) * 32] = nxt.x;
+            ring[((wv + 1) & rmask) * 32] = nxt.y;
+            ring[((wv + 2) & rmask) * 32] = nxt.z;
+            ring[((wv + 3) & rmask) * 32] = nxt.w;
+            nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
+            if (j + 1 < nch) nxt = sp[(size_t)(j + 1) * 32];
+        }
+        const uint32_t w0 = ring[(wv & rmask) * 32];
+        const uint32_t hi1 = ring[((wv - a1o) & rmask) * 32];
+        const uint32_t hi2 = ring[((wv - a2o) & rmask) * 32];
+        const uint32_t w1 = __funnelshift_rc(lo1, hi1, s1o);
+        const uint32_t w2 = __funnelshift_rc(lo2, hi2, s2o);
+        lo1 = hi1;
+        lo2 = hi2;
+        const int tbase = wv * 4;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int t = tbase + i;
+            const uint32_t e0 = (w0 >> (8 * i)) & 63u, e1 = (w1 >> (8 * i)) & 63u, e2 = (w2 >> (8 * i)) & 63u;
+            const char* p0 = hp + e0 * 128u;
+            const char* p1 = hp + e1 * 128u;
+            const char* p2 = hp + e2 * 128u;
+            const double hy0 = *reinterpret_cast<const double*>(p0);
+            const double lr0 = *reinterpret_cast<const double*>(p0 + kLl);
+            const double pa0 = *reinterpret_cast<const double*>(p0 + 2 * kLl);
+            const double hy1 = *reinterpret_cast<const double*>(p1);
+            const double lr1 = *reinterpret_cast<const double*>(p1 + kLl);
+            const double pa1 = *reinterpret_cast<const double*>(p1 + 2 * kLl);
+            const double hy2 = *reinterpret_cast<const double*>(p2);
+            const double lr2 = *reinterpret_cast<const double*>(p2 + kLl);
+            const double pa2 = *reinterpret_cast<const double*>(p2 + 2 * kLl);
+            const int ch0 = (int)((ks.charge_plus >> (e0 & 31u)) & 1u) - (int)((ks.charge_minus >> (e0 & 31u)) & 1u);
+            const int ch1 = (int)((ks.charge_plus >> (e1 & 31u)) & 1u) - (int)((ks.charge_minus >> (e1 & 31u)) & 1u);
+            const int ch2 = (int)((ks.charge_plus >> (e2 & 31u)) & 1u) - (int)((ks.charge_minus >> (e2 & 31u)) & 1u);
+            if (t < n) {
+                sh = sh + hy0;  // mean() :1584, sequential
+                csum += ch0;
+            }
+            // window sums of the zero-padded sequence: lead centre p = t-w, lag centre p-(2w+1)
+            SLh = (SLh + hy0) - hy1;
+            SGh = (SGh + hy1) - hy2;
+            Th = (Th + SLh) - SGh;
+            SLl = (SLl + lr0) - lr1;
+            SGl = (SGl + lr1) - lr2;
+            Tl = (Tl + SLl) - SGl;
+            Dp = Dp + ((pa0 + pa2) - (pa1 + pa1));  // exact: PAPA log-odds live on a 2^-k grid
+            Tp = Tp + Dp;
+            SLc += ch0 - ch1;
+            SGc += ch1 - ch2;
+            Tac += abs(SLc) - abs(SGc);
+            const int p = t - w;
+            // FoldIndex run scan :5010-5059 over i in [halfw, n-halfw)
+            if (p >= halfw && p < n - halfw) {
+                const int cnt = full - max(0, w - p) - max(0, p + w - (n - 1));
+                // sign of fi[p] = cc0*hydro + cc1*|charge| + cc2, scaled by the tap count (> 0)
+                const double fis = (ks.cc0 * SLh + ks.cc1 * u2d((uint32_t)abs(SLc))) + ks.cc2 * u2d((uint32_t)cnt);
+                const bool neg = fis < 0;
+                if (neg && fi_run_start < 0) fi_run_start = (p == halfw) ? 0 : p;
+                const bool last = (p == n - halfw - 1);
+                if (fi_run_start >= 0 && (!neg || last)) {
+                    const int stop = neg ? (n - 1) : (p - 1);
+                    const int len = stop - fi_run_start + 1;
+                    if (len >= 5) {
+                        fi_numaa += len;
+                        fi_maxrun = max(fi_maxrun, len);
+                    }
+                    fi_run_start = -1;
+                }
+            }
+            // PAPA centre k = p - w: first strict maximum of Tp/W among centres with fix2 < 0 (:4941-4948)
+            const int k = p - w;
+            if (k >= w && k <= n - w - 1) {
+                const int ml = 2 * w - k, mr = 2 * w - (n - 1 - k);
+                const int W = Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0);
+                const double Wd = u2d((uint32_t)W);
+                // Tp/Wd > Tb/Wb  <=>  Tp*Wb > Tb*Wd (both positive); the products are exact (grid units * small ints)
+                if (pcen < 0 || Tp * Wb > Tb * Wd) {
+                    const double vfi = (ks.cc0 * Th + ks.cc1 * u2d((uint32_t)Tac)) + ks.cc2 * Wd;
+                    if (vfi < 0) {
+                        Tb = Tp;
+                        Wb = Wd;
+                        pcen = k;
+                        pfix = vfi / Wd;
+                        pllr2 = Tl / Wd;
+                    }
+                }
+            }
+        }
+    }
+
+    if (prot < 0) return;
+    plaac_summary* r = g.out + prot;
+    if (n < 1) {
+        r->fi_numaa = r->fi_maxrun = r->papa_center = 0;
+        r->fi_meanhydro = r->fi_meancharge = r->fi_meancombo = 0;
+        r->papa_combo = r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = 0;
+        return;
+    }
+    const double mh = (1.0 * sh) / (double)n;
+    const double mc = (1.0 * (double)csum) / (double)n;
+    r->fi_meanhydro = mh;
+    r->fi_meancharge = mc;
+    r->fi_meancombo = (ks.cc2 + ks.cc1 * fabs(mc)) + ks.cc0 * mh;
+    r->fi_numaa = fi_numaa;
+    r->fi_maxrun = fi_maxrun;
+    r->papa_center = pcen;
+    if (pcen >= 0) {
+        const double prop = Tb / Wb;
+        r->papa_combo = prop;
+        r->papa_prop = prop;
+        r->papa_fi = pfix;
+        r->papa_llr2 = pllr2;
+        // plaacllr[pcen]: 2w+1 taps in reference order (:2604-2620); pcen is interior, all taps in range
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(sp);
+        const double* lt = &S.llrB[0][lane & 15];
+        double sc = 0.0, den = 0.0;
+        for (int j = pcen - w; j <= pcen + w; j++) {
+            den = den + 1.0;
+            sc = sc + 1.0 * lt[(size_t)(sb[(size_t)(j >> 4) * 512 + (j & 15)] & 31) * 16];
+        }
+        r->papa_llr = sc / den;
+    } else {
+        r->papa_combo = -INFINITY;
+        r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = nan("");
+    }
+}
+
+__global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemV2& S = *reinterpret_cast<SmemV2*>(smem_raw);
+    uint32_t* ring_all = reinterpret_cast<uint32_t*>(smem_raw + sizeof(SmemV2));
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const DeviceTables* T = g.tabs;
+    for (int i = tid; i <= PLAAC_LUT_LEN; i += blockDim.x) {
+        const double l0 = i < PLAAC_LUT_LEN ? T->lut[i] : 0.0;
+        const double l1 = i + 1 < PLAAC_LUT_LEN ? T->lut[i + 1] : 0.0;
+        S.lut2[i] = make_double2(l0, l1);
+    }
+    for (int i = tid; i < 32 * 8; i += blockDim.x) S.lepair[i >> 3][i & 7] = make_double2(T->le0[i >> 3], T->le1[i >> 3]);
+    for (int i = tid; i < 32 * 16; i += blockDim.x) S.llrA[i >> 4][i & 15] = T->llr[i >> 4];
+    for (int i = tid; i < kTabN * 16; i += blockDim.x) {
+        S.hydB[i >> 4][i & 15] = T->hyd[i >> 4];
+        S.llrB[i >> 4][i & 15] = T->llr[i >> 4];
+        S.papB[i >> 4][i & 15] = T->pap[i >> 4];
+    }
+    uint32_t* ring = ring_all + (size_t)wid * g.ring_words * 32 + lane;
+    constexpr uint32_t kPadW = 0x01010101u * kPad;
+    for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
+    __syncthreads();
+
+    const int role = wid >= g.nwr;
+    const int64_t b = (int64_t)blockIdx.x * g.nwr + (role ? wid - g.nwr : wid);
+    if (b >= g.bv.nbuckets) return;
+    if (role == 0)
+        role_a(g, S, ring, lane, b);
+    else
+        role_b(g, S, ring, lane, b);
+}
+
+// ------------------------------------------------------------------------------------------------ CORE search
+// The -1e6-masked window search of plaac.java:816-833 (hss2 :1206-1257 in reference order: the masking
+// constant pollutes the sequential prefix sums, and the jar's COREscore/COREstart carry that pollution),
+// then the PrD expansion and PRDscore :851-873.  One lane per listed protein (about 5 % of all).
+__global__ void __launch_bounds__(128)
+k_core_search(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs, plaac_summary* __restrict__ out,
+              const int32_t* __restrict__ core_list, const int32_t* __restrict__ core_count)
+{
+    __shared__ double llr_s[32][16];
+    for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) llr_s[i >> 4][i & 15] = tabs->llr[i >> 4];
+    __syncthreads();
+    const int total = *core_count;
+    const int c = ks.core_len;
+    const double big_neg = ks.big_neg;
+    const double* lt = &llr_s[0][threadIdx.x & 15];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int32_t rank = core_list[idx];
+        const int64_t b = rank >> 5;
+        const int lane = rank & 31;
+        const int32_t prot = bv.order[rank];
+        const int n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
+        const int64_t cb = bv.chunk_base[b];
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(bv.stream + cb * 32 + lane);
+        const uint32_t* vw = bv.tbw + cb * 32 + lane;
+        auto code_at = [&](int i) -> int { return sb[(size_t)(i >> 4) * 512 + (i & 15)] & 31; };
+        auto vit_at = [&](int i) -> int { return (vw[(size_t)(i >> 4) * 32] >> (i & 15)) & 1; };
+        double ps = 0.0, psl = 0.0, best = 0.0;
+        int bstop = c - 1;
+        // lead and lag cursors walk their own 16-residue slots
+        uint4 lead = make_uint4(0, 0, 0, 0), lag = lead;
+        uint32_t vlead = 0, vlag = 0;
+        for (int i = 0; i < n; i++) {
+            if ((i & 15) == 0) {
+                lead = *reinterpret_cast<const uint4*>(sb + (size_t)(i >> 4) * 512);
+                vlead = vw[(size_t)(i >> 4) * 32];
+            }
+            const int k = i - c;
+            if (k >= 0 && ((k & 15) == 0 || i == c)) {
+                lag = *reinterpret_cast<const uint4*>(sb + (size_t)(k >> 4) * 512);
+                vlag = vw[(size_t)(k >> 4) * 32];
+            }
+            const uint32_t lw = ((i & 12) == 0) ? lead.x : ((i & 12) == 4) ? lead.y : ((i & 12) == 8) ? lead.z : lead.w;
+            const int code = (lw >> ((i & 3) * 8)) & 31;
+            const double x = ((vlead >> (i & 15)) & 1) ? lt[code * 16] : big_neg;
+            ps = ps + x;
+            if (k >= 0) {
+                const uint32_t gw = ((k & 12) == 0) ? lag.x : ((k & 12) == 4) ? lag.y : ((k & 12) == 8) ? lag.z : lag.w;
+                const int codel = (gw >> ((k & 3) * 8)) & 31;
+                const double xl = ((vlag >> (k & 15)) & 1) ? lt[codel * 16] : big_neg;
+                psl = psl + xl;
+                const double d = ps - psl;
+                if (d > best) {
+                    best = d;
+                    bstop = i;
+                }
+            } else if (i == c - 1) {
+                best = ps;
+            }
+        }
+        if (best > big_neg / 2) {
+            const int s = bstop - c + 1, e = bstop;
+            int a0 = s, a1 = e;
+            while (a0 >= 0 && vit_at(a0) == 1) a0--;
+            a0++;
+            while (a1 < n && vit_at(a1) == 1) a1++;
+            a1--;
+            double sc = 0.0;
+            for (int kk = a0; kk <= a1; kk++) sc = sc + lt[code_at(kk) * 16];
+            plaac_summary* r = out + prot;
+            r->core_start = s;
+            r->core_end = e;
+            r->core_score = best;
+            r->prd_start = a0;
+            r->prd_end = a1;
+            r->prd_score = sc;
+        }
+    }
+}
+
+}  // namespace plaac
