@@ -180,7 +180,7 @@ int setup_scalars(plaac_ctx* ctx)
     else if (memcmp(P.le0, P.le[0], sizeof(P.le0)) != 0)
         ctx->v2_why = "hmm0 emissions differ from hmm1 state 0";
     else {
-        const size_t fixed2 = sizeof(SmemV2);
+        const size_t fixed2 = (size_t)kV2FixedBytes + kV2AlignSlack;
         if (fixed2 + 2 * per_warp <= limit) {
             int nwr = (int)std::min<size_t>(kV2MaxThreads / 64, (limit - fixed2) / (2 * per_warp));
             ctx->v2_nwr = nwr;
@@ -299,7 +299,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     const int pack_blocks = (int)std::min<int64_t>((nbuckets + 7) / 8, (int64_t)ctx->sm_count * 8);
     k_pack<<<pack_blocks, 256, 0, st>>>(d_codes, d_offsets, off_base, (const int32_t*)s.order.p,
                                         (const int64_t*)s.chunk_base.p, nprot, nbuckets, ctx->ks.adjust_prolines,
-                                        (uint4*)s.stream_buf.p, (int*)s.errflag.p);
+                                        ctx->ks.charge_plus, ctx->ks.charge_minus, (uint4*)s.stream_buf.p,
+                                        (int*)s.errflag.p);
     ctx->stats.kernel_launches += 1;
 
     BatchView bv;

@@ -116,12 +116,14 @@ __device__ __forceinline__ uint32_t sel8(const uint4& a, const uint4& b, int i)
     return (i & 4) ? hi : lo;
 }
 
+// Ext byte layout: bits 4:0 residue code (22 = pad), bit 5 PAPA proline mask, bits 7:6 charge class.
 // One warp per bucket.  Lane l streams protein order[32b+l]: aligned 16-byte loads, byte realignment with
 // funnel shifts, SWAR sanitising / padding / PAPA proline flags, one coalesced 512-byte store per slot.
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
        int64_t off_base, const int32_t* __restrict__ order, const int64_t* __restrict__ chunk_base, int64_t nprot,
-       int64_t nbuckets, int adjust_prolines, uint4* __restrict__ stream, int* __restrict__ errflag)
+       int64_t nbuckets, int adjust_prolines, uint32_t charge_plus, uint32_t charge_minus, uint4* __restrict__ stream,
+       int* __restrict__ errflag)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -174,6 +176,15 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
                     carry = eq;
                     w |= flag >> 2;  // bit 7 -> bit 5 (kPapaMaskBit)
                 }
+                // charge class in bits 7:6 of every byte: 01 = +1, 11 = -1 (so (int8)byte >> 6 is the charge)
+                uint32_t cb = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t cd = (w >> (8 * i)) & 31u;
+                    const uint32_t pl = (charge_plus >> cd) & 1u, mi = (charge_minus >> cd) & 1u;
+                    cb |= ((pl << 6) | (mi * 0xc0u)) << (8 * i);
+                }
+                w |= cb;
                 o[q] = w;
             }
             stream[(cb + j) * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);

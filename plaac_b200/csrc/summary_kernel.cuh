@@ -246,7 +246,7 @@ k_score_summary(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs
         {
             const double hy1 = S.hyd[c1], hy2 = S.hyd[c2];
             const double lr1 = S.llr[c1], lr2 = S.llr[c2];
-            const double pa0 = S.pap[e0], pa1 = S.pap[e1], pa2 = S.pap[e2];
+            const double pa0 = S.pap[e0 & 63], pa1 = S.pap[e1 & 63], pa2 = S.pap[e2 & 63];
             const int ch0 = code_charge(ks.charge_plus, ks.charge_minus, c0);
             const int ch1 = code_charge(ks.charge_plus, ks.charge_minus, c1);
             const int ch2 = code_charge(ks.charge_plus, ks.charge_minus, c2);

@@ -14,11 +14,13 @@
 //   role B (sliding windows as running sums; |delta| ~1e-13, DESIGN.md "tolerances"):
 //     FoldIndex runs, means                           disorderreport :4866-5068
 //     PAPA centre search on the twice-smoothed tracks slidingaverage :2585-2662, :4941-4948
+//     the values reported at the PAPA centre (PAPAllr, PAPAllr2) are evaluated once per protein
 //
 // Shared-memory traffic is the scarce resource (one 128-byte wavefront per cycle per SM), so every
 // per-code table is replicated per bank group (conflict-free for any code pattern) and the 4001-entry
-// log-sum-exp LUT is stored as {lut[d], lut[d+1]} pairs (one 16-byte load per lookup).  Integer <->
-// double conversions use the 2^52 bit trick on the FP64 pipe instead of the slow XU conversion unit.
+// log-sum-exp LUT is stored as {lut[d], lut[d+1]} pairs (one 16-byte load per lookup).  Table bases are
+// aligned so that "base | code bits" forms the address in one LOP3.  Integer -> double conversions use the
+// 2^52 bit trick on the FP64 pipe instead of the slow XU conversion unit.
 #pragma once
 #include "common.cuh"
 
@@ -26,14 +28,39 @@ namespace plaac {
 
 constexpr int kV2MaxThreads = 768;
 
-struct SmemV2 {
-    double2 lut2[PLAAC_LUT_LEN + 1];  // {lut[d], lut[d+1]}
-    double2 lepair[32][8];            // [code][lane & 7]   {le0, le1}
-    double llrA[32][16];              // [code][lane & 15]
-    double hydB[kTabN][16];           // [ext code][lane & 15]
-    double llrB[kTabN][16];
-    double papB[kTabN][16];
-};
+// Byte offsets from an 8 KB-aligned shared-memory base.
+constexpr uint32_t kOffHydB = 0;         // double [64 ext codes][16 lane copies]
+constexpr uint32_t kOffPapB = 8192;      // double [64][16]
+constexpr uint32_t kOffLlrB = 16384;     // double [64][16]   (tail loops only)
+constexpr uint32_t kOffLeA = 24576;      // double2 [32 codes][8 lane copies]  {le0, le1}
+constexpr uint32_t kOffLlrA = 28672;     // double [32][16]
+constexpr uint32_t kOffLut2 = 32768;     // double2 [4002]  {lut[d], lut[d+1]}
+constexpr uint32_t kV2FixedBytes = kOffLut2 + (PLAAC_LUT_LEN + 1) * 16;
+constexpr uint32_t kV2AlignSlack = 8192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64_off(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(uint32_t addr)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ double u2d(uint32_t v)
 {
@@ -42,19 +69,17 @@ __device__ __forceinline__ double u2d(uint32_t v)
 }
 
 // logeapeb :1024-1047 for finite-or-(-Inf) arguments, given loglut[0] == ln 2 bit for bit (checked at
-// plaac_create): the a == b branch (a + ln2) then equals the interpolation at c = 0, so one compare suffices.
-__device__ __forceinline__ double lse_lut2(double a, double b, const double2* __restrict__ lut2)
+// plaac_create): the a == b branch (a + ln2) then equals the interpolation at c = 0.  c = |a - b| is the
+// reference's (a - b) or (b - a) bit for bit; the larger argument is picked from the sign of a - b.
+__device__ __forceinline__ double lse_lut2(double a, double b, uint32_t lut_addr)
 {
-    const bool gt = a > b;
-    const double hi = gt ? a : b;
-    const double lo = gt ? b : a;
-    const double c = hi - lo;
+    const double d = a - b;
+    const double hi = (__double2hiint(d) < 0) ? b : a;  // d < 0 (or -0 never occurs: a == b gives +0)
+    const double c = fabs(d);
     const double x = 100.0 * c;
     const bool in = c < 40.0;
-    int dex = __double2int_rd(x);
-    dex = min(dex, PLAAC_LUT_LEN - 1);
-    dex = max(dex, 0);
-    const double2 l = lut2[dex];
+    const int dex = min(__double2int_rd(x), PLAAC_LUT_LEN - 1);  // x >= 0, NaN -> 0
+    const double2 l = lds_v2f64(lut_addr + (uint32_t)dex * 16u);
     const double f1 = x - u2d((uint32_t)dex);  // 100*c - dex
     const double f0 = 1.0 - f1;                // == (dex + 1) - 100*c exactly (both are exact differences)
     const double r = hi + (f1 * l.y + f0 * l.x);
@@ -73,7 +98,7 @@ struct V2Args {
 };
 
 // ------------------------------------------------------------------------------------------------ role A
-__device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_t* ring, int lane, int64_t b)
+__device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t* ring, int lane, int64_t b)
 {
     const KScalars& ks = g.ks;
     const BatchView& bv = g.bv;
@@ -92,8 +117,9 @@ __device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_
     uint32_t* tbp = bv.tbw + cb * 32 + lane;
     const int c = ks.core_len, mw = ks.mw_window;
 
-    const char* lep = reinterpret_cast<const char*>(&S.lepair[0][lane & 7]);
-    const char* llp = reinterpret_cast<const char*>(&S.llrA[0][lane & 15]);
+    const uint32_t le_base = sbase + kOffLeA + (uint32_t)(lane & 7) * 16u;
+    const uint32_t ll_base = sbase + kOffLlrA + (uint32_t)(lane & 15) * 8u;
+    const uint32_t lut_addr = sbase + kOffLut2;
 
     double s0 = 0, s1 = 0, a0 = 0, a1 = 0, sum0 = 0;
     double ps = 0, psl = 0, llr_best = -INFINITY;
@@ -131,14 +157,14 @@ __device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int t = tbase + i;
-            const uint32_t c0 = (w0 >> (8 * i)) & 31u;
-            const uint32_t cc = (wc >> (8 * i)) & 31u;
-            const uint32_t cm = (wm >> (8 * i)) & 31u;
-            const double2 le = *reinterpret_cast<const double2*>(lep + c0 * 128u);
-            const double lr0 = *reinterpret_cast<const double*>(llp + c0 * 128u);
-            const double lrc = *reinterpret_cast<const double*>(llp + cc * 128u);
+            // code bits 4:0 of byte i moved to address bits 11:7
+            const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (31u << 7);
+            const uint32_t kc = (i == 0 ? (wc << 7) : (wc >> (8 * i - 7))) & (31u << 7);
+            const double2 le = lds_v2f64(le_base | k0);
+            const double lr0 = lds_f64(ll_base | k0);
+            const double lrc = lds_f64(ll_base | kc);
             psl = psl + lrc;  // == psum[t-c+1]  (pad codes add +0.0)
-            qn += (int)((ks.qn_mask >> c0) & 1u) - (int)((ks.qn_mask >> cm) & 1u);
+            qn += (int)((ks.qn_mask >> ((w0 >> (8 * i)) & 31u)) & 1u) - (int)((ks.qn_mask >> ((wm >> (8 * i)) & 31u)) & 1u);
             if (t < n) {
                 if (t == 0) {
                     s0 = ks.li0 + le.x;
@@ -153,8 +179,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_
                     s0 = (tb0 ? v10 : v00) + le.x;
                     s1 = (tb1 ? v11 : v01) + le.y;
                     tbacc |= ((uint32_t)tb0 | ((uint32_t)tb1 << 1)) << ((t & 15) * 2);
-                    const double f0 = lse_lut2(ks.lt00 + a0, ks.lt10 + a1, S.lut2) + le.x;
-                    const double f1 = lse_lut2(ks.lt01 + a0, ks.lt11 + a1, S.lut2) + le.y;
+                    const double f0 = lse_lut2(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
+                    const double f1 = lse_lut2(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
                     a0 = f0;
                     a1 = f1;
                     sum0 = sum0 + le.x;
@@ -208,7 +234,7 @@ __device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_
     const double e0v = s0 + ks.lf0, e1v = s1 + ks.lf1;
     const int vlast = e1v > e0v ? 1 : 0;
     const double lvit = vlast ? e1v : e0v;
-    const double lmarg = lse_lut2(a0 + ks.lf0, a1 + ks.lf1, S.lut2);
+    const double lmarg = lse_lut2(a0 + ks.lf0, a1 + ks.lf1, lut_addr);
     r->hmm_all = lmarg - sum0;
     r->hmm_vit = lvit - sum0;
 
@@ -240,7 +266,7 @@ __device__ __forceinline__ void role_a(const V2Args& g, const SmemV2& S, uint32_
 }
 
 // ------------------------------------------------------------------------------------------------ role B
-__device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_t* ring, int lane, int64_t b)
+__device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t* ring, int lane, int64_t b)
 {
     const KScalars& ks = g.ks;
     const BatchView& bv = g.bv;
@@ -262,9 +288,9 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
     const int a2o = off2 >> 2, s2o = 8 * (4 - (off2 & 3));
     const int full = 2 * w + 1;
     const int Wfull = full * full;
+    const double cc2full = ks.cc2 * (double)full;
 
-    const char* hp = reinterpret_cast<const char*>(&S.hydB[0][lane & 15]);
-    constexpr uint32_t kLl = sizeof(double) * kTabN * 16;  // hydB -> llrB -> papB are consecutive
+    const uint32_t hb = sbase + kOffHydB + (uint32_t)(lane & 15) * 8u;
 
     int nmax = n;
 #pragma unroll
@@ -274,12 +300,14 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
 
     double sh = 0;
     int csum = 0;
-    double SLh = 0, SGh = 0, Th = 0, SLl = 0, SGl = 0, Tl = 0, Dp = 0, Tp = 0;
+    double SLh = 0, SGh = 0, Th = 0, Dp = 0, Tp = 0;
     int SLc = 0, SGc = 0, Tac = 0;
-    double Tb = 0, Wb = 1, pfix = 0, pllr2 = 0;
+    double Tb = 0, Wb = 1, vfib = 0;
     int pcen = -1;
     int halfw = ks.h_fi;
     if (halfw > n / 2) halfw = n / 2;
+    const int fi_hi = n - halfw;     // FoldIndex scan is over p in [halfw, fi_hi)
+    const int edge_hi = n - 1 - w;   // windows centred beyond this are clipped on the right
     int fi_run_start = -1, fi_numaa = 0, fi_maxrun = 0;
     uint32_t lo1 = kPadW, lo2 = kPadW;
 
@@ -307,22 +335,16 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int t = tbase + i;
-            const uint32_t e0 = (w0 >> (8 * i)) & 63u, e1 = (w1 >> (8 * i)) & 63u, e2 = (w2 >> (8 * i)) & 63u;
-            const char* p0 = hp + e0 * 128u;
-            const char* p1 = hp + e1 * 128u;
-            const char* p2 = hp + e2 * 128u;
-            const double hy0 = *reinterpret_cast<const double*>(p0);
-            const double lr0 = *reinterpret_cast<const double*>(p0 + kLl);
-            const double pa0 = *reinterpret_cast<const double*>(p0 + 2 * kLl);
-            const double hy1 = *reinterpret_cast<const double*>(p1);
-            const double lr1 = *reinterpret_cast<const double*>(p1 + kLl);
-            const double pa1 = *reinterpret_cast<const double*>(p1 + 2 * kLl);
-            const double hy2 = *reinterpret_cast<const double*>(p2);
-            const double lr2 = *reinterpret_cast<const double*>(p2 + kLl);
-            const double pa2 = *reinterpret_cast<const double*>(p2 + 2 * kLl);
-            const int ch0 = (int)((ks.charge_plus >> (e0 & 31u)) & 1u) - (int)((ks.charge_minus >> (e0 & 31u)) & 1u);
-            const int ch1 = (int)((ks.charge_plus >> (e1 & 31u)) & 1u) - (int)((ks.charge_minus >> (e1 & 31u)) & 1u);
-            const int ch2 = (int)((ks.charge_plus >> (e2 & 31u)) & 1u) - (int)((ks.charge_minus >> (e2 & 31u)) & 1u);
+            // ext code bits 5:0 of byte i -> address bits 12:7; charge = sign-extended bits 7:6
+            const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (63u << 7);
+            const uint32_t k1 = (i == 0 ? (w1 << 7) : (w1 >> (8 * i - 7))) & (63u << 7);
+            const uint32_t k2 = (i == 0 ? (w2 << 7) : (w2 >> (8 * i - 7))) & (63u << 7);
+            const int ch0 = (int)(w0 << (24 - 8 * i)) >> 30;
+            const int ch1 = (int)(w1 << (24 - 8 * i)) >> 30;
+            const int ch2 = (int)(w2 << (24 - 8 * i)) >> 30;
+            const double hy0 = lds_f64(hb | k0), pa0 = lds_f64_off<kOffPapB>(hb | k0);
+            const double hy1 = lds_f64(hb | k1), pa1 = lds_f64_off<kOffPapB>(hb | k1);
+            const double hy2 = lds_f64(hb | k2), pa2 = lds_f64_off<kOffPapB>(hb | k2);
             if (t < n) {
                 sh = sh + hy0;  // mean() :1584, sequential
                 csum += ch0;
@@ -331,23 +353,22 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
             SLh = (SLh + hy0) - hy1;
             SGh = (SGh + hy1) - hy2;
             Th = (Th + SLh) - SGh;
-            SLl = (SLl + lr0) - lr1;
-            SGl = (SGl + lr1) - lr2;
-            Tl = (Tl + SLl) - SGl;
             Dp = Dp + ((pa0 + pa2) - (pa1 + pa1));  // exact: PAPA log-odds live on a 2^-k grid
             Tp = Tp + Dp;
             SLc += ch0 - ch1;
             SGc += ch1 - ch2;
-            Tac += abs(SLc) - abs(SGc);
+            const int aSL = abs(SLc);
+            Tac += aSL - abs(SGc);
             const int p = t - w;
-            // FoldIndex run scan :5010-5059 over i in [halfw, n-halfw)
-            if (p >= halfw && p < n - halfw) {
-                const int cnt = full - max(0, w - p) - max(0, p + w - (n - 1));
-                // sign of fi[p] = cc0*hydro + cc1*|charge| + cc2, scaled by the tap count (> 0)
-                const double fis = (ks.cc0 * SLh + ks.cc1 * u2d((uint32_t)abs(SLc))) + ks.cc2 * u2d((uint32_t)cnt);
+            // FoldIndex run scan :5010-5059 over i in [halfw, n-halfw):
+            // sign of fi[p] = cc0*hydro + cc1*|charge| + cc2, scaled by the tap count (> 0)
+            if (p >= halfw && p < fi_hi) {
+                double c2 = cc2full;
+                if (p < w || p > edge_hi) c2 = ks.cc2 * u2d((uint32_t)(full - max(0, w - p) - max(0, p - edge_hi)));
+                const double fis = (ks.cc0 * SLh + ks.cc1 * u2d((uint32_t)aSL)) + c2;
                 const bool neg = fis < 0;
                 if (neg && fi_run_start < 0) fi_run_start = (p == halfw) ? 0 : p;
-                const bool last = (p == n - halfw - 1);
+                const bool last = (p == fi_hi - 1);
                 if (fi_run_start >= 0 && (!neg || last)) {
                     const int stop = neg ? (n - 1) : (p - 1);
                     const int len = stop - fi_run_start + 1;
@@ -360,20 +381,19 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
             }
             // PAPA centre k = p - w: first strict maximum of Tp/W among centres with fix2 < 0 (:4941-4948)
             const int k = p - w;
-            if (k >= w && k <= n - w - 1) {
-                const int ml = 2 * w - k, mr = 2 * w - (n - 1 - k);
-                const int W = Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0);
-                const double Wd = u2d((uint32_t)W);
-                // Tp/Wd > Tb/Wb  <=>  Tp*Wb > Tb*Wd (both positive); the products are exact (grid units * small ints)
-                if (pcen < 0 || Tp * Wb > Tb * Wd) {
-                    const double vfi = (ks.cc0 * Th + ks.cc1 * u2d((uint32_t)Tac)) + ks.cc2 * Wd;
-                    if (vfi < 0) {
-                        Tb = Tp;
-                        Wb = Wd;
-                        pcen = k;
-                        pfix = vfi / Wd;
-                        pllr2 = Tl / Wd;
-                    }
+            if (k >= w && k <= edge_hi) {
+                double Wd = (double)Wfull;
+                if (k < 2 * w || k > edge_hi - w) {
+                    const int ml = 2 * w - k, mr = k - (edge_hi - w);
+                    Wd = u2d((uint32_t)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0)));
+                }
+                // Tp/Wd > Tb/Wb  <=>  Tp*Wb > Tb*Wd (both positive); products of grid units and small ints
+                const double vfi = (ks.cc0 * Th + ks.cc1 * u2d((uint32_t)Tac)) + ks.cc2 * Wd;
+                if ((pcen < 0 || Tp * Wb > Tb * Wd) && vfi < 0) {
+                    Tb = Tp;
+                    Wb = Wd;
+                    vfib = vfi;
+                    pcen = k;
                 }
             }
         }
@@ -399,17 +419,24 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
         const double prop = Tb / Wb;
         r->papa_combo = prop;
         r->papa_prop = prop;
-        r->papa_fi = pfix;
-        r->papa_llr2 = pllr2;
-        // plaacllr[pcen]: 2w+1 taps in reference order (:2604-2620); pcen is interior, all taps in range
+        r->papa_fi = vfib / Wb;
+        // PAPAllr = plaacllr[pcen]: 2w+1 taps in reference order (:2604-2620; pcen is interior).
+        // PAPAllr2 = plaacllrx2[pcen] = sum_q (2w+1-|q-pcen|) llr[q] / W over the zero-padded sequence.
         const uint8_t* sb = reinterpret_cast<const uint8_t*>(sp);
-        const double* lt = &S.llrB[0][lane & 15];
-        double sc = 0.0, den = 0.0;
-        for (int j = pcen - w; j <= pcen + w; j++) {
-            den = den + 1.0;
-            sc = sc + 1.0 * lt[(size_t)(sb[(size_t)(j >> 4) * 512 + (j & 15)] & 31) * 16];
+        const uint32_t lb = sbase + kOffLlrB + (uint32_t)(lane & 15) * 8u;
+        double sc = 0.0, den = 0.0, t2 = 0.0;
+        for (int q = pcen - 2 * w; q <= pcen + 2 * w; q++) {
+            if (q < 0 || q >= n) continue;
+            const double x = lds_f64(lb + (uint32_t)(sb[(size_t)(q >> 4) * 512 + (q & 15)] & 63) * 128u);
+            const int dist = abs(q - pcen);
+            if (dist <= w) {
+                den = den + 1.0;
+                sc = sc + 1.0 * x;
+            }
+            t2 = t2 + x * (double)(full - dist);
         }
         r->papa_llr = sc / den;
+        r->papa_llr2 = t2 / Wb;
     } else {
         r->papa_combo = -INFINITY;
         r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = nan("");
@@ -419,22 +446,32 @@ __device__ __forceinline__ void role_b(const V2Args& g, const SmemV2& S, uint32_
 __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemV2& S = *reinterpret_cast<SmemV2*>(smem_raw);
-    uint32_t* ring_all = reinterpret_cast<uint32_t*>(smem_raw + sizeof(SmemV2));
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + kV2AlignSlack - 1) & ~(kV2AlignSlack - 1);
+    unsigned char* sm = smem_raw + (sbase - raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const DeviceTables* T = g.tabs;
-    for (int i = tid; i <= PLAAC_LUT_LEN; i += blockDim.x) {
-        const double l0 = i < PLAAC_LUT_LEN ? T->lut[i] : 0.0;
-        const double l1 = i + 1 < PLAAC_LUT_LEN ? T->lut[i + 1] : 0.0;
-        S.lut2[i] = make_double2(l0, l1);
+    {
+        double2* lut2 = reinterpret_cast<double2*>(sm + kOffLut2);
+        for (int i = tid; i <= PLAAC_LUT_LEN; i += blockDim.x) {
+            const double l0 = i < PLAAC_LUT_LEN ? T->lut[i] : 0.0;
+            const double l1 = i + 1 < PLAAC_LUT_LEN ? T->lut[i + 1] : 0.0;
+            lut2[i] = make_double2(l0, l1);
+        }
+        double2* le = reinterpret_cast<double2*>(sm + kOffLeA);
+        for (int i = tid; i < 32 * 8; i += blockDim.x) le[i] = make_double2(T->le0[i >> 3], T->le1[i >> 3]);
+        double* la = reinterpret_cast<double*>(sm + kOffLlrA);
+        for (int i = tid; i < 32 * 16; i += blockDim.x) la[i] = T->llr[i >> 4];
+        double* hy = reinterpret_cast<double*>(sm + kOffHydB);
+        double* pa = reinterpret_cast<double*>(sm + kOffPapB);
+        double* lb = reinterpret_cast<double*>(sm + kOffLlrB);
+        for (int i = tid; i < kTabN * 16; i += blockDim.x) {
+            hy[i] = T->hyd[i >> 4];
+            pa[i] = T->pap[i >> 4];
+            lb[i] = T->llr[i >> 4];
+        }
     }
-    for (int i = tid; i < 32 * 8; i += blockDim.x) S.lepair[i >> 3][i & 7] = make_double2(T->le0[i >> 3], T->le1[i >> 3]);
-    for (int i = tid; i < 32 * 16; i += blockDim.x) S.llrA[i >> 4][i & 15] = T->llr[i >> 4];
-    for (int i = tid; i < kTabN * 16; i += blockDim.x) {
-        S.hydB[i >> 4][i & 15] = T->hyd[i >> 4];
-        S.llrB[i >> 4][i & 15] = T->llr[i >> 4];
-        S.papB[i >> 4][i & 15] = T->pap[i >> 4];
-    }
+    uint32_t* ring_all = reinterpret_cast<uint32_t*>(sm + kV2FixedBytes);
     uint32_t* ring = ring_all + (size_t)wid * g.ring_words * 32 + lane;
     constexpr uint32_t kPadW = 0x01010101u * kPad;
     for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
@@ -444,9 +481,9 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
     const int64_t b = (int64_t)blockIdx.x * g.nwr + (role ? wid - g.nwr : wid);
     if (b >= g.bv.nbuckets) return;
     if (role == 0)
-        role_a(g, S, ring, lane, b);
+        role_a(g, sbase, ring, lane, b);
     else
-        role_b(g, S, ring, lane, b);
+        role_b(g, sbase, ring, lane, b);
 }
 
 // ------------------------------------------------------------------------------------------------ CORE search
