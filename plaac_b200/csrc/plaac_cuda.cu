@@ -52,6 +52,7 @@ struct plaac_ctx {
     size_t smem_bytes = 0;
     int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
     size_t v2_smem_bytes = 0;
+    int v2_always_in = 0;      // forward recurrence provably keeps |a-b| < 40 (no LUT range test needed)
     int variant = 0;           // 0 auto, 1 = v1 (reference-order anchor), 2 = v2
     std::string v2_why;
     int sm_count = 0;
@@ -187,6 +188,22 @@ int setup_scalars(plaac_ctx* ctx)
             ctx->v2_smem_bytes = fixed2 + per_warp * 2 * nwr;
         } else
             ctx->v2_why = "ring does not fit beside the v2 tables";
+        // Range of d = a0 - a1 in the forward recurrence: alpha0/alpha1 is a Moebius image of the previous
+        // ratio, so for t >= 1  d in [lt10 - lt11 + min(le0-le1), lt00 - lt01 + max(le0-le1)], and the two
+        // log-sum-exp arguments differ by (lt0i - lt1i) + d.  If that is safely below 40 the LUT range test
+        // (logeapeb's `c < 40`, plaac.java:1027) can never fail and the kernel skips it.
+        double dmin = INFINITY, dmax = -INFINITY;
+        for (int cidx = 0; cidx < PLAAC_NAA; cidx++) {
+            const double dl = P.le[0][cidx] - P.le[1][cidx];
+            dmin = std::min(dmin, dl);
+            dmax = std::max(dmax, dl);
+        }
+        const double m1 = P.lt[1][0] - P.lt[1][1], m2 = P.lt[0][0] - P.lt[0][1], m0 = P.li[0] - P.li[1];
+        const double lo = std::min(std::min(m1, m2), m0) + dmin;
+        const double hi = std::max(std::max(m1, m2), m0) + dmax;
+        const double dabs = std::max(std::fabs(lo), std::fabs(hi));
+        const double targ = std::max(std::fabs(P.lt[0][0] - P.lt[1][0]), std::fabs(P.lt[0][1] - P.lt[1][1])) + dabs;
+        ctx->v2_always_in = (std::isfinite(targ) && targ < 39.0) ? 1 : 0;
     }
     return PLAAC_OK;
 }
@@ -330,6 +347,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         g.nwr = ctx->v2_nwr;
         g.core_list = (int32_t*)s.core_list.p;
         g.core_count = (int32_t*)s.core_count.p;
+        g.always_in = ctx->v2_always_in;
         const unsigned grid = (unsigned)((nbuckets + g.nwr - 1) / g.nwr);
         k_score_summary_v2<<<grid, g.nwr * 64, ctx->v2_smem_bytes, st>>>(g);
         k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);

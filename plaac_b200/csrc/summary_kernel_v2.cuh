@@ -22,6 +22,8 @@
 // aligned so that "base | code bits" forms the address in one LOP3.  Integer -> double conversions use the
 // 2^52 bit trick on the FP64 pipe instead of the slow XU conversion unit.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace plaac {
@@ -71,12 +73,21 @@ __device__ __forceinline__ double u2d(uint32_t v)
 // logeapeb :1024-1047 for finite-or-(-Inf) arguments, given loglut[0] == ln 2 bit for bit (checked at
 // plaac_create): the a == b branch (a + ln2) then equals the interpolation at c = 0.  c = |a - b| is the
 // reference's (a - b) or (b - a) bit for bit; the larger argument is picked from the sign of a - b.
+template <bool ALWAYS_IN>
 __device__ __forceinline__ double lse_lut2(double a, double b, uint32_t lut_addr)
 {
     const double d = a - b;
-    const double hi = (__double2hiint(d) < 0) ? b : a;  // d < 0 (or -0 never occurs: a == b gives +0)
+    const double hi = (__double2hiint(d) < 0) ? b : a;  // a == b gives +0: hi = a
     const double c = fabs(d);
     const double x = 100.0 * c;
+    if (ALWAYS_IN) {
+        // plaac_create proved |a - b| < 40 for every reachable argument pair of the recurrence
+        const int dex = __double2int_rd(x);
+        const double2 l = lds_v2f64(lut_addr + (uint32_t)dex * 16u);
+        const double f1 = x - u2d((uint32_t)dex);
+        const double f0 = 1.0 - f1;
+        return hi + (f1 * l.y + f0 * l.x);
+    }
     const bool in = c < 40.0;
     const int dex = min(__double2int_rd(x), PLAAC_LUT_LEN - 1);  // x >= 0, NaN -> 0
     const double2 l = lds_v2f64(lut_addr + (uint32_t)dex * 16u);
@@ -95,6 +106,7 @@ struct V2Args {
     int nwr;              // warps per role
     int32_t* core_list;   // ranks needing the CORE search
     int32_t* core_count;
+    int always_in;        // 1: |a-b| < 40 is guaranteed inside the forward recurrence (bound checked on the host)
 };
 
 // ------------------------------------------------------------------------------------------------ role A
@@ -135,6 +147,65 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     uint4 nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
     if (nch > 0) nxt = sp[0];
     const int nwords = nch * 4;  // nch*16 >= nmax
+    int nmin = (prot >= 0) ? n : 0x7fffffff;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, d));
+    const int fast_lo = max(max(c, mw), 1);  // every window is full and t > 0 from here on
+
+    // one residue step; FAST: every lane has t in [max(c,mw), n) so all range tests are known
+    auto step = [&](auto fast_tag, auto in_tag, int t, int i, uint32_t w0, uint32_t wc, uint32_t wm) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        constexpr bool AIN = decltype(in_tag)::value;
+        // code bits 4:0 of byte i moved to address bits 11:7
+        const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (31u << 7);
+        const uint32_t kc = (i == 0 ? (wc << 7) : (wc >> (8 * i - 7))) & (31u << 7);
+        const double2 le = lds_v2f64(le_base | k0);
+        const double lr0 = lds_f64(ll_base | k0);
+        const double lrc = lds_f64(ll_base | kc);
+        psl = psl + lrc;  // == psum[t-c+1]  (pad codes add +0.0)
+        qn += (int)((ks.qn_mask >> ((w0 >> (8 * i)) & 31u)) & 1u) - (int)((ks.qn_mask >> ((wm >> (8 * i)) & 31u)) & 1u);
+        uint32_t bits = 0;
+        if (FAST || t < n) {
+            if (!FAST && t == 0) {
+                s0 = ks.li0 + le.x;
+                s1 = ks.li1 + le.y;
+                a0 = s0;
+                a1 = s1;
+                sum0 = le.x;
+            } else {
+                const double v00 = ks.lt00 + s0, v10 = ks.lt10 + s1;
+                const double v01 = ks.lt01 + s0, v11 = ks.lt11 + s1;
+                const bool tb0 = v10 > v00, tb1 = v11 > v01;
+                s0 = (tb0 ? v10 : v00) + le.x;
+                s1 = (tb1 ? v11 : v01) + le.y;
+                bits = (uint32_t)tb0 | ((uint32_t)tb1 << 1);
+                const double f0 = lse_lut2<AIN>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
+                const double f1 = lse_lut2<AIN>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
+                a0 = f0;
+                a1 = f1;
+                sum0 = sum0 + le.x;
+            }
+            ps = ps + lr0;
+            if (FAST || t >= c - 1) {
+                const double d = ps - psl;
+                if ((!FAST && t == c - 1) || d > llr_best) {
+                    llr_best = d;
+                    llr_stop = t;
+                }
+            }
+            if (FAST || t >= mw - 1) {
+                if ((!FAST && t == mw - 1) || qn > mw_best) {
+                    mw_best = qn;
+                    mw_stop = t;
+                }
+            } else if (t == n - 1) {
+                mw_best = qn;
+                mw_stop = t;
+            }
+        }
+        tbacc = __funnelshift_r(tbacc, bits, 2);  // after 16 steps the bits of residue 16j+i sit at 2i
+    };
+
 #pragma unroll 1
     for (int wv = 0; wv < nwords; wv++) {
         if ((wv & 3) == 0) {
@@ -154,55 +225,17 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
         lo_c = hi_c;
         lo_m = hi_m;
         const int tbase = wv * 4;
+        if (tbase >= fast_lo && tbase + 3 < nmin) {  // warp-uniform
+            if (g.always_in) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int t = tbase + i;
-            // code bits 4:0 of byte i moved to address bits 11:7
-            const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (31u << 7);
-            const uint32_t kc = (i == 0 ? (wc << 7) : (wc >> (8 * i - 7))) & (31u << 7);
-            const double2 le = lds_v2f64(le_base | k0);
-            const double lr0 = lds_f64(ll_base | k0);
-            const double lrc = lds_f64(ll_base | kc);
-            psl = psl + lrc;  // == psum[t-c+1]  (pad codes add +0.0)
-            qn += (int)((ks.qn_mask >> ((w0 >> (8 * i)) & 31u)) & 1u) - (int)((ks.qn_mask >> ((wm >> (8 * i)) & 31u)) & 1u);
-            if (t < n) {
-                if (t == 0) {
-                    s0 = ks.li0 + le.x;
-                    s1 = ks.li1 + le.y;
-                    a0 = s0;
-                    a1 = s1;
-                    sum0 = le.x;
-                } else {
-                    const double v00 = ks.lt00 + s0, v10 = ks.lt10 + s1;
-                    const double v01 = ks.lt01 + s0, v11 = ks.lt11 + s1;
-                    const bool tb0 = v10 > v00, tb1 = v11 > v01;
-                    s0 = (tb0 ? v10 : v00) + le.x;
-                    s1 = (tb1 ? v11 : v01) + le.y;
-                    tbacc |= ((uint32_t)tb0 | ((uint32_t)tb1 << 1)) << ((t & 15) * 2);
-                    const double f0 = lse_lut2(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
-                    const double f1 = lse_lut2(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
-                    a0 = f0;
-                    a1 = f1;
-                    sum0 = sum0 + le.x;
-                }
-                ps = ps + lr0;
-                if (t >= c - 1) {
-                    const double d = ps - psl;
-                    if (t == c - 1 || d > llr_best) {
-                        llr_best = d;
-                        llr_stop = t;
-                    }
-                }
-                if (t >= mw - 1) {
-                    if (t == mw - 1 || qn > mw_best) {
-                        mw_best = qn;
-                        mw_stop = t;
-                    }
-                } else if (t == n - 1) {
-                    mw_best = qn;
-                    mw_stop = t;
-                }
+                for (int i = 0; i < 4; i++) step(std::true_type{}, std::true_type{}, tbase + i, i, w0, wc, wm);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) step(std::true_type{}, std::false_type{}, tbase + i, i, w0, wc, wm);
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) step(std::false_type{}, std::false_type{}, tbase + i, i, w0, wc, wm);
         }
         if ((wv & 3) == 3) {
             tbp[(size_t)(wv >> 2) * 32] = tbacc;
@@ -234,7 +267,7 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     const double e0v = s0 + ks.lf0, e1v = s1 + ks.lf1;
     const int vlast = e1v > e0v ? 1 : 0;
     const double lvit = vlast ? e1v : e0v;
-    const double lmarg = lse_lut2(a0 + ks.lf0, a1 + ks.lf1, lut_addr);
+    const double lmarg = lse_lut2<false>(a0 + ks.lf0, a1 + ks.lf1, lut_addr);
     r->hmm_all = lmarg - sum0;
     r->hmm_vit = lvit - sum0;
 
@@ -308,8 +341,100 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
     if (halfw > n / 2) halfw = n / 2;
     const int fi_hi = n - halfw;     // FoldIndex scan is over p in [halfw, fi_hi)
     const int edge_hi = n - 1 - w;   // windows centred beyond this are clipped on the right
-    int fi_run_start = -1, fi_numaa = 0, fi_maxrun = 0;
+    int fi_run = 0, fi_numaa = 0, fi_maxrun = 0;  // fi_run: length of the open run of fi < 0 (snaps included)
     uint32_t lo1 = kPadW, lo2 = kPadW;
+    const double WfullD = (double)Wfull;
+    const double cc2W = ks.cc2 * WfullD;
+    const double cc0 = ks.cc0, cc1 = ks.cc1;
+
+    int nmin = (prot >= 0) ? n : 0x7fffffff;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, d));
+    const int fast_lo = 4 * w;  // from here on p = t-w >= 3w and k = t-2w >= 2w: no left-edge effects
+
+    // one residue step; FAST: 4w <= t < n for every lane, so every window below is unclipped and in range
+    auto step = [&](auto fast_tag, int t, int i, uint32_t w0, uint32_t w1, uint32_t w2) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        // ext code bits 5:0 of byte i -> address bits 12:7; charge = sign-extended bits 7:6
+        const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (63u << 7);
+        const uint32_t k1 = (i == 0 ? (w1 << 7) : (w1 >> (8 * i - 7))) & (63u << 7);
+        const uint32_t k2 = (i == 0 ? (w2 << 7) : (w2 >> (8 * i - 7))) & (63u << 7);
+        const int ch0 = (int)(w0 << (24 - 8 * i)) >> 30;
+        const int ch1 = (int)(w1 << (24 - 8 * i)) >> 30;
+        const int ch2 = (int)(w2 << (24 - 8 * i)) >> 30;
+        const double hy0 = lds_f64(hb | k0), pa0 = lds_f64_off<kOffPapB>(hb | k0);
+        const double hy1 = lds_f64(hb | k1), pa1 = lds_f64_off<kOffPapB>(hb | k1);
+        const double hy2 = lds_f64(hb | k2), pa2 = lds_f64_off<kOffPapB>(hb | k2);
+        if (FAST || t < n) {
+            sh = sh + hy0;  // mean() :1584, sequential
+            csum += ch0;
+        }
+        // window sums of the zero-padded sequence: lead centre p = t-w, lag centre p-(2w+1)
+        SLh = (SLh + hy0) - hy1;
+        SGh = (SGh + hy1) - hy2;
+        Th = (Th + SLh) - SGh;
+        Dp = Dp + ((pa0 + pa2) - (pa1 + pa1));  // exact: PAPA log-odds live on a 2^-k grid
+        Tp = Tp + Dp;
+        SLc += ch0 - ch1;
+        SGc += ch1 - ch2;
+        const int aSL = abs(SLc);
+        Tac += aSL - abs(SGc);
+        const int p = t - w;
+        // FoldIndex run scan :5010-5059 over i in [halfw, n-halfw):
+        // sign of fi[p] = cc0*hydro + cc1*|charge| + cc2, scaled by the tap count (> 0)
+        if (FAST) {
+            const double fis = (cc0 * SLh + cc1 * u2d((uint32_t)aSL)) + cc2full;
+            const bool neg = fis < 0;
+            const int closed = (!neg && fi_run >= 5) ? fi_run : 0;
+            fi_numaa += closed;
+            fi_maxrun = max(fi_maxrun, closed);
+            fi_run = neg ? fi_run + 1 : 0;
+        } else if (p >= halfw && p < fi_hi) {
+            double c2 = cc2full;
+            if (p < w || p > edge_hi) c2 = ks.cc2 * u2d((uint32_t)(full - max(0, w - p) - max(0, p - edge_hi)));
+            const double fis = (cc0 * SLh + cc1 * u2d((uint32_t)aSL)) + c2;
+            const bool neg = fis < 0;
+            const bool last = (p == fi_hi - 1);
+            // a run that starts at the first scanned position is snapped back to residue 0,
+            // one that reaches the last scanned position is snapped forward to residue n-1
+            if (neg) fi_run = (fi_run == 0 && p == halfw) ? halfw + 1 : fi_run + 1;
+            if (!neg || last) {
+                const int len = fi_run + ((neg && last) ? (n - 1 - p) : 0);
+                if (len >= 5) {
+                    fi_numaa += len;
+                    fi_maxrun = max(fi_maxrun, len);
+                }
+                fi_run = 0;
+            }
+        }
+        // PAPA centre k = p - w: first strict maximum of Tp/W among centres with fix2 < 0 (:4941-4948)
+        // Tp/Wd > Tb/Wb  <=>  Tp*Wb > Tb*Wd (both positive); products of grid units and small ints
+        if (FAST) {
+            const double vfi = (cc0 * Th + cc1 * u2d((uint32_t)Tac)) + cc2W;
+            if ((pcen < 0 || Tp * Wb > Tb * WfullD) && vfi < 0) {
+                Tb = Tp;
+                Wb = WfullD;
+                vfib = vfi;
+                pcen = t - 2 * w;
+            }
+        } else {
+            const int k = p - w;
+            if (k >= w && k <= edge_hi) {
+                double Wd = WfullD;
+                if (k < 2 * w || k > edge_hi - w) {
+                    const int ml = 2 * w - k, mr = k - (edge_hi - w);
+                    Wd = u2d((uint32_t)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0)));
+                }
+                const double vfi = (cc0 * Th + cc1 * u2d((uint32_t)Tac)) + ks.cc2 * Wd;
+                if ((pcen < 0 || Tp * Wb > Tb * Wd) && vfi < 0) {
+                    Tb = Tp;
+                    Wb = Wd;
+                    vfib = vfi;
+                    pcen = k;
+                }
+            }
+        }
+    };
 
     uint4 nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
     if (nch > 0) nxt = sp[0];
@@ -332,70 +457,12 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         lo1 = hi1;
         lo2 = hi2;
         const int tbase = wv * 4;
+        if (tbase >= fast_lo && tbase + 3 < nmin) {  // warp-uniform
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int t = tbase + i;
-            // ext code bits 5:0 of byte i -> address bits 12:7; charge = sign-extended bits 7:6
-            const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (63u << 7);
-            const uint32_t k1 = (i == 0 ? (w1 << 7) : (w1 >> (8 * i - 7))) & (63u << 7);
-            const uint32_t k2 = (i == 0 ? (w2 << 7) : (w2 >> (8 * i - 7))) & (63u << 7);
-            const int ch0 = (int)(w0 << (24 - 8 * i)) >> 30;
-            const int ch1 = (int)(w1 << (24 - 8 * i)) >> 30;
-            const int ch2 = (int)(w2 << (24 - 8 * i)) >> 30;
-            const double hy0 = lds_f64(hb | k0), pa0 = lds_f64_off<kOffPapB>(hb | k0);
-            const double hy1 = lds_f64(hb | k1), pa1 = lds_f64_off<kOffPapB>(hb | k1);
-            const double hy2 = lds_f64(hb | k2), pa2 = lds_f64_off<kOffPapB>(hb | k2);
-            if (t < n) {
-                sh = sh + hy0;  // mean() :1584, sequential
-                csum += ch0;
-            }
-            // window sums of the zero-padded sequence: lead centre p = t-w, lag centre p-(2w+1)
-            SLh = (SLh + hy0) - hy1;
-            SGh = (SGh + hy1) - hy2;
-            Th = (Th + SLh) - SGh;
-            Dp = Dp + ((pa0 + pa2) - (pa1 + pa1));  // exact: PAPA log-odds live on a 2^-k grid
-            Tp = Tp + Dp;
-            SLc += ch0 - ch1;
-            SGc += ch1 - ch2;
-            const int aSL = abs(SLc);
-            Tac += aSL - abs(SGc);
-            const int p = t - w;
-            // FoldIndex run scan :5010-5059 over i in [halfw, n-halfw):
-            // sign of fi[p] = cc0*hydro + cc1*|charge| + cc2, scaled by the tap count (> 0)
-            if (p >= halfw && p < fi_hi) {
-                double c2 = cc2full;
-                if (p < w || p > edge_hi) c2 = ks.cc2 * u2d((uint32_t)(full - max(0, w - p) - max(0, p - edge_hi)));
-                const double fis = (ks.cc0 * SLh + ks.cc1 * u2d((uint32_t)aSL)) + c2;
-                const bool neg = fis < 0;
-                if (neg && fi_run_start < 0) fi_run_start = (p == halfw) ? 0 : p;
-                const bool last = (p == fi_hi - 1);
-                if (fi_run_start >= 0 && (!neg || last)) {
-                    const int stop = neg ? (n - 1) : (p - 1);
-                    const int len = stop - fi_run_start + 1;
-                    if (len >= 5) {
-                        fi_numaa += len;
-                        fi_maxrun = max(fi_maxrun, len);
-                    }
-                    fi_run_start = -1;
-                }
-            }
-            // PAPA centre k = p - w: first strict maximum of Tp/W among centres with fix2 < 0 (:4941-4948)
-            const int k = p - w;
-            if (k >= w && k <= edge_hi) {
-                double Wd = (double)Wfull;
-                if (k < 2 * w || k > edge_hi - w) {
-                    const int ml = 2 * w - k, mr = k - (edge_hi - w);
-                    Wd = u2d((uint32_t)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0)));
-                }
-                // Tp/Wd > Tb/Wb  <=>  Tp*Wb > Tb*Wd (both positive); products of grid units and small ints
-                const double vfi = (ks.cc0 * Th + ks.cc1 * u2d((uint32_t)Tac)) + ks.cc2 * Wd;
-                if ((pcen < 0 || Tp * Wb > Tb * Wd) && vfi < 0) {
-                    Tb = Tp;
-                    Wb = Wd;
-                    vfib = vfi;
-                    pcen = k;
-                }
-            }
+            for (int i = 0; i < 4; i++) step(std::true_type{}, tbase + i, i, w0, w1, w2);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) step(std::false_type{}, tbase + i, i, w0, w1, w2);
         }
     }
 
