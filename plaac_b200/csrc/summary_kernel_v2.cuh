@@ -457,7 +457,8 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         lo1 = hi1;
         lo2 = hi2;
         const int tbase = wv * 4;
-        if (tbase >= fast_lo && tbase + 3 < nmin) {  // warp-uniform
+        // warp-uniform; t <= nmin-2 keeps the last scanned FoldIndex position (p = n-1-halfw) out of the fast path
+        if (tbase >= fast_lo && tbase + 3 < nmin - 1) {
 #pragma unroll
             for (int i = 0; i < 4; i++) step(std::true_type{}, tbase + i, i, w0, w1, w2);
         } else {
