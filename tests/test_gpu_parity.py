@@ -215,3 +215,66 @@ def test_throughput_kernel_against_reference_order_anchor_at_scale():
         assert ra[f].tobytes() == rb[f].tobytes(), f
     for f in ("papa_prop", "papa_fi", "papa_llr", "papa_llr2", "papa_combo"):
         assert parity.close(rb[f][same_cen], ra[f][same_cen], parity.SCALE[f]).all(), f
+
+
+# ----------------------------------------------------------------------------- per-residue mode (config 2)
+def _check_residue(got, ref, what=""):
+    for k in orc.RESIDUE_U8:
+        bad = np.nonzero(got[k] != ref[k])[0]
+        assert len(bad) == 0, (what, k, len(bad), bad[:5])
+    for k in orc.RESIDUE_F64:
+        assert (np.isnan(got[k]) == np.isnan(ref[k])).all(), (what, k, "NaN pattern")
+        ok = parity.close(got[k], ref[k], parity.SCALE[k])
+        assert ok.all(), (what, k, int((~ok).sum()), got[k][~ok][:3], ref[k][~ok][:3])
+
+
+def test_per_residue_against_golden_fixture(scorer, golden):
+    seqs = [plaac_b200.encode(p["seq"]) for p in golden["proteins"]]
+    codes, offs = plaac_b200.pack(seqs)
+    summ, res = scorer.score(codes, offs, per_residue=True)
+    for i, prot in enumerate(golden["proteins"]):
+        lo = int(offs[i])
+        for k, vals in prot["residue"].items():
+            for j, v in zip(prot["residue_idx"], vals):
+                x = res[k][lo + j]
+                if v is None:
+                    assert x != x, (prot["name"], k, j)
+                elif k in orc.RESIDUE_U8:
+                    assert int(x) == int(v), (prot["name"], k, j)
+                else:
+                    assert parity.close(x, v, parity.SCALE[k]), (prot["name"], k, j, x, v)
+        runs = lambda bits: [[int(a), int(b)] for a, b in zip(
+            np.nonzero(np.diff(np.r_[0, bits.astype(np.int64), 0]) == 1)[0],
+            np.nonzero(np.diff(np.r_[0, bits.astype(np.int64), 0]) == -1)[0] - 1)]
+        assert runs(res["vit"][lo:int(offs[i + 1])]) == prot["vit_runs"]
+        assert runs(res["map"][lo:int(offs[i + 1])]) == prot["map_runs"]
+    # the summary rows of the same call are the summary-mode rows
+    assert summ.tobytes() == scorer.score(codes, offs).tobytes()
+
+
+def test_per_residue_yeast_sized(scorer):
+    """Config 2: yeast-proteome-sized set with per-residue Viterbi parse and posterior output."""
+    codes, offs = synth.proteome(6000, seed=1001)
+    _, got = scorer.score(codes, offs, per_residue=True)
+    ref = orc.residue_batch(orc.make_params(), codes, offs, nthreads=NT)
+    _check_residue(got, ref, "yeast-sized per-residue")
+
+
+def test_per_residue_edge_cases_and_chunking():
+    codes, offs = synth.edge_cases()
+    sc = plaac_b200.Scorer()
+    sc.set_chunk(max_residues=3000, max_proteins=7)
+    _, got = sc.score(codes, offs, per_residue=True)
+    sc.close()
+    ref = orc.residue_batch(orc.make_params(), codes, offs)
+    _check_residue(got, ref, "edge cases per-residue")
+
+
+def test_per_residue_long_and_other_params():
+    codes, offs = synth.long_proteins(lengths=(35000,))
+    kw = dict(core_len=30, ww1=21, ww2=21, alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS)
+    sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    _, got = sc.score(codes, offs, per_residue=True)
+    sc.close()
+    ref = orc.residue_batch(orc.make_params(**kw), codes, offs)
+    _check_residue(got, ref, "long per-residue")
