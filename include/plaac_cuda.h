@@ -134,6 +134,20 @@ int plaac_score_device(plaac_ctx *ctx, const uint8_t *d_codes, const int64_t *d_
 int plaac_sync(plaac_ctx *ctx);
 void *plaac_stream(plaac_ctx *ctx); /* cudaStream_t of the ctx */
 
+/* ---- multi-GPU: proteins are independent, so the batch is cut into contiguous,
+ * residue-balanced shards, one per ctx (each ctx on its own GPU), scored concurrently by one host thread per
+ * ctx, each writing its records / per-residue rows straight into the caller's arrays at the input position.
+ * No collective, no gather copy.  The reference has no counterpart (the jar is single-threaded). */
+
+/* Shard plan: bounds[0..nshards], bounds[0] = 0, bounds[nshards] = nprot, shard k = proteins
+ * [bounds[k], bounds[k+1]).  Balanced on (residues + 64 per protein).  Pure host arithmetic (no GPU needed). */
+int plaac_shard_plan(const int64_t *offsets, int64_t nprot, int nshards, int64_t *bounds);
+
+/* Same contract as plaac_score() with nctx contexts.  Returns the first non-zero shard return code
+ * (its text is on that shard's ctx); all shards are always joined before returning. */
+int plaac_score_multi(plaac_ctx *const *ctxs, int nctx, const uint8_t *codes, const int64_t *offsets, int64_t nprot,
+                      plaac_summary *summaries, const plaac_residue_out *per_res);
+
 /* Host-side parameter chain for hosts that do not have their own (the C++ CLI, Python tests): what
  * plaac.java main computes between :310 and :518 -- bg/fg mixing with alpha (:449-458), the 1e-5
  * pseudo-frequency for X and * (:490-496), llr (:497-500), prionhmm1/prionhmm0 (:968-1001) through

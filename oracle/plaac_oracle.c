@@ -672,23 +672,56 @@ int orc_max_threads(void)
 #endif
 }
 
-/* java.util.Formatter "%.<d>f": BigDecimal(x).setScale(d, HALF_UP).  C's printf
- * rounds the exact binary value half-to-even, so the two differ only when the
- * exact value is a tie, i.e. x * 2^(d+1) ... more precisely x*10^d has
- * fractional part exactly 1/2, which (x being a dyadic rational) needs
- * x * 2 * 10^d to be an odd integer => x * 2^(d+1) is an odd integer. */
+/* java.util.Formatter "%.<d>f" (plaac.java:899-945, :638-641).  The JDK does NOT round the exact binary
+ * value: Formatter hands the double to sun.misc.FormattedFloatingDecimal, which takes the SHORTEST decimal
+ * digit string that identifies the double (the digits of Double.toString) and rounds THAT half-up
+ * (applyPrecision).  So 1.0005 (binary 1.000499999999999989...) prints as 1.001 where C prints 1.000.
+ * Restated here: shortest round-trip digits via "%.{p}e", then schoolbook half-up on the digit string. */
 int orc_java_fmt(char *buf, int buflen, double x, int d)
 {
     if (isnan(x)) return snprintf(buf, buflen, "NaN");
     if (isinf(x)) return snprintf(buf, buflen, x > 0 ? "Infinity" : "-Infinity");
+    char sci[64];
     double ax = fabs(x);
-    if (ax < 4503599627370496.0 /* 2^52 */) {
-        double s = ldexp(ax, d + 1); /* exact */
-        if (s == floor(s) && fmod(s, 2.0) == 1.0) {
-            /* exact tie: round half up (away from zero); nudge by one ulp-ish step */
-            double up = nextafter(ax, INFINITY);
-            return snprintf(buf, buflen, "%s%.*f", x < 0 ? "-" : "", d, up);
+    int p;
+    for (p = 0; p < 17; p++) {
+        snprintf(sci, sizeof sci, "%.*e", p, ax);
+        if (strtod(sci, NULL) == ax) break;
+    }
+    char digits[32];
+    int nd = 0;
+    const char *q = sci;
+    for (; *q && *q != 'e'; q++)
+        if (*q != '.') digits[nd++] = *q;
+    int point = atoi(q + 1) + 1; /* digits before the decimal point */
+    int keep = point + d;
+    char out[400];
+    int no = 0;
+    if (keep <= 0) {
+        for (int i = 0; i < d + 1; i++) out[no++] = '0';
+        if (keep == 0 && nd > 0 && digits[0] >= '5') out[no - 1] = '1';
+    } else {
+        for (int i = 0; i < keep; i++) out[no++] = i < nd ? digits[i] : '0';
+        if (keep < nd && digits[keep] >= '5') {
+            int i = no - 1;
+            while (i >= 0 && out[i] == '9') out[i--] = '0';
+            if (i >= 0)
+                out[i]++;
+            else {
+                memmove(out + 1, out, (size_t)no);
+                out[0] = '1';
+                no++;
+            }
+        }
+        while (no - d <= 0) {
+            memmove(out + 1, out, (size_t)no);
+            out[0] = '0';
+            no++;
         }
     }
-    return snprintf(buf, buflen, "%.*f", d, x);
+    out[no] = 0;
+    int intd = no - d;
+    if (d > 0)
+        return snprintf(buf, buflen, "%s%.*s.%s", signbit(x) ? "-" : "", intd, out, out + intd);
+    return snprintf(buf, buflen, "%s%s", signbit(x) ? "-" : "", out);
 }

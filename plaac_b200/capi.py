@@ -99,6 +99,10 @@ def lib():
         L.plaac_set_kernel_variant.argtypes = [vp, C.c_int]
         L.plaac_get_stats.restype = C.c_int
         L.plaac_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.plaac_shard_plan.restype = C.c_int
+        L.plaac_shard_plan.argtypes = [vp, i64, C.c_int, vp]
+        L.plaac_score_multi.restype = C.c_int
+        L.plaac_score_multi.argtypes = [C.POINTER(vp), C.c_int, vp, vp, i64, vp, C.POINTER(ResidueOut)]
         L.plaac_bench_synth_lengths.restype = C.c_int
         L.plaac_bench_synth_lengths.argtypes = [vp, C.c_uint64, i64, i64, dbl, dbl, i32, i32, vp]
         L.plaac_bench_synth_residues.restype = C.c_int
@@ -229,3 +233,49 @@ class Scorer:
         s = Stats()
         self._check(lib().plaac_get_stats(self._h, C.byref(s)))
         return s
+
+
+def shard_plan(offsets: np.ndarray, nshards: int) -> np.ndarray:
+    """plaac_shard_plan: contiguous, residue-balanced shard bounds (nshards+1 protein indices).  Host arithmetic only."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    bounds = np.zeros(nshards + 1, dtype=np.int64)
+    rc = lib().plaac_shard_plan(offsets.ctypes.data, len(offsets) - 1, nshards, bounds.ctypes.data)
+    if rc != 0:
+        raise PlaacError(rc, "plaac_shard_plan failed")
+    return bounds
+
+
+class MultiScorer:
+    """One ctx per GPU of this box, driven from one process through plaac_score_multi (one host thread per GPU)."""
+
+    def __init__(self, params: Params | None = None, devices=None):
+        n = lib().plaac_device_count()
+        if devices is None:
+            devices = list(range(n))
+        if not devices:
+            raise PlaacError(-5, "no CUDA device (there is no CPU fallback)")
+        self.scorers = [Scorer(params, d) for d in devices]
+
+    def close(self):
+        for s in self.scorers:
+            s.close()
+        self.scorers = []
+
+    def score(self, codes: np.ndarray, offsets: np.ndarray, per_residue: bool = False):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        nprot = len(offsets) - 1
+        out = np.zeros(nprot, dtype=SUMMARY_DTYPE)
+        res, ro = None, None
+        if per_residue:
+            ntot = int(offsets[-1] - offsets[0])
+            res = {n: np.zeros(ntot, dtype=np.uint8) for n in RESIDUE_U8}
+            res.update({n: np.zeros(ntot, dtype=np.float64) for n in RESIDUE_F64})
+            ro = C.byref(ResidueOut(**{n: a.ctypes.data for n, a in res.items()}))
+        handles = (C.c_void_p * len(self.scorers))(*[s._h for s in self.scorers])
+        rc = lib().plaac_score_multi(handles, len(self.scorers), codes.ctypes.data, offsets.ctypes.data, nprot,
+                                     out.ctypes.data, ro)
+        if rc != 0:
+            msgs = [lib().plaac_last_error(s._h).decode() for s in self.scorers]
+            raise PlaacError(rc, "; ".join(m for m in msgs if m) or lib().plaac_last_error(None).decode())
+        return (out, res) if per_residue else out

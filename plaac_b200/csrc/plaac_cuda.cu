@@ -640,3 +640,74 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ multi-GPU
+#include <thread>
+
+extern "C" {
+
+int plaac_shard_plan(const int64_t* offsets, int64_t nprot, int nshards, int64_t* bounds)
+{
+    if (!offsets || !bounds || nprot < 0 || nshards < 1) return PLAAC_E_INVALID;
+    constexpr int64_t kPerProtein = 64;  // per-record overhead in residue equivalents
+    const int64_t base = offsets[0];
+    auto cost = [&](int64_t i) { return (offsets[i] - base) + kPerProtein * i; };  // monotone prefix cost
+    const int64_t total = cost(nprot);
+    bounds[0] = 0;
+    for (int k = 1; k < nshards; k++) {
+        const int64_t target = (int64_t)(((__int128)total * k) / nshards);
+        int64_t lo = bounds[k - 1], hi = nprot;  // first i with cost(i) >= target
+        while (lo < hi) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if (cost(mid) >= target)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        bounds[k] = lo;
+    }
+    bounds[nshards] = nprot;
+    return PLAAC_OK;
+}
+
+int plaac_score_multi(plaac_ctx* const* ctxs, int nctx, const uint8_t* codes, const int64_t* offsets, int64_t nprot,
+                      plaac_summary* summaries, const plaac_residue_out* per_res)
+{
+    if (!ctxs || nctx < 1) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi: no contexts");
+    for (int k = 0; k < nctx; k++)
+        if (!ctxs[k]) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi: NULL ctx %d", k);
+    if (nctx == 1) return plaac_score(ctxs[0], codes, offsets, nprot, summaries, per_res);
+    if (nprot < 0 || !offsets) return fail(ctxs[0], PLAAC_E_INVALID, "plaac_score_multi: bad offsets/nprot");
+    if (nprot == 0) return PLAAC_OK;
+    std::vector<int64_t> bounds((size_t)nctx + 1);
+    plaac_shard_plan(offsets, nprot, nctx, bounds.data());
+    std::vector<int> rcs((size_t)nctx, PLAAC_OK);
+    std::vector<std::thread> threads;
+    for (int k = 0; k < nctx; k++) {
+        const int64_t lo = bounds[k], hi = bounds[k + 1];
+        if (hi <= lo) continue;
+        threads.emplace_back([=, &rcs]() {
+            plaac_residue_out shifted;
+            const plaac_residue_out* pr = nullptr;
+            if (per_res) {
+                const int64_t o = offsets[lo] - offsets[0];
+                shifted = *per_res;
+                uint8_t** u8s[2] = {&shifted.vit, &shifted.map};
+                for (auto p : u8s)
+                    if (*p) *p += o;
+                double** f64s[10] = {&shifted.charge, &shifted.hydro,   &shifted.fi,     &shifted.plaac,   &shifted.papa,
+                                     &shifted.fix2,   &shifted.plaacx2, &shifted.papax2, &shifted.post_bg, &shifted.post_prd};
+                for (auto p : f64s)
+                    if (*p) *p += o;
+                pr = &shifted;
+            }
+            rcs[k] = plaac_score(ctxs[k], codes, offsets + lo, hi - lo, summaries ? summaries + lo : nullptr, pr);
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int k = 0; k < nctx; k++)
+        if (rcs[k] != PLAAC_OK) return rcs[k];
+    return PLAAC_OK;
+}
+
+}  // extern "C"
