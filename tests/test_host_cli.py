@@ -31,6 +31,7 @@ def run(cli, *args, stdin=None):
 
 def java_fmt(x, d):
     """java.util.Formatter %.<d>f: half-up on the shortest round-trip digits (= Python's repr digits)."""
+    x = float(x)
     if math.isnan(x):
         return "NaN"
     if math.isinf(x):
