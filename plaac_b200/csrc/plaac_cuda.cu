@@ -332,9 +332,9 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
 
     const bool use_v2 = ctx->variant == 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);
     if (d_summaries && use_v2) {
-        if ((rc = ensure(ctx, s.core_list, sizeof(int32_t) * nprot))) return rc;
-        if ((rc = ensure(ctx, s.core_count, sizeof(int32_t)))) return rc;
-        CU(ctx, cudaMemsetAsync(s.core_count.p, 0, sizeof(int32_t), st));
+        if ((rc = ensure(ctx, s.core_list, sizeof(int32_t) * 2 * nprot))) return rc;
+        if ((rc = ensure(ctx, s.core_count, 16))) return rc;  // [0] CORE list length, [8] work-queue counter
+        CU(ctx, cudaMemsetAsync(s.core_count.p, 0, 16, st));
     }
     CU(ctx, cudaEventRecord(s.ev_b, st));
     if (d_summaries && use_v2) {
@@ -348,9 +348,16 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         g.core_list = (int32_t*)s.core_list.p;
         g.core_count = (int32_t*)s.core_count.p;
         g.always_in = ctx->v2_always_in;
-        const unsigned grid = (unsigned)((nbuckets + g.nwr - 1) / g.nwr);
+        g.work_counter = (unsigned long long*)((char*)s.core_count.p + 8);
+        const int64_t nitems = 2 * nbuckets, wpc = 2 * g.nwr;
+        const unsigned grid = (unsigned)std::min<int64_t>((nitems + wpc - 1) / wpc, ctx->sm_count);  // 1 CTA per SM
         k_score_summary_v2<<<grid, g.nwr * 64, ctx->v2_smem_bytes, st>>>(g);
-        k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
+        // masked stretches can be jumped exactly when the masking constant is a negative integer (it is -1e6)
+        const double bn = ctx->ks.big_neg;
+        if (bn < 0 && bn == std::floor(bn) && bn >= -4194304.0)
+            k_core_search_jump<<<ctx->sm_count * 8, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
+        else
+            k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
         ctx->stats.kernel_launches += 2;
         ctx->stats.score_launches += 1;
     } else if (d_summaries) {

@@ -107,6 +107,7 @@ struct V2Args {
     int32_t* core_list;   // ranks needing the CORE search
     int32_t* core_count;
     int always_in;        // 1: |a-b| < 40 is guaranteed inside the forward recurrence (bound checked on the host)
+    unsigned long long* work_counter;  // zeroed before the launch
 };
 
 // ------------------------------------------------------------------------------------------------ role A
@@ -134,10 +135,12 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     const uint32_t lut_addr = sbase + kOffLut2;
 
     double s0 = 0, s1 = 0, a0 = 0, a1 = 0, sum0 = 0;
-    double ps = 0, psl = 0, llr_best = -INFINITY;
+    // Sentinels: until the first complete window (t = c-1 resp. mw-1, always taken in the generic path, which
+    // assigns unconditionally) no candidate can beat +Inf / INT_MAX, so the fast path needs no range test.
+    double ps = 0, psl = 0, llr_best = INFINITY;
     int llr_stop = -2;
-    int qn = 0, mw_best = 0, mw_stop = -1;
-    uint32_t tbacc = 0;
+    int qn = 0, mw_best = 0x7fffffff, mw_stop = -1;
+    uint32_t acc0 = 0, acc1 = 0;  // traceback bit planes, newest residue at bit 31
 
     // lagged byte streams: position t - off, off = 4*a + b
     const int ac = c >> 2, sc_ = 8 * (4 - (c & 3));
@@ -150,9 +153,9 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     int nmin = (prot >= 0) ? n : 0x7fffffff;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, d));
-    const int fast_lo = max(max(c, mw), 1);  // every window is full and t > 0 from here on
+    const int wv_c1 = (c - 1) >> 2, wv_m1 = (mw - 1) >> 2;  // words holding the first complete LLR / MW window
 
-    // one residue step; FAST: every lane has t in [max(c,mw), n) so all range tests are known
+    // one residue step; FAST: every lane has 0 < t < n-1 and t is not the first complete window of either search
     auto step = [&](auto fast_tag, auto in_tag, int t, int i, uint32_t w0, uint32_t wc, uint32_t wm) {
         constexpr bool FAST = decltype(fast_tag)::value;
         constexpr bool AIN = decltype(in_tag)::value;
@@ -164,7 +167,7 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
         const double lrc = lds_f64(ll_base | kc);
         psl = psl + lrc;  // == psum[t-c+1]  (pad codes add +0.0)
         qn += (int)((ks.qn_mask >> ((w0 >> (8 * i)) & 31u)) & 1u) - (int)((ks.qn_mask >> ((wm >> (8 * i)) & 31u)) & 1u);
-        uint32_t bits = 0;
+        uint32_t tb0u = 0, tb1u = 0;
         if (FAST || t < n) {
             if (!FAST && t == 0) {
                 s0 = ks.li0 + le.x;
@@ -178,7 +181,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
                 const bool tb0 = v10 > v00, tb1 = v11 > v01;
                 s0 = (tb0 ? v10 : v00) + le.x;
                 s1 = (tb1 ? v11 : v01) + le.y;
-                bits = (uint32_t)tb0 | ((uint32_t)tb1 << 1);
+                tb0u = tb0;
+                tb1u = tb1;
                 const double f0 = lse_lut2<AIN>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
                 const double f1 = lse_lut2<AIN>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
                 a0 = f0;
@@ -203,7 +207,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
                 mw_stop = t;
             }
         }
-        tbacc = __funnelshift_r(tbacc, bits, 2);  // after 16 steps the bits of residue 16j+i sit at 2i
+        acc0 = __funnelshift_r(acc0, tb0u, 1);  // after 16 steps the bit of residue 16j+i sits at 16+i
+        acc1 = __funnelshift_r(acc1, tb1u, 1);
     };
 
 #pragma unroll 1
@@ -225,7 +230,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
         lo_c = hi_c;
         lo_m = hi_m;
         const int tbase = wv * 4;
-        if (tbase >= fast_lo && tbase + 3 < nmin) {  // warp-uniform
+        // warp-uniform; t = nmin-1 stays generic so the "whole protein is one MW window" case (n < mw) is seen there
+        if (wv != 0 && wv != wv_c1 && wv != wv_m1 && tbase + 3 < nmin - 1) {
             if (g.always_in) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) step(std::true_type{}, std::true_type{}, tbase + i, i, w0, wc, wm);
@@ -238,8 +244,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
             for (int i = 0; i < 4; i++) step(std::false_type{}, std::false_type{}, tbase + i, i, w0, wc, wm);
         }
         if ((wv & 3) == 3) {
-            tbp[(size_t)(wv >> 2) * 32] = tbacc;
-            tbacc = 0;
+            // low half: predecessor-of-state-0 bits of the slot's 16 residues, high half: predecessor-of-state-1 bits
+            tbp[(size_t)(wv >> 2) * 32] = __byte_perm(acc0, acc1, 0x7632);
         }
     }
 
@@ -271,17 +277,48 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     r->hmm_all = lmarg - sum0;
     r->hmm_vit = lvit - sum0;
 
-    // traceback :3110-3113 + longestrun :1787-1804; the Viterbi bits replace the traceback words
+    // traceback :3110-3113 + longestrun :1787-1804, 16 residues at a time; the Viterbi bits replace the
+    // traceback words.  Residue i of a slot maps the state at i to the state at i-1: f_i = (P0[i], P1[i]).
+    // state_i = (f_{i+1} o ... o f_hi)(state_hi): a suffix scan of 2->2 maps (Kogge-Stone on two bit planes).
     int v = vlast, cur = 0, mx = 0;
-    for (int j = (n - 1) >> 4; j >= 0; j--) {
-        const uint32_t tw = tbp[(size_t)j * 32];
-        uint32_t vb = 0;
-        const int hi = (j == ((n - 1) >> 4)) ? ((n - 1) & 15) : 15;
-        for (int i = hi; i >= 0; i--) {
-            vb |= (uint32_t)v << i;
-            cur = v ? cur + 1 : 0;
+    const int jlast = (n - 1) >> 4;
+    int jhi = -1, jlo = 0;  // highest / lowest slot holding a Viterbi-1 residue
+    uint32_t tw_next = tbp[(size_t)jlast * 32];
+    for (int j = jlast; j >= 0; j--) {
+        const uint32_t tw = tw_next;
+        if (j > 0) tw_next = tbp[(size_t)(j - 1) * 32];
+        const int hi = (j == jlast) ? ((n - 1) & 15) : 15;
+        const uint32_t valid = (2u << hi) - 1u;  // residues 0..hi of the slot
+        const uint32_t below = valid >> 1;       // residues 0..hi-1
+        const uint32_t P0 = tw & 0xffffu, P1 = tw >> 16;
+        uint32_t A0 = (P0 >> 1) & below;                           // S_i(0), S_i = f_{i+1} for i < hi, identity above
+        uint32_t A1 = ((P1 >> 1) & below) | (0xffffu & ~below);    // S_i(1)
+#pragma unroll
+        for (int sft = 1; sft < 16; sft <<= 1) {
+            const uint32_t B0 = A0 >> sft;                                      // S_{i+sft}, identity shifted in
+            const uint32_t B1 = (A1 >> sft) | (0xffffu & ~(0xffffu >> sft));
+            const uint32_t n0 = (B0 & A1) | (~B0 & A0);                         // (S_i o S_{i+sft})(0)
+            const uint32_t n1 = (B1 & A1) | (~B1 & A0);
+            A0 = n0;
+            A1 = n1;
+        }
+        const uint32_t vb = (v ? A1 : A0) & valid;
+        v = (int)(((vb & 1u) ? P1 : P0) & 1u);  // state of the residue before this slot
+        if (vb == valid) {
+            cur += hi + 1;
             mx = max(mx, cur);
-            v = (tw >> (2 * i + v)) & 1;
+        } else if (vb == 0) {
+            cur = 0;
+        } else {
+            mx = max(mx, cur + __clz((int)~(vb << (31 - hi))));  // run entering from above continues downward
+            int len = 0;
+            for (uint32_t x = vb; x; x &= x >> 1) len++;
+            mx = max(mx, len);
+            cur = __ffs((int)~vb) - 1;  // ones at the bottom continue into the next slot
+        }
+        if (vb) {
+            if (jhi < 0) jhi = j;
+            jlo = j;
         }
         tbp[(size_t)j * 32] = vb;
     }
@@ -294,7 +331,9 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     r->prd_score = 0.0;
     if (mx >= c && n >= c) {
         const int slot = atomicAdd(g.core_count, 1);
-        g.core_list[slot] = (int32_t)rank;
+        g.core_list[2 * slot] = (int32_t)rank;
+        // slots the CORE search has to visit (everything outside is masked); 16 bits each, else the whole protein
+        g.core_list[2 * slot + 1] = (jhi < 65536) ? (jlo | (jhi << 16)) : (int32_t)0xffff0000;
     }
 }
 
@@ -490,12 +529,31 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         r->papa_fi = vfib / Wb;
         // PAPAllr = plaacllr[pcen]: 2w+1 taps in reference order (:2604-2620; pcen is interior).
         // PAPAllr2 = plaacllrx2[pcen] = sum_q (2w+1-|q-pcen|) llr[q] / W over the zero-padded sequence.
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(sp);
+        // The 4w+1 residues around the centre are re-staged into the lane's ring column (whole 16-byte slots,
+        // independent loads first), so the tap loop below reads shared memory only.
         const uint32_t lb = sbase + kOffLlrB + (uint32_t)(lane & 15) * 8u;
+        const int q0 = max(pcen - 2 * w, 0), q1 = min(pcen + 2 * w, n - 1);
+        const int j0 = q0 >> 4, j1 = q1 >> 4;
+        for (int jb = j0; jb <= j1; jb += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (jb + u <= j1) ? sp[(size_t)(jb + u) * 32] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (jb + u <= j1) {
+                    const int wi = (jb + u - j0) * 4;
+                    ring[(wi + 0) * 32] = v[u].x;
+                    ring[(wi + 1) * 32] = v[u].y;
+                    ring[(wi + 2) * 32] = v[u].z;
+                    ring[(wi + 3) * 32] = v[u].w;
+                }
+            }
+        }
         double sc = 0.0, den = 0.0, t2 = 0.0;
-        for (int q = pcen - 2 * w; q <= pcen + 2 * w; q++) {
-            if (q < 0 || q >= n) continue;
-            const double x = lds_f64(lb + (uint32_t)(sb[(size_t)(q >> 4) * 512 + (q & 15)] & 63) * 128u);
+        for (int q = q0; q <= q1; q++) {
+            const int rel = q - (j0 << 4);
+            const uint32_t e = (ring[(rel >> 2) * 32] >> ((rel & 3) * 8)) & 63u;
+            const double x = lds_f64(lb + e * 128u);
             const int dist = abs(q - pcen);
             if (dist <= w) {
                 den = den + 1.0;
@@ -542,16 +600,24 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
     uint32_t* ring_all = reinterpret_cast<uint32_t*>(sm + kV2FixedBytes);
     uint32_t* ring = ring_all + (size_t)wid * g.ring_words * 32 + lane;
     constexpr uint32_t kPadW = 0x01010101u * kPad;
-    for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
     __syncthreads();
 
-    const int role = wid >= g.nwr;
-    const int64_t b = (int64_t)blockIdx.x * g.nwr + (role ? wid - g.nwr : wid);
-    if (b >= g.bv.nbuckets) return;
-    if (role == 0)
-        role_a(g, sbase, ring, lane, b);
-    else
-        role_b(g, sbase, ring, lane, b);
+    // Persistent warps: work item = (bucket, role), handed out by one global counter in bucket order (longest
+    // buckets first, roles alternating), so every SM keeps all its warps busy with a balanced A/B mix until the
+    // queue is empty.  The first round is assigned statically to save one atomic round trip.
+    const int64_t nitems = 2 * g.bv.nbuckets;
+    int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    const int64_t first_dynamic = (int64_t)gridDim.x * (blockDim.x >> 5);
+    while (item < nitems) {
+        for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
+        if (item & 1)
+            role_b(g, sbase, ring, lane, item >> 1);
+        else
+            role_a(g, sbase, ring, lane, item >> 1);
+        unsigned long long nx = 0;
+        if (lane == 0) nx = atomicAdd(g.work_counter, 1ull);
+        item = first_dynamic + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ CORE search
@@ -570,7 +636,7 @@ k_core_search(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs, 
     const double big_neg = ks.big_neg;
     const double* lt = &llr_s[0][threadIdx.x & 15];
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int32_t rank = core_list[idx];
+        const int32_t rank = core_list[2 * idx];
         const int64_t b = rank >> 5;
         const int lane = rank & 31;
         const int32_t prot = bv.order[rank];
@@ -629,6 +695,132 @@ k_core_search(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs, 
             r->prd_start = a0;
             r->prd_end = a1;
             r->prd_score = sc;
+        }
+    }
+}
+
+// k masked residues add the masking constant B to the sequential prefix sum k times (hss2 :1230-1233 on the
+// masked sequence of :816-831).  For a negative INTEGER B (checked on the host) one such addition is exact
+// whenever the result stays inside the binade of ps: both operands are then multiples of the result's ulp.
+// So whole stretches are applied as one exact step and only the additions that cross into the next binade
+// (about one per power of two) are done one by one -- bit-identical to the jar's k rounded additions.
+__device__ __forceinline__ double masked_jump(double ps, int k, double B)
+{
+    const double aB = -B;
+    while (k > 0) {
+        double m = 0.0;
+        if (ps < 0.0) {
+            const double aps = -ps;
+            const int ebits = (__double2hiint(aps) >> 20) & 0x7ff;
+            const double lim = __hiloint2double((ebits + 1) << 20, 0);  // next power of two above |ps|
+            const double room = lim - aps;                             // exact (same binade)
+            m = floor(room / aB);
+            if (m * aB > room) m -= 1.0;                               // m * aB is an exact integer product
+        }
+        if (m >= 1.0) {
+            const double mm = fmin(m, (double)k);
+            ps = ps - mm * aB;  // exact
+            k -= (int)mm;
+        } else {
+            ps = ps + B;  // the rounded addition, as the reference does it
+            k -= 1;
+        }
+    }
+    return ps;
+}
+
+// Same search as k_core_search with the masked stretches jumped (needs big_neg to be a negative integer).
+// Only windows inside Viterbi runs can win (every other window is below big_neg/2 and a listed protein has a run
+// of at least c residues), so d = psum[i+1] - psum[i-c+1] is evaluated there only; the lagged prefix sum restarts
+// from the lead value at each run start and replays the same additions, so it has the jar's bits.
+__global__ void __launch_bounds__(128)
+k_core_search_jump(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs, plaac_summary* __restrict__ out,
+                   const int32_t* __restrict__ core_list, const int32_t* __restrict__ core_count)
+{
+    __shared__ double llr_s[32][16];
+    for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) llr_s[i >> 4][i & 15] = tabs->llr[i >> 4];
+    __syncthreads();
+    const int total = *core_count;
+    const int c = ks.core_len;
+    const double big_neg = ks.big_neg;
+    const double* lt = &llr_s[0][threadIdx.x & 15];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int32_t rank = core_list[2 * idx];
+        const uint32_t span = (uint32_t)core_list[2 * idx + 1];
+        const int64_t b = rank >> 5;
+        const int lane = rank & 31;
+        const int32_t prot = bv.order[rank];
+        const int n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
+        const int64_t cb = bv.chunk_base[b];
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(bv.stream + cb * 32 + lane);
+        const uint32_t* vw = bv.tbw + cb * 32 + lane;
+        auto code_at = [&](int i) -> int { return sb[(size_t)(i >> 4) * 512 + (i & 15)] & 31; };
+        // One loop iteration = one Viterbi-1 residue (or one step to the next 16-residue word); masked residues
+        // cost nothing: the gap before a residue is applied as one jump.  PRDscore (:870-872, a sequential sum
+        // from the run start) and the PrD bounds (:861-866, the enclosing run) are carried along per run.
+        double ps = 0.0, lag = 0.0, best = -INFINITY, runsum = 0.0, prd_sc = 0.0;
+        int bstop = -1, run = 0, last = 0, run_start = 0, prd_s = -1, prd_e = -2;
+        bool hit = false;
+        const int nslots = min((n + 15) >> 4, (int)(span >> 16) + 1);  // nothing but masked residues beyond
+        int j = (int)(span & 0xffffu) - 1;                              // ... and before (one jump from residue 0)
+        uint32_t bits = 0, vnext = vw[(size_t)(j + 1) * 32];
+        uint4 cw = make_uint4(0, 0, 0, 0);
+        while (true) {
+            if (bits == 0) {
+                if (++j >= nslots) break;
+                const int nb = min(16, n - 16 * j);
+                bits = vnext & ((1u << nb) - 1u);
+                if (j + 1 < nslots) vnext = vw[(size_t)(j + 1) * 32];
+                if (bits) cw = *reinterpret_cast<const uint4*>(sb + (size_t)j * 512);
+                continue;
+            }
+            const int i = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int p = 16 * j + i;
+            if (p != last) {  // masked residues since the previous Viterbi-1 residue: the run (if any) ended
+                if (hit) {
+                    prd_s = run_start;
+                    prd_e = last - 1;
+                    prd_sc = runsum;
+                    hit = false;
+                }
+                ps = masked_jump(ps, p - last, big_neg);
+                run = 0;
+            }
+            if (run == 0) {
+                lag = ps;
+                run_start = p;
+                runsum = 0.0;
+            }
+            const uint32_t w = ((i & 12) == 0) ? cw.x : ((i & 12) == 4) ? cw.y : ((i & 12) == 8) ? cw.z : cw.w;
+            const double x = lt[((w >> ((i & 3) * 8)) & 31) * 16];
+            ps = ps + x;
+            runsum = runsum + x;
+            if (run >= c - 1) {
+                const double d = ps - lag;
+                if (d > best) {
+                    best = d;
+                    bstop = p;
+                    hit = true;
+                }
+                lag = lag + lt[code_at(p - c + 1) * 16];
+            }
+            run++;
+            last = p + 1;
+        }
+        if (hit) {
+            prd_s = run_start;
+            prd_e = last - 1;
+            prd_sc = runsum;
+        }
+        if (best > big_neg / 2) {
+            plaac_summary* r = out + prot;
+            r->core_start = bstop - c + 1;
+            r->core_end = bstop;
+            r->core_score = best;
+            r->prd_start = prd_s;
+            r->prd_end = prd_e;
+            r->prd_score = prd_sc;
         }
     }
 }
