@@ -298,10 +298,11 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     CU(ctx, cudaEventRecord(s.ev_a, st));
     CU(ctx, cudaMemsetAsync(s.hist.p, 0, sizeof(int32_t) * (kHistBins + 1), st));
     const int tb = 256;
-    const unsigned gp = (unsigned)((nprot + tb - 1) / tb);
-    k_len_hist<<<gp, tb, 0, st>>>(d_offsets, nprot, (int32_t*)s.hist.p);
+    const unsigned g_hist = (unsigned)std::min<int64_t>(ctx->sm_count, (nprot + 4095) / 4096);
+    const unsigned g_scat = (unsigned)std::min<int64_t>(ctx->sm_count, (nprot + kScatterTile - 1) / kScatterTile);
+    k_len_hist<<<g_hist, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, (int32_t*)s.hist.p);
     k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.hist.p, (int64_t*)s.cursor.p, kHistBins + 1);
-    k_scatter<<<gp, tb, 0, st>>>(d_offsets, nprot, (int64_t*)s.cursor.p, (int32_t*)s.order.p);
+    k_scatter<<<g_scat, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, (int64_t*)s.cursor.p, (int32_t*)s.order.p);
     const unsigned gb = (unsigned)((nbuckets * 32 + tb - 1) / tb);
     k_bucket_chunks<<<gb, tb, 0, st>>>(d_offsets, (const int32_t*)s.order.p, nprot, nbuckets, (int32_t*)s.nchunks.p);
     k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.nchunks.p, (int64_t*)s.chunk_base.p, nbuckets);
@@ -455,6 +456,13 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         e = cudaFuncSetAttribute(k_score_summary_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->v2_smem_bytes);
         if (e != cudaSuccess) {
             ctx->err = std::string("cudaFuncSetAttribute(k_score_summary_v2): ") + cudaGetErrorString(e);
+            return bail(PLAAC_E_CUDA);
+        }
+    }
+    for (const void* fn : {(const void*)k_len_hist, (const void*)k_scatter}) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes);
+        if (e != cudaSuccess) {
+            ctx->err = std::string("cudaFuncSetAttribute(prep kernels): ") + cudaGetErrorString(e);
             return bail(PLAAC_E_CUDA);
         }
     }

@@ -17,11 +17,27 @@ __device__ __forceinline__ int len_bin(int64_t len)
     return len >= kHistBins ? 0 : (int)(kHistBins - len);
 }
 
-__global__ void k_len_hist(const int64_t* __restrict__ offsets, int64_t nprot, int32_t* __restrict__ hist)
+// Length histogram.  Lengths cluster in a few hundred bins, so global atomics serialise on a handful of L2
+// sectors; each CTA therefore counts its contiguous share of the proteins in a private shared-memory histogram
+// (kHistBins+1 counters, dynamic shared memory) and flushes only its non-zero bins.
+constexpr int kPrepThreads = 1024;
+constexpr size_t kHistSmemBytes = sizeof(int32_t) * (kHistBins + 1);
+
+__global__ void __launch_bounds__(kPrepThreads)
+k_len_hist(const int64_t* __restrict__ offsets, int64_t nprot, int32_t* __restrict__ hist)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nprot) return;
-    atomicAdd(&hist[len_bin(offsets[i + 1] - offsets[i])], 1);
+    extern __shared__ int32_t sh_hist[];
+    for (int i = threadIdx.x; i <= kHistBins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    const int64_t per = (nprot + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = per * blockIdx.x, hi = min(nprot, lo + per);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        atomicAdd(&sh_hist[len_bin(offsets[i + 1] - offsets[i])], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= kHistBins; i += blockDim.x) {
+        const int32_t v = sh_hist[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
 }
 
 // Single-CTA exclusive scan, out[0..n] (n+1 values, out[n] = total).  n is small here (bins, buckets).
@@ -77,14 +93,57 @@ __global__ void __launch_bounds__(1024) k_scan_exclusive(const TIn* __restrict__
     if (tid == 0) out[n] = carry_s;
 }
 
-__global__ void k_scatter(const int64_t* __restrict__ offsets, int64_t nprot, int64_t* __restrict__ cursor,
-                          int32_t* __restrict__ order)
+// Counting-sort scatter.  A CTA ranks a tile of kScatterTile proteins inside shared memory (one shared atomic
+// each), reserves one global range per (tile, bin) with a single global atomic, and writes order[].  The order
+// inside a bin is arbitrary (results are per protein; nothing depends on it).
+constexpr int kScatterPer = 8;
+constexpr int kScatterTile = kPrepThreads * kScatterPer;
+
+__global__ void __launch_bounds__(kPrepThreads)
+k_scatter(const int64_t* __restrict__ offsets, int64_t nprot, int64_t* __restrict__ cursor, int32_t* __restrict__ order)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nprot) return;
-    int b = len_bin(offsets[i + 1] - offsets[i]);
-    unsigned long long r = atomicAdd((unsigned long long*)&cursor[b], 1ull);
-    order[r] = (int32_t)i;
+    extern __shared__ int32_t sh_cnt[];  // per bin: count during ranking, then the reserved global base
+    for (int i = threadIdx.x; i <= kHistBins; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    const int64_t ntiles = (nprot + kScatterTile - 1) / kScatterTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base_i = tile * kScatterTile;
+        int bin[kScatterPer], rk[kScatterPer];
+#pragma unroll
+        for (int k = 0; k < kScatterPer; k++) {
+            const int64_t i = base_i + (int64_t)k * kPrepThreads + threadIdx.x;
+            bin[k] = -1;
+            rk[k] = 0;
+            if (i < nprot) {
+                bin[k] = len_bin(offsets[i + 1] - offsets[i]);
+                rk[k] = atomicAdd(&sh_cnt[bin[k]], 1);
+            }
+        }
+        __syncthreads();
+        // the first arrival of every bin reserves the tile's range
+        int32_t reserved[kScatterPer];
+#pragma unroll
+        for (int k = 0; k < kScatterPer; k++) {
+            reserved[k] = 0;
+            if (bin[k] >= 0 && rk[k] == 0)
+                reserved[k] = (int32_t)atomicAdd((unsigned long long*)&cursor[bin[k]], (unsigned long long)sh_cnt[bin[k]]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScatterPer; k++)
+            if (bin[k] >= 0 && rk[k] == 0) sh_cnt[bin[k]] = reserved[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScatterPer; k++) {
+            const int64_t i = base_i + (int64_t)k * kPrepThreads + threadIdx.x;
+            if (bin[k] >= 0) order[sh_cnt[bin[k]] + rk[k]] = (int32_t)i;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScatterPer; k++)
+            if (bin[k] >= 0 && rk[k] == 0) sh_cnt[bin[k]] = 0;
+        __syncthreads();
+    }
 }
 
 // One warp per bucket: slots needed = ceil(max length / 16).
@@ -108,17 +167,34 @@ __global__ void k_bucket_chunks(const int64_t* __restrict__ offsets, const int32
     if (lane == 0) nchunks[b] = (int32_t)((len + kChunk - 1) / kChunk);
 }
 
-__device__ __forceinline__ uint32_t sel8(const uint4& a, const uint4& b, int i)
+// SWAR helpers on 4 packed bytes that are all < 0x80.
+__device__ __forceinline__ uint32_t bytes_zero(uint32_t x)
 {
-    // word i (0..7) of the 32-byte pair {a,b}; i is per-lane dynamic
-    uint32_t lo = (i & 2) ? ((i & 1) ? a.w : a.z) : ((i & 1) ? a.y : a.x);
-    uint32_t hi = (i & 2) ? ((i & 1) ? b.w : b.z) : ((i & 1) ? b.y : b.x);
-    return (i & 4) ? hi : lo;
+    // 0x80 in every zero byte of x; exact when no byte of x is 0x80 (borrows cannot cross a byte whose top bit
+    // is forced on), which holds for sanitised codes xor a code pattern or xor 0xff
+    return ~((x | 0x80808080u) - 0x01010101u) & ~x & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t code)
+{
+    // 0x80 in every byte of w that equals `code`
+    return bytes_zero(w ^ (code * 0x01010101u));
+}
+__device__ __forceinline__ uint32_t bytes_in_set(uint32_t w, uint32_t set)
+{
+    // 0x80 in every byte of w whose value is a member of the 32-bit code set (warp-uniform loop over the members)
+    uint32_t r = 0;
+    while (set) {
+        const uint32_t c = (uint32_t)__ffs((int)set) - 1u;
+        set &= set - 1u;
+        r |= bytes_eq(w, c);
+    }
+    return r;
 }
 
 // Ext byte layout: bits 4:0 residue code (22 = pad), bit 5 PAPA proline mask, bits 7:6 charge class.
-// One warp per bucket.  Lane l streams protein order[32b+l]: aligned 16-byte loads, byte realignment with
-// funnel shifts, SWAR sanitising / padding / PAPA proline flags, one coalesced 512-byte store per slot.
+// One warp per bucket.  Lane l streams protein order[32b+l]: aligned 16-byte loads two blocks ahead, a
+// two-level word barrel shifter + funnel shifts for the byte realignment, SWAR sanitising / padding / PAPA
+// proline flags / charge classes, one coalesced 512-byte store per slot.
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
        int64_t off_base, const int32_t* __restrict__ order, const int64_t* __restrict__ chunk_base, int64_t nprot,
@@ -128,6 +204,15 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     constexpr uint32_t kPadW = 0x01010101u * kPad;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    // up to two codes per charge class are matched with straight-line SWAR compares (PLAAC has D,E / K,R);
+    // 0xffffffff never matches a sanitised byte
+    const bool small_sets = __popc(charge_plus) <= 2 && __popc(charge_minus) <= 2;
+    uint32_t cp0 = 0xffffffffu, cp1 = 0xffffffffu, cm0 = 0xffffffffu, cm1 = 0xffffffffu;
+    if (charge_plus) cp0 = ((uint32_t)__ffs((int)charge_plus) - 1u) * 0x01010101u;
+    if (charge_plus & (charge_plus - 1u)) cp1 = (31u - (uint32_t)__clz((int)charge_plus)) * 0x01010101u;
+    if (charge_minus) cm0 = ((uint32_t)__ffs((int)charge_minus) - 1u) * 0x01010101u;
+    if (charge_minus & (charge_minus - 1u)) cm1 = (31u - (uint32_t)__clz((int)charge_minus)) * 0x01010101u;
     for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nbuckets; b += warps) {
         const int64_t r = b * 32 + lane;
         int64_t n = 0;
@@ -141,62 +226,65 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
         const int nch = (int)(chunk_base[b + 1] - cb);
         const int sh = (int)((uintptr_t)src & 15);
         const uint4* ap = (const uint4*)(src - sh);
-        const int s4 = sh >> 2, s1 = (sh & 3) * 8;
-        uint4 A = make_uint4(0, 0, 0, 0), B = A;
-        if (n > 0) A = __ldg(ap);
-        uint32_t carry = 0;  // eq13 bits of the previous word (positions before the current one)
-        bool bad_any = false;
+        const bool s4b1 = (sh & 8) != 0, s4b0 = (sh & 4) != 0;
+        const int s1 = (sh & 3) * 8;
+        const int64_t nblk = (n + sh + 15) >> 4;  // aligned 16-byte blocks that hold the protein
+        uint4 A = nblk > 0 ? __ldg(ap) : zero4;
+        uint4 B = nblk > 1 ? __ldg(ap + 1) : zero4;
+        uint32_t carry = 0;  // proline bits of the previous word (positions before the current one)
+        uint32_t bad_any = 0;
+        uint4* dst = stream + cb * 32 + lane;
         for (int j = 0; j < nch; j++) {
-            const int64_t pos0 = (int64_t)j * kChunk;
-            // B is needed when the 16 source bytes straddle into the next aligned block and are still in range
-            B = make_uint4(0, 0, 0, 0);
-            if (sh != 0 && (pos0 + (16 - sh)) < n) B = __ldg(ap + j + 1);
-            uint32_t o[4];
+            const uint4 C = ((int64_t)j + 2 < nblk) ? __ldg(ap + j + 2) : zero4;  // in flight while slot j is packed
+            // bytes sh .. sh+15 of the 32-byte pair {A, B}
+            uint32_t W0 = A.x, W1 = A.y, W2 = A.z, W3 = A.w, W4 = B.x, W5 = B.y, W6 = B.z, W7 = B.w;
+            if (s4b1) {
+                W0 = W2; W1 = W3; W2 = W4; W3 = W5; W4 = W6; W5 = W7;
+            }
+            if (s4b0) {
+                W0 = W1; W1 = W2; W2 = W3; W3 = W4; W4 = W5;
+            }
+            uint32_t o[4] = {__funnelshift_r(W0, W1, s1), __funnelshift_r(W1, W2, s1), __funnelshift_r(W2, W3, s1),
+                             __funnelshift_r(W3, W4, s1)};
+            const int64_t rem = n - (int64_t)j * kChunk;  // valid bytes from this slot on
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                uint32_t w0 = sel8(A, B, q + s4);
-                uint32_t w1 = sel8(A, B, (q + s4 + 1) & 7);
-                uint32_t w = __funnelshift_r(w0, w1, s1);
-                // sanitise: bytes > 21 are invalid input -> X (0) and flag the error
-                uint32_t bad = (w & 0x80808080u) | (((w & 0x7f7f7f7fu) + 0x6a6a6a6au) & 0x80808080u);
-                int64_t rem = n - (pos0 + 4 * q);
-                uint32_t vmask = rem >= 4 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (8 * (int)rem)) - 1u));
-                bad &= vmask;
-                bad_any |= (bad != 0);
-                uint32_t badbytes = (bad >> 7) * 0xffu;
-                w &= ~badbytes;
+                uint32_t w = o[q];
+                uint32_t vmask = 0xffffffffu;
+                if (rem < 16) {
+                    const int64_t rq = rem - 4 * q;
+                    vmask = rq >= 4 ? 0xffffffffu : (rq <= 0 ? 0u : ((1u << (8 * (int)rq)) - 1u));
+                }
+                // sanitise: bytes > 21 are invalid input -> X (0), flagged
+                const uint32_t bad = ((w & 0x80808080u) | (((w & 0x7f7f7f7fu) + 0x6a6a6a6au) & 0x80808080u)) & vmask;
+                if (bad) {
+                    bad_any = 1;
+                    w &= ~((bad >> 7) * 0xffu);
+                }
                 w = (w & vmask) | (kPadW & ~vmask);
+                uint32_t ext = w;
                 if (adjust_prolines) {
-                    uint32_t x = w ^ 0x0d0d0d0du;
-                    uint32_t t = (x | 0x80808080u) - 0x01010101u;
-                    uint32_t eq = ~t & 0x80808080u;
-                    uint32_t prev1 = (eq << 8) | (carry >> 24);
-                    uint32_t prev2 = (eq << 16) | (carry >> 16);
-                    uint32_t flag = eq & (prev1 | prev2);
+                    const uint32_t eq = bytes_eq(w, 13u);
+                    const uint32_t prev1 = __funnelshift_l(carry, eq, 8);   // proline one position earlier
+                    const uint32_t prev2 = __funnelshift_l(carry, eq, 16);  // two positions earlier
                     carry = eq;
-                    w |= flag >> 2;  // bit 7 -> bit 5 (kPapaMaskBit)
+                    ext |= (eq & (prev1 | prev2)) >> 2;  // bit 7 -> bit 5 (kPapaMaskBit)
                 }
                 // charge class in bits 7:6 of every byte: 01 = +1, 11 = -1 (so (int8)byte >> 6 is the charge)
-                uint32_t cb = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t cd = (w >> (8 * i)) & 31u;
-                    const uint32_t pl = (charge_plus >> cd) & 1u, mi = (charge_minus >> cd) & 1u;
-                    cb |= ((pl << 6) | (mi * 0xc0u)) << (8 * i);
+                uint32_t pl, mi;
+                if (small_sets) {
+                    pl = bytes_zero(w ^ cp0) | bytes_zero(w ^ cp1);
+                    mi = bytes_zero(w ^ cm0) | bytes_zero(w ^ cm1);
+                } else {
+                    pl = bytes_in_set(w, charge_plus);
+                    mi = bytes_in_set(w, charge_minus);
                 }
-                w |= cb;
-                o[q] = w;
+                ext |= (pl >> 1) | mi | (mi >> 1);
+                o[q] = ext;
             }
-            stream[(cb + j) * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
-            // next aligned block becomes A
-            if (sh != 0) {
-                A = B;
-                // if B was not loaded because the protein ended, A is zeros: fine (masked as pad)
-                if (!(pos0 + (16 - sh) < n)) A = make_uint4(0, 0, 0, 0);
-            } else {
-                A = make_uint4(0, 0, 0, 0);
-                if (pos0 + 16 < n) A = __ldg(ap + j + 1);
-            }
+            __stcs(dst + (size_t)j * 32, make_uint4(o[0], o[1], o[2], o[3]));  // streaming: keep L2 for the reads
+            A = B;
+            B = C;
         }
         if (bad_any) atomicOr(errflag, 1);
     }
