@@ -57,7 +57,7 @@ struct plaac_ctx {
     std::string v2_why;
     int sm_count = 0;
     plaac_stats stats;
-    int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
+    int64_t chunk_res = (int64_t)128 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
     std::string err;
     int last_slot = 0;
 };
@@ -281,7 +281,7 @@ void slot_free(Slot& s)
 // subtracted to index d_codes.  Contains ONE stream synchronisation (the padded stream size).
 int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_offsets, int64_t off_base,
               int64_t nprot, int64_t ntotal, plaac_summary* d_summaries, const plaac_residue_out* d_res,
-              int64_t res_base)
+              int64_t res_base, int64_t slots_bound = -1)
 {
     if (nprot == 0) return PLAAC_OK;
     if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins in one device batch");
@@ -308,9 +308,13 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.nchunks.p, (int64_t*)s.chunk_base.p, nbuckets);
     ctx->stats.kernel_launches += 5;
     CU(ctx, cudaMemcpyAsync(s.h_total, (int64_t*)s.chunk_base.p + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
-    const int64_t slots = *s.h_total;
-    ctx->stats.last_padded_slots = slots * 32;
+    int64_t slots = slots_bound;
+    if (slots < 0) {
+        // the caller knows nothing about the lengths (device-resident offsets): wait for the exact padded size
+        CU(ctx, cudaStreamSynchronize(st));
+        slots = *s.h_total;
+        ctx->stats.last_padded_slots = slots * 32;
+    }
     if ((rc = ensure(ctx, s.stream_buf, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint4)))) return rc;
     if ((rc = ensure(ctx, s.tbw, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint32_t)))) return rc;
 
@@ -383,6 +387,7 @@ int finish_slot(plaac_ctx* ctx, Slot& s)
 {
     CU(ctx, cudaMemcpyAsync(s.h_err, s.errflag.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CU(ctx, cudaStreamSynchronize(s.stream));
+    ctx->stats.last_padded_slots = *s.h_total * 32;
     if (*s.h_err) {
         cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream);
         return fail(ctx, PLAAC_E_INVALID, "input contains residue codes > 21 (treated as X)");
@@ -573,11 +578,7 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
     if (nprot == 0) return PLAAC_OK;
     if (!offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
     if (!summaries && !per_res) return fail(ctx, PLAAC_E_INVALID, "no output requested");
-    for (int64_t i = 0; i < nprot; i++) {
-        if (offsets[i + 1] < offsets[i]) return fail(ctx, PLAAC_E_INVALID, "offsets not monotone at protein %lld", (long long)i);
-        if (offsets[i + 1] - offsets[i] > 0x7fffff00LL) return fail(ctx, PLAAC_E_INVALID, "protein %lld longer than 2^31", (long long)i);
-    }
-    if (!codes && offsets[nprot] > offsets[0]) return fail(ctx, PLAAC_E_INVALID, "NULL codes");
+    if (!codes && offsets[nprot] != offsets[0]) return fail(ctx, PLAAC_E_INVALID, "NULL codes");
     CU(ctx, cudaSetDevice(ctx->device));
 
     // Chunking: bounded device footprint, two slots so chunk i+1's H2D overlaps chunk i's kernels/D2H.
@@ -593,11 +594,33 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         return finish_slot(ctx, ctx->slot[i]);
     };
     while (start < nprot && rc == PLAAC_OK) {
+        // Cut the next chunk; validate it and collect what bounds its padded size while walking its offsets (the
+        // walk overlaps the previous chunk's copies and kernels).
         int64_t end = start;
         const int64_t base = offsets[start];
-        while (end < nprot && end - start < max_prot && (end == start || offsets[end + 1] - base <= max_res)) end++;
+        int64_t lmax = 0, nlong = 0;
+        while (end < nprot && end - start < max_prot) {
+            const int64_t len = offsets[end + 1] - offsets[end];
+            if (len < 0) {
+                rc = fail(ctx, PLAAC_E_INVALID, "offsets not monotone at protein %lld", (long long)end);
+                break;
+            }
+            if (len > 0x7fffff00LL) {
+                rc = fail(ctx, PLAAC_E_INVALID, "protein %lld longer than 2^31", (long long)end);
+                break;
+            }
+            if (end != start && offsets[end + 1] - base > max_res) break;
+            lmax = std::max(lmax, len);
+            nlong += len >= kHistBins;
+            end++;
+        }
+        if (rc != PLAAC_OK) break;
         const int64_t np = end - start;
         const int64_t nres = offsets[end] - base;
+        // Upper bound of the bucketed stream (in 32-lane slots), so no host sync is needed for its size: proteins
+        // are sorted by length, hence every bucket's longest member is no longer than the shortest member of the
+        // bucket before it; only the first bucket and the buckets of unsorted >= 32768-residue proteins pay Lmax.
+        const int64_t slots_bound = ((nlong + 31) / 32 + 2) * ((lmax + kChunk - 1) / kChunk) + (nres + 15 * np) / (32 * kChunk) + 1;
         Slot& s = ctx->slot[which];
         if ((rc = drain(which))) break;
         if ((rc = ensure(ctx, s.codes, (size_t)nres + 64))) break;
@@ -626,7 +649,7 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         if (nres > 0) CU(ctx, cudaMemcpyAsync(s.codes.p, codes + base, (size_t)nres, cudaMemcpyHostToDevice, s.stream));
         CU(ctx, cudaMemcpyAsync(s.offsets.p, offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
         rc = run_batch(ctx, s, (const uint8_t*)s.codes.p, (const int64_t*)s.offsets.p, base, np, nres,
-                       summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base);
+                       summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base, slots_bound);
         if (rc) break;
         if (summaries)
             CU(ctx, cudaMemcpyAsync(summaries + start, s.summaries.p, sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));
