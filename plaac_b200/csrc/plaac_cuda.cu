@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "residue_kernel.cuh"
+#include "residue_kernel_v2.cuh"
 #include "summary_kernel.cuh"
 #include "summary_kernel_v2.cuh"
 
@@ -34,6 +35,9 @@ struct Slot {
     DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, errflag, core_list, core_count;
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
+    DevBuf res_b0, res_b1, res_mapw;   // per-residue scratch: backward planes, MAP bit words
+    cudaStream_t aux1 = nullptr, aux2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
     int64_t* h_total = nullptr;        // pinned
     int* h_err = nullptr;              // pinned
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
@@ -53,6 +57,7 @@ struct plaac_ctx {
     int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
     size_t v2_smem_bytes = 0;
     int v2_always_in = 0;      // forward recurrence provably keeps |a-b| < 40 (no LUT range test needed)
+    ResidueV2Plan res_plan;
     int variant = 0;           // 0 auto, 1 = v1 (reference-order anchor), 2 = v2
     std::string v2_why;
     int sm_count = 0;
@@ -258,6 +263,11 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     CU(ctx, cudaEventCreate(&s.ev_b));
     CU(ctx, cudaEventCreate(&s.ev_c));
     CU(ctx, cudaEventCreate(&s.ev_d));
+    CU(ctx, cudaStreamCreateWithFlags(&s.aux1, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamCreateWithFlags(&s.aux2, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_j1, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_j2, cudaEventDisableTiming));
     int rc = ensure(ctx, s.errflag, sizeof(int));
     if (rc) return rc;
     CU(ctx, cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream));
@@ -267,12 +277,15 @@ int slot_init(plaac_ctx* ctx, Slot& s)
 void slot_free(Slot& s)
 {
     for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.errflag,
-                      &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64})
+                      &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
+                      &s.res_b1, &s.res_mapw})
         release(*b);
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
-    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d})
+    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_fork, s.ev_j1, s.ev_j2})
         if (e) cudaEventDestroy(e);
+    for (cudaStream_t a : {s.aux1, s.aux2})
+        if (a) cudaStreamDestroy(a);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -374,7 +387,37 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     }
     CU(ctx, cudaEventRecord(s.ev_c, st));
     if (d_res) {
-        rc = launch_residue(ctx->ks, ctx->d_tabs, bv, *d_res, res_base, ctx->sm_count, st, &ctx->stats.kernel_launches);
+        const bool res_v2 = ctx->res_plan.ok && ctx->v2_nwr > 0 && ctx->variant != 1;
+        if (res_v2) {
+            const size_t nslots = (size_t)std::max<int64_t>(slots, 1);
+            if ((rc = ensure(ctx, s.res_b0, nslots * 512 * sizeof(double)))) return rc;
+            if ((rc = ensure(ctx, s.res_b1, nslots * 512 * sizeof(double)))) return rc;
+            if ((rc = ensure(ctx, s.res_mapw, nslots * 32 * sizeof(uint32_t)))) return rc;
+            ResArgs ra;
+            ra.bv = bv;
+            ra.ks = ctx->ks;
+            ra.tabs = ctx->d_tabs;
+            ra.out = *d_res;
+            ra.res_base = res_base;
+            ra.B0 = (double*)s.res_b0.p;
+            ra.B1 = (double*)s.res_b1.p;
+            ra.mapw = (uint32_t*)s.res_mapw.p;
+            TrackArgs ta;
+            ta.codes = d_codes;
+            ta.offsets = d_offsets;
+            ta.off_base = off_base;
+            ta.res_base = res_base;
+            ta.nprot = nprot;
+            ta.ks = ctx->ks;
+            ta.tabs = ctx->d_tabs;
+            ta.out = *d_res;
+            ta.nx = ctx->res_plan.nx;
+            ta.per_x = ctx->res_plan.per_x;
+            ta.per_s = ctx->res_plan.per_s;
+            rc = launch_residue_v2(ctx->res_plan, ra, ta, ctx->sm_count, st, s.aux1, s.aux2, s.ev_fork, s.ev_j1, s.ev_j2,
+                                   &ctx->stats.kernel_launches);
+        } else
+            rc = launch_residue(ctx->ks, ctx->d_tabs, bv, *d_res, res_base, ctx->sm_count, st, &ctx->stats.kernel_launches);
         if (rc != PLAAC_OK) return fail(ctx, rc, "per-residue kernels failed to launch");
     }
     CU(ctx, cudaEventRecord(s.ev_d, st));
@@ -471,7 +514,9 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
             return bail(PLAAC_E_CUDA);
         }
     }
-    rc = residue_setup(ctx->ks, ctx->ring_words);
+    ctx->res_plan = residue_v2_plan(ctx->ks);
+    rc = residue_v2_setup(ctx->res_plan);
+    if (rc == PLAAC_OK) rc = residue_setup(ctx->ks, ctx->ring_words);
     if (rc != PLAAC_OK) {
         ctx->err = "cudaFuncSetAttribute(per-residue kernels) failed";
         return bail(rc);

@@ -1,0 +1,547 @@
+// Per-residue mode (plotsomefastas, plaac.java:610-647), throughput version.
+//
+// The two posterior columns need the ABSOLUTE forward and backward variables of the lookup-table recurrences in the
+// reference's operation order (exp((a+b) - lpseq), posteriorl :3349-3411): the LUT error accumulates along the
+// sequence, so there is no associative shortcut that reproduces the jar to 1e-9.  Each recurrence therefore stays
+// one sequential chain per protein (lane = protein on the length-bucketed stream, as in the summary kernels) and the
+// mode is organised around memory traffic instead:
+//
+//   k_res_vit     Viterbi max-plus recurrence (viterbidecodel :3077-3121), traceback bits, SWAR traceback -> Viterbi
+//                 bits, one 32-bit word per 16 residues per lane
+//   k_res_bwd     backward recurrence (:3378-3391) -> scratch planes B0/B1 in the bucketed layout
+//                 [slot][residue-in-slot][lane]: every warp store is one 256-byte line
+//   k_res_fwd     forward recurrence (:3356-3367); lpseq is known at residue 0 because the backward pass is already
+//                 complete, so the posteriors and the MAP bit (mapdecodel :4032-4045) come out in the same sweep.
+//                 16-residue tiles are transposed through shared memory and written protein-major as 128-byte runs
+//   k_res_bits    Viterbi/MAP bit words -> one byte per residue, protein-major, coalesced
+//   k_res_tracks  the eight disorderreport tracks (:4866-4903, slidingaverage :2585-2662) from fp64 prefix sums: one
+//                 warp per protein walks tiles of 256 consecutive residues (+2w halo each side); pass-1 window sums
+//                 are differences of a prefix sum of per-residue values, pass-2 sums are differences of a prefix sum
+//                 of the pass-1 sums (sum-of-window-sums identity).  All loads and stores are coalesced.
+//
+// k_res_vit / k_res_bwd are independent and run on two streams; k_res_tracks overlaps both.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "summary_kernel_v2.cuh"
+
+namespace plaac {
+
+constexpr int kResThreads = 256;   // k_res_vit, k_res_bits
+constexpr int kResHmmThreads = 512;  // k_res_bwd, k_res_fwd (one 64 KB LUT per CTA)
+constexpr uint32_t kResOffLe = 0;                                     // double2 [32 codes][8 lane copies] {le0, le1}
+constexpr uint32_t kResOffLut2 = 4096;                                // double2 [4002]
+constexpr uint32_t kResFixedBytes = kResOffLut2 + (PLAAC_LUT_LEN + 1) * 16;
+constexpr int kTilePitch = 33;                                        // doubles per tile row (conflict-free transpose)
+constexpr uint32_t kResTileBytes = 2 * 16 * kTilePitch * 8;           // per warp: two 16 x 32 tiles
+
+struct ResArgs {
+    BatchView bv;
+    KScalars ks;
+    const DeviceTables* tabs;
+    plaac_residue_out out;
+    int64_t res_base;    // residue index of out.*[0]
+    double* B0;          // backward variables, bucketed layout
+    double* B1;
+    uint32_t* mapw;      // MAP bits, one word per slot per lane
+};
+
+__device__ __forceinline__ void res_stage_tables(unsigned char* sm, const DeviceTables* T)
+{
+    double2* lut2 = reinterpret_cast<double2*>(sm + kResOffLut2);
+    for (int i = threadIdx.x; i <= PLAAC_LUT_LEN; i += blockDim.x) {
+        const double l0 = i < PLAAC_LUT_LEN ? T->lut[i] : 0.0;
+        const double l1 = i + 1 < PLAAC_LUT_LEN ? T->lut[i + 1] : 0.0;
+        lut2[i] = make_double2(l0, l1);
+    }
+    double2* le = reinterpret_cast<double2*>(sm + kResOffLe);
+    for (int i = threadIdx.x; i < 32 * 8; i += blockDim.x) le[i] = make_double2(T->le0[i >> 3], T->le1[i >> 3]);
+    __syncthreads();
+}
+
+struct LaneView {
+    int n;
+    int32_t prot;
+    int64_t cb;
+    int nch;
+    int64_t base;  // residue 0 of the protein in the output arrays
+};
+
+__device__ __forceinline__ LaneView lane_view(const BatchView& bv, int64_t b, int lane, int64_t res_base)
+{
+    LaneView v;
+    const int64_t rank = b * 32 + lane;
+    v.n = 0;
+    v.prot = -1;
+    v.base = 0;
+    if (rank < bv.nprot) {
+        v.prot = bv.order[rank];
+        const int64_t o = bv.offsets[v.prot];
+        v.n = (int)(bv.offsets[v.prot + 1] - o);
+        v.base = o - res_base;
+    }
+    v.cb = bv.chunk_base[b];
+    v.nch = (int)(bv.chunk_base[b + 1] - v.cb);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int q)
+{
+    return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
+}
+
+// ------------------------------------------------------------------------------------------------ Viterbi
+__global__ void __launch_bounds__(kResThreads) k_res_vit(ResArgs g)
+{
+    __shared__ double2 le_s[32][8];
+    for (int i = threadIdx.x; i < 32 * 8; i += blockDim.x) le_s[i >> 3][i & 7] = make_double2(g.tabs->le0[i >> 3], g.tabs->le1[i >> 3]);
+    __syncthreads();
+    const KScalars& ks = g.ks;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < g.bv.nbuckets; b += warps) {
+        const LaneView L = lane_view(g.bv, b, lane, g.res_base);
+        const int n = L.n;
+        const uint4* sp = g.bv.stream + L.cb * 32 + lane;
+        uint32_t* tbp = g.bv.tbw + L.cb * 32 + lane;
+        double s0 = 0, s1 = 0;
+        uint32_t acc0 = 0, acc1 = 0;
+        uint4 nxt = L.nch > 0 ? sp[0] : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < L.nch; j++) {
+            const uint4 cw = nxt;
+            if (j + 1 < L.nch) nxt = sp[(size_t)(j + 1) * 32];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int t = 16 * j + i;
+                const uint32_t cd = (word_of(cw, i >> 2) >> ((i & 3) * 8)) & 31u;
+                const double2 le = le_s[cd][lane & 7];
+                uint32_t tb0u = 0, tb1u = 0;
+                if (t < n) {
+                    if (t == 0) {
+                        s0 = ks.li0 + le.x;
+                        s1 = ks.li1 + le.y;
+                    } else {
+                        const double v00 = ks.lt00 + s0, v10 = ks.lt10 + s1;
+                        const double v01 = ks.lt01 + s0, v11 = ks.lt11 + s1;
+                        const bool tb0 = v10 > v00, tb1 = v11 > v01;
+                        s0 = (tb0 ? v10 : v00) + le.x;
+                        s1 = (tb1 ? v11 : v01) + le.y;
+                        tb0u = tb0;
+                        tb1u = tb1;
+                    }
+                }
+                acc0 = __funnelshift_r(acc0, tb0u, 1);
+                acc1 = __funnelshift_r(acc1, tb1u, 1);
+            }
+            tbp[(size_t)j * 32] = __byte_perm(acc0, acc1, 0x7632);
+        }
+        if (n < 1) continue;
+        // traceback (:3102-3113) as a suffix scan of 2->2 maps per 16-residue word (see summary_kernel_v2.cuh)
+        int v = (s1 + ks.lf1 > s0 + ks.lf0) ? 1 : 0;
+        const int jlast = (n - 1) >> 4;
+        uint32_t tw_next = tbp[(size_t)jlast * 32];
+        for (int j = jlast; j >= 0; j--) {
+            const uint32_t tw = tw_next;
+            if (j > 0) tw_next = tbp[(size_t)(j - 1) * 32];
+            const int hi = (j == jlast) ? ((n - 1) & 15) : 15;
+            const uint32_t valid = (2u << hi) - 1u, below = valid >> 1;
+            const uint32_t P0 = tw & 0xffffu, P1 = tw >> 16;
+            uint32_t A0 = (P0 >> 1) & below;
+            uint32_t A1 = ((P1 >> 1) & below) | (0xffffu & ~below);
+#pragma unroll
+            for (int sft = 1; sft < 16; sft <<= 1) {
+                const uint32_t B0 = A0 >> sft;
+                const uint32_t B1 = (A1 >> sft) | (0xffffu & ~(0xffffu >> sft));
+                const uint32_t n0 = (B0 & A1) | (~B0 & A0);
+                const uint32_t n1 = (B1 & A1) | (~B1 & A0);
+                A0 = n0;
+                A1 = n1;
+            }
+            const uint32_t vb = (v ? A1 : A0) & valid;
+            v = (int)(((vb & 1u) ? P1 : P0) & 1u);
+            tbp[(size_t)j * 32] = vb;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(kResHmmThreads) k_res_bwd(ResArgs g)
+{
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    res_stage_tables(res_smem, g.tabs);
+    const uint32_t sbase = smem_u32(res_smem);
+    const KScalars& ks = g.ks;
+    const int lane = threadIdx.x & 31;
+    const uint32_t le_base = sbase + kResOffLe + (uint32_t)(lane & 7) * 16u;
+    const uint32_t lut_addr = sbase + kResOffLut2;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < g.bv.nbuckets; b += warps) {
+        const LaneView L = lane_view(g.bv, b, lane, g.res_base);
+        const int n = L.n;
+        const uint4* sp = g.bv.stream + L.cb * 32 + lane;
+        double* B0 = g.B0 + (size_t)L.cb * 512 + lane;
+        double* B1 = g.B1 + (size_t)L.cb * 512 + lane;
+        double b0 = 0, b1 = 0;
+        uint32_t cnext = 0;  // code of residue t+1
+        uint4 nxt = L.nch > 0 ? sp[(size_t)(L.nch - 1) * 32] : make_uint4(0, 0, 0, 0);
+        for (int j = L.nch - 1; j >= 0; j--) {
+            const uint4 cw = nxt;
+            if (j > 0) nxt = sp[(size_t)(j - 1) * 32];
+#pragma unroll
+            for (int i = 15; i >= 0; i--) {
+                const int t = 16 * j + i;
+                const uint32_t cd = (word_of(cw, i >> 2) >> ((i & 3) * 8)) & 31u;
+                if (t < n) {
+                    if (t == n - 1) {
+                        b0 = ks.lf0;  // :3379-3381
+                        b1 = ks.lf1;
+                    } else {
+                        // b[i][t] = LSE_k( (lt[i][k] + b[k][t+1]) + le[k][aa[t+1]] ), k ascending (:3384-3389)
+                        const double2 le = lds_v2f64(le_base + (cnext << 7));
+                        const double x0 = (ks.lt00 + b0) + le.x, x1 = (ks.lt01 + b1) + le.y;
+                        const double y0 = (ks.lt10 + b0) + le.x, y1 = (ks.lt11 + b1) + le.y;
+                        b0 = lse_lut2<false>(x0, x1, lut_addr);
+                        b1 = lse_lut2<false>(y0, y1, lut_addr);
+                    }
+                    B0[((size_t)j * 16 + i) * 32] = b0;
+                    B1[((size_t)j * 16 + i) * 32] = b1;
+                    cnext = cd;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward + posteriors
+__global__ void __launch_bounds__(kResHmmThreads) k_res_fwd(ResArgs g)
+{
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    res_stage_tables(res_smem, g.tabs);
+    const uint32_t sbase = smem_u32(res_smem);
+    const KScalars& ks = g.ks;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t le_base = sbase + kResOffLe + (uint32_t)(lane & 7) * 16u;
+    const uint32_t lut_addr = sbase + kResOffLut2;
+    double* tile0 = reinterpret_cast<double*>(res_smem + kResFixedBytes + (size_t)wid * kResTileBytes);
+    double* tile1 = tile0 + 16 * kTilePitch;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < g.bv.nbuckets; b += warps) {
+        const LaneView L = lane_view(g.bv, b, lane, g.res_base);
+        const int n = L.n;
+        const uint4* sp = g.bv.stream + L.cb * 32 + lane;
+        const double* B0 = g.B0 + (size_t)L.cb * 512 + lane;
+        const double* B1 = g.B1 + (size_t)L.cb * 512 + lane;
+        uint32_t* mw = g.mapw + L.cb * 32 + lane;
+        double a0 = 0, a1 = 0, lpseq = 0;
+        uint4 nxt = L.nch > 0 ? sp[0] : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < L.nch; j++) {
+            const uint4 cw = nxt;
+            if (j + 1 < L.nch) nxt = sp[(size_t)(j + 1) * 32];
+            uint32_t mapbits = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int t = 16 * j + i;
+                const uint32_t cd = (word_of(cw, i >> 2) >> ((i & 3) * 8)) & 31u;
+                double p0 = 0, p1 = 0;
+                if (t < n) {
+                    const double2 le = lds_v2f64(le_base + (cd << 7));
+                    if (t == 0) {
+                        a0 = ks.li0 + le.x;  // :3356-3358
+                        a1 = ks.li1 + le.y;
+                    } else {
+                        const double f0 = lse_lut2<false>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;  // :3359-3367
+                        const double f1 = lse_lut2<false>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
+                        a0 = f0;
+                        a1 = f1;
+                    }
+                    const double ab0 = a0 + B0[((size_t)j * 16 + i) * 32];
+                    const double ab1 = a1 + B1[((size_t)j * 16 + i) * 32];
+                    if (t == 0) lpseq = lse_lut2<false>(ab0, ab1, lut_addr);  // :3393-3396
+                    p0 = exp(ab0 - lpseq);                                    // :3401-3405
+                    p1 = exp(ab1 - lpseq);
+                    mapbits |= (p1 > p0 ? 1u : 0u) << i;                      // :4036-4040
+                }
+                tile0[i * kTilePitch + lane] = p0;
+                tile1[i * kTilePitch + lane] = p1;
+            }
+            mw[(size_t)j * 32] = mapbits;
+            __syncwarp();
+            // protein-major write-out: lanes 0-15 carry 16 consecutive post_bg values of protein q, lanes 16-31 post_prd
+            const int half = lane >> 4, ii = lane & 15;
+            const double* tsrc = (half ? tile1 : tile0) + ii * kTilePitch;
+            double* const dsts = half ? g.out.post_prd : g.out.post_bg;
+#pragma unroll 4
+            for (int q = 0; q < 32; q++) {
+                const int nq = __shfl_sync(0xffffffffu, n, q);
+                const int64_t bq = __shfl_sync(0xffffffffu, L.base, q);
+                if (16 * j + ii < nq) dsts[bq + 16 * j + ii] = tsrc[q];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ bit words -> bytes
+__global__ void __launch_bounds__(kResThreads) k_res_bits(ResArgs g)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int64_t b = blockIdx.x; b < g.bv.nbuckets; b += gridDim.x) {
+        const int64_t cb = g.bv.chunk_base[b];
+        for (int q = wid; q < 32; q += nw) {
+            const int64_t rank = b * 32 + q;
+            if (rank >= g.bv.nprot) break;
+            const int32_t prot = g.bv.order[rank];
+            const int64_t o = g.bv.offsets[prot];
+            const int n = (int)(g.bv.offsets[prot + 1] - o);
+            const int64_t base = o - g.res_base;
+            const uint32_t* vw = g.bv.tbw + cb * 32 + q;
+            const uint32_t* mw = g.mapw + cb * 32 + q;
+            for (int t = lane; t < n; t += 32) {
+                const size_t w = (size_t)(t >> 4) * 32;
+                if (g.out.vit) g.out.vit[base + t] = (uint8_t)((vw[w] >> (t & 15)) & 1u);
+                if (g.out.map) g.out.map[base + t] = (uint8_t)((mw[w] >> (t & 15)) & 1u);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tracks
+constexpr int kTrackTile = 256;
+constexpr int kTrackWarps = 4;
+
+// inclusive prefix sum of arr[0..len) in place; lane `lane` owns the contiguous run [lane*per, lane*per+per)
+template <typename T>
+__device__ __forceinline__ void warp_scan_inplace(T* arr, int len, int per, int lane)
+{
+    const int lo = lane * per, hi = min(lo + per, len);
+    T run = 0;
+    for (int e = lo; e < hi; e++) {
+        run = run + arr[e];
+        arr[e] = run;
+    }
+    T inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = inc + o;
+    }
+    T ex = __shfl_up_sync(0xffffffffu, inc, 1);  // sum of the runs of the lower lanes
+    if (lane == 0) ex = 0;
+    if (lane > 0)
+        for (int e = lo; e < hi; e++) arr[e] = arr[e] + ex;
+    __syncwarp();
+}
+
+struct TrackArgs {
+    const uint8_t* codes;     // protein-major, 1 byte per residue
+    const int64_t* offsets;
+    int64_t off_base;         // offsets are relative to this residue index for `codes`
+    int64_t res_base;         // ... and to this one for the output arrays
+    int64_t nprot;
+    KScalars ks;
+    const DeviceTables* tabs;
+    plaac_residue_out out;
+    int nx;                   // kTrackTile + 4w
+    int per_x, per_s;         // elements per lane of the two scans (odd: conflict-free)
+};
+
+__global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
+{
+    extern __shared__ __align__(16) unsigned char trk_smem[];
+    __shared__ double tab_h[32], tab_l[32], tab_p[32];
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+        tab_h[i] = g.tabs->hyd[i];
+        tab_l[i] = g.tabs->llr[i];
+        tab_p[i] = g.tabs->pap[i];
+    }
+    __syncthreads();
+    const KScalars& ks = g.ks;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int w = ks.w, full = 2 * w + 1, Wfull = full * full;
+    const int NX = g.nx, NS = kTrackTile + 2 * w;
+    // per-warp arrays: X* (NX) are reused for the second-level prefix sums
+    const size_t per_warp = (size_t)NX * (3 * 8 + 4) + (size_t)NS * (3 * 8 + 4) + 64;
+    unsigned char* base = trk_smem + (size_t)wid * ((per_warp + 15) & ~(size_t)15);
+    double* Xh = reinterpret_cast<double*>(base);
+    double* Xl = Xh + NX;
+    double* Xp = Xl + NX;
+    double* Sh = Xp + NX;
+    double* Sl = Sh + NS;
+    double* Sp = Sl + NS;
+    int* Xc = reinterpret_cast<int*>(Sp + NS);
+    int* Sc = Xc + NX;
+
+    const int64_t warps = (int64_t)gridDim.x * kTrackWarps;
+    for (int64_t p = (int64_t)blockIdx.x * kTrackWarps + wid; p < g.nprot; p += warps) {
+        const int64_t o = g.offsets[p];
+        const int n = (int)(g.offsets[p + 1] - o);
+        const uint8_t* src = g.codes + (o - g.off_base);
+        const int64_t ob = o - g.res_base;
+        for (int t0 = 0; t0 < n; t0 += kTrackTile) {
+            const int u_lo = t0 - 2 * w;  // residue of X*[0]
+            // 1. per-residue values, zero outside the protein
+            for (int e = lane; e < NX; e += 32) {
+                const int u = u_lo + e;
+                double h = 0, l = 0, pp = 0;
+                int ch = 0;
+                if (u >= 0 && u < n) {
+                    uint32_t cd = src[u];
+                    if (cd > 21u) cd = 0;  // invalid input is scored as X (and reported by k_pack)
+                    h = tab_h[cd];
+                    l = tab_l[cd];
+                    pp = tab_p[cd];
+                    // PAPA proline rule (:2652-2655): the second proline of PP / PxP is not scored
+                    if (ks.adjust_prolines && cd == 13u && ((u >= 1 && src[u - 1] == 13) || (u >= 2 && src[u - 2] == 13))) pp = 0.0;
+                    ch = (int)((ks.charge_plus >> cd) & 1u) - (int)((ks.charge_minus >> cd) & 1u);
+                }
+                Xh[e] = h;
+                Xl[e] = l;
+                Xp[e] = pp;
+                Xc[e] = ch;
+            }
+            __syncwarp();
+            warp_scan_inplace(Xh, NX, g.per_x, lane);
+            warp_scan_inplace(Xl, NX, g.per_x, lane);
+            warp_scan_inplace(Xp, NX, g.per_x, lane);
+            warp_scan_inplace(Xc, NX, g.per_x, lane);
+            // 2. pass-1 window sums for centres t0-w .. t0+T+w-1 and the five pass-1 tracks
+            for (int idx = lane; idx < NS; idx += 32) {
+                const int pc = t0 - w + idx;
+                double sh = 0, sl = 0, sp_ = 0;
+                int scv = 0;
+                if (pc >= 0 && pc < n) {
+                    const int ehi = min(pc + w, u_lo + NX - 1) - u_lo;  // beyond the protein everything is zero
+                    const int elo = pc - w - 1 - u_lo;                   // >= -1
+                    sh = Xh[ehi] - (elo >= 0 ? Xh[elo] : 0.0);
+                    sl = Xl[ehi] - (elo >= 0 ? Xl[elo] : 0.0);
+                    sp_ = Xp[ehi] - (elo >= 0 ? Xp[elo] : 0.0);
+                    scv = Xc[ehi] - (elo >= 0 ? Xc[elo] : 0);
+                    if (pc >= t0 && pc < t0 + kTrackTile) {
+                        const double cnt = (double)(full - max(0, w - pc) - max(0, pc + w - (n - 1)));
+                        const double hyd = sh / cnt;
+                        const double chg = (double)scv / cnt;
+                        const double fi_p = (ks.cc0 * hyd + ks.cc1 * fabs(chg)) + ks.cc2;
+                        g.out.hydro[ob + pc] = hyd;
+                        g.out.charge[ob + pc] = chg;
+                        g.out.fi[ob + pc] = fi_p;
+                        g.out.plaac[ob + pc] = sl / cnt;
+                        g.out.papa[ob + pc] = sp_ / cnt;
+                        if (n == 1) {  // w clips to 0: the second pass returns the value itself (:2588-2589)
+                            g.out.fix2[ob] = fi_p;
+                            g.out.plaacx2[ob] = sl / cnt;
+                            g.out.papax2[ob] = sp_ / cnt;
+                        }
+                    }
+                }
+                Sh[idx] = sh;
+                Sl[idx] = sl;
+                Sp[idx] = sp_;
+                Sc[idx] = abs(scv);
+            }
+            __syncwarp();
+            warp_scan_inplace(Sh, NS, g.per_s, lane);
+            warp_scan_inplace(Sl, NS, g.per_s, lane);
+            warp_scan_inplace(Sp, NS, g.per_s, lane);
+            warp_scan_inplace(Sc, NS, g.per_s, lane);
+            // 3. pass-2 tracks for centres t0 .. t0+T-1 (NaN outside [w, n-1-w], :2596-2601)
+            if (n > 1) {
+                for (int idx = lane; idx < kTrackTile; idx += 32) {
+                    const int k = t0 + idx;
+                    if (k >= n) break;
+                    double f2 = nan(""), l2 = f2, p2 = f2;
+                    if (k >= w && k <= n - 1 - w) {
+                        const int ehi = idx + 2 * w;  // centre k+w in S* coordinates (S*[0] is centre t0-w)
+                        const int elo = idx - 1;      // centre k-w-1
+                        const double Th = Sh[ehi] - (elo >= 0 ? Sh[elo] : 0.0);
+                        const double Tl = Sl[ehi] - (elo >= 0 ? Sl[elo] : 0.0);
+                        const double Tp = Sp[ehi] - (elo >= 0 ? Sp[elo] : 0.0);
+                        const int Tac = Sc[ehi] - (elo >= 0 ? Sc[elo] : 0);
+                        const int ml = 2 * w - k, mr = 2 * w - (n - 1 - k);
+                        const double Wd = (double)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0));
+                        f2 = ((ks.cc0 * Th + ks.cc1 * (double)Tac) + ks.cc2 * Wd) / Wd;
+                        l2 = Tl / Wd;
+                        p2 = Tp / Wd;
+                    }
+                    g.out.fix2[ob + k] = f2;
+                    g.out.plaacx2[ob + k] = l2;
+                    g.out.papax2[ob + k] = p2;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct ResidueV2Plan {
+    bool ok = false;           // false: parameters outside what these kernels support (fall back to residue_kernel.cuh)
+    size_t fwd_smem = 0, bwd_smem = 0, trk_smem = 0;
+    int nx = 0, per_x = 0, per_s = 0;
+};
+
+inline ResidueV2Plan residue_v2_plan(const KScalars& ks)
+{
+    ResidueV2Plan P;
+    P.bwd_smem = kResFixedBytes;
+    P.fwd_smem = kResFixedBytes + (size_t)(kResHmmThreads / 32) * kResTileBytes;
+    P.nx = kTrackTile + 4 * ks.w;
+    const int ns = kTrackTile + 2 * ks.w;
+    P.per_x = ((P.nx + 31) / 32) | 1;
+    P.per_s = ((ns + 31) / 32) | 1;
+    const size_t per_warp = ((size_t)P.nx * 28 + (size_t)ns * 28 + 64 + 15) & ~(size_t)15;
+    P.trk_smem = per_warp * kTrackWarps;
+    P.ok = P.trk_smem <= 200 * 1024 && P.fwd_smem <= 227 * 1024;
+    return P;
+}
+
+inline int residue_v2_setup(const ResidueV2Plan& P)
+{
+    if (!P.ok) return PLAAC_OK;
+    if (cudaFuncSetAttribute(k_res_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bwd_smem) != cudaSuccess) return PLAAC_E_CUDA;
+    if (cudaFuncSetAttribute(k_res_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.fwd_smem) != cudaSuccess) return PLAAC_E_CUDA;
+    if (cudaFuncSetAttribute(k_res_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.trk_smem) != cudaSuccess) return PLAAC_E_CUDA;
+    return PLAAC_OK;
+}
+
+// All five kernels on `st`; aux streams (may be NULL) let the independent ones overlap:
+//   st:   vit -------------------------> bits
+//   aux1: bwd -> fwd (needs bwd) ------/
+//   aux2: tracks ----------------------/
+inline int launch_residue_v2(const ResidueV2Plan& P, const ResArgs& ra, const TrackArgs& ta, int sm_count, cudaStream_t st,
+                             cudaStream_t aux1, cudaStream_t aux2, cudaEvent_t ev_fork, cudaEvent_t ev_j1, cudaEvent_t ev_j2,
+                             int64_t* launches)
+{
+    const plaac_residue_out& out = ra.out;
+    if (!out.post_bg || !out.post_prd || !out.charge || !out.hydro || !out.fi || !out.plaac || !out.papa || !out.fix2 ||
+        !out.plaacx2 || !out.papax2)
+        return PLAAC_E_INVALID;
+    const int64_t nb = ra.bv.nbuckets;
+    const bool fork = aux1 && aux2;
+    cudaStream_t s1 = fork ? aux1 : st, s2 = fork ? aux2 : st;
+    if (fork) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(s1, ev_fork, 0);
+        cudaStreamWaitEvent(s2, ev_fork, 0);
+    }
+    const unsigned g_vit = (unsigned)std::min<int64_t>((nb + kResThreads / 32 - 1) / (kResThreads / 32), (int64_t)sm_count * 8);
+    const unsigned g_hmm = (unsigned)std::min<int64_t>((nb + kResHmmThreads / 32 - 1) / (kResHmmThreads / 32), (int64_t)sm_count * 2);
+    const unsigned g_fwd = (unsigned)std::min<int64_t>((nb + kResHmmThreads / 32 - 1) / (kResHmmThreads / 32), (int64_t)sm_count);
+    const unsigned g_trk = (unsigned)std::min<int64_t>((ta.nprot + kTrackWarps - 1) / kTrackWarps, (int64_t)sm_count * 8);
+    const unsigned g_bits = (unsigned)std::min<int64_t>(nb, (int64_t)sm_count * 8);
+    k_res_vit<<<g_vit, kResThreads, 0, st>>>(ra);
+    k_res_bwd<<<g_hmm, kResHmmThreads, P.bwd_smem, s1>>>(ra);
+    k_res_fwd<<<g_fwd, kResHmmThreads, P.fwd_smem, s1>>>(ra);
+    k_res_tracks<<<g_trk, kTrackWarps * 32, P.trk_smem, s2>>>(ta);
+    if (fork) {
+        cudaEventRecord(ev_j1, s1);
+        cudaEventRecord(ev_j2, s2);
+        cudaStreamWaitEvent(st, ev_j1, 0);
+        cudaStreamWaitEvent(st, ev_j2, 0);
+    }
+    k_res_bits<<<g_bits, kResThreads, 0, st>>>(ra);
+    if (launches) *launches += 5;
+    return cudaGetLastError() == cudaSuccess ? PLAAC_OK : PLAAC_E_CUDA;
+}
+
+}  // namespace plaac
