@@ -34,6 +34,8 @@ struct BatchView {
     const int32_t* order;     // sorted rank -> protein index (descending length)
     const int64_t* offsets;   // nprot+1
     const int64_t* chunk_base;  // nbuckets+1, in slots-of-32-lanes
+    const int32_t* slot_bucket; // bucket of every 32-lane slot (written by k_pack)
+    int64_t nslots;           // chunk_base[nbuckets] if the host knows it, else an upper bound
     int64_t nprot;
     int64_t nbuckets;
     int64_t off_base;         // offsets[] are relative to this residue index

@@ -32,10 +32,10 @@ struct DevBuf {
 // One set of device work buffers; plaac_score() uses two of them to overlap copies with compute.
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, errflag, core_list, core_count;
+    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count;
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
-    DevBuf res_b0, res_b1, res_mapw;   // per-residue scratch: backward planes, MAP bit words
+    DevBuf res_b0, res_b1, res_a0, res_a1, res_mapw, res_lpseq;  // per-residue scratch (bucketed layout)
     cudaStream_t aux1 = nullptr, aux2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
     int64_t* h_total = nullptr;        // pinned
@@ -276,9 +276,9 @@ int slot_init(plaac_ctx* ctx, Slot& s)
 
 void slot_free(Slot& s)
 {
-    for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.errflag,
+    for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
                       &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
-                      &s.res_b1, &s.res_mapw})
+                      &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq})
         release(*b);
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
@@ -330,12 +330,13 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     }
     if ((rc = ensure(ctx, s.stream_buf, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint4)))) return rc;
     if ((rc = ensure(ctx, s.tbw, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(ctx, s.slot_bucket, (size_t)std::max<int64_t>(slots, 1) * sizeof(int32_t)))) return rc;
 
     const int pack_blocks = (int)std::min<int64_t>((nbuckets + 7) / 8, (int64_t)ctx->sm_count * 8);
     k_pack<<<pack_blocks, 256, 0, st>>>(d_codes, d_offsets, off_base, (const int32_t*)s.order.p,
                                         (const int64_t*)s.chunk_base.p, nprot, nbuckets, ctx->ks.adjust_prolines,
                                         ctx->ks.charge_plus, ctx->ks.charge_minus, (uint4*)s.stream_buf.p,
-                                        (int*)s.errflag.p);
+                                        (int32_t*)s.slot_bucket.p, (int*)s.errflag.p);
     ctx->stats.kernel_launches += 1;
 
     BatchView bv;
@@ -344,6 +345,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     bv.order = (const int32_t*)s.order.p;
     bv.offsets = d_offsets;
     bv.chunk_base = (const int64_t*)s.chunk_base.p;
+    bv.slot_bucket = (const int32_t*)s.slot_bucket.p;
+    bv.nslots = slots;
     bv.nprot = nprot;
     bv.nbuckets = nbuckets;
     bv.off_base = off_base;
@@ -392,7 +395,10 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             const size_t nslots = (size_t)std::max<int64_t>(slots, 1);
             if ((rc = ensure(ctx, s.res_b0, nslots * 512 * sizeof(double)))) return rc;
             if ((rc = ensure(ctx, s.res_b1, nslots * 512 * sizeof(double)))) return rc;
+            if ((rc = ensure(ctx, s.res_a0, nslots * 512 * sizeof(double)))) return rc;
+            if ((rc = ensure(ctx, s.res_a1, nslots * 512 * sizeof(double)))) return rc;
             if ((rc = ensure(ctx, s.res_mapw, nslots * 32 * sizeof(uint32_t)))) return rc;
+            if ((rc = ensure(ctx, s.res_lpseq, (size_t)nbuckets * 32 * sizeof(double)))) return rc;
             ResArgs ra;
             ra.bv = bv;
             ra.ks = ctx->ks;
@@ -401,7 +407,10 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             ra.res_base = res_base;
             ra.B0 = (double*)s.res_b0.p;
             ra.B1 = (double*)s.res_b1.p;
+            ra.A0 = (double*)s.res_a0.p;
+            ra.A1 = (double*)s.res_a1.p;
             ra.mapw = (uint32_t*)s.res_mapw.p;
+            ra.lpseq = (double*)s.res_lpseq.p;
             TrackArgs ta;
             ta.codes = d_codes;
             ta.offsets = d_offsets;

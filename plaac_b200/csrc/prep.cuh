@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256)
 k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
        int64_t off_base, const int32_t* __restrict__ order, const int64_t* __restrict__ chunk_base, int64_t nprot,
        int64_t nbuckets, int adjust_prolines, uint32_t charge_plus, uint32_t charge_minus, uint4* __restrict__ stream,
-       int* __restrict__ errflag)
+       int32_t* __restrict__ slot_bucket, int* __restrict__ errflag)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -234,6 +234,7 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
         uint32_t carry = 0;  // proline bits of the previous word (positions before the current one)
         uint32_t bad_any = 0;
         uint4* dst = stream + cb * 32 + lane;
+        for (int j = lane; j < nch; j += 32) slot_bucket[cb + j] = (int32_t)b;
         for (int j = 0; j < nch; j++) {
             const uint4 C = ((int64_t)j + 2 < nblk) ? __ldg(ap + j + 2) : zero4;  // in flight while slot j is packed
             // bytes sh .. sh+15 of the 32-byte pair {A, B}

@@ -10,25 +10,30 @@
 //                 bits, one 32-bit word per 16 residues per lane
 //   k_res_bwd     backward recurrence (:3378-3391) -> scratch planes B0/B1 in the bucketed layout
 //                 [slot][residue-in-slot][lane]: every warp store is one 256-byte line
-//   k_res_fwd     forward recurrence (:3356-3367); lpseq is known at residue 0 because the backward pass is already
-//                 complete, so the posteriors and the MAP bit (mapdecodel :4032-4045) come out in the same sweep.
-//                 16-residue tiles are transposed through shared memory and written protein-major as 128-byte runs
+//   k_res_fwd     forward recurrence (:3356-3367) -> scratch planes A0/A1, same layout.  The three recurrences are
+//                 independent chains and run concurrently on three streams
+//   k_res_lpseq   lpseq per protein (:3393-3396)
+//   k_res_post    fully parallel, one warp per 16-residue x 32-protein slot: pp = exp((a+b) - lpseq) (:3401-3405) and
+//                 the MAP bit (mapdecodel :4032-4045); tiles are transposed through shared memory and written
+//                 protein-major as 128-byte runs
 //   k_res_bits    Viterbi/MAP bit words -> one byte per residue, protein-major, coalesced
 //   k_res_tracks  the eight disorderreport tracks (:4866-4903, slidingaverage :2585-2662) from fp64 prefix sums: one
 //                 warp per protein walks tiles of 256 consecutive residues (+2w halo each side); pass-1 window sums
 //                 are differences of a prefix sum of per-residue values, pass-2 sums are differences of a prefix sum
 //                 of the pass-1 sums (sum-of-window-sums identity).  All loads and stores are coalesced.
 //
-// k_res_vit / k_res_bwd are independent and run on two streams; k_res_tracks overlaps both.
+// Scratch traffic: 32 B/aa written and read once; output 82 B/aa.
 #pragma once
 #include <algorithm>
 
 #include "common.cuh"
+#include "residue_kernel.cuh"
 #include "summary_kernel_v2.cuh"
 
 namespace plaac {
 
 constexpr int kResThreads = 256;   // k_res_vit, k_res_bits
+constexpr int kResPostThreads = 128;
 constexpr int kResHmmThreads = 512;  // k_res_bwd, k_res_fwd (one 64 KB LUT per CTA)
 constexpr uint32_t kResOffLe = 0;                                     // double2 [32 codes][8 lane copies] {le0, le1}
 constexpr uint32_t kResOffLut2 = 4096;                                // double2 [4002]
@@ -42,9 +47,12 @@ struct ResArgs {
     const DeviceTables* tabs;
     plaac_residue_out out;
     int64_t res_base;    // residue index of out.*[0]
-    double* B0;          // backward variables, bucketed layout
+    double* B0;          // backward variables, bucketed layout [slot][residue in slot][lane]
     double* B1;
+    double* A0;          // forward variables, same layout
+    double* A1;
     uint32_t* mapw;      // MAP bits, one word per slot per lane
+    double* lpseq;       // per rank
 };
 
 __device__ __forceinline__ void res_stage_tables(unsigned char* sm, const DeviceTables* T)
@@ -213,37 +221,32 @@ __global__ void __launch_bounds__(kResHmmThreads) k_res_bwd(ResArgs g)
     }
 }
 
-// ------------------------------------------------------------------------------------------------ forward + posteriors
+// ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(kResHmmThreads) k_res_fwd(ResArgs g)
 {
     extern __shared__ __align__(16) unsigned char res_smem[];
     res_stage_tables(res_smem, g.tabs);
     const uint32_t sbase = smem_u32(res_smem);
     const KScalars& ks = g.ks;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const uint32_t le_base = sbase + kResOffLe + (uint32_t)(lane & 7) * 16u;
     const uint32_t lut_addr = sbase + kResOffLut2;
-    double* tile0 = reinterpret_cast<double*>(res_smem + kResFixedBytes + (size_t)wid * kResTileBytes);
-    double* tile1 = tile0 + 16 * kTilePitch;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < g.bv.nbuckets; b += warps) {
         const LaneView L = lane_view(g.bv, b, lane, g.res_base);
         const int n = L.n;
         const uint4* sp = g.bv.stream + L.cb * 32 + lane;
-        const double* B0 = g.B0 + (size_t)L.cb * 512 + lane;
-        const double* B1 = g.B1 + (size_t)L.cb * 512 + lane;
-        uint32_t* mw = g.mapw + L.cb * 32 + lane;
-        double a0 = 0, a1 = 0, lpseq = 0;
+        double* A0 = g.A0 + (size_t)L.cb * 512 + lane;
+        double* A1 = g.A1 + (size_t)L.cb * 512 + lane;
+        double a0 = 0, a1 = 0;
         uint4 nxt = L.nch > 0 ? sp[0] : make_uint4(0, 0, 0, 0);
         for (int j = 0; j < L.nch; j++) {
             const uint4 cw = nxt;
             if (j + 1 < L.nch) nxt = sp[(size_t)(j + 1) * 32];
-            uint32_t mapbits = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int t = 16 * j + i;
                 const uint32_t cd = (word_of(cw, i >> 2) >> ((i & 3) * 8)) & 31u;
-                double p0 = 0, p1 = 0;
                 if (t < n) {
                     const double2 le = lds_v2f64(le_base + (cd << 7));
                     if (t == 0) {
@@ -255,30 +258,77 @@ __global__ void __launch_bounds__(kResHmmThreads) k_res_fwd(ResArgs g)
                         a0 = f0;
                         a1 = f1;
                     }
-                    const double ab0 = a0 + B0[((size_t)j * 16 + i) * 32];
-                    const double ab1 = a1 + B1[((size_t)j * 16 + i) * 32];
-                    if (t == 0) lpseq = lse_lut2<false>(ab0, ab1, lut_addr);  // :3393-3396
-                    p0 = exp(ab0 - lpseq);                                    // :3401-3405
-                    p1 = exp(ab1 - lpseq);
-                    mapbits |= (p1 > p0 ? 1u : 0u) << i;                      // :4036-4040
+                    A0[((size_t)j * 16 + i) * 32] = a0;
+                    A1[((size_t)j * 16 + i) * 32] = a1;
                 }
-                tile0[i * kTilePitch + lane] = p0;
-                tile1[i * kTilePitch + lane] = p1;
             }
-            mw[(size_t)j * 32] = mapbits;
-            __syncwarp();
-            // protein-major write-out: lanes 0-15 carry 16 consecutive post_bg values of protein q, lanes 16-31 post_prd
-            const int half = lane >> 4, ii = lane & 15;
-            const double* tsrc = (half ? tile1 : tile0) + ii * kTilePitch;
-            double* const dsts = half ? g.out.post_prd : g.out.post_bg;
-#pragma unroll 4
-            for (int q = 0; q < 32; q++) {
-                const int nq = __shfl_sync(0xffffffffu, n, q);
-                const int64_t bq = __shfl_sync(0xffffffffu, L.base, q);
-                if (16 * j + ii < nq) dsts[bq + 16 * j + ii] = tsrc[q];
-            }
-            __syncwarp();
         }
+    }
+}
+
+// lpseq = logeapeb(a[0][0] + b[0][0], a[1][0] + b[1][0]) per protein (:3393-3396); lane = rank
+__global__ void __launch_bounds__(256) k_res_lpseq(ResArgs g)
+{
+    const int64_t rank = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rank >= g.bv.nprot) return;
+    const size_t at = (size_t)g.bv.chunk_base[rank >> 5] * 512 + (size_t)(rank & 31);
+    g.lpseq[rank] = lse_lut_g(g.A0[at] + g.B0[at], g.A1[at] + g.B1[at], g.tabs->lut, g.ks.ln2);
+}
+
+// ------------------------------------------------------------------------------------------------ posteriors + MAP
+// Fully parallel: one warp per 32-lane slot (16 residues of 32 proteins).  pp = exp((a + b) - lpseq) (:3401-3405),
+// MAP bit = pp1 > pp0 (:4036-4040).  The 16 x 32 tiles are transposed through shared memory and written
+// protein-major: lanes 0-15 carry 16 consecutive post_bg values of one protein, lanes 16-31 its post_prd values.
+__global__ void __launch_bounds__(kResPostThreads) k_res_post(ResArgs g)
+{
+    __shared__ double tiles[kResPostThreads / 32][2][16 * kTilePitch];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* tile0 = tiles[wid][0];
+    double* tile1 = tiles[wid][1];
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = g.bv.chunk_base[g.bv.nbuckets];
+    for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < total; s += warps) {
+        const int64_t b = g.bv.slot_bucket[s];
+        const int j = (int)(s - g.bv.chunk_base[b]);
+        const int64_t rank = b * 32 + lane;
+        int n = 0;
+        int64_t base = 0;
+        double lpseq = 0;
+        if (rank < g.bv.nprot) {
+            const int32_t prot = g.bv.order[rank];
+            const int64_t o = g.bv.offsets[prot];
+            n = (int)(g.bv.offsets[prot + 1] - o);
+            base = o - g.res_base;
+            lpseq = g.lpseq[rank];
+        }
+        const size_t at = (size_t)s * 512 + lane;
+        double a0[16], a1[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const bool in = 16 * j + i < n;
+            a0[i] = in ? g.A0[at + (size_t)i * 32] + g.B0[at + (size_t)i * 32] : 0.0;
+            a1[i] = in ? g.A1[at + (size_t)i * 32] + g.B1[at + (size_t)i * 32] : 0.0;
+        }
+        uint32_t mapbits = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const double p0 = exp(a0[i] - lpseq), p1 = exp(a1[i] - lpseq);
+            if (16 * j + i < n) mapbits |= (p1 > p0 ? 1u : 0u) << i;
+            tile0[i * kTilePitch + lane] = p0;
+            tile1[i * kTilePitch + lane] = p1;
+        }
+        g.mapw[(size_t)s * 32 + lane] = mapbits;
+        __syncwarp();
+        const int half = lane >> 4, ii = lane & 15;
+        const double* tsrc = (half ? tile1 : tile0) + ii * kTilePitch;
+        double* const dsts = half ? g.out.post_prd : g.out.post_bg;
+#pragma unroll 8
+        for (int q = 0; q < 32; q++) {
+            const int nq = __shfl_sync(0xffffffffu, n, q);
+            const int64_t bq = __shfl_sync(0xffffffffu, base, q);
+            if (16 * j + ii < nq) dsts[bq + 16 * j + ii] = tsrc[q];
+        }
+        __syncwarp();
     }
 }
 
@@ -333,6 +383,50 @@ __device__ __forceinline__ void warp_scan_inplace(T* arr, int len, int per, int 
     __syncwarp();
 }
 
+// the four tracks scanned together: four independent dependency chains per lane instead of one
+__device__ __forceinline__ void warp_scan4_inplace(double* a, double* b, double* c, int* d, int len, int per, int lane)
+{
+    const int lo = lane * per, hi = min(lo + per, len);
+    double ra = 0, rb = 0, rc = 0;
+    int rd = 0;
+    for (int e = lo; e < hi; e++) {
+        ra = ra + a[e];
+        rb = rb + b[e];
+        rc = rc + c[e];
+        rd = rd + d[e];
+        a[e] = ra;
+        b[e] = rb;
+        c[e] = rc;
+        d[e] = rd;
+    }
+    double ia = ra, ib = rb, ic = rc;
+    int id = rd;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const double oa = __shfl_up_sync(0xffffffffu, ia, s), ob = __shfl_up_sync(0xffffffffu, ib, s);
+        const double oc = __shfl_up_sync(0xffffffffu, ic, s);
+        const int od = __shfl_up_sync(0xffffffffu, id, s);
+        if (lane >= s) {
+            ia = ia + oa;
+            ib = ib + ob;
+            ic = ic + oc;
+            id = id + od;
+        }
+    }
+    double ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
+    double ec = __shfl_up_sync(0xffffffffu, ic, 1);
+    int ed = __shfl_up_sync(0xffffffffu, id, 1);
+    if (lane > 0) {
+        for (int e = lo; e < hi; e++) {
+            a[e] = a[e] + ea;
+            b[e] = b[e] + eb;
+            c[e] = c[e] + ec;
+            d[e] = d[e] + ed;
+        }
+    }
+    __syncwarp();
+}
+
 struct TrackArgs {
     const uint8_t* codes;     // protein-major, 1 byte per residue
     const int64_t* offsets;
@@ -360,8 +454,9 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int w = ks.w, full = 2 * w + 1, Wfull = full * full;
     const int NX = g.nx, NS = kTrackTile + 2 * w;
+    const double rfull = 1.0 / (double)full, rWfull = 1.0 / (double)Wfull;
     // per-warp arrays: X* (NX) are reused for the second-level prefix sums
-    const size_t per_warp = (size_t)NX * (3 * 8 + 4) + (size_t)NS * (3 * 8 + 4) + 64;
+    const size_t per_warp = (size_t)NX * (3 * 8 + 4) + (size_t)NS * (3 * 8 + 4) + (size_t)NX + 64;
     unsigned char* base = trk_smem + (size_t)wid * ((per_warp + 15) & ~(size_t)15);
     double* Xh = reinterpret_cast<double*>(base);
     double* Xl = Xh + NX;
@@ -371,6 +466,7 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
     double* Sp = Sl + NS;
     int* Xc = reinterpret_cast<int*>(Sp + NS);
     int* Sc = Xc + NX;
+    uint8_t* Cd = reinterpret_cast<uint8_t*>(Sc + NS);
 
     const int64_t warps = (int64_t)gridDim.x * kTrackWarps;
     for (int64_t p = (int64_t)blockIdx.x * kTrackWarps + wid; p < g.nprot; p += warps) {
@@ -380,57 +476,69 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
         const int64_t ob = o - g.res_base;
         for (int t0 = 0; t0 < n; t0 += kTrackTile) {
             const int u_lo = t0 - 2 * w;  // residue of X*[0]
-            // 1. per-residue values, zero outside the protein
-            for (int e = lane; e < NX; e += 32) {
-                const int u = u_lo + e;
-                double h = 0, l = 0, pp = 0;
-                int ch = 0;
-                if (u >= 0 && u < n) {
-                    uint32_t cd = src[u];
-                    if (cd > 21u) cd = 0;  // invalid input is scored as X (and reported by k_pack)
-                    h = tab_h[cd];
-                    l = tab_l[cd];
-                    pp = tab_p[cd];
-                    // PAPA proline rule (:2652-2655): the second proline of PP / PxP is not scored
-                    if (ks.adjust_prolines && cd == 13u && ((u >= 1 && src[u - 1] == 13) || (u >= 2 && src[u - 2] == 13))) pp = 0.0;
-                    ch = (int)((ks.charge_plus >> cd) & 1u) - (int)((ks.charge_minus >> cd) & 1u);
+            // the last tile of a protein is shorter: nothing beyond residue n-1 has to be staged or scanned (prefix
+            // sums stay constant there; reads clamp to the last element)
+            const int NXe = min(NX, n - u_lo), NSe = min(NS, n - (t0 - w));
+            const int per_x = ((NXe + 31) >> 5) | 1, per_s = ((NSe + 31) >> 5) | 1;
+            // 0. codes of residues u_lo-2 .. u_lo+NX-1 into shared memory (independent loads, issued together)
+            for (int e0 = 0; e0 < NXe + 2; e0 += 32 * 12) {
+                uint8_t cdv[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    const int e = e0 + 32 * k + lane;
+                    const int u = u_lo - 2 + e;
+                    cdv[k] = (e < NXe + 2 && u >= 0) ? src[u] : (uint8_t)0xff;
                 }
-                Xh[e] = h;
-                Xl[e] = l;
-                Xp[e] = pp;
-                Xc[e] = ch;
+#pragma unroll
+                for (int k = 0; k < 12; k++) {
+                    const int e = e0 + 32 * k + lane;
+                    // outside the protein: pad; invalid input (> 21) is scored as X and reported by k_pack
+                    if (e < NXe + 2) Cd[e] = cdv[k] == 0xff ? (uint8_t)kPad : (cdv[k] > 21 ? (uint8_t)0 : cdv[k]);
+                }
             }
             __syncwarp();
-            warp_scan_inplace(Xh, NX, g.per_x, lane);
-            warp_scan_inplace(Xl, NX, g.per_x, lane);
-            warp_scan_inplace(Xp, NX, g.per_x, lane);
-            warp_scan_inplace(Xc, NX, g.per_x, lane);
+            // 1. per-residue values, zero outside the protein (pad code: all tables are 0)
+            for (int e = lane; e < NXe; e += 32) {
+                const uint32_t cd = Cd[e + 2];
+                double pp = tab_p[cd];
+                // PAPA proline rule (:2652-2655): the second proline of PP / PxP is not scored
+                if (ks.adjust_prolines && cd == 13u && (Cd[e + 1] == 13 || Cd[e] == 13)) pp = 0.0;
+                Xh[e] = tab_h[cd];
+                Xl[e] = tab_l[cd];
+                Xp[e] = pp;
+                Xc[e] = (int)((ks.charge_plus >> cd) & 1u) - (int)((ks.charge_minus >> cd) & 1u);
+            }
+            __syncwarp();
+            warp_scan4_inplace(Xh, Xl, Xp, Xc, NXe, per_x, lane);
             // 2. pass-1 window sums for centres t0-w .. t0+T+w-1 and the five pass-1 tracks
-            for (int idx = lane; idx < NS; idx += 32) {
+            for (int idx = lane; idx < NSe; idx += 32) {
                 const int pc = t0 - w + idx;
                 double sh = 0, sl = 0, sp_ = 0;
                 int scv = 0;
                 if (pc >= 0 && pc < n) {
-                    const int ehi = min(pc + w, u_lo + NX - 1) - u_lo;  // beyond the protein everything is zero
+                    const int ehi = min(pc + w, n - 1) - u_lo;  // beyond the protein everything is zero
                     const int elo = pc - w - 1 - u_lo;                   // >= -1
                     sh = Xh[ehi] - (elo >= 0 ? Xh[elo] : 0.0);
                     sl = Xl[ehi] - (elo >= 0 ? Xl[elo] : 0.0);
                     sp_ = Xp[ehi] - (elo >= 0 ? Xp[elo] : 0.0);
                     scv = Xc[ehi] - (elo >= 0 ? Xc[elo] : 0);
                     if (pc >= t0 && pc < t0 + kTrackTile) {
-                        const double cnt = (double)(full - max(0, w - pc) - max(0, pc + w - (n - 1)));
-                        const double hyd = sh / cnt;
-                        const double chg = (double)scv / cnt;
+                        // one reciprocal per residue instead of four divisions (1 ulp, far inside the 1e-9 bar);
+                        // interior windows have the full tap count and use the precomputed reciprocal
+                        const int cnt = full - max(0, w - pc) - max(0, pc + w - (n - 1));
+                        const double rc = cnt == full ? rfull : 1.0 / (double)cnt;
+                        const double hyd = sh * rc;
+                        const double chg = (double)scv * rc;
                         const double fi_p = (ks.cc0 * hyd + ks.cc1 * fabs(chg)) + ks.cc2;
                         g.out.hydro[ob + pc] = hyd;
                         g.out.charge[ob + pc] = chg;
                         g.out.fi[ob + pc] = fi_p;
-                        g.out.plaac[ob + pc] = sl / cnt;
-                        g.out.papa[ob + pc] = sp_ / cnt;
+                        g.out.plaac[ob + pc] = sl * rc;
+                        g.out.papa[ob + pc] = sp_ * rc;
                         if (n == 1) {  // w clips to 0: the second pass returns the value itself (:2588-2589)
                             g.out.fix2[ob] = fi_p;
-                            g.out.plaacx2[ob] = sl / cnt;
-                            g.out.papax2[ob] = sp_ / cnt;
+                            g.out.plaacx2[ob] = sl * rc;
+                            g.out.papax2[ob] = sp_ * rc;
                         }
                     }
                 }
@@ -440,10 +548,7 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
                 Sc[idx] = abs(scv);
             }
             __syncwarp();
-            warp_scan_inplace(Sh, NS, g.per_s, lane);
-            warp_scan_inplace(Sl, NS, g.per_s, lane);
-            warp_scan_inplace(Sp, NS, g.per_s, lane);
-            warp_scan_inplace(Sc, NS, g.per_s, lane);
+            warp_scan4_inplace(Sh, Sl, Sp, Sc, NSe, per_s, lane);
             // 3. pass-2 tracks for centres t0 .. t0+T-1 (NaN outside [w, n-1-w], :2596-2601)
             if (n > 1) {
                 for (int idx = lane; idx < kTrackTile; idx += 32) {
@@ -458,10 +563,12 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
                         const double Tp = Sp[ehi] - (elo >= 0 ? Sp[elo] : 0.0);
                         const int Tac = Sc[ehi] - (elo >= 0 ? Sc[elo] : 0);
                         const int ml = 2 * w - k, mr = 2 * w - (n - 1 - k);
-                        const double Wd = (double)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0));
-                        f2 = ((ks.cc0 * Th + ks.cc1 * (double)Tac) + ks.cc2 * Wd) / Wd;
-                        l2 = Tl / Wd;
-                        p2 = Tp / Wd;
+                        const int Wi = Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0);
+                        const double Wd = (double)Wi;
+                        const double rW = Wi == Wfull ? rWfull : 1.0 / Wd;
+                        f2 = ((ks.cc0 * Th + ks.cc1 * (double)Tac) + ks.cc2 * Wd) * rW;
+                        l2 = Tl * rW;
+                        p2 = Tp * rW;
                     }
                     g.out.fix2[ob + k] = f2;
                     g.out.plaacx2[ob + k] = l2;
@@ -484,12 +591,12 @@ inline ResidueV2Plan residue_v2_plan(const KScalars& ks)
 {
     ResidueV2Plan P;
     P.bwd_smem = kResFixedBytes;
-    P.fwd_smem = kResFixedBytes + (size_t)(kResHmmThreads / 32) * kResTileBytes;
+    P.fwd_smem = kResFixedBytes;
     P.nx = kTrackTile + 4 * ks.w;
     const int ns = kTrackTile + 2 * ks.w;
     P.per_x = ((P.nx + 31) / 32) | 1;
     P.per_s = ((ns + 31) / 32) | 1;
-    const size_t per_warp = ((size_t)P.nx * 28 + (size_t)ns * 28 + 64 + 15) & ~(size_t)15;
+    const size_t per_warp = ((size_t)P.nx * 28 + (size_t)ns * 28 + (size_t)P.nx + 64 + 15) & ~(size_t)15;
     P.trk_smem = per_warp * kTrackWarps;
     P.ok = P.trk_smem <= 200 * 1024 && P.fwd_smem <= 227 * 1024;
     return P;
@@ -504,10 +611,10 @@ inline int residue_v2_setup(const ResidueV2Plan& P)
     return PLAAC_OK;
 }
 
-// All five kernels on `st`; aux streams (may be NULL) let the independent ones overlap:
-//   st:   vit -------------------------> bits
-//   aux1: bwd -> fwd (needs bwd) ------/
-//   aux2: tracks ----------------------/
+// Kernel order; aux streams (may be NULL) let the independent recurrences overlap:
+//   st:   vit -> tracks --\
+//   aux1: bwd ------------+--> lpseq -> post -> bits   (on st)
+//   aux2: fwd ------------/
 inline int launch_residue_v2(const ResidueV2Plan& P, const ResArgs& ra, const TrackArgs& ta, int sm_count, cudaStream_t st,
                              cudaStream_t aux1, cudaStream_t aux2, cudaEvent_t ev_fork, cudaEvent_t ev_j1, cudaEvent_t ev_j2,
                              int64_t* launches)
@@ -526,21 +633,23 @@ inline int launch_residue_v2(const ResidueV2Plan& P, const ResArgs& ra, const Tr
     }
     const unsigned g_vit = (unsigned)std::min<int64_t>((nb + kResThreads / 32 - 1) / (kResThreads / 32), (int64_t)sm_count * 8);
     const unsigned g_hmm = (unsigned)std::min<int64_t>((nb + kResHmmThreads / 32 - 1) / (kResHmmThreads / 32), (int64_t)sm_count * 2);
-    const unsigned g_fwd = (unsigned)std::min<int64_t>((nb + kResHmmThreads / 32 - 1) / (kResHmmThreads / 32), (int64_t)sm_count);
     const unsigned g_trk = (unsigned)std::min<int64_t>((ta.nprot + kTrackWarps - 1) / kTrackWarps, (int64_t)sm_count * 8);
     const unsigned g_bits = (unsigned)std::min<int64_t>(nb, (int64_t)sm_count * 8);
-    k_res_vit<<<g_vit, kResThreads, 0, st>>>(ra);
+    const unsigned g_post = (unsigned)std::min<int64_t>((ra.bv.nslots + kResPostThreads / 32 - 1) / (kResPostThreads / 32) + 1, (int64_t)sm_count * 12);
     k_res_bwd<<<g_hmm, kResHmmThreads, P.bwd_smem, s1>>>(ra);
-    k_res_fwd<<<g_fwd, kResHmmThreads, P.fwd_smem, s1>>>(ra);
-    k_res_tracks<<<g_trk, kTrackWarps * 32, P.trk_smem, s2>>>(ta);
+    k_res_fwd<<<g_hmm, kResHmmThreads, P.fwd_smem, s2>>>(ra);
+    k_res_vit<<<g_vit, kResThreads, 0, st>>>(ra);
+    k_res_tracks<<<g_trk, kTrackWarps * 32, P.trk_smem, st>>>(ta);
     if (fork) {
         cudaEventRecord(ev_j1, s1);
         cudaEventRecord(ev_j2, s2);
         cudaStreamWaitEvent(st, ev_j1, 0);
         cudaStreamWaitEvent(st, ev_j2, 0);
     }
+    k_res_lpseq<<<(unsigned)((ra.bv.nprot + 255) / 256), 256, 0, st>>>(ra);
+    k_res_post<<<g_post, kResPostThreads, 0, st>>>(ra);
     k_res_bits<<<g_bits, kResThreads, 0, st>>>(ra);
-    if (launches) *launches += 5;
+    if (launches) *launches += 7;
     return cudaGetLastError() == cudaSuccess ? PLAAC_OK : PLAAC_E_CUDA;
 }
 
