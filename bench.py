@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample-proteins", type=int, default=0, help="0 = sized automatically")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-residue", action="store_true", help="skip the config-2 (per-residue mode) side measurement")
     return ap.parse_args()
 
 
@@ -297,7 +298,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": "k_score_summary",
+        "bound": "fp64", "kernel": "k_score_summary_v2 (+ k_core_search_jump, same event bracket)",
         "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
         "frac": achieved_ops / peak_ops, "traffic": traffic,
         "note": "fp64 pipe binds (SURVEY 8d): achieved = 67 algorithmic fp64 ops/residue x residues per launch / "
@@ -342,6 +343,11 @@ def main():
         e2e["matches_device_path"] = same
         del h_codes, h_offsets, h_sum
 
+    # ---- config 2 side measurement: per-residue mode (rank 0, N=1 only) -----------------------------
+    per_res = None
+    if rank == 0 and world == 1 and not args.no_per_residue:
+        per_res = measure_per_residue(L, scorer, dev, hbm_peak)
+
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,13 +374,59 @@ def main():
             "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "residues_per_gpu": ntotal, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "per_residue_mode": per_res,
             "timing": "CUDA events on the library stream around K steps, max over ranks; wall %.3f s" % wall,
         }
         print(json.dumps(line), flush=True)
     scorer.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_per_residue(L, scorer, dev, hbm_peak):
+    """Config 2 (per-residue table: VIT, MAP, 8 tracks, 2 posteriors = 82 B/residue out), device-resident:
+    the yeast-proteome-sized set the config names, and a 200k-protein batch for the bandwidth view."""
+    import numpy as np
+    import torch
+
+    import plaac_b200
+
+    out = {}
+    for tag, nprot in (("yeast_sized_6k", 6000), ("batch_200k", 200000)):
+        lens = torch.empty(nprot, dtype=torch.int64, device=dev)
+        L.plaac_bench_synth_lengths(None, 1001, 0, nprot, math.log(407.0), 0.66, MIN_LEN, MAX_LEN, lens.data_ptr())
+        offsets = torch.zeros(nprot + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens, 0, out=offsets[1:])
+        ntotal = int(offsets[-1].item())
+        codes = torch.empty(ntotal + 64, dtype=torch.uint8, device=dev)
+        bg = np.array(BG_SCER, dtype=np.float64)
+        prd = np.array(PRD_28, dtype=np.float64)
+        L.plaac_bench_synth_residues(None, 1001, 0, nprot, offsets.data_ptr(), bg.ctypes.data, prd.ctypes.data, PRD_RATE,
+                                     X_RATE, codes.data_ptr())
+        u8 = torch.empty(2 * ntotal, dtype=torch.uint8, device=dev)
+        f64 = torch.empty(10 * ntotal, dtype=torch.float64, device=dev)
+        ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + ntotal}
+        for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+            ptrs[nm] = f64.data_ptr() + 8 * k * ntotal
+        torch.cuda.synchronize()
+
+        def f():
+            scorer.score_device(codes.data_ptr(), offsets.data_ptr(), nprot, ntotal, 0, residue_ptrs=ptrs, sync=True)
+
+        for _ in range(3):
+            f()
+        ms = []
+        for _ in range(5):
+            f()
+            ms.append(scorer.stats().last_total_ms)
+        t = sum(ms) / len(ms) * 1e-3
+        out[tag] = {"proteins": nprot, "residues": ntotal, "ms": t * 1e3, "residues_per_s": ntotal / t,
+                    "hbm_out_gbs": 82.0 * ntotal / t / 1e9, "frac_of_hbm_write_roofline": 83.0 * ntotal / t / 1e9 / hbm_peak}
+        del u8, f64, codes, offsets, lens
+    out["note"] = ("device-resident, CUDA-event time of the whole per-residue pipeline inside the library; 83 algorithmic "
+                   "bytes/residue (1 in + 82 out) against the measured HBM peak; the 6k set is latency-bound by the "
+                   "sequential forward/backward chains of its longest proteins")
+    return out
 
 
 class C_double:
