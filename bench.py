@@ -133,6 +133,14 @@ def cpu_sample(nprot, seed):
     return codes, offsets
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the box's size)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_oracle(nprot, nthreads, full_jar_work, repeats=1):
     from oracle import orc
 
@@ -155,7 +163,7 @@ def run_reference(args, rank, world):
         return
     from oracle import orc
 
-    nthreads = orc.max_threads()
+    nthreads = host_threads()
     nprot = args.cpu_sample_proteins or 3000 * nthreads
     codes, offsets = cpu_sample(nprot, SEED)
     P = orc.make_params()
@@ -200,6 +208,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO; stdout carries the one JSON line only
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -353,7 +364,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import orc
 
-        nthreads = orc.max_threads()
+        nthreads = host_threads()
         n1 = args.cpu_sample_proteins or 6000
         nres1, dt1 = time_oracle(n1, 1, 1)
         nall = args.cpu_sample_proteins or 3000 * nthreads
