@@ -346,9 +346,10 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": res_total * args.steps / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": int(ntotal + 8 * (nprot + 1)), "d2h_bytes_per_step": int(160 * nprot),
+               "h2d_bytes_per_step": int(res_total + 8 * (nprot + 1) * world), "d2h_bytes_per_step": int(160 * nprot * world),
                "ms_per_step": float(tt[0]) / args.steps * 1e3,
-               "note": "plaac_score() on pinned host buffers, per rank; wall clock between barriers, max over ranks"}
+               "note": "plaac_score() on pinned host buffers in every rank (each GPU on its own PCIe link); byte counts are "
+                       "whole-job totals; wall clock between barriers, max over ranks"}
         # sanity: both paths produce the same records
         same = bool((h_sum.view(torch.int32)[:40] == summaries.cpu().view(torch.int32)[:40]).all())
         e2e["matches_device_path"] = same

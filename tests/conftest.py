@@ -18,3 +18,15 @@ def golden():
 
     with open(os.path.join(ROOT, "tests", "golden", "classic_prions.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_artifacts():
+    """The CUDA library, host CLI and oracle are built in-tree (git-ignored); build them if this checkout is fresh.
+    nvcc cross-compiles without a GPU."""
+    from oracle import orc
+    from plaac_b200 import build as pb
+
+    pb.build_lib()
+    pb.build_cli()
+    orc.build()
