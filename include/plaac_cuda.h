@@ -148,6 +148,32 @@ int plaac_shard_plan(const int64_t *offsets, int64_t nprot, int nshards, int64_t
 int plaac_score_multi(plaac_ctx *const *ctxs, int nctx, const uint8_t *codes, const int64_t *offsets, int64_t nprot,
                       plaac_summary *summaries, const plaac_residue_out *per_res);
 
+/* ---- GPU FASTA ingest and background counts --------------------------------
+ * Replaces fastareader (plaac.java:4302-4375) + string2aa (:1764-1769) + the terminal '*' strip (:758) for a whole
+ * file image, and computeaafreq/isvalidprotein (:1655-1739) for the background counts.  Reader semantics are the
+ * jar's: \n, \r, \r\n line ends; sequence lines are not trimmed; an empty line ends the record and everything up to
+ * the next '>' line is skipped.  Records with an empty sequence are kept (offsets[i+1] == offsets[i]) so that names
+ * stay aligned; the host prints no row for them (:762). */
+typedef struct plaac_fasta_index {
+    int64_t nrec;       /* records found in the text (may exceed max_rec: then only max_rec were stored) */
+    int64_t nres;       /* residues written to codes */
+} plaac_fasta_index;
+
+/* HOST text in, HOST arrays out.  codes: capacity nbytes; offsets: max_rec+1; name_pos/name_len/flags: max_rec
+ * (any of the three may be NULL).  flags bit 0: the jar trims this name (found after an empty line or at file start,
+ * :4362); bit 1: a terminal '*' was stripped.  bg_counts (22 doubles, may be NULL) receives the residue counts of the
+ * valid records exactly as computeaafreq(file) would (64-bit accumulation). */
+int plaac_ingest_fasta(plaac_ctx *ctx, const char *text, int64_t nbytes, uint8_t *codes, int64_t *offsets,
+                       int64_t *name_pos, int32_t *name_len, uint8_t *flags, int64_t max_rec, plaac_fasta_index *index,
+                       double *bg_counts);
+
+/* DEVICE text in, DEVICE arrays out (same capacities; d_bg_counts: 22 x uint64, may be NULL).  The outputs feed
+ * plaac_score_device directly.  index is written on return (one small D2H).  d_flags must be 4-byte aligned and its
+ * capacity a multiple of 4 bytes (bits are set with word-wide atomics). */
+int plaac_ingest_fasta_device(plaac_ctx *ctx, const char *d_text, int64_t nbytes, uint8_t *d_codes, int64_t *d_offsets,
+                              int64_t *d_name_pos, int32_t *d_name_len, uint8_t *d_flags, int64_t max_rec,
+                              plaac_fasta_index *index, uint64_t *d_bg_counts);
+
 /* Host-side parameter chain for hosts that do not have their own (the C++ CLI, Python tests): what
  * plaac.java main computes between :310 and :518 -- bg/fg mixing with alpha (:449-458), the 1e-5
  * pseudo-frequency for X and * (:490-496), llr (:497-500), prionhmm1/prionhmm0 (:968-1001) through

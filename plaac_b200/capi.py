@@ -63,6 +63,10 @@ class Stats(C.Structure):
                 ("last_score_ms", C.c_float), ("last_padded_slots", C.c_int64)]
 
 
+class FastaIndex(C.Structure):
+    _fields_ = [("nrec", C.c_int64), ("nres", C.c_int64)]
+
+
 _lib = None
 
 
@@ -99,6 +103,10 @@ def lib():
         L.plaac_set_kernel_variant.argtypes = [vp, C.c_int]
         L.plaac_get_stats.restype = C.c_int
         L.plaac_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.plaac_ingest_fasta.restype = C.c_int
+        L.plaac_ingest_fasta.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(FastaIndex), vp]
+        L.plaac_ingest_fasta_device.restype = C.c_int
+        L.plaac_ingest_fasta_device.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, C.POINTER(FastaIndex), vp]
         L.plaac_shard_plan.restype = C.c_int
         L.plaac_shard_plan.argtypes = [vp, i64, C.c_int, vp]
         L.plaac_score_multi.restype = C.c_int
@@ -215,6 +223,35 @@ class Scorer:
         self._check(lib().plaac_score_device(self._h, d_codes_ptr, d_offsets_ptr, nprot, ntotal, d_summaries_ptr, ro))
         if sync:
             self.sync()
+
+    def ingest_fasta(self, text: bytes, max_rec: int | None = None, bg_counts: bool = False):
+        """GPU FASTA ingest (plaac_ingest_fasta): raw file bytes -> dict(codes, offsets, names, flags[, bg_counts]).
+        Names are cut from the text with the jar's trimming rule (flag bit 0)."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        n = len(buf)
+        if max_rec is None:
+            max_rec = int(text.count(b">")) + 1
+        codes = np.zeros(max(n, 1), dtype=np.uint8)
+        offsets = np.zeros(max_rec + 1, dtype=np.int64)
+        npos = np.zeros(max(max_rec, 1), dtype=np.int64)
+        nlen = np.zeros(max(max_rec, 1), dtype=np.int32)
+        flags = np.zeros(max(max_rec, 1) + 8, dtype=np.uint8)
+        idx = FastaIndex()
+        bg = np.zeros(NAA, dtype=np.float64) if bg_counts else None
+        self._check(lib().plaac_ingest_fasta(self._h, buf.ctypes.data if n else None, n, codes.ctypes.data, offsets.ctypes.data,
+                                             npos.ctypes.data, nlen.ctypes.data, flags.ctypes.data, max_rec, C.byref(idx),
+                                             bg.ctypes.data if bg is not None else None))
+        nrec = int(idx.nrec)
+        names = []
+        for r in range(nrec):
+            nm = text[int(npos[r]):int(npos[r]) + int(nlen[r])]
+            if flags[r] & 1:  # String.trim() of the whole '>' line: only the tail can change
+                nm = nm.rstrip(b"".join(bytes([c]) for c in range(33)))
+            names.append(nm.decode("latin-1"))
+        out = {"codes": codes[:int(idx.nres)], "offsets": offsets[:nrec + 1], "names": names, "flags": flags[:nrec]}
+        if bg is not None:
+            out["bg_counts"] = bg
+        return out
 
     def set_chunk(self, max_residues=0, max_proteins=0):
         self._check(lib().plaac_set_chunk(self._h, max_residues, max_proteins))

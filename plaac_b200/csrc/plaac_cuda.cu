@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "prep.cuh"
+#include "ingest.cuh"
 #include "residue_kernel.cuh"
 #include "residue_kernel_v2.cuh"
 #include "summary_kernel.cuh"
@@ -36,6 +37,8 @@ struct Slot {
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
     DevBuf res_b0, res_b1, res_a0, res_a1, res_mapw, res_lpseq;  // per-residue scratch (bucketed layout)
+    DevBuf ing_agg, ing_cnt, ing_base, ing_misc;                 // FASTA ingest scratch
+    DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
     cudaStream_t aux1 = nullptr, aux2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
     int64_t* h_total = nullptr;        // pinned
@@ -278,7 +281,9 @@ void slot_free(Slot& s)
 {
     for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
                       &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
-                      &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq})
+                      &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
+                      &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
+                      &s.ing_hist})
         release(*b);
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
@@ -799,6 +804,136 @@ int plaac_score_multi(plaac_ctx* const* ctxs, int nctx, const uint8_t* codes, co
     for (auto& t : threads) t.join();
     for (int k = 0; k < nctx; k++)
         if (rcs[k] != PLAAC_OK) return rcs[k];
+    return PLAAC_OK;
+}
+
+}  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------ FASTA ingest
+extern "C" {
+
+int plaac_ingest_fasta_device(plaac_ctx* ctx, const char* d_text, int64_t nbytes, uint8_t* d_codes, int64_t* d_offsets,
+                              int64_t* d_name_pos, int32_t* d_name_len, uint8_t* d_flags, int64_t max_rec,
+                              plaac_fasta_index* index, uint64_t* d_bg_counts)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_ingest_fasta_device: NULL ctx");
+    if (nbytes < 0 || max_rec < 0 || !index) return fail(ctx, PLAAC_E_INVALID, "bad size / NULL index");
+    if (nbytes > 0 && (!d_text || !d_codes)) return fail(ctx, PLAAC_E_INVALID, "NULL text/codes");
+    if (!d_offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    index->nrec = index->nres = 0;
+    const long long ntiles = (nbytes + kIngTile - 1) / kIngTile;
+    int rc;
+    if ((rc = ensure(ctx, s.ing_agg, sizeof(Ing3) * (size_t)std::max<long long>(ntiles, 1)))) return rc;
+    if ((rc = ensure(ctx, s.ing_cnt, sizeof(int32_t) * (size_t)std::max<long long>(ntiles, 1)))) return rc;
+    if ((rc = ensure(ctx, s.ing_base, sizeof(int64_t) * (size_t)(ntiles + 1)))) return rc;
+    if ((rc = ensure(ctx, s.ing_misc, sizeof(Ing3) + 64))) return rc;
+    // flags are OR-ed into: zero them (rounded up to whole words); also used internally when the caller passes NULL
+    uint8_t* flags = d_flags;
+    int64_t* npos = d_name_pos;
+    int32_t* nlen = d_name_len;
+    const size_t cap = (size_t)std::max<int64_t>(max_rec, 1);
+    if (!flags) {
+        if ((rc = ensure(ctx, s.ing_flags, cap + 8))) return rc;
+        flags = (uint8_t*)s.ing_flags.p;
+    }
+    if (!npos) {
+        if ((rc = ensure(ctx, s.ing_npos, sizeof(int64_t) * cap))) return rc;
+        npos = (int64_t*)s.ing_npos.p;
+    }
+    if (!nlen) {
+        if ((rc = ensure(ctx, s.ing_nlen, sizeof(int32_t) * cap))) return rc;
+        nlen = (int32_t*)s.ing_nlen.p;
+    }
+    if (((uintptr_t)flags & 3) != 0) return fail(ctx, PLAAC_E_INVALID, "flags must be 4-byte aligned");
+    CU(ctx, cudaMemsetAsync(flags, 0, (size_t)max_rec, st));
+    Ing3 grand;
+    grand.ls = grand.mk = -1;
+    grand.nh = 0;
+    long long total = 0;
+    if (ntiles > 0) {
+        const unsigned char* t = (const unsigned char*)d_text;
+        k_ing_reduce<<<(unsigned)ntiles, kIngThreads, 0, st>>>(t, nbytes, (Ing3*)s.ing_agg.p);
+        k_ing_scan3<<<1, 1024, 0, st>>>((Ing3*)s.ing_agg.p, ntiles, (Ing3*)s.ing_misc.p);
+        IngOut out;
+        out.codes = d_codes;
+        out.offsets = (long long*)d_offsets;
+        out.name_pos = (long long*)npos;
+        out.name_len = nlen;
+        out.flags = flags;
+        out.max_rec = max_rec;
+        k_ing_apply<0><<<(unsigned)ntiles, kIngThreads, 0, st>>>(t, nbytes, (const Ing3*)s.ing_agg.p, (int32_t*)s.ing_cnt.p,
+                                                                  nullptr, out);
+        k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.ing_cnt.p, (int64_t*)s.ing_base.p, ntiles);
+        k_ing_apply<1><<<(unsigned)ntiles, kIngThreads, 0, st>>>(t, nbytes, (const Ing3*)s.ing_agg.p, nullptr,
+                                                                  (const long long*)s.ing_base.p, out);
+        ctx->stats.kernel_launches += 5;
+        CU(ctx, cudaMemcpyAsync(&grand, s.ing_misc.p, sizeof(Ing3), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaMemcpyAsync(&total, (int64_t*)s.ing_base.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    }
+    index->nrec = grand.nh;
+    index->nres = total;
+    const int64_t stored = std::min<int64_t>(grand.nh, max_rec);
+    // closing offset of the last stored record
+    if (stored == grand.nh) {
+        CU(ctx, cudaMemcpyAsync(d_offsets + stored, &total, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    } else {
+        // truncated: record `stored` exists in the text; its start is the end of the last stored one.  Re-deriving
+        // it would need its header; report the truncation instead.
+        return fail(ctx, PLAAC_E_INVALID, "FASTA holds %lld records but max_rec is %lld", (long long)grand.nh,
+                    (long long)max_rec);
+    }
+    if (d_bg_counts) {
+        CU(ctx, cudaMemsetAsync(d_bg_counts, 0, sizeof(uint64_t) * PLAAC_NAA, st));
+        if (stored > 0) {
+            const unsigned grid = (unsigned)std::min<int64_t>((stored + 7) / 8, (int64_t)ctx->sm_count * 8);
+            k_bg_hist<<<grid, 256, 0, st>>>(d_codes, (const long long*)d_offsets, flags, stored,
+                                            (unsigned long long*)d_bg_counts);
+            ctx->stats.kernel_launches += 1;
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    CU(ctx, cudaGetLastError());
+    return PLAAC_OK;
+}
+
+int plaac_ingest_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, uint8_t* codes, int64_t* offsets, int64_t* name_pos,
+                       int32_t* name_len, uint8_t* flags, int64_t max_rec, plaac_fasta_index* index, double* bg_counts)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_ingest_fasta: NULL ctx");
+    if (nbytes < 0 || max_rec < 0 || !index || !offsets) return fail(ctx, PLAAC_E_INVALID, "bad size / NULL argument");
+    if (nbytes > 0 && (!text || !codes)) return fail(ctx, PLAAC_E_INVALID, "NULL text/codes");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    int rc;
+    const size_t cap = (size_t)std::max<int64_t>(max_rec, 1);
+    if ((rc = ensure(ctx, s.ing_text, (size_t)nbytes + 64))) return rc;
+    if ((rc = ensure(ctx, s.ing_codes, (size_t)nbytes + 64))) return rc;
+    if ((rc = ensure(ctx, s.ing_offsets, sizeof(int64_t) * (cap + 1)))) return rc;
+    if ((rc = ensure(ctx, s.ing_npos, sizeof(int64_t) * cap))) return rc;
+    if ((rc = ensure(ctx, s.ing_nlen, sizeof(int32_t) * cap))) return rc;
+    if ((rc = ensure(ctx, s.ing_flags, cap + 8))) return rc;
+    if ((rc = ensure(ctx, s.ing_hist, sizeof(uint64_t) * PLAAC_NAA))) return rc;
+    if (nbytes > 0) CU(ctx, cudaMemcpyAsync(s.ing_text.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, s.stream));
+    rc = plaac_ingest_fasta_device(ctx, (const char*)s.ing_text.p, nbytes, (uint8_t*)s.ing_codes.p, (int64_t*)s.ing_offsets.p,
+                                   (int64_t*)s.ing_npos.p, (int32_t*)s.ing_nlen.p, (uint8_t*)s.ing_flags.p, max_rec, index,
+                                   bg_counts ? (uint64_t*)s.ing_hist.p : nullptr);
+    if (rc != PLAAC_OK) return rc;
+    const size_t nrec = (size_t)index->nrec;
+    if (index->nres > 0) CU(ctx, cudaMemcpy(codes, s.ing_codes.p, (size_t)index->nres, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(offsets, s.ing_offsets.p, sizeof(int64_t) * (nrec + 1), cudaMemcpyDeviceToHost));
+    if (name_pos && nrec) CU(ctx, cudaMemcpy(name_pos, s.ing_npos.p, sizeof(int64_t) * nrec, cudaMemcpyDeviceToHost));
+    if (name_len && nrec) CU(ctx, cudaMemcpy(name_len, s.ing_nlen.p, sizeof(int32_t) * nrec, cudaMemcpyDeviceToHost));
+    if (flags && nrec) CU(ctx, cudaMemcpy(flags, s.ing_flags.p, nrec, cudaMemcpyDeviceToHost));
+    if (bg_counts) {
+        uint64_t h[PLAAC_NAA];
+        CU(ctx, cudaMemcpy(h, s.ing_hist.p, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < PLAAC_NAA; i++) bg_counts[i] = (double)h[i];
+    }
     return PLAAC_OK;
 }
 
