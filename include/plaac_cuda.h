@@ -174,6 +174,14 @@ int plaac_ingest_fasta_device(plaac_ctx *ctx, const char *d_text, int64_t nbytes
                               int64_t *d_name_pos, int32_t *d_name_len, uint8_t *d_flags, int64_t max_rec,
                               plaac_fasta_index *index, uint64_t *d_bg_counts);
 
+/* FASTA text in, summary records out: plaac_ingest_fasta_device + plaac_score_device without the codes ever leaving
+ * the GPU on the way in (H2D = the file bytes).  All pointers are HOST buffers: summaries, offsets, name_pos, name_len and flags as in
+ * plaac_ingest_fasta (capacity max_rec), codes (capacity nbytes, may be NULL) receives the residue codes for the
+ * string columns the host prints.  Replaces the whole loop of scoreallfastas (:755-948) for one file image. */
+int plaac_score_fasta(plaac_ctx *ctx, const char *text, int64_t nbytes, int64_t max_rec, plaac_summary *summaries,
+                      uint8_t *codes, int64_t *offsets, int64_t *name_pos, int32_t *name_len, uint8_t *flags,
+                      plaac_fasta_index *index, double *bg_counts);
+
 /* Host-side parameter chain for hosts that do not have their own (the C++ CLI, Python tests): what
  * plaac.java main computes between :310 and :518 -- bg/fg mixing with alpha (:449-458), the 1e-5
  * pseudo-frequency for X and * (:490-496), llr (:497-500), prionhmm1/prionhmm0 (:968-1001) through

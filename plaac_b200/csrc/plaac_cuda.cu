@@ -938,3 +938,55 @@ int plaac_ingest_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, uint8_t
 }
 
 }  // extern "C"
+
+
+extern "C" int plaac_score_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, int64_t max_rec, plaac_summary* summaries,
+                                 uint8_t* codes, int64_t* offsets, int64_t* name_pos, int32_t* name_len, uint8_t* flags,
+                                 plaac_fasta_index* index, double* bg_counts)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_fasta: NULL ctx");
+    if (nbytes < 0 || max_rec < 0 || !index || !offsets || !summaries) return fail(ctx, PLAAC_E_INVALID, "bad size / NULL argument");
+    if (nbytes > 0 && !text) return fail(ctx, PLAAC_E_INVALID, "NULL text");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    int rc;
+    const size_t cap = (size_t)std::max<int64_t>(max_rec, 1);
+    if ((rc = ensure(ctx, s.ing_text, (size_t)nbytes + 64))) return rc;
+    if ((rc = ensure(ctx, s.ing_codes, (size_t)nbytes + 64))) return rc;
+    if ((rc = ensure(ctx, s.ing_offsets, sizeof(int64_t) * (cap + 1)))) return rc;
+    if ((rc = ensure(ctx, s.ing_npos, sizeof(int64_t) * cap))) return rc;
+    if ((rc = ensure(ctx, s.ing_nlen, sizeof(int32_t) * cap))) return rc;
+    if ((rc = ensure(ctx, s.ing_flags, cap + 8))) return rc;
+    if ((rc = ensure(ctx, s.ing_hist, sizeof(uint64_t) * PLAAC_NAA))) return rc;
+    if (nbytes > 0) CU(ctx, cudaMemcpyAsync(s.ing_text.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, s.stream));
+    rc = plaac_ingest_fasta_device(ctx, (const char*)s.ing_text.p, nbytes, (uint8_t*)s.ing_codes.p, (int64_t*)s.ing_offsets.p,
+                                   (int64_t*)s.ing_npos.p, (int32_t*)s.ing_nlen.p, (uint8_t*)s.ing_flags.p, max_rec, index,
+                                   bg_counts ? (uint64_t*)s.ing_hist.p : nullptr);
+    if (rc != PLAAC_OK) return rc;
+    const size_t nrec = (size_t)index->nrec;
+    if (nrec > 0) {
+        if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * nrec))) return rc;
+        rc = plaac_score_device(ctx, (const uint8_t*)s.ing_codes.p, (const int64_t*)s.ing_offsets.p, (int64_t)nrec, index->nres,
+                                (plaac_summary*)s.summaries.p, nullptr);
+        if (rc != PLAAC_OK) return rc;
+        // the index arrays travel back while the scoring kernels run
+        cudaStream_t cp = s.aux1;
+        if (codes && index->nres > 0) CU(ctx, cudaMemcpyAsync(codes, s.ing_codes.p, (size_t)index->nres, cudaMemcpyDeviceToHost, cp));
+        CU(ctx, cudaMemcpyAsync(offsets, s.ing_offsets.p, sizeof(int64_t) * (nrec + 1), cudaMemcpyDeviceToHost, cp));
+        if (name_pos) CU(ctx, cudaMemcpyAsync(name_pos, s.ing_npos.p, sizeof(int64_t) * nrec, cudaMemcpyDeviceToHost, cp));
+        if (name_len) CU(ctx, cudaMemcpyAsync(name_len, s.ing_nlen.p, sizeof(int32_t) * nrec, cudaMemcpyDeviceToHost, cp));
+        if (flags) CU(ctx, cudaMemcpyAsync(flags, s.ing_flags.p, nrec, cudaMemcpyDeviceToHost, cp));
+        CU(ctx, cudaMemcpyAsync(summaries, s.summaries.p, sizeof(plaac_summary) * nrec, cudaMemcpyDeviceToHost, s.stream));
+        rc = plaac_sync(ctx);
+        CU(ctx, cudaStreamSynchronize(cp));
+        if (rc != PLAAC_OK) return rc;
+    } else {
+        CU(ctx, cudaMemcpy(offsets, s.ing_offsets.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    if (bg_counts) {
+        uint64_t h[PLAAC_NAA];
+        CU(ctx, cudaMemcpy(h, s.ing_hist.p, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < PLAAC_NAA; i++) bg_counts[i] = (double)h[i];
+    }
+    return PLAAC_OK;
+}

@@ -9,6 +9,8 @@
 //   --device D      GPU index when --gpus is 1 (default 0)
 //   --batch-mb M    residues per scoring batch in MiB (default 256)
 //   --compat-F      keep the jar's -F bug (plaac.java:388 reads the -B file name)
+//   --gpu-ingest    parse the FASTA on the GPU as well (plaac_score_fasta): the file goes to the device as raw bytes in
+//                   record-aligned pieces of --batch-mb; summary table only, one GPU
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -307,6 +309,7 @@ struct Options {
     int gpus = 1, device = 0;
     int64_t batch_res = (int64_t)256 << 20;
     bool compat_F = false;
+    bool gpu_ingest = false;
 };
 
 struct Scorers {
@@ -350,24 +353,16 @@ int die(const Scorers& S, int rc, const char* what)
     return 2;
 }
 
-int score_summary_batch(const Options& o, Scorers& S, Batch& B)
+void print_summary_row(const Options& o, const std::string& name, const plaac_summary& s, const uint8_t* aa, std::string& line)
 {
-    if (B.nprot() == 0) return 0;
-    std::vector<plaac_summary> sum((size_t)B.nprot());
-    const int rc = plaac_score_multi(S.ctx.data(), (int)S.ctx.size(), B.codes.data(), B.offsets.data(), B.nprot(),
-                                     sum.data(), nullptr);
-    if (rc != PLAAC_OK) return die(S, rc, "plaac_score");
-    std::string line;
-    for (int64_t i = 0; i < B.nprot(); i++) {
-        const plaac_summary& s = sum[(size_t)i];
-        const uint8_t* aa = B.codes.data() + B.offsets[(size_t)i];
+    {
         const int n = s.prot_len;
-        if (n < 1) continue;  // :762
+        if (n < 1) return;  // :762
         const int llrlen = s.llr_end - s.llr_start + 1;
         const double llr = inf2nan(s.llr);
         const int prdlen = s.prd_end - s.prd_start + 1;
         line.clear();
-        line += B.names[(size_t)i];
+        line += name;
         auto I = [&](long v) { line += "\t" + std::to_string(v); };
         auto F = [&](double v) { line += "\t" + jfmt(v, 3); };
         I(s.mw_score), I(s.mw_start + 1), I(s.mw_end + 1), I(s.mw_end - s.mw_start + 1);
@@ -387,7 +382,121 @@ int score_summary_batch(const Options& o, Scorers& S, Batch& B)
         line.push_back('\n');
         std::fwrite(line.data(), 1, line.size(), stdout);
     }
+}
+
+int score_summary_batch(const Options& o, Scorers& S, Batch& B)
+{
+    if (B.nprot() == 0) return 0;
+    std::vector<plaac_summary> sum((size_t)B.nprot());
+    const int rc = plaac_score_multi(S.ctx.data(), (int)S.ctx.size(), B.codes.data(), B.offsets.data(), B.nprot(),
+                                     sum.data(), nullptr);
+    if (rc != PLAAC_OK) return die(S, rc, "plaac_score");
+    std::string line;
+    for (int64_t i = 0; i < B.nprot(); i++)
+        print_summary_row(o, B.names[(size_t)i], sum[(size_t)i], B.codes.data() + B.offsets[(size_t)i], line);
     B.clear();
+    return 0;
+}
+
+// --gpu-ingest: the file is cut into pieces that end right before a '>' line; each piece is parsed, encoded and scored
+// on the GPU (plaac_score_fasta).  The jar trims a record name only when the reader found it after an empty line or
+// at the file start (:4362); for the first record of a later piece that context lies in the previous piece, so the
+// host re-derives it from the piece's last lines.
+int score_fasta_gpu(const Options& o, Scorers& S, bool count_only, double* bg_total)
+{
+    std::ifstream in(o.inputfile, std::ios::binary);
+    if (!in.good()) {
+        std::printf("# Couldn't open %s\n", o.inputfile.c_str());
+        return 0;
+    }
+    const size_t piece = (size_t)std::max<int64_t>(o.batch_res, 1 << 20);
+    std::string buf, carry;
+    std::vector<plaac_summary> sum;
+    std::vector<uint8_t> codes, flags;
+    std::vector<int64_t> offsets, npos;
+    std::vector<int32_t> nlen;
+    std::string line, name;
+    bool prev_open = false;  // the previous piece ended inside a record (its last marker line was a header)
+    bool first = true;
+    while (true) {
+        buf = carry;
+        carry.clear();
+        const size_t old = buf.size();
+        buf.resize(old + piece);
+        in.read(&buf[old], (std::streamsize)piece);
+        buf.resize(old + (size_t)in.gcount());
+        const bool eof = in.gcount() < (std::streamsize)piece;
+        if (buf.empty()) break;
+        size_t cut = buf.size();
+        if (!eof) {
+            // last line start that begins with '>' (not at 0): cut there
+            size_t k = buf.size();
+            cut = 0;
+            while (k > 1) {
+                k--;
+                if (buf[k] == '>' && (buf[k - 1] == '\n' || buf[k - 1] == '\r')) {
+                    cut = k;
+                    break;
+                }
+            }
+            if (cut == 0) {  // no record boundary inside: keep reading into the same piece
+                carry.swap(buf);
+                continue;
+            }
+            carry.assign(buf, cut, std::string::npos);
+            buf.resize(cut);
+        }
+        size_t maxrec = 1;
+        for (char c : buf) maxrec += c == '>';
+        sum.resize(maxrec);
+        codes.resize(buf.size() + 16);
+        offsets.resize(maxrec + 1);
+        npos.resize(maxrec);
+        nlen.resize(maxrec);
+        flags.assign(maxrec + 8, 0);
+        plaac_fasta_index idx;
+        double bg[PLAAC_NAA];
+        const int rc = plaac_score_fasta(S.ctx[0], buf.data(), (int64_t)buf.size(), (int64_t)maxrec, sum.data(), codes.data(),
+                                         offsets.data(), npos.data(), nlen.data(), flags.data(), &idx, bg);
+        if (rc != PLAAC_OK) return die(S, rc, "plaac_score_fasta");
+        if (bg_total)
+            for (int i = 0; i < PLAAC_NAA; i++) bg_total[i] += bg[i];
+        if (!count_only) {
+            for (int64_t r = 0; r < idx.nrec; r++) {
+                name.assign(buf, (size_t)npos[(size_t)r], (size_t)nlen[(size_t)r]);
+                bool trim = (flags[(size_t)r] & 1) != 0;
+                if (r == 0 && !first && prev_open) trim = false;  // found by nextfasta in the jar: untrimmed
+                if (trim)
+                    while (!name.empty() && (unsigned char)name.back() <= ' ') name.pop_back();
+                print_summary_row(o, name, sum[(size_t)r], codes.data() + offsets[(size_t)r], line);
+            }
+        }
+        // state at the end of this piece: walk back over its last lines to the latest header-or-empty line
+        {
+            prev_open = false;
+            size_t e = buf.size();
+            while (e > 0) {
+                size_t ls = e;  // start of the line that ends at e
+                if (ls > 0 && buf[ls - 1] == '\n') ls--;
+                if (ls > 0 && buf[ls - 1] == '\r') ls--;
+                const size_t line_end = ls;
+                while (ls > 0 && buf[ls - 1] != '\n' && buf[ls - 1] != '\r') ls--;
+                if (line_end == ls) {  // empty line
+                    if (e == buf.size() && line_end == e) {  // no terminator at all: e is just the end of the buffer
+                        if (ls == 0) break;
+                    } else
+                        break;
+                } else if (buf[ls] == '>') {
+                    prev_open = true;
+                    break;
+                }
+                e = ls;
+            }
+            if (idx.nrec == 0 && !first) prev_open = prev_open;  // a piece without records cannot open one
+        }
+        first = false;
+        if (eof) break;
+    }
     return 0;
 }
 
@@ -492,6 +601,8 @@ int main(int argc, char** argv)
             o.batch_res = (int64_t)std::atoll(val("--batch-mb")) << 20;
         else if (a == "--compat-F")
             o.compat_F = true;
+        else if (a == "--gpu-ingest")
+            o.gpu_ingest = true;
         else if (a == "--format-check") {
             // test hook: lines "decimals value" on stdin -> the Java-formatted value on stdout
             int d;
@@ -610,6 +721,7 @@ int main(int argc, char** argv)
         std::puts(kSummaryHeader);
         std::fflush(stdout);
         if ((rc = open_devices())) return rc;
+        if (o.gpu_ingest) return score_fasta_gpu(o, S, false, nullptr);
         FastaReader fr(o.inputfile);
         while (fr.hasmore()) {
             name = fr.name();

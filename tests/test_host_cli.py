@@ -231,3 +231,30 @@ def test_per_residue_table_end_to_end(cli, tmp_path, golden):
     r = run(cli, "-i", str(fa), "-s", "-p", "all")
     ids = [l.split("\t")[0] for l in r.stdout.split("\n")[1:] if l and not l.startswith("#")]
     assert sorted(set(ids), key=int) == ["1", "2", "3", "4"]
+
+
+@pytest.mark.gpu
+def test_gpu_ingest_path_prints_the_same_table(cli, tmp_path, golden):
+    """--gpu-ingest (FASTA parsed, encoded and scored on the GPU, in record-aligned pieces) == the host reader path,
+    including name trimming at piece boundaries."""
+    rng = np.random.default_rng(8)
+    parts = []
+    for k, p in enumerate(golden["proteins"]):
+        parts.append(f">{p['name']} trailing blanks  \n{p['seq']}*\n".encode())
+    for r in range(600):
+        term = [b"\n", b"\r\n"][r % 2]
+        parts.append(b">r%d  name with spaces \t" % r + term)
+        seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYqnx "), int(rng.integers(0, 1500)))).encode()
+        for j in range(0, len(seq), 70):
+            parts.append(seq[j:j + 70] + term)
+        if r % 9 == 0:
+            parts.append(term + b"ignored after blank" + term)
+    fa = tmp_path / "messy.fa"
+    fa.write_bytes(b"".join(parts))
+    a = run(cli, "-i", str(fa), "-s")
+    b = run(cli, "-i", str(fa), "-s", "--gpu-ingest")
+    c = run(cli, "-i", str(fa), "-s", "--gpu-ingest", "--batch-mb", "1")  # many pieces
+    assert a.returncode == 0 and b.returncode == 0 and c.returncode == 0, (a.stderr, b.stderr, c.stderr)
+    assert len(a.stdout.split("\n")) > 500
+    assert a.stdout == b.stdout
+    assert a.stdout == c.stdout
