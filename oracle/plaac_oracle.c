@@ -1,6 +1,6 @@
 /*
  * plaac_oracle.c -- CPU restatement of the PLAAC per-protein scoring path.
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see plaac_oracle.h).
+ * TEST INFRASTRUCTURE ONLY; parity pinned against the jar's own bytecode (see plaac_oracle.h).
  *
  * Written against cli/src/plaac.java of whitehead/plaac ("plaac.java:N" below).
  * Arithmetic is IEEE double, one rounding per Java operator, evaluated left to

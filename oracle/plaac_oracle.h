@@ -6,13 +6,17 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs use it, and only as the checker / CPU baseline.
  *
- * PARITY UNPINNED: the reference (whitehead/plaac, cli/src/plaac.java) ships
- * no tests and no golden outputs, and there is no JVM in this image, so
- * plaac.jar cannot be executed.  This restatement follows plaac.java line by
- * line in the reference's own operation order (sequential psum, 41-tap window
- * loops, lookup-table log-sum-exp); it is cross-checked against an
- * independent pure-Python restatement (oracle/plaac_oracle_py.py) and the
- * provisional known answers of SURVEY.md Appendix B.
+ * PARITY PINNED AGAINST THE REFERENCE'S OWN BYTECODE (with one stated caveat).  The reference ships no tests
+ * and no golden outputs, and there is no JVM in this image, so plaac.jar cannot be *launched*.  Its class files
+ * can be interpreted, though: tests/golden/minijvm.py executes web/bin/plaac.jar's plaac.main() unmodified on
+ * the reference's own cli/example/four_classic_prions.fasta and on 44 edge-case proteins (summary table and
+ * `-p all` per-residue table, default and non-default flags) and tests/golden/jar_vectors.json.gz holds every
+ * value the jar handed to System.out.format() at full precision.  This restatement reproduces ALL of them bit
+ * for bit (tests/test_jar_vectors.py).  Caveat: the JDK natives behind the bytecode (Math.log/exp/floor...) are
+ * this box's libm in both cases; a real JVM's Math.log/exp may differ from libm in the last ulp of the tables.
+ * The restatement follows plaac.java line by line in the reference's own operation order (sequential psum,
+ * 41-tap window loops, lookup-table log-sum-exp); it is also cross-checked against an independent pure-Python
+ * restatement (oracle/plaac_oracle_py.py) and the provisional known answers of SURVEY.md Appendix B.
  *
  * Every function cites the plaac.java lines it follows.
  */

@@ -1,7 +1,7 @@
 """Pure-Python second restatement of the PLAAC scoring path (small inputs only).
 
-TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (no JVM here, reference has no
-goldens).  Written independently of oracle/plaac_oracle.c, from
+TEST INFRASTRUCTURE ONLY.  The C oracle is pinned against the jar's own bytecode (tests/test_jar_vectors.py);
+this file is the second, independent restatement it is cross-checked with.  Written independently of oracle/plaac_oracle.c, from
 cli/src/plaac.java directly, with plain Python floats (IEEE double, one
 rounding per operator, no numpy reductions) so the two restatements
 cross-check each other.  Citations are plaac.java line numbers.
