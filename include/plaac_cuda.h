@@ -182,6 +182,24 @@ int plaac_score_fasta(plaac_ctx *ctx, const char *text, int64_t nbytes, int64_t 
                       uint8_t *codes, int64_t *offsets, int64_t *name_pos, int32_t *name_len, uint8_t *flags,
                       plaac_fasta_index *index, double *bg_counts);
 
+/* ---- on-device ranking and compact output ---------------------------------------
+ * The order the reference's web front end gives the table before it paginates (web/lib/server.rb:222-229):
+ * COREscore descending, then LLR descending, rows without a CORE (COREscore NaN) last; equal rows keep input
+ * order (the Ruby sort_by is unstable there, so any order of equal rows is one of its possible outputs).
+ * order[k] = input index of the row ranked k; *n_core (may be NULL) = number of rows with a CORE, i.e. the head
+ * order[0 .. n_core) is "every protein with a CORE, best first".  Values are compared at full precision (the web
+ * compares the 3-decimal text).  flags: PLAAC_RANK_WEB_QUIRKS reproduces Ruby's "-Infinity".to_f == 0.0, which
+ * ranks the LLR of proteins shorter than the core length as 0 instead of last. */
+#define PLAAC_RANK_WEB_QUIRKS 1
+int plaac_rank_device(plaac_ctx *ctx, const plaac_summary *d_summaries, int64_t nprot, int flags, int32_t *d_order,
+                      int64_t *n_core);
+/* d_out[k] = d_summaries[d_order[k]] for k < count: ship the head of the ranking instead of 160 B x nprot.
+ * Enqueued on the ctx stream (plaac_sync before reading). */
+int plaac_gather_device(plaac_ctx *ctx, const plaac_summary *d_summaries, const int32_t *d_order, int64_t count,
+                        plaac_summary *d_out);
+/* HOST records in, HOST order out. */
+int plaac_rank(plaac_ctx *ctx, const plaac_summary *summaries, int64_t nprot, int flags, int32_t *order, int64_t *n_core);
+
 /* Host-side parameter chain for hosts that do not have their own (the C++ CLI, Python tests): what
  * plaac.java main computes between :310 and :518 -- bg/fg mixing with alpha (:449-458), the 1e-5
  * pseudo-frequency for X and * (:490-496), llr (:497-500), prionhmm1/prionhmm0 (:968-1001) through

@@ -67,6 +67,8 @@ class FastaIndex(C.Structure):
     _fields_ = [("nrec", C.c_int64), ("nres", C.c_int64)]
 
 
+RANK_WEB_QUIRKS = 1
+
 _lib = None
 
 
@@ -111,6 +113,14 @@ def lib():
         L.plaac_shard_plan.argtypes = [vp, i64, C.c_int, vp]
         L.plaac_score_multi.restype = C.c_int
         L.plaac_score_multi.argtypes = [C.POINTER(vp), C.c_int, vp, vp, i64, vp, C.POINTER(ResidueOut)]
+        L.plaac_score_fasta.restype = C.c_int
+        L.plaac_score_fasta.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, C.POINTER(FastaIndex), vp]
+        L.plaac_rank.restype = C.c_int
+        L.plaac_rank.argtypes = [vp, vp, i64, C.c_int, vp, C.POINTER(i64)]
+        L.plaac_rank_device.restype = C.c_int
+        L.plaac_rank_device.argtypes = [vp, vp, i64, C.c_int, vp, C.POINTER(i64)]
+        L.plaac_gather_device.restype = C.c_int
+        L.plaac_gather_device.argtypes = [vp, vp, vp, i64, vp]
         L.plaac_bench_synth_lengths.restype = C.c_int
         L.plaac_bench_synth_lengths.argtypes = [vp, C.c_uint64, i64, i64, dbl, dbl, i32, i32, vp]
         L.plaac_bench_synth_residues.restype = C.c_int
@@ -252,6 +262,26 @@ class Scorer:
         if bg is not None:
             out["bg_counts"] = bg
         return out
+
+    def rank(self, summaries: np.ndarray, web_quirks: bool = False):
+        """plaac_rank: the web front end's order (web/lib/server.rb:222-229) -> (order int32[nprot], n_core)."""
+        summaries = np.ascontiguousarray(summaries, dtype=SUMMARY_DTYPE)
+        order = np.zeros(len(summaries), dtype=np.int32)
+        ncore = C.c_int64(0)
+        self._check(lib().plaac_rank(self._h, summaries.ctypes.data, len(summaries), RANK_WEB_QUIRKS if web_quirks else 0,
+                                     order.ctypes.data, C.byref(ncore)))
+        return order, int(ncore.value)
+
+    def rank_device(self, d_summaries_ptr: int, nprot: int, d_order_ptr: int, web_quirks: bool = False) -> int:
+        ncore = C.c_int64(0)
+        self._check(lib().plaac_rank_device(self._h, d_summaries_ptr, nprot, RANK_WEB_QUIRKS if web_quirks else 0,
+                                            d_order_ptr, C.byref(ncore)))
+        return int(ncore.value)
+
+    def gather_device(self, d_summaries_ptr: int, d_order_ptr: int, count: int, d_out_ptr: int, sync: bool = True):
+        self._check(lib().plaac_gather_device(self._h, d_summaries_ptr, d_order_ptr, count, d_out_ptr))
+        if sync:
+            self._check(lib().plaac_sync(self._h))
 
     def set_chunk(self, max_residues=0, max_proteins=0):
         self._check(lib().plaac_set_chunk(self._h, max_residues, max_proteins))

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "ingest.cuh"
+#include "rank.cuh"
 #include "residue_kernel.cuh"
 #include "residue_kernel_v2.cuh"
 #include "summary_kernel.cuh"
@@ -39,6 +40,7 @@ struct Slot {
     DevBuf res_b0, res_b1, res_a0, res_a1, res_mapw, res_lpseq;  // per-residue scratch (bucketed layout)
     DevBuf ing_agg, ing_cnt, ing_base, ing_misc;                 // FASTA ingest scratch
     DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
+    DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
     cudaStream_t aux1 = nullptr, aux2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
     int64_t* h_total = nullptr;        // pinned
@@ -283,7 +285,8 @@ void slot_free(Slot& s)
                       &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
-                      &s.ing_hist})
+                      &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
+                      &s.rk_order})
         release(*b);
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
@@ -990,3 +993,119 @@ extern "C" int plaac_score_fasta(plaac_ctx* ctx, const char* text, int64_t nbyte
     }
     return PLAAC_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------ ranking (N4)
+namespace {
+
+// One stable radix pass over the first n rows of buffer pair `cur`; the result lands in pair cur ^ 1.
+template <bool SPLIT>
+int rank_pass(plaac_ctx* ctx, Slot& s, int64_t n, int shift, int cur)
+{
+    const int64_t ntiles = (n + kRankTile - 1) / kRankTile;
+    int rc;
+    if ((rc = ensure(ctx, s.rk_hist, sizeof(int32_t) * (size_t)(kRankDigits * ntiles)))) return rc;
+    if ((rc = ensure(ctx, s.rk_offs, sizeof(int64_t) * (size_t)(kRankDigits * ntiles + 1)))) return rc;
+    cudaStream_t st = s.stream;
+    k_rank_hist<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>((const uint64_t*)s.rk_keys[cur].p, n, shift,
+                                                                  (int32_t*)s.rk_hist.p, ntiles);
+    k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.rk_hist.p, (int64_t*)s.rk_offs.p, kRankDigits * ntiles);
+    k_rank_scatter<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>(
+        (const uint64_t*)s.rk_keys[cur].p, (const int32_t*)s.rk_vals[cur].p, (uint64_t*)s.rk_keys[cur ^ 1].p,
+        (int32_t*)s.rk_vals[cur ^ 1].p, n, shift, (const int64_t*)s.rk_offs.p, ntiles);
+    ctx->stats.kernel_launches += 3;
+    CU(ctx, cudaGetLastError());
+    return PLAAC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plaac_rank_device(plaac_ctx* ctx, const plaac_summary* d_summaries, int64_t nprot, int flags, int32_t* d_order,
+                      int64_t* n_core)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank_device: NULL ctx");
+    if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
+    if (n_core) *n_core = 0;
+    if (nprot == 0) return PLAAC_OK;
+    if (!d_summaries || !d_order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    int rc;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = ensure(ctx, s.rk_keys[k], sizeof(uint64_t) * (size_t)nprot))) return rc;
+        if ((rc = ensure(ctx, s.rk_vals[k], sizeof(int32_t) * (size_t)nprot))) return rc;
+    }
+    const unsigned gk = (unsigned)((nprot + 255) / 256);
+    int cur = 0;
+    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 0, (flags & PLAAC_RANK_WEB_QUIRKS) ? 1 : 0, (uint64_t*)s.rk_keys[cur].p,
+                                    (int32_t*)s.rk_vals[cur].p);
+    ctx->stats.kernel_launches += 1;
+    for (int shift = 0; shift < 64; shift += 8) {
+        if ((rc = rank_pass<false>(ctx, s, nprot, shift, cur))) return rc;
+        cur ^= 1;
+    }
+    // CORE proteins first (stable), then order them by COREscore
+    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 1, 0, (uint64_t*)s.rk_keys[cur].p, (int32_t*)s.rk_vals[cur].p);
+    ctx->stats.kernel_launches += 1;
+    if ((rc = rank_pass<true>(ctx, s, nprot, 0, cur))) return rc;
+    cur ^= 1;
+    const int64_t ntiles = (nprot + kRankTile - 1) / kRankTile;
+    int64_t ncore = 0;  // rows with digit 0 = output base of (digit 1, tile 0)
+    CU(ctx, cudaMemcpyAsync(&ncore, (const int64_t*)s.rk_offs.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (ncore > 1) {
+        // the tail (no CORE) must stay where it is: park it in d_order before the two buffers start to alternate
+        const int tail_src = cur;
+        if (nprot > ncore)
+            CU(ctx, cudaMemcpyAsync(d_order + ncore, (const int32_t*)s.rk_vals[tail_src].p + ncore,
+                                    sizeof(int32_t) * (size_t)(nprot - ncore), cudaMemcpyDeviceToDevice, st));
+        for (int shift = 0; shift < 64; shift += 8) {
+            if ((rc = rank_pass<false>(ctx, s, ncore, shift, cur))) return rc;
+            cur ^= 1;
+        }
+        CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)ncore, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)nprot, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    if (n_core) *n_core = ncore;
+    return PLAAC_OK;
+}
+
+int plaac_gather_device(plaac_ctx* ctx, const plaac_summary* d_summaries, const int32_t* d_order, int64_t count,
+                        plaac_summary* d_out)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_gather_device: NULL ctx");
+    if (count < 0) return fail(ctx, PLAAC_E_INVALID, "negative count");
+    if (count == 0) return PLAAC_OK;
+    if (!d_summaries || !d_order || !d_out) return fail(ctx, PLAAC_E_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int64_t threads = count * (int64_t)(sizeof(plaac_summary) / 8);
+    k_rank_gather<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->slot[0].stream>>>(d_summaries, d_order, count, d_out);
+    ctx->stats.kernel_launches += 1;
+    CU(ctx, cudaGetLastError());
+    return PLAAC_OK;
+}
+
+int plaac_rank(plaac_ctx* ctx, const plaac_summary* summaries, int64_t nprot, int flags, int32_t* order, int64_t* n_core)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank: NULL ctx");
+    if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
+    if (n_core) *n_core = 0;
+    if (nprot == 0) return PLAAC_OK;
+    if (!summaries || !order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    int rc;
+    if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * (size_t)nprot))) return rc;
+    if ((rc = ensure(ctx, s.rk_order, sizeof(int32_t) * (size_t)nprot))) return rc;
+    CU(ctx, cudaMemcpyAsync(s.summaries.p, summaries, sizeof(plaac_summary) * (size_t)nprot, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = plaac_rank_device(ctx, (const plaac_summary*)s.summaries.p, nprot, flags, (int32_t*)s.rk_order.p, n_core))) return rc;
+    CU(ctx, cudaMemcpy(order, s.rk_order.p, sizeof(int32_t) * (size_t)nprot, cudaMemcpyDeviceToHost));
+    return PLAAC_OK;
+}
+
+}  // extern "C"
