@@ -217,6 +217,15 @@ void plaac_encode_host(const char *chars, int64_t n, uint8_t *codes);
 /* Tuning/testing knob for plaac_score(): upper bounds of one device chunk (0 = keep default). */
 int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
 
+/* Long-sequence path (BASELINE config 5; summary mode): proteins of at least min_len residues are scored by one CTA
+ * each, cut into <= 384 chunks (csrc/long_kernel.cuh): a warp-shuffle scan of 2x2 max-plus chunk matrices and
+ * warm-started LUT forward chunks fix the absolute magnitudes, then both recurrences are re-run chunk-parallel in the
+ * jar's own binade, where every rounding commutes with the chunk's shift, so the combined HMMall / HMMvit / Viterbi
+ * path have the jar's bits.  min_len = 0 switches the path off (every protein on the bucketed kernel); values below
+ * 1024 or below four times the longest window are raised to that.  Default 4096.  warm: forward warm-up length,
+ * 0 keeps the current value (default 256); a negative value redoes every forward chunk sequentially (testing). */
+int plaac_set_long_path(plaac_ctx *ctx, int64_t min_len, int warm);
+
 /* Kernel selection for testing: 0 = automatic (default), 1 = the reference-order anchor kernel (one fused
  * kernel, every recurrence in plaac.java's operation order, slower), 2 = the throughput kernel (needs
  * loglut[0] == ln2 and le0 == le[0], true for tables built as plaac.java builds them). */
@@ -231,6 +240,8 @@ typedef struct plaac_stats {
     float last_total_ms;       /* whole pipeline of the last device call */
     float last_score_ms;       /* dominant kernel of the last device call */
     int64_t last_padded_slots; /* 16-byte lane slots in the bucketed stream of the last call */
+    int64_t long_proteins;     /* proteins scored by the long-sequence path so far */
+    int64_t long_redone_chunks; /* forward chunks of that path redone sequentially (warm-up had not coalesced) */
 } plaac_stats;
 int plaac_get_stats(plaac_ctx *ctx, plaac_stats *out);
 

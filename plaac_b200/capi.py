@@ -60,7 +60,8 @@ class ResidueOut(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("score_launches", C.c_int64), ("last_total_ms", C.c_float),
-                ("last_score_ms", C.c_float), ("last_padded_slots", C.c_int64)]
+                ("last_score_ms", C.c_float), ("last_padded_slots", C.c_int64), ("long_proteins", C.c_int64),
+                ("long_redone_chunks", C.c_int64)]
 
 
 class FastaIndex(C.Structure):
@@ -101,6 +102,8 @@ def lib():
         L.plaac_encode_host.argtypes = [vp, i64, vp]
         L.plaac_set_chunk.restype = C.c_int
         L.plaac_set_chunk.argtypes = [vp, i64, i64]
+        L.plaac_set_long_path.restype = C.c_int
+        L.plaac_set_long_path.argtypes = [vp, i64, C.c_int]
         L.plaac_set_kernel_variant.restype = C.c_int
         L.plaac_set_kernel_variant.argtypes = [vp, C.c_int]
         L.plaac_get_stats.restype = C.c_int
@@ -285,6 +288,11 @@ class Scorer:
 
     def set_chunk(self, max_residues=0, max_proteins=0):
         self._check(lib().plaac_set_chunk(self._h, max_residues, max_proteins))
+
+    def set_long_path(self, min_len: int, warm: int = 0):
+        """plaac_set_long_path: length threshold of the chunked long-sequence path (0 = off); warm < 0 forces its
+        sequential forward fallback."""
+        self._check(lib().plaac_set_long_path(self._h, min_len, warm))
 
     def set_kernel_variant(self, variant: int):
         """0 auto, 1 reference-order anchor kernel, 2 throughput kernel."""

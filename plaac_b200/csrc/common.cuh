@@ -39,6 +39,10 @@ struct BatchView {
     int64_t nprot;
     int64_t nbuckets;
     int64_t off_base;         // offsets[] are relative to this residue index
+    int64_t long_min;         // proteins at least this long belong to the long-sequence path: empty for the bucketed one
 };
+
+// Length of a protein as the bucketed path sees it.
+__device__ __forceinline__ int64_t eff_len(int64_t len, int64_t long_min) { return len >= long_min ? 0 : len; }
 
 }  // namespace plaac

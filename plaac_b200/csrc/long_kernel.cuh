@@ -1,0 +1,761 @@
+// Long-sequence path (BASELINE config 5: titin-length and 100k-residue proteins; summary mode).
+//
+// In the bucketed kernel one lane walks one protein, so a lone long protein costs its full dependent chain
+// (~150 ns per residue: 15 ms for 100k residues).  Here ONE CTA owns one long protein and cuts it into <= 384
+// chunks, one lane per chunk, 32 consecutive chunks per warp:
+//
+//   Viterbi   (viterbidecodel :3077-3121) pass 1: every chunk runs the max-plus recurrence from both unit start
+//             vectors, which gives its 2x2 max-plus transfer matrix; the chunk matrices are combined by a warp-shuffle
+//             Kogge-Stone SCAN of 2x2 max-plus matrices with a carry across groups of 32 chunks.
+//   forward   (posteriorl :3349-3375 with the LUT log-sum-exp :1024-1047) the LUT recurrence is not associative,
+//             but d = a1 - a0 forgets its start: pass 1 re-runs the recurrence from `warm` residues
+//             before each chunk and prefix-sums the chunk increments of a0 (warp-shuffle scan).
+//   Pass 1 is exact mathematics but NOT the jar's rounding: at |s| ~ 3e5 every addition of the jar rounds to
+//   ulp = 5.8e-11 and the dropped low bits of lt/le are the same at every step, so the jar's HMMall/HMMvit carry a
+//   systematic drift (3e-7 at n = 100k, measured) that a chunk-local frame does not have.  Pass 2 therefore re-runs
+//   both recurrences in the jar's own binade, started from pass 1's absolute values: every addition has an operand of
+//   the running magnitude, rounding is monotone and commutes with shifts by multiples of the ulp, hence a chunk
+//   reproduces the jar's sequential values up to an EXACT shift.  Viterbi transfer entries and forward increments are
+//   then exact multiples of the ulp and their ordered combination is the jar's number BIT FOR BIT.  The forward chunk
+//   is accepted only if it enters with exactly the bits of d the previous chunk left with (the quantised recurrence
+//   coalesces during the warm-up); chunks in which the magnitude crosses a power of two (about one per binade), and
+//   chunks that failed that test, are redone sequentially from the exact values.
+//   windows   (disorderreport :4866-5068) the running window sums restart 2w residues before the chunk; FoldIndex
+//             runs and the PAPA first-strict-maximum are reduced per chunk and merged in chunk order.
+//   Three single lanes on other warps meanwhile walk the whole protein for the columns that are plain sequential
+//   fp64 sums in plaac.java's order: the psum[] LLR window search (hss2 :1206-1257), hmm0's log-emission sum, the
+//   hydropathy mean, and the Q/N window.  The -1e6-masked CORE search runs last on the Viterbi bits with the exact
+//   binade jumps of k_core_search_jump.
+//
+// Result: every column has the bits of the bucketed kernel, which has the bits of the jar.
+#pragma once
+#include "common.cuh"
+#include "summary_kernel_v2.cuh"
+
+namespace plaac {
+
+constexpr int kLongThreads = 512;
+constexpr int kLongChunkWarps = 12;
+constexpr int kLongMaxChunks = kLongChunkWarps * 32;
+constexpr int kLongMinChunk = 256;
+constexpr int kLongPadTail = 128;  // ext bytes past the end are pad codes
+
+struct LongArgs {
+    const uint8_t* codes;
+    const int64_t* offsets;
+    int64_t off_base;
+    const int32_t* list;         // protein indices
+    const int64_t* scratch_off;  // per listed protein, multiple of 128
+    KScalars ks;
+    const DeviceTables* tabs;
+    plaac_summary* out;
+    uint8_t* ext;   // ext code per residue (same byte layout as the bucketed stream)
+    uint8_t* tb;    // 4 traceback bits per residue: variant A (P0, P1), variant B (P0, P1)
+    unsigned long long* redone;  // statistics: forward chunks redone sequentially because d had not coalesced
+    uint32_t* vit;  // Viterbi bits, one word per 32 residues
+    int* errflag;
+    int warm;       // forward warm-up length
+    int force_seq_forward;  // testing: always take the sequential forward fallback
+};
+
+struct LongShared {
+    double2 lut2[PLAAC_LUT_LEN + 1];
+    double2 le[32];
+    double llr[kTabN], hyd[kTabN], pap[kTabN];
+    // per chunk
+    double M[4][kLongMaxChunks];       // Viterbi transfer matrix: [0] 0->0, [1] 0->1, [2] 1->0, [3] 1->1
+    double Sa[2][kLongMaxChunks];      // pass 1: approximate Viterbi scores at the chunk's last residue
+    double f_inc[kLongMaxChunks], f_mid[kLongMaxChunks], f_dentry[kLongMaxChunks], f_dexit[kLongMaxChunks];
+    double A_cs[kLongMaxChunks], A_ts[kLongMaxChunks], A_end;  // pass 1: forward a0 before the chunk / at its warm-up start
+    double p_tb[kLongMaxChunks], p_wb[kLongMaxChunks], p_vfi[kLongMaxChunks];
+    int p_cen[kLongMaxChunks];
+    int fi_pre[kLongMaxChunks], fi_suf[kLongMaxChunks], fi_sum[kLongMaxChunks], fi_max[kLongMaxChunks];
+    int v_pre[kLongMaxChunks], v_suf[kLongMaxChunks], v_max[kLongMaxChunks];
+    unsigned char fi_all[kLongMaxChunks], v_all[kLongMaxChunks], choice[kLongMaxChunks], endstate[kLongMaxChunks],
+        variant[kLongMaxChunks], cross_v[kLongMaxChunks], cross_f[kLongMaxChunks];
+    // results of the single-lane walks and the combines
+    double llr_best, sum0, sh, lvit, lmarg;
+    int llr_stop, csum, mw_best, mw_stop, vlast, fwd_redone;
+    int fi_numaa, fi_maxrun, pcen;
+    double pTb, pWb, pVfi;
+};
+
+// Proteins of at least long_min residues are scored by k_long_score; the bucketed path sees them as empty.
+__global__ void __launch_bounds__(256)
+k_long_select(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_min, int32_t* __restrict__ list,
+              int64_t* __restrict__ scratch_off, unsigned long long* __restrict__ counters /* [0] count, [1] scratch cursor */)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nprot) return;
+    const int64_t len = offsets[i + 1] - offsets[i];
+    if (len < long_min) return;
+    const unsigned long long slot = atomicAdd(&counters[0], 1ull);
+    const unsigned long long need = (unsigned long long)((len + kLongPadTail + 127) & ~(int64_t)127);
+    list[slot] = (int32_t)i;
+    scratch_off[slot] = (int64_t)atomicAdd(&counters[1], need);
+}
+
+// barrier of the chunk warps only: the single-lane walks on the other warps take longer and join at the end
+__device__ __forceinline__ void long_chunk_bar()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(kLongChunkWarps * 32) : "memory");
+}
+
+struct MP2 {  // 2x2 max-plus matrix
+    double m00, m01, m10, m11;
+};
+__device__ __forceinline__ MP2 mp_mul(const MP2& a, const MP2& b)
+{
+    MP2 r;  // (a (x) b)[i][e] = max_m a[i][m] + b[m][e]
+    r.m00 = fmax(a.m00 + b.m00, a.m01 + b.m10);
+    r.m01 = fmax(a.m00 + b.m01, a.m01 + b.m11);
+    r.m10 = fmax(a.m10 + b.m00, a.m11 + b.m10);
+    r.m11 = fmax(a.m10 + b.m01, a.m11 + b.m11);
+    return r;
+}
+__device__ __forceinline__ MP2 mp_shfl_up(const MP2& a, int d)
+{
+    MP2 r;
+    r.m00 = __shfl_up_sync(0xffffffffu, a.m00, d);
+    r.m01 = __shfl_up_sync(0xffffffffu, a.m01, d);
+    r.m10 = __shfl_up_sync(0xffffffffu, a.m10, d);
+    r.m11 = __shfl_up_sync(0xffffffffu, a.m11, d);
+    return r;
+}
+
+__global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
+{
+    extern __shared__ __align__(16) unsigned char long_smem[];
+    LongShared& sm = *reinterpret_cast<LongShared*>(long_smem);
+    const KScalars& ks = g.ks;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t prot = g.list[blockIdx.x];
+    const int64_t so = g.scratch_off[blockIdx.x];
+    const int n = (int)(g.offsets[prot + 1] - g.offsets[prot]);
+    const uint8_t* src = g.codes + (g.offsets[prot] - g.off_base);
+    uint8_t* ext = g.ext + so;
+    uint8_t* tb = g.tb + so;
+    uint32_t* vit = g.vit + (so >> 5);
+    const int c = ks.core_len, w = ks.w, mw = ks.mw_window;
+
+    // ---- tables
+    {
+        const DeviceTables* T = g.tabs;
+        for (int i = tid; i <= PLAAC_LUT_LEN; i += kLongThreads) {
+            const double l0 = i < PLAAC_LUT_LEN ? T->lut[i] : 0.0;
+            const double l1 = i + 1 < PLAAC_LUT_LEN ? T->lut[i + 1] : 0.0;
+            sm.lut2[i] = make_double2(l0, l1);
+        }
+        if (tid < 32) sm.le[tid] = make_double2(T->le0[tid], T->le1[tid]);
+        if (tid < kTabN) {
+            sm.llr[tid] = T->llr[tid];
+            sm.hyd[tid] = T->hyd[tid];
+            sm.pap[tid] = T->pap[tid];
+        }
+    }
+    // ---- phase 0: ext codes (k_pack's byte layout: code | PAPA proline mask << 5 | charge class << 6)
+    {
+        int bad = 0;
+        for (int i = tid; i < n; i += kLongThreads) {
+            uint32_t cd = src[i];
+            if (cd > 21u) {
+                bad = 1;
+                cd = 0;
+            }
+            uint32_t e = cd;
+            if (ks.adjust_prolines && cd == 13u && ((i >= 1 && src[i - 1] == 13) || (i >= 2 && src[i - 2] == 13)))
+                e |= (uint32_t)kPapaMaskBit;
+            if ((ks.charge_plus >> cd) & 1u)
+                e |= 0x40u;
+            else if ((ks.charge_minus >> cd) & 1u)
+                e |= 0xc0u;
+            ext[i] = (uint8_t)e;
+        }
+        for (int i = n + tid; i < n + kLongPadTail; i += kLongThreads) ext[i] = (uint8_t)kPad;
+        if (bad) atomicOr(g.errflag, 1);
+    }
+    __syncthreads();
+
+    // chunk geometry: C is a multiple of 32, K <= kLongMaxChunks chunks
+    int C = (n + kLongMaxChunks - 1) / kLongMaxChunks;
+    C = max(kLongMinChunk, (C + 31) & ~31);
+    const int K = (n + C - 1) / C;
+    const uint32_t lut_addr = smem_u32(&sm.lut2[0]);
+
+    const int warm = max(1, min(g.warm, C));
+    if (wid < kLongChunkWarps) {
+        const int k = tid;
+        const bool live = k < K;
+        const int cs = k * C, ce = min(n, cs + C);
+        // ================= pass 1: chunk-local frame =================
+        if (live) {
+            // ---- Viterbi: the chunk's 2x2 max-plus transfer matrix (first chunk: the true chain, with its traceback)
+            {
+                double a0, a1, b0 = -INFINITY, b1 = 0.0;
+                int t0 = cs;
+                if (k == 0) {
+                    const double2 le = sm.le[ext[0] & 31];
+                    a0 = ks.li0 + le.x;
+                    a1 = ks.li1 + le.y;
+                    b1 = -INFINITY;
+                    tb[0] = 0;
+                    t0 = 1;
+                } else {
+                    a0 = 0.0;
+                    a1 = -INFINITY;
+                }
+                for (int t = t0; t < ce; t++) {
+                    const double2 le = sm.le[ext[t] & 31];
+                    const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
+                    const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
+                    const bool pA0 = vA10 > vA00, pA1 = vA11 > vA01;
+                    a0 = (pA0 ? vA10 : vA00) + le.x;
+                    a1 = (pA1 ? vA11 : vA01) + le.y;
+                    b0 = fmax(vB00, vB10) + le.x;
+                    b1 = fmax(vB01, vB11) + le.y;
+                    if (k == 0) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
+                }
+                sm.M[0][k] = a0;
+                sm.M[1][k] = a1;
+                sm.M[2][k] = b0;
+                sm.M[3][k] = b1;
+            }
+            // ---- forward LUT recurrence from `warm` residues before the chunk (first chunk: the true chain)
+            {
+                const int ts = (k == 0) ? 0 : max(0, cs - warm);
+                const int tmid = ce - warm;  // where the next chunk's warm-up starts
+                const double2 le0 = sm.le[ext[ts] & 31];
+                double a0 = ks.li0 + le0.x, a1 = ks.li1 + le0.y;
+                double e_a0 = 0.0, m_a0 = a0;
+                for (int t = ts + 1; t < ce; t++) {
+                    if (t == cs) e_a0 = a0;
+                    const double2 le = sm.le[ext[t] & 31];
+                    const double f0 = lse_lut2<false>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
+                    const double f1 = lse_lut2<false>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
+                    a0 = f0;
+                    a1 = f1;
+                    if (t == tmid) m_a0 = a0;
+                }
+                sm.f_inc[k] = a0 - e_a0;   // first chunk: e_a0 = 0, absolute values
+                sm.f_mid[k] = m_a0 - e_a0;
+                if (k == 0) sm.f_dexit[0] = a1 - a0;
+            }
+            // ---- sliding windows: FoldIndex runs and the PAPA centre over the positions this chunk owns
+            {
+                const int off1 = 2 * w + 1, off2 = 4 * w + 2;
+                const int full = 2 * w + 1, Wfull = full * full;
+                const int t_start = max(0, cs - 2 * w);
+                const int t_last = min(ce + 2 * w, n + w) - 1;
+                int halfw = ks.h_fi;
+                if (halfw > n / 2) halfw = n / 2;
+                const int fi_hi = n - halfw, edge_hi = n - 1 - w;
+                double SLh = 0, SGh = 0, Th = 0, Dp = 0, Tp = 0;
+                int SLc = 0, SGc = 0, Tac = 0;
+                double Tb = 0, Wb = 1, vfib = 0;
+                int pcen = -1;
+                int cur = 0, pre = 0, insum = 0, inmax = 0;
+                bool all = true;
+                for (int t = t_start; t <= t_last; t++) {
+                    const uint32_t e0 = (t < n) ? ext[t] : (uint32_t)kPad;
+                    const uint32_t e1 = (t - off1 >= t_start) ? ext[t - off1] : (uint32_t)kPad;
+                    const uint32_t e2 = (t - off2 >= t_start) ? ext[t - off2] : (uint32_t)kPad;
+                    const double hy0 = sm.hyd[e0 & 63], hy1 = sm.hyd[e1 & 63], hy2 = sm.hyd[e2 & 63];
+                    const double pa0 = sm.pap[e0 & 63], pa1 = sm.pap[e1 & 63], pa2 = sm.pap[e2 & 63];
+                    const int ch0 = (int)(int8_t)e0 >> 6, ch1 = (int)(int8_t)e1 >> 6, ch2 = (int)(int8_t)e2 >> 6;
+                    SLh = (SLh + hy0) - hy1;
+                    SGh = (SGh + hy1) - hy2;
+                    Th = (Th + SLh) - SGh;
+                    Dp = Dp + ((pa0 + pa2) - (pa1 + pa1));
+                    Tp = Tp + Dp;
+                    SLc += ch0 - ch1;
+                    SGc += ch1 - ch2;
+                    const int aSL = abs(SLc);
+                    Tac += aSL - abs(SGc);
+                    const int p = t - w;
+                    if (p >= cs && p < ce && p >= halfw && p < fi_hi) {
+                        const double c2 = ks.cc2 * (double)(full - max(0, w - p) - max(0, p - edge_hi));
+                        const double fis = (ks.cc0 * SLh + ks.cc1 * (double)aSL) + c2;
+                        if (fis < 0) {
+                            cur += 1;
+                            if (p == halfw) cur += halfw;           // a run from the first scanned position snaps to 0
+                            if (p == fi_hi - 1) cur += n - 1 - p;   // one reaching the last scanned position snaps to n-1
+                        } else {
+                            if (all) {
+                                pre = cur;
+                                all = false;
+                            } else if (cur >= 5) {
+                                insum += cur;
+                                inmax = max(inmax, cur);
+                            }
+                            cur = 0;
+                        }
+                    }
+                    const int kk = p - w;
+                    if (kk >= cs && kk < ce && kk >= w && kk <= edge_hi) {
+                        const int ml = 2 * w - kk, mr = kk - (edge_hi - w);
+                        const double Wd =
+                            (double)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0));
+                        const double vfi = (ks.cc0 * Th + ks.cc1 * (double)Tac) + ks.cc2 * Wd;
+                        if ((pcen < 0 || Tp * Wb > Tb * Wd) && vfi < 0) {
+                            Tb = Tp;
+                            Wb = Wd;
+                            vfib = vfi;
+                            pcen = kk;
+                        }
+                    }
+                }
+                sm.fi_all[k] = all ? 1 : 0;
+                sm.fi_pre[k] = all ? cur : pre;
+                sm.fi_suf[k] = cur;
+                sm.fi_sum[k] = insum;
+                sm.fi_max[k] = inmax;
+                sm.p_cen[k] = pcen;
+                sm.p_tb[k] = Tb;
+                sm.p_wb[k] = Wb;
+                sm.p_vfi[k] = vfib;
+            }
+        }
+        long_chunk_bar();
+        // ================= combine 1: approximate absolute values (they only fix the binade of pass 2) =================
+        if (wid == 0) {
+            // Scan of the 2x2 max-plus chunk matrices: S_k = S_0 (x) M_1 (x) ... (x) M_k, 32 chunks per round with the
+            // running product of all earlier rounds as carry (Kogge-Stone over warp shuffles).
+            double c0 = sm.M[0][0], c1 = sm.M[1][0];
+            if (lane == 0) {
+                sm.Sa[0][0] = c0;
+                sm.Sa[1][0] = c1;
+            }
+            for (int base = 1; base < K; base += 32) {
+                const int kk = base + lane;
+                MP2 m;
+                if (kk < K) {
+                    m.m00 = sm.M[0][kk];
+                    m.m01 = sm.M[1][kk];
+                    m.m10 = sm.M[2][kk];
+                    m.m11 = sm.M[3][kk];
+                } else {
+                    m.m00 = 0.0;
+                    m.m01 = -INFINITY;
+                    m.m10 = -INFINITY;
+                    m.m11 = 0.0;
+                }
+                MP2 p = m;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const MP2 o = mp_shfl_up(p, d);
+                    if (lane >= d) p = mp_mul(o, p);
+                }
+                const double s0 = fmax(c0 + p.m00, c1 + p.m10), s1 = fmax(c0 + p.m01, c1 + p.m11);
+                if (kk < K) {
+                    sm.Sa[0][kk] = s0;
+                    sm.Sa[1][kk] = s1;
+                }
+                c0 = __shfl_sync(0xffffffffu, s0, 31);
+                c1 = __shfl_sync(0xffffffffu, s1, 31);
+            }
+        } else if (wid == 1) {
+            // prefix sums of the forward increments (warp-shuffle scan with carry): a0 at cs-1 and at the warm-up start
+            double carry = 0.0;
+            for (int base = 0; base < K; base += 32) {
+                const int kk = base + lane;
+                const double v = kk < K ? sm.f_inc[kk] : 0.0;
+                double inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                if (kk < K) {
+                    const double before = carry + (inc - v);      // a0 at cs-1 (0 for the first chunk)
+                    sm.A_cs[kk] = before;
+                    if (kk + 1 < K) sm.A_ts[kk + 1] = before + sm.f_mid[kk];
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) sm.A_end = carry;
+        }
+        long_chunk_bar();
+        // ================= pass 2: the jar's own binade =================
+        // Every fp64 addition of the two recurrences has one operand of the running magnitude |s| ~ 3t, so it rounds
+        // to a multiple of ulp(|s|); rounding is monotone and commutes with shifts by multiples of that ulp as long as
+        // no operand changes its binade.  Re-run from an approximate absolute value, a chunk therefore reproduces the
+        // jar's sequential values up to an EXACT shift: Viterbi transfer entries and forward increments become exact
+        // multiples of the ulp and their ordered combination is the jar's number bit for bit.  Chunks in which the
+        // magnitude crosses a power of two (about one per binade) are redone sequentially from the exact values.
+        if (live && k >= 1) {
+            {
+                const double lo = fmin(fabs(sm.Sa[0][k - 1]), fabs(sm.Sa[1][k - 1])) - 64.0;
+                const double hi = fmax(fabs(sm.Sa[0][k]), fabs(sm.Sa[1][k])) + 64.0;
+                const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20);
+                sm.cross_v[k] = cross ? 1 : 0;
+                if (!cross) {
+                    const double R = sm.Sa[0][k - 1];
+                    double a0 = R, a1 = -INFINITY, b0 = -INFINITY, b1 = R;
+                    for (int t = cs; t < ce; t++) {
+                        const double2 le = sm.le[ext[t] & 31];
+                        const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
+                        const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
+                        const bool pA0 = vA10 > vA00, pA1 = vA11 > vA01, pB0 = vB10 > vB00, pB1 = vB11 > vB01;
+                        a0 = (pA0 ? vA10 : vA00) + le.x;
+                        a1 = (pA1 ? vA11 : vA01) + le.y;
+                        b0 = (pB0 ? vB10 : vB00) + le.x;
+                        b1 = (pB1 ? vB11 : vB01) + le.y;
+                        tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
+                    }
+                    sm.M[0][k] = a0;  // values at the chunk's last residue had the chunk been entered in state 0 with score R
+                    sm.M[1][k] = a1;
+                    sm.M[2][k] = b0;  // ... in state 1 with score R
+                    sm.M[3][k] = b1;
+                }
+            }
+            {
+                const double lo = fabs(sm.A_cs[k]) - 64.0;
+                const double hi = fabs(k + 1 < K ? sm.A_cs[k + 1] : sm.A_end) + 64.0;
+                const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20);
+                sm.cross_f[k] = cross ? 1 : 0;
+                if (!cross) {
+                    const int ts = max(0, cs - warm);
+                    const double2 le0 = sm.le[ext[ts] & 31];
+                    double a0 = ks.li0 + le0.x, a1 = ks.li1 + le0.y;
+                    if (ts > 0) {
+                        a1 = sm.A_ts[k] + (a1 - a0);
+                        a0 = sm.A_ts[k];
+                    }
+                    double e_a0 = 0.0, e_d = 0.0;
+                    for (int t = ts + 1; t < ce; t++) {
+                        if (t == cs) {
+                            e_a0 = a0;
+                            e_d = a1 - a0;
+                        }
+                        const double2 le = sm.le[ext[t] & 31];
+                        const double f0 = lse_lut2<false>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
+                        const double f1 = lse_lut2<false>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
+                        a0 = f0;
+                        a1 = f1;
+                    }
+                    sm.f_inc[k] = a0 - e_a0;  // exact: both are multiples of the same ulp
+                    sm.f_dentry[k] = e_d;
+                    sm.f_dexit[k] = a1 - a0;
+                }
+            }
+        }
+        long_chunk_bar();
+        // ================= combine 2: exact, in chunk order =================
+        if (wid == 0 && lane == 0) {
+            double S0 = sm.M[0][0], S1 = sm.M[1][0];
+            sm.choice[0] = 0;
+            for (int kk = 1; kk < K; kk++) {
+                const int s = kk * C, e = min(n, s + C);
+                if (sm.cross_v[kk]) {
+                    for (int t = s; t < e; t++) {
+                        const double2 le = sm.le[ext[t] & 31];
+                        const double v00 = ks.lt00 + S0, v10 = ks.lt10 + S1, v01 = ks.lt01 + S0, v11 = ks.lt11 + S1;
+                        const bool p0 = v10 > v00, p1 = v11 > v01;
+                        S0 = (p0 ? v10 : v00) + le.x;
+                        S1 = (p1 ? v11 : v01) + le.y;
+                        tb[t] = (uint8_t)((int)p0 | ((int)p1 << 1));
+                    }
+                } else {
+                    const double R = sm.Sa[0][kk - 1];
+                    const double d0 = S0 - R, d1 = S1 - R;  // exact shifts
+                    const double x00 = d0 + sm.M[0][kk], x10 = d1 + sm.M[2][kk];
+                    const double x01 = d0 + sm.M[1][kk], x11 = d1 + sm.M[3][kk];
+                    const int ch0 = x10 > x00 ? 1 : 0, ch1 = x11 > x01 ? 1 : 0;
+                    S0 = ch0 ? x10 : x00;
+                    S1 = ch1 ? x11 : x01;
+                    sm.choice[kk] = (unsigned char)(ch0 | (ch1 << 1));
+                }
+            }
+            const double e0v = S0 + ks.lf0, e1v = S1 + ks.lf1;
+            const int vlast = e1v > e0v ? 1 : 0;
+            sm.vlast = vlast;
+            sm.lvit = vlast ? e1v : e0v;
+            int e = vlast;
+            for (int kk = K - 1; kk >= 1; kk--) {
+                sm.endstate[kk] = (unsigned char)e;
+                if (sm.cross_v[kk]) {
+                    const int s = kk * C, en = min(n, s + C);
+                    for (int t = en - 1; t >= s; t--) e = (tb[t] >> e) & 1;
+                    sm.variant[kk] = 0;
+                } else {
+                    const int v = (sm.choice[kk] >> e) & 1;
+                    sm.variant[kk] = (unsigned char)v;
+                    e = v;  // state at the last residue of the previous chunk
+                }
+            }
+            sm.endstate[0] = (unsigned char)e;
+            sm.variant[0] = 0;
+        } else if (wid == 1 && lane == 0) {
+            // forward: the chunk's trajectory is the jar's iff it enters the chunk with the bits of d the previous
+            // chunk left with; then its increment is added exactly.  Otherwise the chunk is redone from the exact values.
+            double A0 = sm.f_inc[0], dex = sm.f_dexit[0];
+            double A1 = A0 + dex;
+            int nfb = 0;
+            for (int kk = 1; kk < K; kk++) {
+                const bool ok = !g.force_seq_forward && !sm.cross_f[kk] &&
+                                __double_as_longlong(sm.f_dentry[kk]) == __double_as_longlong(dex);
+                if (ok) {
+                    A0 = A0 + sm.f_inc[kk];
+                    dex = sm.f_dexit[kk];
+                    A1 = A0 + dex;
+                } else {
+                    const int s = kk * C, e = min(n, s + C);
+                    for (int t = s; t < e; t++) {
+                        const double2 le = sm.le[ext[t] & 31];
+                        const double f0 = lse_lut2<false>(ks.lt00 + A0, ks.lt10 + A1, lut_addr) + le.x;
+                        const double f1 = lse_lut2<false>(ks.lt01 + A0, ks.lt11 + A1, lut_addr) + le.y;
+                        A0 = f0;
+                        A1 = f1;
+                    }
+                    dex = A1 - A0;
+                    nfb += sm.cross_f[kk] ? 0 : 1;
+                }
+            }
+            sm.fwd_redone = nfb;
+            sm.lmarg = lse_lut2<false>(A0 + ks.lf0, A1 + ks.lf1, lut_addr);
+        } else if (wid == 2 && lane == 0) {
+        // FoldIndex runs (:5010-5059) and PAPA centre (:4941-4948) merged in chunk order
+        int open = 0, num = 0, mx = 0;
+        int pcen = -1;
+        double Tb = 0, Wb = 1, vfib = 0;
+        for (int k = 0; k < K; k++) {
+            if (sm.fi_all[k])
+                open += sm.fi_pre[k];
+            else {
+                const int r = open + sm.fi_pre[k];
+                if (r >= 5) {
+                    num += r;
+                    mx = max(mx, r);
+                }
+                num += sm.fi_sum[k];
+                mx = max(mx, sm.fi_max[k]);
+                open = sm.fi_suf[k];
+            }
+            if (sm.p_cen[k] >= 0 && (pcen < 0 || sm.p_tb[k] * Wb > Tb * sm.p_wb[k])) {
+                Tb = sm.p_tb[k];
+                Wb = sm.p_wb[k];
+                vfib = sm.p_vfi[k];
+                pcen = sm.p_cen[k];
+            }
+        }
+        if (open >= 5) {
+            num += open;
+            mx = max(mx, open);
+        }
+        sm.fi_numaa = num;
+        sm.fi_maxrun = mx;
+        sm.pcen = pcen;
+        sm.pTb = Tb;
+        sm.pWb = Wb;
+        sm.pVfi = vfib;
+        }
+        long_chunk_bar();
+        // ---- traceback of every chunk in parallel (:3110-3113) + run statistics for longestrun (:1787-1804)
+        if (live) {
+            int v = sm.endstate[k];
+            const int sh = 2 * sm.variant[k];
+            int cur = 0, suf = 0, inmax = 0;
+            bool closed = false;
+            uint32_t word = 0;
+            for (int t = ce - 1; t >= cs; t--) {
+                word |= (uint32_t)v << (t & 31);
+                if (v)
+                    cur++;
+                else {
+                    if (!closed) {
+                        suf = cur;
+                        closed = true;
+                    } else
+                        inmax = max(inmax, cur);
+                    cur = 0;
+                }
+                if ((t & 31) == 0) {
+                    vit[t >> 5] = word;
+                    word = 0;
+                }
+                v = (tb[t] >> (sh + v)) & 1;
+            }
+            sm.v_all[k] = closed ? 0 : 1;
+            sm.v_pre[k] = cur;
+            sm.v_suf[k] = closed ? suf : cur;
+            sm.v_max[k] = inmax;
+        }
+    } else if (lane == 0) {
+        if (wid == kLongChunkWarps) {
+            // ---- LLR window search, hss2 :1206-1257 with min == max == c, sequential psum[] in reference order
+            double ps = 0, psl = 0, best = 0;
+            int stop = -2;
+#pragma unroll 4
+            for (int t = 0; t < n; t++) {
+                ps = ps + sm.llr[ext[t] & 31];
+                if (t >= c) psl = psl + sm.llr[ext[t - c] & 31];
+                if (t >= c - 1) {
+                    const double d = ps - psl;
+                    if (t == c - 1 || d > best) {
+                        best = d;
+                        stop = t;
+                    }
+                }
+            }
+            sm.llr_best = best;
+            sm.llr_stop = stop;
+        } else if (wid == kLongChunkWarps + 1) {
+            // ---- hmm0's log-emission sum (= its Viterbi and marginal log-probability), mean hydropathy and charge
+            double sum0 = sm.le[ext[0] & 31].x, sh = sm.hyd[ext[0] & 63];
+            int cs_ = (int)(int8_t)ext[0] >> 6;
+            sh = 0.0 + sh;
+#pragma unroll 4
+            for (int t = 1; t < n; t++) {
+                const uint32_t e = ext[t];
+                sum0 = sum0 + sm.le[e & 31].x;
+                sh = sh + sm.hyd[e & 63];
+                cs_ += (int)(int8_t)e >> 6;
+            }
+            sm.sum0 = sum0;
+            sm.sh = sh;
+            sm.csum = cs_;
+        } else if (wid == kLongChunkWarps + 2) {
+            // ---- Q/N window :764-771 (n >= mw here): first strict maximum of the count in [t-mw+1, t]
+            int qn = 0, best = 0, stop = -1;
+#pragma unroll 4
+            for (int t = 0; t < n; t++) {
+                qn += (int)((ks.qn_mask >> (ext[t] & 31)) & 1u);
+                if (t >= mw) qn -= (int)((ks.qn_mask >> (ext[t - mw] & 31)) & 1u);
+                if (t >= mw - 1 && (t == mw - 1 || qn > best)) {
+                    best = qn;
+                    stop = t;
+                }
+            }
+            sm.mw_best = best;
+            sm.mw_stop = stop;
+        }
+    }
+    __syncthreads();
+
+    if (tid != 0) return;
+    if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
+    plaac_summary* r = g.out + prot;
+    r->prot_len = n;
+    r->mw_score = sm.mw_best;
+    r->mw_start = sm.mw_stop - mw + 1;
+    r->mw_end = sm.mw_stop;
+    r->llr = sm.llr_best;
+    r->llr_start = sm.llr_stop - c + 1;
+    r->llr_end = sm.llr_stop;
+    r->hmm_all = sm.lmarg - sm.sum0;
+    r->hmm_vit = sm.lvit - sm.sum0;
+    const double mh = (1.0 * sm.sh) / (double)n;
+    const double mc = (1.0 * (double)sm.csum) / (double)n;
+    r->fi_meanhydro = mh;
+    r->fi_meancharge = mc;
+    r->fi_meancombo = (ks.cc2 + ks.cc1 * fabs(mc)) + ks.cc0 * mh;
+    r->fi_numaa = sm.fi_numaa;
+    r->fi_maxrun = sm.fi_maxrun;
+    const int pcen = sm.pcen;
+    r->papa_center = pcen;
+    if (pcen >= 0) {
+        const double prop = sm.pTb / sm.pWb;
+        r->papa_combo = prop;
+        r->papa_prop = prop;
+        r->papa_fi = sm.pVfi / sm.pWb;
+        const int full = 2 * w + 1;
+        const int q0 = max(pcen - 2 * w, 0), q1 = min(pcen + 2 * w, n - 1);
+        double sc = 0.0, den = 0.0, t2 = 0.0;
+        for (int q = q0; q <= q1; q++) {
+            const double x = sm.llr[ext[q] & 63];
+            const int dist = abs(q - pcen);
+            if (dist <= w) {
+                den = den + 1.0;
+                sc = sc + 1.0 * x;
+            }
+            t2 = t2 + x * (double)(full - dist);
+        }
+        r->papa_llr = sc / den;
+        r->papa_llr2 = t2 / sm.pWb;
+    } else {
+        r->papa_combo = -INFINITY;
+        r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = nan("");
+    }
+    // longestrun
+    int open = 0, mx = 0;
+    for (int k = 0; k < K; k++) {
+        if (sm.v_all[k])
+            open += sm.v_pre[k];
+        else {
+            mx = max(mx, max(open + sm.v_pre[k], sm.v_max[k]));
+            open = sm.v_suf[k];
+        }
+    }
+    mx = max(mx, open);
+    r->vit_maxrun = mx;
+    r->core_start = -1;
+    r->core_end = -2;
+    r->prd_start = -1;
+    r->prd_end = -2;
+    r->core_score = nan("");
+    r->prd_score = 0.0;
+    if (mx < c) return;
+    // ---- CORE search on the masked sequence (:816-833), PrD expansion and PRDscore (:851-873), in reference order;
+    // masked stretches are applied as exact binade jumps when the masking constant is a negative integer.
+    const double big_neg = ks.big_neg;
+    const bool can_jump = big_neg < 0 && big_neg == floor(big_neg) && big_neg >= -4194304.0;
+    double ps = 0.0, lag = 0.0, best = -INFINITY, runsum = 0.0, prd_sc = 0.0;
+    int bstop = -1, run = 0, last = 0, run_start = 0, prd_s = -1, prd_e = -2;
+    bool hit = false;
+    const int nwords = (n + 31) >> 5;
+    for (int j = 0; j < nwords; j++) {
+        uint32_t bits = vit[j];
+        while (bits) {
+            const int i = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int p = 32 * j + i;
+            if (p != last) {
+                if (hit) {
+                    prd_s = run_start;
+                    prd_e = last - 1;
+                    prd_sc = runsum;
+                    hit = false;
+                }
+                if (can_jump)
+                    ps = masked_jump(ps, p - last, big_neg);
+                else
+                    for (int q = last; q < p; q++) ps = ps + big_neg;
+                run = 0;
+            }
+            if (run == 0) {
+                lag = ps;
+                run_start = p;
+                runsum = 0.0;
+            }
+            const double x = sm.llr[ext[p] & 31];
+            ps = ps + x;
+            runsum = runsum + x;
+            if (run >= c - 1) {
+                const double d = ps - lag;
+                if (d > best) {
+                    best = d;
+                    bstop = p;
+                    hit = true;
+                }
+                lag = lag + sm.llr[ext[p - c + 1] & 31];
+            }
+            run++;
+            last = p + 1;
+        }
+    }
+    if (hit) {
+        prd_s = run_start;
+        prd_e = last - 1;
+        prd_sc = runsum;
+    }
+    if (best > big_neg / 2) {
+        r->core_start = bstop - c + 1;
+        r->core_end = bstop;
+        r->core_score = best;
+        r->prd_start = prd_s;
+        r->prd_end = prd_e;
+        r->prd_score = prd_sc;
+    }
+}
+
+}  // namespace plaac

@@ -19,6 +19,7 @@
 #include "residue_kernel_v2.cuh"
 #include "summary_kernel.cuh"
 #include "summary_kernel_v2.cuh"
+#include "long_kernel.cuh"
 
 using namespace plaac;
 
@@ -41,6 +42,8 @@ struct Slot {
     DevBuf ing_agg, ing_cnt, ing_base, ing_misc;                 // FASTA ingest scratch
     DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
     DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
+    DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_tb, lg_vit;                             // long-sequence path
+    unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues
     cudaStream_t aux1 = nullptr, aux2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
     int64_t* h_total = nullptr;        // pinned
@@ -68,6 +71,8 @@ struct plaac_ctx {
     int sm_count = 0;
     plaac_stats stats;
     int64_t chunk_res = (int64_t)128 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
+    int64_t long_min = 4096;   // proteins at least this long take the long-sequence path (0 = off)
+    int long_warm = 256;       // forward warm-up of that path
     std::string err;
     int last_slot = 0;
 };
@@ -264,6 +269,7 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(ctx, cudaMallocHost((void**)&s.h_total, sizeof(int64_t)));
     CU(ctx, cudaMallocHost((void**)&s.h_err, sizeof(int)));
+    CU(ctx, cudaMallocHost((void**)&s.h_long, 2 * sizeof(unsigned long long)));
     CU(ctx, cudaEventCreate(&s.ev_a));
     CU(ctx, cudaEventCreate(&s.ev_b));
     CU(ctx, cudaEventCreate(&s.ev_c));
@@ -276,6 +282,8 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     int rc = ensure(ctx, s.errflag, sizeof(int));
     if (rc) return rc;
     CU(ctx, cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream));
+    if ((rc = ensure(ctx, s.lg_cnt, 32))) return rc;
+    CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 32, s.stream));
     return PLAAC_OK;
 }
 
@@ -286,8 +294,9 @@ void slot_free(Slot& s)
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
-                      &s.rk_order})
+                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_tb, &s.lg_vit})
         release(*b);
+    if (s.h_long) cudaFreeHost(s.h_long);
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
     for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_fork, s.ev_j1, s.ev_j2})
@@ -298,18 +307,47 @@ void slot_free(Slot& s)
     s = Slot();
 }
 
+// Threshold of the long-sequence path for this ctx (0 = off): it needs every window to be far shorter than a protein.
+int64_t effective_long_min(const plaac_ctx* ctx)
+{
+    if (ctx->long_min <= 0 || ctx->v2_nwr <= 0) return 0;
+    const int64_t maxoff = std::max<int64_t>(std::max(4 * ctx->ks.w + 2, ctx->ks.core_len), ctx->ks.mw_window);
+    return std::max<int64_t>(std::max<int64_t>(ctx->long_min, 1024), 4 * maxoff);
+}
+
 // Enqueue the whole device pipeline for one batch on slot s.  d_offsets are absolute; off_base is
 // subtracted to index d_codes.  Contains ONE stream synchronisation (the padded stream size).
 int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_offsets, int64_t off_base,
               int64_t nprot, int64_t ntotal, plaac_summary* d_summaries, const plaac_residue_out* d_res,
-              int64_t res_base, int64_t slots_bound = -1)
+              int64_t res_base, int64_t slots_bound = -1, int64_t nlong_known = -1, int64_t long_scratch_known = -1)
 {
     if (nprot == 0) return PLAAC_OK;
     if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins in one device batch");
-    (void)ntotal;
     cudaStream_t st = s.stream;
     const int64_t nbuckets = (nprot + 31) / 32;
     int rc;
+    const bool use_v2 = ctx->variant == 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);
+    // Long-sequence path: summary mode of the throughput kernel only.
+    const int64_t long_min = effective_long_min(ctx);
+    const bool use_long = d_summaries && !d_res && use_v2 && long_min > 0 && ntotal >= long_min && nlong_known != 0;
+    const int64_t lm = use_long ? long_min : INT64_MAX;
+    int64_t nlong = 0, long_scratch = 0;
+    if (use_long) {
+        const int64_t cap = ntotal / long_min + 1;
+        if ((rc = ensure(ctx, s.lg_list, sizeof(int32_t) * (size_t)cap))) return rc;
+        if ((rc = ensure(ctx, s.lg_off, sizeof(int64_t) * (size_t)cap))) return rc;
+        if ((rc = ensure(ctx, s.lg_cnt, 32))) return rc;  // [0] count, [1] scratch cursor, [2] redone chunks (cumulative)
+        CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 16, st));
+        k_long_select<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, long_min, (int32_t*)s.lg_list.p,
+                                                                      (int64_t*)s.lg_off.p, (unsigned long long*)s.lg_cnt.p);
+        ctx->stats.kernel_launches += 1;
+        if (nlong_known >= 0) {
+            nlong = nlong_known;
+            long_scratch = long_scratch_known;
+        } else {
+            CU(ctx, cudaMemcpyAsync(s.h_long, s.lg_cnt.p, 16, cudaMemcpyDeviceToHost, st));  // read after the sync below
+        }
+    }
     if ((rc = ensure(ctx, s.hist, sizeof(int32_t) * (kHistBins + 1)))) return rc;
     if ((rc = ensure(ctx, s.cursor, sizeof(int64_t) * (kHistBins + 2)))) return rc;
     if ((rc = ensure(ctx, s.order, sizeof(int32_t) * nprot))) return rc;
@@ -321,11 +359,11 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     const int tb = 256;
     const unsigned g_hist = (unsigned)std::min<int64_t>(ctx->sm_count, (nprot + 4095) / 4096);
     const unsigned g_scat = (unsigned)std::min<int64_t>(ctx->sm_count, (nprot + kScatterTile - 1) / kScatterTile);
-    k_len_hist<<<g_hist, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, (int32_t*)s.hist.p);
+    k_len_hist<<<g_hist, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, lm, (int32_t*)s.hist.p);
     k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.hist.p, (int64_t*)s.cursor.p, kHistBins + 1);
-    k_scatter<<<g_scat, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, (int64_t*)s.cursor.p, (int32_t*)s.order.p);
+    k_scatter<<<g_scat, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, lm, (int64_t*)s.cursor.p, (int32_t*)s.order.p);
     const unsigned gb = (unsigned)((nbuckets * 32 + tb - 1) / tb);
-    k_bucket_chunks<<<gb, tb, 0, st>>>(d_offsets, (const int32_t*)s.order.p, nprot, nbuckets, (int32_t*)s.nchunks.p);
+    k_bucket_chunks<<<gb, tb, 0, st>>>(d_offsets, (const int32_t*)s.order.p, nprot, nbuckets, lm, (int32_t*)s.nchunks.p);
     k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.nchunks.p, (int64_t*)s.chunk_base.p, nbuckets);
     ctx->stats.kernel_launches += 5;
     CU(ctx, cudaMemcpyAsync(s.h_total, (int64_t*)s.chunk_base.p + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -335,6 +373,14 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         CU(ctx, cudaStreamSynchronize(st));
         slots = *s.h_total;
         ctx->stats.last_padded_slots = slots * 32;
+        if (use_long && nlong_known < 0) {
+            nlong = (int64_t)s.h_long[0];
+            long_scratch = (int64_t)s.h_long[1];
+        }
+    } else if (use_long && nlong_known < 0) {
+        CU(ctx, cudaStreamSynchronize(st));
+        nlong = (int64_t)s.h_long[0];
+        long_scratch = (int64_t)s.h_long[1];
     }
     if ((rc = ensure(ctx, s.stream_buf, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint4)))) return rc;
     if ((rc = ensure(ctx, s.tbw, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint32_t)))) return rc;
@@ -342,7 +388,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
 
     const int pack_blocks = (int)std::min<int64_t>((nbuckets + 7) / 8, (int64_t)ctx->sm_count * 8);
     k_pack<<<pack_blocks, 256, 0, st>>>(d_codes, d_offsets, off_base, (const int32_t*)s.order.p,
-                                        (const int64_t*)s.chunk_base.p, nprot, nbuckets, ctx->ks.adjust_prolines,
+                                        (const int64_t*)s.chunk_base.p, nprot, nbuckets, lm, ctx->ks.adjust_prolines,
                                         ctx->ks.charge_plus, ctx->ks.charge_minus, (uint4*)s.stream_buf.p,
                                         (int32_t*)s.slot_bucket.p, (int*)s.errflag.p);
     ctx->stats.kernel_launches += 1;
@@ -358,8 +404,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     bv.nprot = nprot;
     bv.nbuckets = nbuckets;
     bv.off_base = off_base;
+    bv.long_min = lm;
 
-    const bool use_v2 = ctx->variant == 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);
     if (d_summaries && use_v2) {
         if ((rc = ensure(ctx, s.core_list, sizeof(int32_t) * 2 * nprot))) return rc;
         if ((rc = ensure(ctx, s.core_count, 16))) return rc;  // [0] CORE list length, [8] work-queue counter
@@ -389,6 +435,30 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
         ctx->stats.kernel_launches += 2;
         ctx->stats.score_launches += 1;
+        if (use_long && nlong > 0) {
+            if ((rc = ensure(ctx, s.lg_ext, (size_t)long_scratch + 256))) return rc;
+            if ((rc = ensure(ctx, s.lg_tb, (size_t)long_scratch + 256))) return rc;
+            if ((rc = ensure(ctx, s.lg_vit, (size_t)long_scratch / 8 + 256))) return rc;
+            LongArgs la;
+            la.codes = d_codes;
+            la.offsets = d_offsets;
+            la.off_base = off_base;
+            la.list = (const int32_t*)s.lg_list.p;
+            la.scratch_off = (const int64_t*)s.lg_off.p;
+            la.ks = ctx->ks;
+            la.tabs = ctx->d_tabs;
+            la.out = d_summaries;
+            la.ext = (uint8_t*)s.lg_ext.p;
+            la.tb = (uint8_t*)s.lg_tb.p;
+            la.vit = (uint32_t*)s.lg_vit.p;
+            la.errflag = (int*)s.errflag.p;
+            la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
+            la.warm = std::max(1, std::abs(ctx->long_warm));
+            la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
+            k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), st>>>(la);
+            ctx->stats.kernel_launches += 1;
+            ctx->stats.long_proteins += nlong;
+        }
     } else if (d_summaries) {
         const unsigned grid = (unsigned)((nbuckets + ctx->nwarps - 1) / ctx->nwarps);
         k_score_summary<<<grid, ctx->nwarps * 32, ctx->smem_bytes, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries,
@@ -512,6 +582,11 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         ctx->err = std::string("table upload: ") + cudaGetErrorString(e);
         return bail(PLAAC_E_CUDA);
     }
+    e = cudaFuncSetAttribute(k_long_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LongShared));
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaFuncSetAttribute(k_long_score): ") + cudaGetErrorString(e);
+        return bail(PLAAC_E_CUDA);
+    }
     e = cudaFuncSetAttribute(k_score_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes);
     if (e != cudaSuccess) {
         ctx->err = std::string("cudaFuncSetAttribute(k_score_summary): ") + cudaGetErrorString(e);
@@ -601,6 +676,15 @@ int plaac_set_chunk(plaac_ctx* ctx, int64_t max_residues, int64_t max_proteins)
     return PLAAC_OK;
 }
 
+int plaac_set_long_path(plaac_ctx* ctx, int64_t min_len, int warm)
+{
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_long_path: NULL ctx");
+    if (min_len < 0) return fail(ctx, PLAAC_E_INVALID, "negative min_len");
+    ctx->long_min = min_len;
+    if (warm != 0) ctx->long_warm = warm;
+    return PLAAC_OK;
+}
+
 int plaac_set_kernel_variant(plaac_ctx* ctx, int variant)
 {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_kernel_variant: NULL ctx");
@@ -614,6 +698,13 @@ int plaac_set_kernel_variant(plaac_ctx* ctx, int variant)
 int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
 {
     if (!ctx || !out) return fail(ctx, PLAAC_E_INVALID, "plaac_get_stats: NULL argument");
+    ctx->stats.long_redone_chunks = 0;
+    for (int i = 0; i < 2; i++) {
+        unsigned long long v = 0;
+        if (ctx->slot[i].lg_cnt.p && cudaSetDevice(ctx->device) == cudaSuccess &&
+            cudaMemcpy(&v, (char*)ctx->slot[i].lg_cnt.p + 16, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess)
+            ctx->stats.long_redone_chunks += (int64_t)v;
+    }
     *out = ctx->stats;
     return PLAAC_OK;
 }
@@ -660,7 +751,8 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         // walk overlaps the previous chunk's copies and kernels).
         int64_t end = start;
         const int64_t base = offsets[start];
-        int64_t lmax = 0, nlong = 0;
+        int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0;
+        const int64_t long_min = per_res ? 0 : effective_long_min(ctx);
         while (end < nprot && end - start < max_prot) {
             const int64_t len = offsets[end + 1] - offsets[end];
             if (len < 0) {
@@ -672,8 +764,14 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
                 break;
             }
             if (end != start && offsets[end + 1] - base > max_res) break;
-            lmax = std::max(lmax, len);
-            nlong += len >= kHistBins;
+            if (long_min > 0 && len >= long_min) {
+                // scored by the long-sequence path; the bucketed stream sees an empty protein
+                nlp++;
+                lp_scratch += (len + kLongPadTail + 127) & ~(int64_t)127;
+            } else {
+                lmax = std::max(lmax, len);
+                nlong += len >= kHistBins;
+            }
             end++;
         }
         if (rc != PLAAC_OK) break;
@@ -711,7 +809,8 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         if (nres > 0) CU(ctx, cudaMemcpyAsync(s.codes.p, codes + base, (size_t)nres, cudaMemcpyHostToDevice, s.stream));
         CU(ctx, cudaMemcpyAsync(s.offsets.p, offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
         rc = run_batch(ctx, s, (const uint8_t*)s.codes.p, (const int64_t*)s.offsets.p, base, np, nres,
-                       summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base, slots_bound);
+                       summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base, slots_bound,
+                       nlp, lp_scratch);
         if (rc) break;
         if (summaries)
             CU(ctx, cudaMemcpyAsync(summaries + start, s.summaries.p, sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));

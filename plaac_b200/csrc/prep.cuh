@@ -24,7 +24,7 @@ constexpr int kPrepThreads = 1024;
 constexpr size_t kHistSmemBytes = sizeof(int32_t) * (kHistBins + 1);
 
 __global__ void __launch_bounds__(kPrepThreads)
-k_len_hist(const int64_t* __restrict__ offsets, int64_t nprot, int32_t* __restrict__ hist)
+k_len_hist(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_min, int32_t* __restrict__ hist)
 {
     extern __shared__ int32_t sh_hist[];
     for (int i = threadIdx.x; i <= kHistBins; i += blockDim.x) sh_hist[i] = 0;
@@ -32,7 +32,7 @@ k_len_hist(const int64_t* __restrict__ offsets, int64_t nprot, int32_t* __restri
     const int64_t per = (nprot + gridDim.x - 1) / gridDim.x;
     const int64_t lo = per * blockIdx.x, hi = min(nprot, lo + per);
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-        atomicAdd(&sh_hist[len_bin(offsets[i + 1] - offsets[i])], 1);
+        atomicAdd(&sh_hist[len_bin(eff_len(offsets[i + 1] - offsets[i], long_min))], 1);
     __syncthreads();
     for (int i = threadIdx.x; i <= kHistBins; i += blockDim.x) {
         const int32_t v = sh_hist[i];
@@ -100,7 +100,8 @@ constexpr int kScatterPer = 8;
 constexpr int kScatterTile = kPrepThreads * kScatterPer;
 
 __global__ void __launch_bounds__(kPrepThreads)
-k_scatter(const int64_t* __restrict__ offsets, int64_t nprot, int64_t* __restrict__ cursor, int32_t* __restrict__ order)
+k_scatter(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_min, int64_t* __restrict__ cursor,
+          int32_t* __restrict__ order)
 {
     extern __shared__ int32_t sh_cnt[];  // per bin: count during ranking, then the reserved global base
     for (int i = threadIdx.x; i <= kHistBins; i += blockDim.x) sh_cnt[i] = 0;
@@ -115,7 +116,7 @@ k_scatter(const int64_t* __restrict__ offsets, int64_t nprot, int64_t* __restric
             bin[k] = -1;
             rk[k] = 0;
             if (i < nprot) {
-                bin[k] = len_bin(offsets[i + 1] - offsets[i]);
+                bin[k] = len_bin(eff_len(offsets[i + 1] - offsets[i], long_min));
                 rk[k] = atomicAdd(&sh_cnt[bin[k]], 1);
             }
         }
@@ -148,7 +149,7 @@ k_scatter(const int64_t* __restrict__ offsets, int64_t nprot, int64_t* __restric
 
 // One warp per bucket: slots needed = ceil(max length / 16).
 __global__ void k_bucket_chunks(const int64_t* __restrict__ offsets, const int32_t* __restrict__ order, int64_t nprot,
-                                int64_t nbuckets, int32_t* __restrict__ nchunks)
+                                int64_t nbuckets, int64_t long_min, int32_t* __restrict__ nchunks)
 {
     int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -157,7 +158,7 @@ __global__ void k_bucket_chunks(const int64_t* __restrict__ offsets, const int32
     int64_t len = 0;
     if (r < nprot) {
         int32_t p = order[r];
-        len = offsets[p + 1] - offsets[p];
+        len = eff_len(offsets[p + 1] - offsets[p], long_min);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -198,7 +199,8 @@ __device__ __forceinline__ uint32_t bytes_in_set(uint32_t w, uint32_t set)
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
        int64_t off_base, const int32_t* __restrict__ order, const int64_t* __restrict__ chunk_base, int64_t nprot,
-       int64_t nbuckets, int adjust_prolines, uint32_t charge_plus, uint32_t charge_minus, uint4* __restrict__ stream,
+       int64_t nbuckets, int64_t long_min, int adjust_prolines, uint32_t charge_plus, uint32_t charge_minus,
+       uint4* __restrict__ stream,
        int32_t* __restrict__ slot_bucket, int* __restrict__ errflag)
 {
     const int lane = threadIdx.x & 31;
@@ -219,7 +221,7 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
         const uint8_t* src = codes;
         if (r < nprot) {
             int32_t p = order[r];
-            n = offsets[p + 1] - offsets[p];
+            n = eff_len(offsets[p + 1] - offsets[p], long_min);
             src = codes + (offsets[p] - off_base);
         }
         const int64_t cb = chunk_base[b];

@@ -122,7 +122,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     int32_t prot = -1;
     if (rank < bv.nprot) {
         prot = bv.order[rank];
-        n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
+        n = (int)eff_len(bv.offsets[prot + 1] - bv.offsets[prot], bv.long_min);
+        if (n == 0 && bv.offsets[prot + 1] != bv.offsets[prot]) prot = -1;  // scored by the long-sequence path
     }
     const int64_t cb = bv.chunk_base[b];
     const int nch = (int)(bv.chunk_base[b + 1] - cb);
@@ -349,7 +350,8 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
     int32_t prot = -1;
     if (rank < bv.nprot) {
         prot = bv.order[rank];
-        n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
+        n = (int)eff_len(bv.offsets[prot + 1] - bv.offsets[prot], bv.long_min);
+        if (n == 0 && bv.offsets[prot + 1] != bv.offsets[prot]) prot = -1;  // scored by the long-sequence path
     }
     const int64_t cb = bv.chunk_base[b];
     const int nch = (int)(bv.chunk_base[b + 1] - cb);

@@ -9,6 +9,9 @@
 //   --device D      GPU index when --gpus is 1 (default 0)
 //   --batch-mb M    residues per scoring batch in MiB (default 256)
 //   --compat-F      keep the jar's -F bug (plaac.java:388 reads the -B file name)
+//   --rank          print the rows of every scoring batch in the web front end's order (COREscore desc, LLR desc, no-CORE
+//                   rows last; web/lib/server.rb:222-229), computed on the GPU (plaac_rank); --rank-core prints only the
+//                   rows with a CORE.  A file that fits one batch (--batch-mb) is ranked as a whole.
 //   --gpu-ingest    parse the FASTA on the GPU as well (plaac_score_fasta): the file goes to the device as raw bytes in
 //                   record-aligned pieces of --batch-mb; summary table only, one GPU
 #include <charconv>
@@ -310,6 +313,7 @@ struct Options {
     int64_t batch_res = (int64_t)256 << 20;
     bool compat_F = false;
     bool gpu_ingest = false;
+    bool rank = false, rank_core_only = false;
 };
 
 struct Scorers {
@@ -392,6 +396,19 @@ int score_summary_batch(const Options& o, Scorers& S, Batch& B)
                                      sum.data(), nullptr);
     if (rc != PLAAC_OK) return die(S, rc, "plaac_score");
     std::string line;
+    if (o.rank) {
+        std::vector<int32_t> order((size_t)B.nprot());
+        int64_t ncore = 0;
+        const int rr = plaac_rank(S.ctx[0], sum.data(), B.nprot(), 0, order.data(), &ncore);
+        if (rr != PLAAC_OK) return die(S, rr, "plaac_rank");
+        const int64_t nshow = o.rank_core_only ? ncore : B.nprot();
+        for (int64_t k = 0; k < nshow; k++) {
+            const size_t i = (size_t)order[(size_t)k];
+            print_summary_row(o, B.names[i], sum[i], B.codes.data() + B.offsets[i], line);
+        }
+        B.clear();
+        return 0;
+    }
     for (int64_t i = 0; i < B.nprot(); i++)
         print_summary_row(o, B.names[(size_t)i], sum[(size_t)i], B.codes.data() + B.offsets[(size_t)i], line);
     B.clear();
@@ -575,7 +592,7 @@ void usage()
     std::puts("  -d               print documentation of the output columns");
     std::puts("  -s               skip the run-time parameter block");
     std::puts("  -p list.txt|all  per-residue table for the listed proteins (one name per line) or for all");
-    std::puts("  --gpus N, --device D, --batch-mb M, --compat-F   (this host only)");
+    std::puts("  --gpus N, --device D, --batch-mb M, --compat-F, --rank, --rank-core, --gpu-ingest   (this host only)");
 }
 
 }  // namespace
@@ -601,6 +618,10 @@ int main(int argc, char** argv)
             o.batch_res = (int64_t)std::atoll(val("--batch-mb")) << 20;
         else if (a == "--compat-F")
             o.compat_F = true;
+        else if (a == "--rank")
+            o.rank = true;
+        else if (a == "--rank-core")
+            o.rank = o.rank_core_only = true;
         else if (a == "--gpu-ingest")
             o.gpu_ingest = true;
         else if (a == "--format-check") {

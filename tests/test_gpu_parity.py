@@ -25,7 +25,7 @@ def scorer():
     s.close()
 
 
-def _check(got, ref, what="", P=None, codes=None, offs=None, max_ties=0):
+def _check(got, ref, what="", P=None, codes=None, offs=None, max_ties=0, reassociated=()):
     if P is not None:
         bad, nties = parity.compare_with_tie_classes(P, codes, offs, got, ref, orc.INT_FIELDS, orc.DBL_FIELDS)
         assert nties <= max_ties, f"{what}: {nties} PAPA tie-class rows (allowed {max_ties})"
@@ -36,6 +36,8 @@ def _check(got, ref, what="", P=None, codes=None, offs=None, max_ties=0):
     for f in parity.REF_ORDER:
         if f == "papa_llr" and P is not None:
             continue  # follows the centre; covered by the tie-class rule
+        if f in reassociated:
+            continue  # long-sequence path: chunk-wise sums, held to the 1e-9 bar only
         assert parity.max_rel(got, ref, f) <= 1e-13, (what, f, parity.max_rel(got, ref, f))
 
 
@@ -102,12 +104,81 @@ def test_human_sized_blended_background(scorer):
 
 
 def test_long_sequences(scorer):
-    """Config 5: 35k and 100k residues."""
+    """Config 5: 35k and 100k residues, through the chunked long-sequence path (scan of 2x2 max-plus matrices for
+    Viterbi, warm-started chunks for the LUT forward recurrence) and, with the path switched off, through the bucketed
+    kernel in plaac.java's own operation order."""
     codes, offs = synth.long_proteins()
-    got = scorer.score(codes, offs)
     ref = orc.score_batch(orc.make_params(), codes, offs, nthreads=2)
-    _check(got, ref, "long sequences")
+    before = scorer.stats().long_proteins
+    got = scorer.score(codes, offs)
+    assert scorer.stats().long_proteins == before + 2
+    _check(got, ref, "long sequences (long path)")
+    print("forward chunks redone:", scorer.stats().long_redone_chunks)
     assert (got["core_start"] >= 0).all()
+    scorer.set_long_path(0)
+    try:
+        got = scorer.score(codes, offs)
+        assert scorer.stats().long_proteins == before + 2
+        _check(got, ref, "long sequences (bucketed kernel)")
+    finally:
+        scorer.set_long_path(4096)
+
+
+def test_long_path_mixed_batch_thresholds_and_fallback():
+    """Proteins on both sides of the threshold in one batch (host and device-resident API), lengths around the chunk
+    geometry, the sequential-forward fallback, and a warm-up too short to forget its start (must be detected)."""
+    rng = np.random.default_rng(77)
+    bg = synth.BG_SCER / synth.BG_SCER.sum()
+    prd = synth.PRD_28 / synth.PRD_28.sum()
+    seqs = []
+    for n in (1023, 1024, 1025, 2047, 2048, 4095, 4096, 4097, 8191, 8192, 8193, 12287, 12288, 12289, 20000, 98303, 98304,
+              98305):
+        s = rng.choice(22, size=n, p=bg).astype(np.uint8)
+        for frac in (0.0, 0.31, 0.77):
+            st = int(n * frac)
+            if rng.random() < 0.7:
+                s[st:st + 120] = rng.choice(22, size=min(120, n - st), p=prd)
+        if n % 2:
+            s[-200:] = rng.choice(22, size=200, p=prd)  # PrD reaching the last residue
+        seqs.append(s)
+    seqs.append(np.full(5000, 14, np.uint8))                                    # poly-Q: plateaus, one Viterbi run
+    seqs.append(np.tile(np.array([13, 1, 13, 13, 12], np.uint8), 1200))        # proline rule across chunk borders
+    seqs.append(rng.integers(1, 21, size=6000).astype(np.uint8))               # uniform composition
+    c2, o2 = synth.proteome(800, seed=5)
+    seqs += [c2[o2[i]:o2[i + 1]] for i in range(800)]
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    codes, offs = plaac_b200.pack(seqs)
+    P = orc.make_params()
+    ref = orc.score_batch(P, codes, offs, nthreads=NT)
+    lens = np.diff(offs)
+    redone = {}
+    for min_len, warm in [(1024, 0), (4096, 0), (1024, -1), (1024, 3)]:
+        sc = plaac_b200.Scorer(device=0)
+        sc.set_long_path(min_len, warm)
+        got = sc.score(codes, offs)
+        st = sc.stats()
+        assert st.long_proteins == int((lens >= min_len).sum())
+        redone[(min_len, warm)] = st.long_redone_chunks
+        _check(got, ref, f"long path min_len={min_len} warm={warm}", P, codes, offs, max_ties=2)
+        sc.close()
+    print("forward chunks redone:", redone)
+    # a 3-residue warm-up cannot forget its start: the entry test must catch (nearly) every chunk
+    assert redone[(1024, 3)] > 10 * max(1, redone[(1024, 0)])
+    # device-resident API (the long list is selected and sized on the device)
+    import torch
+
+    sc = plaac_b200.Scorer(device=0)
+    sc.set_long_path(2048)
+    d_codes = torch.from_numpy(codes).cuda()
+    d_offs = torch.from_numpy(offs).cuda()
+    d_out = torch.zeros((len(lens), 160), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    sc.score_device(d_codes.data_ptr(), d_offs.data_ptr(), len(lens), int(offs[-1]), d_out.data_ptr())
+    got = d_out.cpu().numpy().reshape(-1).view(plaac_b200.SUMMARY_DTYPE)
+    assert sc.stats().long_proteins == int((lens >= 2048).sum())
+    _check(got, ref, "long path, device API", P, codes, offs, max_ties=2)
+    sc.close()
 
 
 @pytest.mark.parametrize("kw", [dict(core_len=30), dict(core_len=100, ww1=21, ww2=21), dict(ww1=40, ww2=40),

@@ -258,3 +258,35 @@ def test_gpu_ingest_path_prints_the_same_table(cli, tmp_path, golden):
     assert len(a.stdout.split("\n")) > 500
     assert a.stdout == b.stdout
     assert a.stdout == c.stdout
+
+
+@pytest.mark.gpu
+def test_rank_option_orders_rows_like_the_web_front_end(cli, tmp_path):
+    """--rank prints the same rows in the order of web/lib/server.rb:222-229; --rank-core only those with a CORE."""
+    from tests import synth
+
+    codes, offs = synth.proteome(400, 31, prd_rate=0.3)
+    names = "XACDEFGHIKLMNPQRSTVWY*"
+    fa = tmp_path / "rank.fa"
+    with open(fa, "w") as f:
+        for i in range(400):
+            f.write(f">p{i}\n" + "".join(names[c] for c in codes[offs[i]:offs[i + 1]]) + "\n")
+    plain = run(cli, "-i", str(fa), "-s")
+    ranked = run(cli, "-i", str(fa), "-s", "--rank")
+    core = run(cli, "-i", str(fa), "-s", "--rank-core")
+    assert plain.returncode == 0 and ranked.returncode == 0 and core.returncode == 0, (ranked.stderr, core.stderr)
+    rows = [l for l in plain.stdout.split("\n") if l and not l.startswith("#")]
+    rrows = [l for l in ranked.stdout.split("\n") if l and not l.startswith("#")]
+    crows = [l for l in core.stdout.split("\n") if l and not l.startswith("#")]
+    assert rows[0] == rrows[0] == crows[0] and sorted(rows) == sorted(rrows)
+    hdr = rows[0].split("\t")
+    ic, il = hdr.index("COREscore"), hdr.index("LLR")
+    body = [r.split("\t") for r in rrows[1:]]
+    ncore = sum(1 for r in body if r[ic] != "NaN")
+    assert 0 < ncore < len(body) and len(crows) - 1 == ncore
+    assert all(r[ic] != "NaN" for r in body[:ncore]) and all(r[ic] == "NaN" for r in body[ncore:])
+    cs = [float(r[ic]) for r in body[:ncore]]
+    assert all(a >= b for a, b in zip(cs, cs[1:]))
+    ls = [float(r[il]) for r in body[ncore:]]
+    assert all(a >= b for a, b in zip(ls, ls[1:]))
+    assert crows[1:] == rrows[1:1 + ncore]
