@@ -22,10 +22,10 @@
 //   chunks that failed that test, are redone sequentially from the exact values.
 //   windows   (disorderreport :4866-5068) the running window sums restart 2w residues before the chunk; FoldIndex
 //             runs and the PAPA first-strict-maximum are reduced per chunk and merged in chunk order.
-//   Three single lanes on other warps meanwhile walk the whole protein for the columns that are plain sequential
-//   fp64 sums in plaac.java's order: the psum[] LLR window search (hss2 :1206-1257), hmm0's log-emission sum, the
-//   hydropathy mean, and the Q/N window.  The -1e6-masked CORE search runs last on the Viterbi bits with the exact
-//   binade jumps of k_core_search_jump.
+//   sums      the plain sequential fp64 sums of plaac.java -- psum[] of the LLR window search (hss2 :1206-1257), hmm0's
+//             log-emission sum, the hydropathy mean -- go through the same two passes (no state besides the sum), the
+//             window maxima are merged in chunk order; the Q/N window is integer work.  The -1e6-masked CORE search
+//             runs last on the Viterbi bits with the exact binade jumps of k_core_search_jump.
 //
 // Result: every column has the bits of the bucketed kernel, which has the bits of the jar.
 #pragma once
@@ -51,6 +51,7 @@ struct LongArgs {
     plaac_summary* out;
     uint8_t* ext;   // ext code per residue (same byte layout as the bucketed stream)
     uint8_t* tb;    // 4 traceback bits per residue: variant A (P0, P1), variant B (P0, P1)
+    long long* dbg_clocks;       // optional: phase time stamps of the CTA with blockIdx 0 (16 slots)
     unsigned long long* redone;  // statistics: forward chunks redone sequentially because d had not coalesced
     uint32_t* vit;  // Viterbi bits, one word per 32 residues
     int* errflag;
@@ -73,7 +74,13 @@ struct LongShared {
     int v_pre[kLongMaxChunks], v_suf[kLongMaxChunks], v_max[kLongMaxChunks];
     unsigned char fi_all[kLongMaxChunks], v_all[kLongMaxChunks], choice[kLongMaxChunks], endstate[kLongMaxChunks],
         variant[kLongMaxChunks], cross_v[kLongMaxChunks], cross_f[kLongMaxChunks];
-    // results of the single-lane walks and the combines
+    // sequential sums (psum[] of the LLR search, hmm0's emission sum, hydropathy sum): [0] LLR, [1] hmm0, [2] hydropathy
+    double q_sum[3][kLongMaxChunks], q_min[3][kLongMaxChunks], q_max[3][kLongMaxChunks];  // pass 1, chunk-local
+    double q_abs[3][kLongMaxChunks];                                                      // pass 1: value before the chunk
+    double q_inc[3][kLongMaxChunks], q_mid[kLongMaxChunks], q_best[kLongMaxChunks];       // pass 2, exact
+    int q_stop[kLongMaxChunks], m_best[kLongMaxChunks], m_stop[kLongMaxChunks], c_sum[kLongMaxChunks];
+    unsigned char cross_q[3][kLongMaxChunks];
+    // results of the combines
     double llr_best, sum0, sh, lvit, lmarg;
     int llr_stop, csum, mw_best, mw_stop, vlast, fwd_redone;
     int fi_numaa, fi_maxrun, pcen;
@@ -123,6 +130,11 @@ __device__ __forceinline__ MP2 mp_shfl_up(const MP2& a, int d)
     return r;
 }
 
+#define LONG_STAMP(i)                                                              \
+    do {                                                                           \
+        if (g.dbg_clocks && tid == 0 && blockIdx.x == 0) g.dbg_clocks[i] = clock64(); \
+    } while (0)
+
 __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
 {
     extern __shared__ __align__(16) unsigned char long_smem[];
@@ -133,9 +145,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     const int64_t so = g.scratch_off[blockIdx.x];
     const int n = (int)(g.offsets[prot + 1] - g.offsets[prot]);
     const uint8_t* src = g.codes + (g.offsets[prot] - g.off_base);
-    uint8_t* ext = g.ext + so;
-    uint8_t* tb = g.tb + so;
-    uint32_t* vit = g.vit + (so >> 5);
+    uint8_t* __restrict__ ext = g.ext + so;
+    uint8_t* __restrict__ tb = g.tb + so;
+    uint32_t* __restrict__ vit = g.vit + (so >> 5);
     const int c = ks.core_len, w = ks.w, mw = ks.mw_window;
 
     // ---- tables
@@ -176,9 +188,10 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     }
     __syncthreads();
 
+    LONG_STAMP(0);
     // chunk geometry: C is a multiple of 32, K <= kLongMaxChunks chunks
     int C = (n + kLongMaxChunks - 1) / kLongMaxChunks;
-    C = max(kLongMinChunk, (C + 31) & ~31);
+    C = max(max(kLongMinChunk, (C + 31) & ~31), ((max(c, mw) + 32) + 31) & ~31);  // a chunk holds a whole CORE / MW window
     const int K = (n + C - 1) / C;
     const uint32_t lut_addr = smem_u32(&sm.lut2[0]);
 
@@ -204,6 +217,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     a0 = 0.0;
                     a1 = -INFINITY;
                 }
+#pragma unroll 8
                 for (int t = t0; t < ce; t++) {
                     const double2 le = sm.le[ext[t] & 31];
                     const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
@@ -220,6 +234,37 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 sm.M[2][k] = b0;
                 sm.M[3][k] = b1;
             }
+            // ---- chunk-local sums of the three sequential-sum columns with their running extremes, charge sum, Q/N window
+            {
+                double q0 = 0, q1 = 0, q2 = 0, mn0 = 0, mn1 = 0, mn2 = 0, mx0 = 0, mx1 = 0, mx2 = 0;
+                int cq = 0;
+                int qn = 0, mbest = -1, mstop = -1;
+                for (int t = max(0, cs - mw); t < cs; t++) qn += (int)((ks.qn_mask >> (ext[t] & 31)) & 1u);
+#pragma unroll 8
+                for (int t = cs; t < ce; t++) {
+                    const uint32_t e = ext[t];
+                    q0 = q0 + sm.llr[e & 31];
+                    q1 = q1 + sm.le[e & 31].x;
+                    q2 = q2 + sm.hyd[e & 63];
+                    mn0 = fmin(mn0, q0), mx0 = fmax(mx0, q0);
+                    mn1 = fmin(mn1, q1), mx1 = fmax(mx1, q1);
+                    mn2 = fmin(mn2, q2), mx2 = fmax(mx2, q2);
+                    cq += (int)(int8_t)e >> 6;
+                    // Q/N window :764-771: first strict maximum of the count in [t-mw+1, t] (n >= mw here)
+                    qn += (int)((ks.qn_mask >> (e & 31)) & 1u);
+                    if (t >= mw) qn -= (int)((ks.qn_mask >> (ext[t - mw] & 31)) & 1u);
+                    if (t >= mw - 1 && qn > mbest) {
+                        mbest = qn;
+                        mstop = t;
+                    }
+                }
+                sm.q_sum[0][k] = q0, sm.q_min[0][k] = mn0, sm.q_max[0][k] = mx0;
+                sm.q_sum[1][k] = q1, sm.q_min[1][k] = mn1, sm.q_max[1][k] = mx1;
+                sm.q_sum[2][k] = q2, sm.q_min[2][k] = mn2, sm.q_max[2][k] = mx2;
+                sm.c_sum[k] = cq;
+                sm.m_best[k] = mbest;
+                sm.m_stop[k] = mstop;
+            }
             // ---- forward LUT recurrence from `warm` residues before the chunk (first chunk: the true chain)
             {
                 const int ts = (k == 0) ? 0 : max(0, cs - warm);
@@ -227,6 +272,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 const double2 le0 = sm.le[ext[ts] & 31];
                 double a0 = ks.li0 + le0.x, a1 = ks.li1 + le0.y;
                 double e_a0 = 0.0, m_a0 = a0;
+#pragma unroll 8
                 for (int t = ts + 1; t < ce; t++) {
                     if (t == cs) e_a0 = a0;
                     const double2 le = sm.le[ext[t] & 31];
@@ -255,6 +301,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 int pcen = -1;
                 int cur = 0, pre = 0, insum = 0, inmax = 0;
                 bool all = true;
+#pragma unroll 8
                 for (int t = t_start; t <= t_last; t++) {
                     const uint32_t e0 = (t < n) ? ext[t] : (uint32_t)kPad;
                     const uint32_t e1 = (t - off1 >= t_start) ? ext[t - off1] : (uint32_t)kPad;
@@ -316,6 +363,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             }
         }
         long_chunk_bar();
+        LONG_STAMP(1);
         // ================= combine 1: approximate absolute values (they only fix the binade of pass 2) =================
         if (wid == 0) {
             // Scan of the 2x2 max-plus chunk matrices: S_k = S_0 (x) M_1 (x) ... (x) M_k, 32 chunks per round with the
@@ -373,8 +421,15 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
             if (lane == 0) sm.A_end = carry;
+        } else if (wid == 2 && lane < 3) {
+            double run = 0.0;
+            for (int kk = 0; kk < K; kk++) {
+                sm.q_abs[lane][kk] = run;
+                run += sm.q_sum[lane][kk];
+            }
         }
         long_chunk_bar();
+        LONG_STAMP(2);
         // ================= pass 2: the jar's own binade =================
         // Every fp64 addition of the two recurrences has one operand of the running magnitude |s| ~ 3t, so it rounds
         // to a multiple of ulp(|s|); rounding is monotone and commutes with shifts by multiples of that ulp as long as
@@ -391,6 +446,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 if (!cross) {
                     const double R = sm.Sa[0][k - 1];
                     double a0 = R, a1 = -INFINITY, b0 = -INFINITY, b1 = R;
+#pragma unroll 8
                     for (int t = cs; t < ce; t++) {
                         const double2 le = sm.le[ext[t] & 31];
                         const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
@@ -422,6 +478,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                         a0 = sm.A_ts[k];
                     }
                     double e_a0 = 0.0, e_d = 0.0;
+#pragma unroll 8
                     for (int t = ts + 1; t < ce; t++) {
                         if (t == cs) {
                             e_a0 = a0;
@@ -439,7 +496,89 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 }
             }
         }
+        if (live) {
+            // ---- the three sequential sums in their own binade (same argument, no state besides the sum itself)
+            // crossing test over every value the running sum takes in the region (for the LLR search the lagged sum
+            // starts c residues before the chunk, i.e. inside the previous chunk)
+            bool cross[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                double mn = sm.q_abs[q][k] + sm.q_min[q][k], mx = sm.q_abs[q][k] + sm.q_max[q][k];
+                if (q == 0 && k >= 1) {
+                    mn = fmin(mn, sm.q_abs[0][k - 1] + sm.q_min[0][k - 1]);
+                    mx = fmax(mx, sm.q_abs[0][k - 1] + sm.q_max[0][k - 1]);
+                }
+                const double lo = fmin(fabs(mn), fabs(mx)) * (1.0 - 1e-6), hi = fmax(fabs(mn), fabs(mx)) * (1.0 + 1e-6);
+                cross[q] = k == 0 || !(mn > 0.0 || mx < 0.0) || !(lo >= 1.0) ||
+                           (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20);
+                sm.cross_q[q][k] = cross[q] ? 1 : 0;
+            }
+            if (k == 0) {
+                // first chunk: the true chains from residue 0 (hss2 :1206-1257, mean() :1584, hmm0's emission sum)
+                double ps = 0, psl = 0, best = 0, mid = 0;
+                int stop = -2;
+                double s0 = 0, shy = 0;
+#pragma unroll 8
+                for (int t = 0; t < ce; t++) {
+                    const uint32_t e = ext[t];
+                    ps = ps + sm.llr[e & 31];
+                    if (t >= c) psl = psl + sm.llr[ext[t - c] & 31];
+                    if (t >= c - 1) {
+                        const double d = ps - psl;
+                        if (t == c - 1 || d > best) {
+                            best = d;
+                            stop = t;
+                        }
+                    }
+                    if (t == ce - c - 1) mid = ps;
+                    s0 = (t == 0) ? sm.le[e & 31].x : s0 + sm.le[e & 31].x;
+                    shy = shy + sm.hyd[e & 63];
+                }
+                sm.q_inc[0][0] = ps, sm.q_mid[0] = mid, sm.q_best[0] = best, sm.q_stop[0] = stop;
+                sm.q_inc[1][0] = s0;
+                sm.q_inc[2][0] = shy;
+            } else {
+                if (!cross[0]) {
+                    double lagsum = 0;
+                    for (int t = cs - c; t < cs; t++) lagsum += sm.llr[ext[t] & 31];
+                    double lag = sm.q_abs[0][k] - lagsum;  // approximate psum before residue cs-c: fixes the frame
+                    double lead = lag;
+                    for (int t = cs - c; t < cs; t++) lead = lead + sm.llr[ext[t] & 31];
+                    const double lead0 = lead;
+                    double best = -INFINITY, mid = lead;
+                    int stop = -1;
+#pragma unroll 8
+                    for (int t = cs; t < ce; t++) {
+                        lead = lead + sm.llr[ext[t] & 31];
+                        lag = lag + sm.llr[ext[t - c] & 31];
+                        const double d = lead - lag;  // exact, and the jar's number
+                        if (d > best) {
+                            best = d;
+                            stop = t;
+                        }
+                        if (t == ce - c - 1) mid = lead;
+                    }
+                    sm.q_inc[0][k] = lead - lead0;
+                    sm.q_mid[k] = mid - lead0;
+                    sm.q_best[k] = best;
+                    sm.q_stop[k] = stop;
+                }
+                if (!cross[1]) {
+                    const double x0 = sm.q_abs[1][k];
+                    double x = x0;
+                    for (int t = cs; t < ce; t++) x = x + sm.le[ext[t] & 31].x;
+                    sm.q_inc[1][k] = x - x0;
+                }
+                if (!cross[2]) {
+                    const double x0 = sm.q_abs[2][k];
+                    double x = x0;
+                    for (int t = cs; t < ce; t++) x = x + sm.hyd[ext[t] & 63];
+                    sm.q_inc[2][k] = x - x0;
+                }
+            }
+        }
         long_chunk_bar();
+        LONG_STAMP(3);
         // ================= combine 2: exact, in chunk order =================
         if (wid == 0 && lane == 0) {
             double S0 = sm.M[0][0], S1 = sm.M[1][0];
@@ -447,6 +586,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             for (int kk = 1; kk < K; kk++) {
                 const int s = kk * C, e = min(n, s + C);
                 if (sm.cross_v[kk]) {
+#pragma unroll 8
                     for (int t = s; t < e; t++) {
                         const double2 le = sm.le[ext[t] & 31];
                         const double v00 = ks.lt00 + S0, v10 = ks.lt10 + S1, v01 = ks.lt01 + S0, v11 = ks.lt11 + S1;
@@ -500,6 +640,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     A1 = A0 + dex;
                 } else {
                     const int s = kk * C, e = min(n, s + C);
+#pragma unroll 8
                     for (int t = s; t < e; t++) {
                         const double2 le = sm.le[ext[t] & 31];
                         const double f0 = lse_lut2<false>(ks.lt00 + A0, ks.lt10 + A1, lut_addr) + le.x;
@@ -513,6 +654,76 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             }
             sm.fwd_redone = nfb;
             sm.lmarg = lse_lut2<false>(A0 + ks.lf0, A1 + ks.lf1, lut_addr);
+        } else if (wid == 3 && lane == 0) {
+            // LLR window search: chunk maxima in order (first strict maximum), crossing chunks redone from exact values
+            double P = sm.q_inc[0][0], Pl = sm.q_mid[0];
+            double best = sm.q_best[0];
+            int stop = sm.q_stop[0];
+            for (int kk = 1; kk < K; kk++) {
+                const int s = kk * C, e = min(n, s + C);
+                double cand, Pl_next = P;
+                int cstop;
+                if (!sm.cross_q[0][kk]) {
+                    cand = sm.q_best[kk];
+                    cstop = sm.q_stop[kk];
+                    Pl_next = P + sm.q_mid[kk];
+                    P = P + sm.q_inc[0][kk];
+                } else {
+                    double lead = P, lag = Pl;
+                    cand = -INFINITY;
+                    cstop = -1;
+#pragma unroll 8
+                    for (int t = s; t < e; t++) {
+                        lead = lead + sm.llr[ext[t] & 31];
+                        lag = lag + sm.llr[ext[t - c] & 31];
+                        const double d = lead - lag;
+                        if (d > cand) {
+                            cand = d;
+                            cstop = t;
+                        }
+                        if (t == e - c - 1) Pl_next = lead;
+                    }
+                    P = lead;
+                }
+                if (cand > best) {
+                    best = cand;
+                    stop = cstop;
+                }
+                Pl = Pl_next;
+            }
+            sm.llr_best = best;
+            sm.llr_stop = stop;
+        } else if (wid == 4 && lane < 2) {
+            // hmm0's emission sum (lane 0) and the hydropathy sum (lane 1)
+            const int q = 1 + lane;
+            double x = sm.q_inc[q][0];
+            for (int kk = 1; kk < K; kk++) {
+                if (!sm.cross_q[q][kk])
+                    x = x + sm.q_inc[q][kk];
+                else {
+                    const int s = kk * C, e = min(n, s + C);
+                    if (q == 1)
+                        for (int t = s; t < e; t++) x = x + sm.le[ext[t] & 31].x;
+                    else
+                        for (int t = s; t < e; t++) x = x + sm.hyd[ext[t] & 63];
+                }
+            }
+            if (q == 1)
+                sm.sum0 = x;
+            else
+                sm.sh = x;
+        } else if (wid == 5 && lane == 0) {
+            int best = sm.m_best[0], stop = sm.m_stop[0], cq = sm.c_sum[0];
+            for (int kk = 1; kk < K; kk++) {
+                if (sm.m_best[kk] > best) {
+                    best = sm.m_best[kk];
+                    stop = sm.m_stop[kk];
+                }
+                cq += sm.c_sum[kk];
+            }
+            sm.mw_best = best;
+            sm.mw_stop = stop;
+            sm.csum = cq;
         } else if (wid == 2 && lane == 0) {
         // FoldIndex runs (:5010-5059) and PAPA centre (:4941-4948) merged in chunk order
         int open = 0, num = 0, mx = 0;
@@ -550,6 +761,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
         sm.pVfi = vfib;
         }
         long_chunk_bar();
+        LONG_STAMP(4);
         // ---- traceback of every chunk in parallel (:3110-3113) + run statistics for longestrun (:1787-1804)
         if (live) {
             int v = sm.endstate[k];
@@ -557,6 +769,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             int cur = 0, suf = 0, inmax = 0;
             bool closed = false;
             uint32_t word = 0;
+#pragma unroll 8
             for (int t = ce - 1; t >= cs; t--) {
                 word |= (uint32_t)v << (t & 31);
                 if (v)
@@ -580,57 +793,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             sm.v_suf[k] = closed ? suf : cur;
             sm.v_max[k] = inmax;
         }
-    } else if (lane == 0) {
-        if (wid == kLongChunkWarps) {
-            // ---- LLR window search, hss2 :1206-1257 with min == max == c, sequential psum[] in reference order
-            double ps = 0, psl = 0, best = 0;
-            int stop = -2;
-#pragma unroll 4
-            for (int t = 0; t < n; t++) {
-                ps = ps + sm.llr[ext[t] & 31];
-                if (t >= c) psl = psl + sm.llr[ext[t - c] & 31];
-                if (t >= c - 1) {
-                    const double d = ps - psl;
-                    if (t == c - 1 || d > best) {
-                        best = d;
-                        stop = t;
-                    }
-                }
-            }
-            sm.llr_best = best;
-            sm.llr_stop = stop;
-        } else if (wid == kLongChunkWarps + 1) {
-            // ---- hmm0's log-emission sum (= its Viterbi and marginal log-probability), mean hydropathy and charge
-            double sum0 = sm.le[ext[0] & 31].x, sh = sm.hyd[ext[0] & 63];
-            int cs_ = (int)(int8_t)ext[0] >> 6;
-            sh = 0.0 + sh;
-#pragma unroll 4
-            for (int t = 1; t < n; t++) {
-                const uint32_t e = ext[t];
-                sum0 = sum0 + sm.le[e & 31].x;
-                sh = sh + sm.hyd[e & 63];
-                cs_ += (int)(int8_t)e >> 6;
-            }
-            sm.sum0 = sum0;
-            sm.sh = sh;
-            sm.csum = cs_;
-        } else if (wid == kLongChunkWarps + 2) {
-            // ---- Q/N window :764-771 (n >= mw here): first strict maximum of the count in [t-mw+1, t]
-            int qn = 0, best = 0, stop = -1;
-#pragma unroll 4
-            for (int t = 0; t < n; t++) {
-                qn += (int)((ks.qn_mask >> (ext[t] & 31)) & 1u);
-                if (t >= mw) qn -= (int)((ks.qn_mask >> (ext[t - mw] & 31)) & 1u);
-                if (t >= mw - 1 && (t == mw - 1 || qn > best)) {
-                    best = qn;
-                    stop = t;
-                }
-            }
-            sm.mw_best = best;
-            sm.mw_stop = stop;
-        }
     }
     __syncthreads();
+    LONG_STAMP(6);
 
     if (tid != 0) return;
     if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
@@ -694,6 +859,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     r->prd_end = -2;
     r->core_score = nan("");
     r->prd_score = 0.0;
+    LONG_STAMP(7);
     if (mx < c) return;
     // ---- CORE search on the masked sequence (:816-833), PrD expansion and PRDscore (:851-873), in reference order;
     // masked stretches are applied as exact binade jumps when the masking constant is a negative integer.
@@ -702,8 +868,16 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     double ps = 0.0, lag = 0.0, best = -INFINITY, runsum = 0.0, prd_sc = 0.0;
     int bstop = -1, run = 0, last = 0, run_start = 0, prd_s = -1, prd_e = -2;
     bool hit = false;
-    const int nwords = (n + 31) >> 5;
+    const int nwords = (n + 31) >> 5, wpc = C >> 5;
     for (int j = 0; j < nwords; j++) {
+        if (j % wpc == 0) {
+            // chunks without a Viterbi-1 residue are one masked stretch: skip their words
+            const int kk = j / wpc;
+            if (!sm.v_all[kk] && sm.v_pre[kk] == 0 && sm.v_suf[kk] == 0 && sm.v_max[kk] == 0) {
+                j += wpc - 1;
+                continue;
+            }
+        }
         uint32_t bits = vit[j];
         while (bits) {
             const int i = __ffs((int)bits) - 1;
@@ -748,6 +922,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
         prd_e = last - 1;
         prd_sc = runsum;
     }
+    LONG_STAMP(8);
     if (best > big_neg / 2) {
         r->core_start = bstop - c + 1;
         r->core_end = bstop;

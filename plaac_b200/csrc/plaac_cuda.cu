@@ -282,8 +282,8 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     int rc = ensure(ctx, s.errflag, sizeof(int));
     if (rc) return rc;
     CU(ctx, cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream));
-    if ((rc = ensure(ctx, s.lg_cnt, 32))) return rc;
-    CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 32, s.stream));
+    if ((rc = ensure(ctx, s.lg_cnt, 32 + 16 * 8))) return rc;
+    CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 32 + 16 * 8, s.stream));
     return PLAAC_OK;
 }
 
@@ -336,7 +336,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         const int64_t cap = ntotal / long_min + 1;
         if ((rc = ensure(ctx, s.lg_list, sizeof(int32_t) * (size_t)cap))) return rc;
         if ((rc = ensure(ctx, s.lg_off, sizeof(int64_t) * (size_t)cap))) return rc;
-        if ((rc = ensure(ctx, s.lg_cnt, 32))) return rc;  // [0] count, [1] scratch cursor, [2] redone chunks (cumulative)
+        if ((rc = ensure(ctx, s.lg_cnt, 32 + 16 * 8))) return rc;  // [0] count, [1] scratch cursor, [2] redone chunks (cumulative)
         CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 16, st));
         k_long_select<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, long_min, (int32_t*)s.lg_list.p,
                                                                       (int64_t*)s.lg_off.p, (unsigned long long*)s.lg_cnt.p);
@@ -453,6 +453,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             la.vit = (uint32_t*)s.lg_vit.p;
             la.errflag = (int*)s.errflag.p;
             la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
+            la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
             la.warm = std::max(1, std::abs(ctx->long_warm));
             la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
             k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), st>>>(la);
@@ -704,6 +705,14 @@ int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
         if (ctx->slot[i].lg_cnt.p && cudaSetDevice(ctx->device) == cudaSuccess &&
             cudaMemcpy(&v, (char*)ctx->slot[i].lg_cnt.p + 16, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess)
             ctx->stats.long_redone_chunks += (int64_t)v;
+    }
+    if (getenv("PLAAC_LONG_CLOCKS") && ctx->slot[0].lg_cnt.p) {
+        long long ck[16];
+        if (cudaMemcpy(ck, (char*)ctx->slot[0].lg_cnt.p + 32, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            std::fprintf(stderr, "long-path clocks (cycles since kernel start):");
+            for (int i = 1; i <= 8; i++) std::fprintf(stderr, " %lld", ck[i] ? ck[i] - ck[0] : 0LL);
+            std::fprintf(stderr, "\n");
+        }
     }
     *out = ctx->stats;
     return PLAAC_OK;

@@ -263,7 +263,7 @@ def test_device_resident_api_and_stats(scorer):
     got = out.cpu().numpy().view(plaac_b200.SUMMARY_DTYPE).reshape(-1)
     assert got.tobytes() == ref.tobytes()
     st = scorer.stats()
-    assert st.kernel_launches - before in (7, 8) and st.last_score_ms > 0 and st.last_total_ms >= st.last_score_ms
+    assert st.kernel_launches - before in (7, 8, 9, 10) and st.last_score_ms > 0 and st.last_total_ms >= st.last_score_ms
 
 
 def test_throughput_kernel_against_reference_order_anchor_at_scale():
