@@ -408,8 +408,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
 
     if (d_summaries && use_v2) {
         if ((rc = ensure(ctx, s.core_list, sizeof(int32_t) * 2 * nprot))) return rc;
-        if ((rc = ensure(ctx, s.core_count, 16))) return rc;  // [0] CORE list length, [8] work-queue counter
-        CU(ctx, cudaMemsetAsync(s.core_count.p, 0, 16, st));
+        if ((rc = ensure(ctx, s.core_count, 32))) return rc;  // [0] CORE list length, [8], [16] work-queue counters of the two roles
+        CU(ctx, cudaMemsetAsync(s.core_count.p, 0, 32, st));
     }
     CU(ctx, cudaEventRecord(s.ev_b, st));
     if (d_summaries && use_v2) {

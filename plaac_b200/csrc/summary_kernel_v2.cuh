@@ -82,9 +82,11 @@ __device__ __forceinline__ double lse_lut2(double a, double b, uint32_t lut_addr
     const double x = 100.0 * c;
     if (ALWAYS_IN) {
         // plaac_create proved |a - b| < 40 for every reachable argument pair of the recurrence
-        const int dex = __double2int_rd(x);
-        const double2 l = lds_v2f64(lut_addr + (uint32_t)dex * 16u);
-        const double f1 = x - u2d((uint32_t)dex);
+        // floor on the FP64 pipe: x + 2^52 rounded DOWN is 2^52 + floor(x) exactly (0 <= x < 2^51), its low word is
+        // the table index and subtracting 2^52 again gives floor(x) as a double -- no F2I, no separate int -> double
+        const double y = __dadd_rd(x, 4503599627370496.0);
+        const double2 l = lds_v2f64(lut_addr + (uint32_t)__double2loint(y) * 16u);
+        const double f1 = x - (y - 4503599627370496.0);
         const double f0 = 1.0 - f1;
         return hi + (f1 * l.y + f0 * l.x);
     }
@@ -607,17 +609,29 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
     // Persistent warps: work item = (bucket, role), handed out by one global counter in bucket order (longest
     // buckets first, roles alternating), so every SM keeps all its warps busy with a balanced A/B mix until the
     // queue is empty.  The first round is assigned statically to save one atomic round trip.
-    const int64_t nitems = 2 * g.bv.nbuckets;
-    int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
-    const int64_t first_dynamic = (int64_t)gridDim.x * (blockDim.x >> 5);
-    while (item < nitems) {
-        for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
-        if (item & 1)
-            role_b(g, sbase, ring, lane, item >> 1);
-        else
-            role_a(g, sbase, ring, lane, item >> 1);
+    // A warp keeps ONE role while that role has buckets left (odd warps: role B), so the two warps a scheduler
+    // partition alternates between mostly run the same loop and the instruction caches hold one role per partition
+    // pair; each role has its own bucket counter and a warp whose role has run dry steals from the other one.
+    const int64_t nb = g.bv.nbuckets;
+    int role = wid & 1;
+    const int64_t per_role = (int64_t)(blockDim.x >> 6);
+    int64_t item = (int64_t)blockIdx.x * per_role + (wid >> 1);
+    const int64_t first_dynamic = (int64_t)gridDim.x * per_role;
+    int switched = 0;
+    while (true) {
+        if (item >= nb) {
+            if (switched) break;
+            switched = 1;
+            role ^= 1;
+        } else {
+            for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
+            if (role)
+                role_b(g, sbase, ring, lane, item);
+            else
+                role_a(g, sbase, ring, lane, item);
+        }
         unsigned long long nx = 0;
-        if (lane == 0) nx = atomicAdd(g.work_counter, 1ull);
+        if (lane == 0) nx = atomicAdd(g.work_counter + role, 1ull);
         item = first_dynamic + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
     }
 }
