@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-per-residue", action="store_true", help="skip the config-2 (per-residue mode) side measurement")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the config-5 (long sequences) and ranking side measurements")
     return ap.parse_args()
 
 
@@ -302,10 +304,13 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one
+    # `ncu --set full` capture of this command (profiles/traffic.json names the capture and its size); scaled by
+    # residues if this run's shard differs from the captured one.
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get("dram_bytes_per_residue") * ntotal if tr.get("dram_bytes_per_residue") else None
+        traffic = float(tr["dram_bytes"]) * ntotal / float(tr["residues"])
     except Exception:
         pass
     roofline = {
@@ -360,6 +365,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_per_residue:
         per_res = measure_per_residue(L, scorer, dev, hbm_peak)
 
+    # ---- config 5 (long sequences) and on-device ranking side measurements (rank 0, N=1 only) -------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = measure_extras(scorer, dev, summaries, nprot)
+
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -387,6 +397,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "residues_per_gpu": ntotal, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "per_residue_mode": per_res,
+            "extras": extras,
             "timing": "CUDA events on the library stream around K steps, max over ranks; wall %.3f s" % wall,
         }
         print(json.dumps(line), flush=True)
@@ -438,6 +449,54 @@ def measure_per_residue(L, scorer, dev, hbm_peak):
     out["note"] = ("device-resident, CUDA-event time of the whole per-residue pipeline inside the library; 83 algorithmic "
                    "bytes/residue (1 in + 82 out) against the measured HBM peak; the 6k set is latency-bound by the "
                    "sequential forward/backward chains of its longest proteins")
+    return out
+
+
+def measure_extras(scorer, dev, summaries, nprot):
+    """Config 5: one 35k- and one 100k-residue protein (background composition, three 150-residue Q/N-rich
+    segments) alone on the GPU, through the chunked long-sequence path and, for contrast, through the bucketed
+    kernel where one lane walks the whole protein.  Ranking: plaac_rank_device over the bench shard's records."""
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(1005)
+    bg = np.array(BG_SCER) / sum(BG_SCER)
+    prd = np.array(PRD_28) / sum(PRD_28)
+    out = {"long_sequences": {}}
+    for n in (35000, 100000):
+        s = rng.choice(22, size=n, p=bg).astype(np.uint8)
+        for frac in (0.10, 0.50, 0.86):
+            st = int(n * frac)
+            s[st:st + 150] = rng.choice(22, size=150, p=prd)
+        d_codes = torch.from_numpy(s).to(dev)
+        d_offs = torch.tensor([0, n], dtype=torch.int64, device=dev)
+        d_out = torch.zeros(160, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        res = {}
+        for tag, min_len in (("long_path_ms", 4096), ("bucketed_kernel_ms", 0)):
+            scorer.set_long_path(min_len)
+            ms = []
+            for it in range(6):
+                scorer.score_device(d_codes.data_ptr(), d_offs.data_ptr(), 1, n, d_out.data_ptr(), sync=True)
+                if it:
+                    ms.append(scorer.stats().last_total_ms)
+            res[tag] = sum(ms) / len(ms)
+        scorer.set_long_path(4096)
+        res["residues_per_s_long_path"] = n / (res["long_path_ms"] * 1e-3)
+        out["long_sequences"]["n%d" % n] = res
+    out["long_sequences"]["note"] = ("whole device pipeline of one call (CUDA events inside the library), a single "
+                                     "protein on the GPU; both paths give the same 160-byte record bit for bit")
+    order = torch.empty(nprot, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ts = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        ncore = scorer.rank_device(summaries.data_ptr(), nprot, order.data_ptr())
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    out["ranking"] = {"records": nprot, "with_core": ncore, "ms": min(ts) * 1e3,
+                      "note": "plaac_rank_device: COREscore desc, LLR desc, no-CORE rows last (web/lib/server.rb:222-229); "
+                              "wall clock around the call (it ends with a stream synchronise)"}
     return out
 
 
