@@ -1,3 +1,1 @@
-python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
-for i in 1 2; do python bench.py --steps 5 --warmup 3 --proteins-per-gpu 4000000 --no-cpu-baseline --no-e2e --no-extras --no-per-residue | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value %.4g ms/step %.2f kernel_ms %.2f frac %.3f share %.3f'%(d['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['roofline']['frac'],d['roofline']['kernel_share_of_step']))"; done
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_score_summary_v2 -c 1 python bench.py --steps 1 --warmup 1 --proteins-per-gpu 4000000 --no-cpu-baseline --no-e2e --no-extras --no-per-residue 2>&1 | grep -i "dram__\|duration"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "long_path_other" 2>&1 | tail -30

@@ -455,18 +455,17 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
     const int w = ks.w, full = 2 * w + 1, Wfull = full * full;
     const int NX = g.nx, NS = kTrackTile + 2 * w;
     const double rfull = 1.0 / (double)full, rWfull = 1.0 / (double)Wfull;
-    // per-warp arrays: X* (NX) are reused for the second-level prefix sums
-    const size_t per_warp = (size_t)NX * (3 * 8 + 4) + (size_t)NS * (3 * 8 + 4) + (size_t)NX + 64;
+    // per-warp arrays; the pass-1 window sums S* (NS <= NX entries) overwrite the prefix sums X* in place, 32 at a
+    // time in ascending order (see step 2), which halves the footprint and lets five CTAs share an SM
+    const size_t per_warp = (size_t)NX * (3 * 8 + 4) + (size_t)NX + 64;
     unsigned char* base = trk_smem + (size_t)wid * ((per_warp + 15) & ~(size_t)15);
     double* Xh = reinterpret_cast<double*>(base);
     double* Xl = Xh + NX;
     double* Xp = Xl + NX;
-    double* Sh = Xp + NX;
-    double* Sl = Sh + NS;
-    double* Sp = Sl + NS;
-    int* Xc = reinterpret_cast<int*>(Sp + NS);
-    int* Sc = Xc + NX;
-    uint8_t* Cd = reinterpret_cast<uint8_t*>(Sc + NS);
+    int* Xc = reinterpret_cast<int*>(Xp + NX);
+    uint8_t* Cd = reinterpret_cast<uint8_t*>(Xc + NX);
+    double *Sh = Xh, *Sl = Xl, *Sp = Xp;
+    int* Sc = Xc;
 
     const int64_t warps = (int64_t)gridDim.x * kTrackWarps;
     for (int64_t p = (int64_t)blockIdx.x * kTrackWarps + wid; p < g.nprot; p += warps) {
@@ -510,18 +509,40 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
             }
             __syncwarp();
             warp_scan4_inplace(Xh, Xl, Xp, Xc, NXe, per_x, lane);
-            // 2. pass-1 window sums for centres t0-w .. t0+T+w-1 and the five pass-1 tracks
-            for (int idx = lane; idx < NSe; idx += 32) {
+            // 2. pass-1 window sums for centres t0-w .. t0+T+w-1 and the five pass-1 tracks.  S*[idx] replaces X*[idx]:
+            // a window needs X*[idx+2w] (not yet overwritten: chunks ascend) and X*[idx-1], which is the own-position
+            // value of the lane below (shuffle; lane 0 takes lane 31's value of the previous chunk).
+            double ch_ = 0, cl_ = 0, cp_ = 0;
+            int cc_ = 0;
+            for (int i0 = 0; i0 < NSe; i0 += 32) {
+                const int idx = i0 + lane;
+                const bool in_rng = idx < NSe;
                 const int pc = t0 - w + idx;
+                const int eo = min(idx, NXe - 1);
+                const double xoh = Xh[eo], xol = Xl[eo], xop = Xp[eo];
+                const int xoc = Xc[eo];
+                double lh = __shfl_up_sync(0xffffffffu, xoh, 1), ll = __shfl_up_sync(0xffffffffu, xol, 1);
+                double lp = __shfl_up_sync(0xffffffffu, xop, 1);
+                int lc = __shfl_up_sync(0xffffffffu, xoc, 1);
+                if (lane == 0) {
+                    lh = ch_;
+                    ll = cl_;
+                    lp = cp_;
+                    lc = cc_;
+                }
+                ch_ = __shfl_sync(0xffffffffu, xoh, 31);
+                cl_ = __shfl_sync(0xffffffffu, xol, 31);
+                cp_ = __shfl_sync(0xffffffffu, xop, 31);
+                cc_ = __shfl_sync(0xffffffffu, xoc, 31);
                 double sh = 0, sl = 0, sp_ = 0;
                 int scv = 0;
-                if (pc >= 0 && pc < n) {
+                if (in_rng && pc >= 0 && pc < n) {
                     const int ehi = min(pc + w, n - 1) - u_lo;  // beyond the protein everything is zero
-                    const int elo = pc - w - 1 - u_lo;                   // >= -1
-                    sh = Xh[ehi] - (elo >= 0 ? Xh[elo] : 0.0);
-                    sl = Xl[ehi] - (elo >= 0 ? Xl[elo] : 0.0);
-                    sp_ = Xp[ehi] - (elo >= 0 ? Xp[elo] : 0.0);
-                    scv = Xc[ehi] - (elo >= 0 ? Xc[elo] : 0);
+                    const int elo = pc - w - 1 - u_lo;          // == idx - 1 >= -1
+                    sh = Xh[ehi] - (elo >= 0 ? lh : 0.0);
+                    sl = Xl[ehi] - (elo >= 0 ? ll : 0.0);
+                    sp_ = Xp[ehi] - (elo >= 0 ? lp : 0.0);
+                    scv = Xc[ehi] - (elo >= 0 ? lc : 0);
                     if (pc >= t0 && pc < t0 + kTrackTile) {
                         // one reciprocal per residue instead of four divisions (1 ulp, far inside the 1e-9 bar);
                         // interior windows have the full tap count and use the precomputed reciprocal
@@ -542,10 +563,13 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
                         }
                     }
                 }
-                Sh[idx] = sh;
-                Sl[idx] = sl;
-                Sp[idx] = sp_;
-                Sc[idx] = abs(scv);
+                __syncwarp();  // every lane of the chunk has read its X* values
+                if (in_rng) {
+                    Sh[idx] = sh;
+                    Sl[idx] = sl;
+                    Sp[idx] = sp_;
+                    Sc[idx] = abs(scv);
+                }
             }
             __syncwarp();
             warp_scan4_inplace(Sh, Sl, Sp, Sc, NSe, per_s, lane);
@@ -596,7 +620,7 @@ inline ResidueV2Plan residue_v2_plan(const KScalars& ks)
     const int ns = kTrackTile + 2 * ks.w;
     P.per_x = ((P.nx + 31) / 32) | 1;
     P.per_s = ((ns + 31) / 32) | 1;
-    const size_t per_warp = ((size_t)P.nx * 28 + (size_t)ns * 28 + (size_t)P.nx + 64 + 15) & ~(size_t)15;
+    const size_t per_warp = ((size_t)P.nx * 28 + (size_t)P.nx + 64 + 15) & ~(size_t)15;
     P.trk_smem = per_warp * kTrackWarps;
     P.ok = P.trk_smem <= 200 * 1024 && P.fwd_smem <= 227 * 1024;
     return P;

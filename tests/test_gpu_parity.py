@@ -349,3 +349,31 @@ def test_per_residue_long_and_other_params():
     sc.close()
     ref = orc.residue_batch(orc.make_params(**kw), codes, offs)
     _check_residue(got, ref, "long per-residue")
+
+
+@pytest.mark.parametrize("kw", [dict(core_len=100, ww1=21, ww2=21), dict(core_len=7, ww1=5, ww2=5),
+                                dict(core_len=30, ww1=40, ww2=40, adjust_prolines=False),
+                                dict(alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS), dict(core_len=250, ww1=61, ww2=61)])
+def test_long_path_other_parameters(kw):
+    """The chunked long-sequence path with other window / core sizes and a blended background: chunk geometry
+    (a chunk holds a whole CORE / MW window), halo widths and the binade-frame passes all depend on them."""
+    rng = np.random.default_rng(123)
+    bg = synth.BG_SCER / synth.BG_SCER.sum()
+    prd = synth.PRD_28 / synth.PRD_28.sum()
+    seqs = []
+    for n in (4096, 5001, 7777, 12345, 30011):
+        s = rng.choice(22, size=n, p=bg).astype(np.uint8)
+        for frac in (0.05, 0.4, 0.93):
+            st = int(n * frac)
+            s[st:st + 260] = rng.choice(22, size=min(260, n - st), p=prd)
+        seqs.append(s)
+    c2, o2 = synth.proteome(300, seed=6)
+    seqs += [c2[o2[i]:o2[i + 1]] for i in range(300)]
+    codes, offs = plaac_b200.pack(seqs)
+    sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    got = sc.score(codes, offs)
+    assert sc.stats().long_proteins == 5
+    sc.close()
+    P = orc.make_params(**kw)
+    ref = orc.score_batch(P, codes, offs, nthreads=NT)
+    _check(got, ref, "long path " + str(kw), P, codes, offs, max_ties=3)
