@@ -126,6 +126,31 @@ def edge_fasta():
     return "\n".join(lines) + "\n"
 
 
+def long_fasta():
+    """Two proteins above the threshold of the chunked long-sequence path (4096): background composition with
+    Q/N-rich segments early, in the middle and reaching the last residue."""
+    rng = np.random.default_rng(20261018)
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    bg = np.array([0.0550, 0.0126, 0.0586, 0.0655, 0.0441, 0.0498, 0.0217, 0.0655, 0.0735, 0.0950, 0.0207, 0.0615, 0.0438,
+                   0.0396, 0.0444, 0.0899, 0.0592, 0.0556, 0.0104, 0.0337])
+    bg /= bg.sum()
+    prd = np.array([0.04865, 0.00219, 0.01638, 0.00783, 0.02537, 0.07603, 0.0181, 0.02018, 0.01641, 0.02639, 0.02975,
+                    0.25885, 0.05126, 0.15178, 0.025, 0.10988, 0.03841, 0.01972, 0.00157, 0.05624])
+    prd /= prd.sum()
+
+    def rnd(n, p):
+        return "".join(rng.choice(list(aa), n, p=p))
+
+    recs = [("long4500", rnd(300, bg) + rnd(140, prd) + rnd(2000, bg) + rnd(90, prd) + rnd(1970, bg)),
+            ("long9000", rnd(4000, bg) + rnd(200, prd) + rnd(4600, bg) + rnd(200, prd))]
+    lines = []
+    for nm, sq in recs:
+        lines.append(">" + nm)
+        for j in range(0, len(sq), 60):
+            lines.append(sq[j:j + 60])
+    return "\n".join(lines) + "\n"
+
+
 def main():
     out = {"generator": "tests/golden/make_jar_vectors.py (reference bytecode web/bin/plaac.jar under minijvm.py)",
            "jar_manifest": "Created-By: 1.7.0_55"}
@@ -153,6 +178,17 @@ def main():
     out["edge_residue_args"] = ["-a", "0.5", "-c", "40", "-w", "21", "-W", "21"]
     out["edge_residue"] = [p for p in parse_residue(ev)]
     print("edge per-residue:", len(out["edge_residue"]), "proteins,", steps, "bytecodes")
+    os.unlink(path)
+    txt = long_fasta()
+    with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+        f.write(txt)
+        path = f.name
+    ev, steps = run_main(["-i", path])
+    rows, params = parse_summary(ev)
+    out["long_fasta"] = txt
+    out["long_summary"] = rows
+    out["long_params"] = params
+    print("long summary:", len(rows), "rows,", steps, "bytecodes")
     os.unlink(path)
     import gzip
 

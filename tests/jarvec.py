@@ -85,6 +85,8 @@ def scenario(which):
         text, kw, rows = J["prions_fasta"], {}, J["prions_summary"]
     elif which == "edge_summary":
         text, kw, rows = J["edge_fasta"], dict(alpha=0.5), J["edge_summary"]
+    elif which == "long_summary":
+        text, kw, rows = J["long_fasta"], {}, J["long_summary"]
     elif which == "prions_residue":
         text, kw, rows = J["prions_fasta"], {}, J["prions_residue"]
     elif which == "edge_residue":

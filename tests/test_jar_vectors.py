@@ -11,7 +11,7 @@ from oracle import orc
 from tests import jarvec, parity
 
 
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary"])
 def test_oracle_summary_is_bit_identical_to_the_jar(which):
     enc, kw, rows = jarvec.scenario(which)
     codes, offs = orc.pack([c for _, c in enc])
@@ -77,14 +77,22 @@ def test_parameter_block_matches_the_jar():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary", "long_summary_bucketed"])
 def test_cuda_summary_against_the_jar(which):
+    """long_summary: 4 500 and 9 000 residues, scored by the chunked long-sequence path (scan of max-plus chunk
+    matrices, warm-started forward chunks, binade-frame second pass) and, `_bucketed`, by the bucketed kernel:
+    both against the numbers the jar's own bytecode produced."""
     import plaac_b200
 
-    enc, kw, rows = jarvec.scenario(which)
+    bucketed = which.endswith("_bucketed")
+    enc, kw, rows = jarvec.scenario(which.replace("_bucketed", ""))
     codes, offs = plaac_b200.pack([c for _, c in enc])
     sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    if bucketed:
+        sc.set_long_path(0)
     got = sc.score(codes, offs)
+    if which.startswith("long"):
+        assert sc.stats().long_proteins == (0 if bucketed else 2)
     sc.close()
     exact = ("LLR", "NLLR", "COREscore", "PRDscore", "HMMall", "HMMvit", "FImeanhydro", "FImeancharge", "FImeancombo")
     nties = 0
