@@ -221,9 +221,15 @@ int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
  * each, cut into <= 384 chunks (csrc/long_kernel.cuh): a warp-shuffle scan of 2x2 max-plus chunk matrices and
  * warm-started LUT forward chunks fix the absolute magnitudes, then both recurrences are re-run chunk-parallel in the
  * jar's own binade, where every rounding commutes with the chunk's shift, so the combined HMMall / HMMvit / Viterbi
- * path have the jar's bits.  min_len = 0 switches the path off (every protein on the bucketed kernel); values below
- * 1024 or below four times the longest window are raised to that.  Default 4096.  warm: forward warm-up length,
- * 0 keeps the current value (default 256); a negative value redoes every forward chunk sequentially (testing). */
+ * path have the jar's bits.  The path is a latency device (a CTA per protein is less efficient per residue than the
+ * bucketed kernel).  min_len > 0: fixed threshold (default 4096; raised to 1024 / four times the longest window if
+ * smaller) -- which path a protein takes then does not depend on its batch, so records are byte-identical however a
+ * proteome is batched or sharded.  min_len = -1: automatic threshold per batch -- the smallest length, at least 1024
+ * residues and at least ntotal/81600 + 220 (a lane's sequential walk of the protein must be a visible part of the
+ * batch's time), that leaves no more long proteins than the GPU has SMs; best latency for small proteomes.
+ * min_len = 0: path off.  warm: forward warm-up length, 0 keeps the current value (default 256); a negative value redoes
+ * every forward chunk sequentially (testing).  Integer and reference-order columns are bit-identical on both paths; the
+ * FoldIndex/PAPA window columns (running sums, restarted per chunk on the long path) agree to rounding (~1e-15). */
 int plaac_set_long_path(plaac_ctx *ctx, int64_t min_len, int warm);
 
 /* Kernel selection for testing: 0 = automatic (default), 1 = the reference-order anchor kernel (one fused

@@ -108,6 +108,34 @@ __device__ __forceinline__ void long_chunk_bar()
     asm volatile("bar.sync 1, %0;" ::"n"(kLongChunkWarps * 32) : "memory");
 }
 
+// Automatic threshold: length bins from 1024 up (256-residue steps to 16384, then powers of two); the host picks the
+// smallest bin edge that leaves at most one wave of long proteins (plaac_cuda.cu: choose_long_threshold).
+constexpr int kLongBins = 78;
+__host__ __device__ __forceinline__ int long_bin(int64_t len)
+{
+    if (len < 1024) return -1;
+    if (len < 16384) return (int)((len - 1024) >> 8);
+    int lg = 14;
+    while (lg < 62 && (len >> (lg + 1)) != 0) lg++;
+    const int b = 60 + (lg - 14);
+    return b < kLongBins ? b : kLongBins - 1;
+}
+inline int64_t long_edge(int b) { return b < 60 ? 1024 + 256 * (int64_t)b : (int64_t)1 << (14 + b - 60); }
+
+// per bin: [b] proteins, [kLongBins + b] scratch bytes, [2 * kLongBins + b] longest member
+__global__ void __launch_bounds__(256)
+k_long_levels(const int64_t* __restrict__ offsets, int64_t nprot, unsigned long long* __restrict__ bins)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nprot) return;
+    const int64_t len = offsets[i + 1] - offsets[i];
+    const int b = long_bin(len);
+    if (b < 0) return;
+    atomicAdd(&bins[b], 1ull);
+    atomicAdd(&bins[kLongBins + b], (unsigned long long)((len + kLongPadTail + 127) & ~(int64_t)127));
+    atomicMax(&bins[2 * kLongBins + b], (unsigned long long)len);
+}
+
 struct MP2 {  // 2x2 max-plus matrix
     double m00, m01, m10, m11;
 };

@@ -43,7 +43,8 @@ struct Slot {
     DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
     DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
     DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_tb, lg_vit;                             // long-sequence path
-    unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues
+    unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues, or 3 x kLongBins bins
+    DevBuf lg_bins;
     cudaStream_t aux1 = nullptr, aux2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
     int64_t* h_total = nullptr;        // pinned
@@ -71,7 +72,9 @@ struct plaac_ctx {
     int sm_count = 0;
     plaac_stats stats;
     int64_t chunk_res = (int64_t)128 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
-    int64_t long_min = 4096;   // proteins at least this long take the long-sequence path (0 = off)
+    // long-sequence path: > 0 fixed threshold (default: which path a protein takes does not depend on its batch, so
+    // records are byte-identical however a proteome is batched or sharded), -1 automatic threshold per batch, 0 off
+    int64_t long_min = 4096;
     int long_warm = 256;       // forward warm-up of that path
     std::string err;
     int last_slot = 0;
@@ -269,7 +272,7 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(ctx, cudaMallocHost((void**)&s.h_total, sizeof(int64_t)));
     CU(ctx, cudaMallocHost((void**)&s.h_err, sizeof(int)));
-    CU(ctx, cudaMallocHost((void**)&s.h_long, 2 * sizeof(unsigned long long)));
+    CU(ctx, cudaMallocHost((void**)&s.h_long, 3 * kLongBins * sizeof(unsigned long long)));
     CU(ctx, cudaEventCreate(&s.ev_a));
     CU(ctx, cudaEventCreate(&s.ev_b));
     CU(ctx, cudaEventCreate(&s.ev_c));
@@ -294,7 +297,7 @@ void slot_free(Slot& s)
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
-                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_tb, &s.lg_vit})
+                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_tb, &s.lg_vit, &s.lg_bins})
         release(*b);
     if (s.h_long) cudaFreeHost(s.h_long);
     if (s.h_total) cudaFreeHost(s.h_total);
@@ -307,7 +310,8 @@ void slot_free(Slot& s)
     s = Slot();
 }
 
-// Threshold of the long-sequence path for this ctx (0 = off): it needs every window to be far shorter than a protein.
+// Fixed threshold of the long-sequence path for this ctx (0 = none): it needs every window to be far shorter than a
+// protein.
 int64_t effective_long_min(const plaac_ctx* ctx)
 {
     if (ctx->long_min <= 0 || ctx->v2_nwr <= 0) return 0;
@@ -315,11 +319,48 @@ int64_t effective_long_min(const plaac_ctx* ctx)
     return std::max<int64_t>(std::max<int64_t>(ctx->long_min, 1024), 4 * maxoff);
 }
 
+// Automatic threshold (long_min == -1).  The long-sequence path is a LATENCY device: one CTA per protein is far less
+// efficient per residue than the bucketed kernel, so a protein goes there only if its sequential walk (~170 ns per
+// residue in a lane of the bucketed kernel) would be a visible part of the batch's time, and only as many proteins
+// as fit one wave of CTAs.  bins: k_long_levels' layout (or the host walk's).  Returns the threshold (0 = none) and
+// the exact count / scratch size / longest remaining protein for it.
+struct LongChoice {
+    int64_t thr = 0, nlong = 0, scratch = 0;
+    int64_t lmax_rest = 0, n_hist_rest = 0;  // among proteins >= 1024 that stay on the bucketed path
+};
+LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long* bins, int64_t ntotal)
+{
+    LongChoice c;
+    const int64_t maxoff = std::max<int64_t>(std::max(4 * ctx->ks.w + 2, ctx->ks.core_len), ctx->ks.mw_window);
+    const int64_t lb = std::max<int64_t>(std::max<int64_t>(1024, 4 * maxoff), ntotal / 81600 + 220);
+    int64_t cnt = 0, scr = 0;
+    int best = -1;
+    for (int b = kLongBins - 1; b >= 0; b--) {  // suffix sums: proteins with len >= long_edge(b)
+        if (long_edge(b) < lb) break;
+        if (cnt + (int64_t)bins[b] > ctx->sm_count) break;
+        cnt += (int64_t)bins[b];
+        scr += (int64_t)bins[kLongBins + b];
+        best = b;
+    }
+    if (best >= 0 && cnt > 0 && ctx->v2_nwr > 0) {
+        c.thr = long_edge(best);
+        c.nlong = cnt;
+        c.scratch = scr;
+    }
+    for (int b = 0; b < (c.thr ? best : kLongBins); b++) {
+        if (!bins[b]) continue;
+        c.lmax_rest = std::max<int64_t>(c.lmax_rest, (int64_t)bins[2 * kLongBins + b]);
+        if (long_edge(b) >= kHistBins) c.n_hist_rest += (int64_t)bins[b];
+    }
+    return c;
+}
+
 // Enqueue the whole device pipeline for one batch on slot s.  d_offsets are absolute; off_base is
 // subtracted to index d_codes.  Contains ONE stream synchronisation (the padded stream size).
 int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_offsets, int64_t off_base,
               int64_t nprot, int64_t ntotal, plaac_summary* d_summaries, const plaac_residue_out* d_res,
-              int64_t res_base, int64_t slots_bound = -1, int64_t nlong_known = -1, int64_t long_scratch_known = -1)
+              int64_t res_base, int64_t slots_bound = -1, int64_t nlong_known = -1, int64_t long_scratch_known = -1,
+              int64_t long_thr_known = -1)
 {
     if (nprot == 0) return PLAAC_OK;
     if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins in one device batch");
@@ -328,7 +369,21 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     int rc;
     const bool use_v2 = ctx->variant == 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);
     // Long-sequence path: summary mode of the throughput kernel only.
-    const int64_t long_min = effective_long_min(ctx);
+    CU(ctx, cudaEventRecord(s.ev_a, st));
+    int64_t long_min = long_thr_known >= 0 ? long_thr_known : effective_long_min(ctx);
+    if (d_summaries && !d_res && use_v2 && ctx->long_min < 0 && long_thr_known < 0 && ntotal >= 1024) {
+        // automatic threshold with device-resident offsets: bin the lengths, let the host choose
+        if ((rc = ensure(ctx, s.lg_bins, 3 * kLongBins * sizeof(unsigned long long)))) return rc;
+        CU(ctx, cudaMemsetAsync(s.lg_bins.p, 0, 3 * kLongBins * sizeof(unsigned long long), st));
+        k_long_levels<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, (unsigned long long*)s.lg_bins.p);
+        ctx->stats.kernel_launches += 1;
+        CU(ctx, cudaMemcpyAsync(s.h_long, s.lg_bins.p, 3 * kLongBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        const LongChoice lc = choose_long_threshold(ctx, s.h_long, ntotal);
+        long_min = lc.thr;
+        nlong_known = lc.nlong;
+        long_scratch_known = lc.scratch;
+    }
     const bool use_long = d_summaries && !d_res && use_v2 && long_min > 0 && ntotal >= long_min && nlong_known != 0;
     const int64_t lm = use_long ? long_min : INT64_MAX;
     int64_t nlong = 0, long_scratch = 0;
@@ -354,7 +409,6 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     if ((rc = ensure(ctx, s.nchunks, sizeof(int32_t) * nbuckets))) return rc;
     if ((rc = ensure(ctx, s.chunk_base, sizeof(int64_t) * (nbuckets + 1)))) return rc;
 
-    CU(ctx, cudaEventRecord(s.ev_a, st));
     CU(ctx, cudaMemsetAsync(s.hist.p, 0, sizeof(int32_t) * (kHistBins + 1), st));
     const int tb = 256;
     const unsigned g_hist = (unsigned)std::min<int64_t>(ctx->sm_count, (nprot + 4095) / 4096);
@@ -412,7 +466,38 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         CU(ctx, cudaMemsetAsync(s.core_count.p, 0, 32, st));
     }
     CU(ctx, cudaEventRecord(s.ev_b, st));
+    bool long_launched = false;
     if (d_summaries && use_v2) {
+        if (use_long && nlong > 0) {
+            if ((rc = ensure(ctx, s.lg_ext, (size_t)long_scratch + 256))) return rc;
+            if ((rc = ensure(ctx, s.lg_tb, (size_t)long_scratch + 256))) return rc;
+            if ((rc = ensure(ctx, s.lg_vit, (size_t)long_scratch / 8 + 256))) return rc;
+            LongArgs la;
+            la.codes = d_codes;
+            la.offsets = d_offsets;
+            la.off_base = off_base;
+            la.list = (const int32_t*)s.lg_list.p;
+            la.scratch_off = (const int64_t*)s.lg_off.p;
+            la.ks = ctx->ks;
+            la.tabs = ctx->d_tabs;
+            la.out = d_summaries;
+            la.ext = (uint8_t*)s.lg_ext.p;
+            la.tb = (uint8_t*)s.lg_tb.p;
+            la.vit = (uint32_t*)s.lg_vit.p;
+            la.errflag = (int*)s.errflag.p;
+            la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
+            la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
+            la.warm = std::max(1, std::abs(ctx->long_warm));
+            la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
+            // on its own stream, launched first: its CTAs (one per long protein) take SMs while the persistent CTAs of
+            // the bucketed kernel start on the others and pick up the rest of the queue as SMs free up
+            CU(ctx, cudaEventRecord(s.ev_fork, st));
+            CU(ctx, cudaStreamWaitEvent(s.aux1, s.ev_fork, 0));
+            k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), s.aux1>>>(la);
+            long_launched = true;
+            ctx->stats.kernel_launches += 1;
+            ctx->stats.long_proteins += nlong;
+        }
         V2Args g;
         g.bv = bv;
         g.ks = ctx->ks;
@@ -435,30 +520,9 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
         ctx->stats.kernel_launches += 2;
         ctx->stats.score_launches += 1;
-        if (use_long && nlong > 0) {
-            if ((rc = ensure(ctx, s.lg_ext, (size_t)long_scratch + 256))) return rc;
-            if ((rc = ensure(ctx, s.lg_tb, (size_t)long_scratch + 256))) return rc;
-            if ((rc = ensure(ctx, s.lg_vit, (size_t)long_scratch / 8 + 256))) return rc;
-            LongArgs la;
-            la.codes = d_codes;
-            la.offsets = d_offsets;
-            la.off_base = off_base;
-            la.list = (const int32_t*)s.lg_list.p;
-            la.scratch_off = (const int64_t*)s.lg_off.p;
-            la.ks = ctx->ks;
-            la.tabs = ctx->d_tabs;
-            la.out = d_summaries;
-            la.ext = (uint8_t*)s.lg_ext.p;
-            la.tb = (uint8_t*)s.lg_tb.p;
-            la.vit = (uint32_t*)s.lg_vit.p;
-            la.errflag = (int*)s.errflag.p;
-            la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
-            la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
-            la.warm = std::max(1, std::abs(ctx->long_warm));
-            la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
-            k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), st>>>(la);
-            ctx->stats.kernel_launches += 1;
-            ctx->stats.long_proteins += nlong;
+        if (long_launched) {
+            CU(ctx, cudaEventRecord(s.ev_j1, s.aux1));
+            CU(ctx, cudaStreamWaitEvent(st, s.ev_j1, 0));
         }
     } else if (d_summaries) {
         const unsigned grid = (unsigned)((nbuckets + ctx->nwarps - 1) / ctx->nwarps);
@@ -680,7 +744,7 @@ int plaac_set_chunk(plaac_ctx* ctx, int64_t max_residues, int64_t max_proteins)
 int plaac_set_long_path(plaac_ctx* ctx, int64_t min_len, int warm)
 {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_long_path: NULL ctx");
-    if (min_len < 0) return fail(ctx, PLAAC_E_INVALID, "negative min_len");
+    if (min_len < -1) return fail(ctx, PLAAC_E_INVALID, "min_len must be -1 (automatic), 0 (off) or a length");
     ctx->long_min = min_len;
     if (warm != 0) ctx->long_warm = warm;
     return PLAAC_OK;
@@ -761,7 +825,10 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         int64_t end = start;
         const int64_t base = offsets[start];
         int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0;
-        const int64_t long_min = per_res ? 0 : effective_long_min(ctx);
+        int64_t long_min = per_res ? 0 : effective_long_min(ctx);
+        const bool long_auto = !per_res && ctx->long_min < 0 && ctx->v2_nwr > 0;
+        unsigned long long bins[3 * kLongBins];
+        if (long_auto) memset(bins, 0, sizeof(bins));
         while (end < nprot && end - start < max_prot) {
             const int64_t len = offsets[end + 1] - offsets[end];
             if (len < 0) {
@@ -773,7 +840,13 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
                 break;
             }
             if (end != start && offsets[end + 1] - base > max_res) break;
-            if (long_min > 0 && len >= long_min) {
+            if (long_auto && len >= 1024) {
+                // decided after the walk (choose_long_threshold)
+                const int b = long_bin(len);
+                bins[b]++;
+                bins[kLongBins + b] += (unsigned long long)((len + kLongPadTail + 127) & ~(int64_t)127);
+                bins[2 * kLongBins + b] = std::max<unsigned long long>(bins[2 * kLongBins + b], (unsigned long long)len);
+            } else if (long_min > 0 && len >= long_min) {
                 // scored by the long-sequence path; the bucketed stream sees an empty protein
                 nlp++;
                 lp_scratch += (len + kLongPadTail + 127) & ~(int64_t)127;
@@ -786,6 +859,15 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         if (rc != PLAAC_OK) break;
         const int64_t np = end - start;
         const int64_t nres = offsets[end] - base;
+        int64_t long_thr = per_res ? 0 : (long_auto ? 0 : long_min);
+        if (long_auto) {
+            const LongChoice lc = choose_long_threshold(ctx, bins, nres);
+            long_thr = lc.thr;
+            nlp = lc.nlong;
+            lp_scratch = lc.scratch;
+            lmax = std::max(lmax, lc.lmax_rest);
+            nlong += lc.n_hist_rest;
+        }
         // Upper bound of the bucketed stream (in 32-lane slots), so no host sync is needed for its size: proteins
         // are sorted by length, hence every bucket's longest member is no longer than the shortest member of the
         // bucket before it; only the first bucket and the buckets of unsorted >= 32768-residue proteins pay Lmax.
@@ -819,7 +901,7 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         CU(ctx, cudaMemcpyAsync(s.offsets.p, offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
         rc = run_batch(ctx, s, (const uint8_t*)s.codes.p, (const int64_t*)s.offsets.p, base, np, nres,
                        summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base, slots_bound,
-                       nlp, lp_scratch);
+                       nlp, lp_scratch, long_thr);
         if (rc) break;
         if (summaries)
             CU(ctx, cudaMemcpyAsync(summaries + start, s.summaries.p, sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));
