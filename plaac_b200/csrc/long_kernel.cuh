@@ -17,9 +17,11 @@
 //   the running magnitude, rounding is monotone and commutes with shifts by multiples of the ulp, hence a chunk
 //   reproduces the jar's sequential values up to an EXACT shift.  Viterbi transfer entries and forward increments are
 //   then exact multiples of the ulp and their ordered combination is the jar's number BIT FOR BIT.  The forward chunk
-//   is accepted only if it enters with exactly the bits of d the previous chunk left with (the quantised recurrence
-//   coalesces during the warm-up); chunks in which the magnitude crosses a power of two (about one per binade), and
-//   chunks that failed that test, are redone sequentially from the exact values.
+//   runs in two frames one ulp apart and the frame is accepted that enters the chunk an EVEN number of ulps from the
+//   exact a0 and with exactly the bits of d the previous chunk left with (round-half-even ties look at the parity of
+//   the sum; the quantised recurrence coalesces during the warm-up); chunks in which the magnitude crosses a power of
+//   two (about one per binade) or lies in a binade where a table constant is an exact tie, and forward chunks without
+//   an acceptable frame, are redone sequentially from the exact values.
 //   windows   (disorderreport :4866-5068) the running window sums restart 2w residues before the chunk; FoldIndex
 //             runs and the PAPA first-strict-maximum are reduced per chunk and merged in chunk order.
 //   sums      the plain sequential fp64 sums of plaac.java -- psum[] of the LLR window search (hss2 :1206-1257), hmm0's
@@ -55,6 +57,12 @@ struct LongArgs {
     unsigned long long* redone;  // statistics: forward chunks redone sequentially because d had not coalesced
     uint32_t* vit;  // Viterbi bits, one word per 32 residues
     int* errflag;
+    // Round-half-even breaks the shift argument exactly at ties (an addend whose bits below the binade's ulp are
+    // 1000...0): the rounding then depends on the parity of the sum.  For the recurrences whose addends are table
+    // constants only, the host lists the binades (bit b: values in [2^b, 2^(b+1))) in which some constant is such a
+    // tie; chunks there are redone sequentially.  [0] Viterbi (lt, le), [1] LLR psum (llr), [2] hmm0 sum (le0),
+    // [3] hydropathy sum.  The forward recurrence has data-dependent addends and handles parity explicitly.
+    unsigned long long tie_mask[4];
     int warm;       // forward warm-up length
     int force_seq_forward;  // testing: always take the sequential forward fallback
 };
@@ -66,7 +74,9 @@ struct LongShared {
     // per chunk
     double M[4][kLongMaxChunks];       // Viterbi transfer matrix: [0] 0->0, [1] 0->1, [2] 1->0, [3] 1->1
     double Sa[2][kLongMaxChunks];      // pass 1: approximate Viterbi scores at the chunk's last residue
-    double f_inc[kLongMaxChunks], f_mid[kLongMaxChunks], f_dentry[kLongMaxChunks], f_dexit[kLongMaxChunks];
+    double f_inc[kLongMaxChunks], f_mid[kLongMaxChunks], f_dexit[kLongMaxChunks];   // pass 1 (f_dexit[0]: true)
+    // pass 2, two frames of opposite parity: increment of a0 over the chunk, a0 and d at entry, d at exit
+    double g_inc[2][kLongMaxChunks], g_ea0[2][kLongMaxChunks], g_den[2][kLongMaxChunks], g_dex[2][kLongMaxChunks];
     double A_cs[kLongMaxChunks], A_ts[kLongMaxChunks], A_end;  // pass 1: forward a0 before the chunk / at its warm-up start
     double p_tb[kLongMaxChunks], p_wb[kLongMaxChunks], p_vfi[kLongMaxChunks];
     int p_cen[kLongMaxChunks];
@@ -469,7 +479,8 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             {
                 const double lo = fmin(fabs(sm.Sa[0][k - 1]), fabs(sm.Sa[1][k - 1])) - 64.0;
                 const double hi = fmax(fabs(sm.Sa[0][k]), fabs(sm.Sa[1][k])) + 64.0;
-                const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20);
+                const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20) ||
+                                   ((g.tie_mask[0] >> (((__double2hiint(lo) >> 20) & 0x7ff) - 1023)) & 1ull);
                 sm.cross_v[k] = cross ? 1 : 0;
                 if (!cross) {
                     const double R = sm.Sa[0][k - 1];
@@ -498,29 +509,49 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20);
                 sm.cross_f[k] = cross ? 1 : 0;
                 if (!cross) {
+                    // Two frames one ulp apart: the shift argument needs the frame to differ from the jar's values by
+                    // an EVEN number of ulps (round-half-even at exact ties looks at the parity of the sum, and the
+                    // interpolation term is a tie about once per 2^15 additions at these magnitudes).  The combine
+                    // step takes the frame of the right parity.
                     const int ts = max(0, cs - warm);
                     const double2 le0 = sm.le[ext[ts] & 31];
                     double a0 = ks.li0 + le0.x, a1 = ks.li1 + le0.y;
+                    double c0 = a0, c1 = a1;
                     if (ts > 0) {
-                        a1 = sm.A_ts[k] + (a1 - a0);
+                        const double u = __hiloint2double((((__double2hiint(fabs(sm.A_cs[k])) >> 20) & 0x7ff) - 52) << 20, 0);
+                        const double dd = a1 - a0;
                         a0 = sm.A_ts[k];
+                        a1 = a0 + dd;
+                        c0 = a0 + u;
+                        c1 = c0 + dd;
                     }
-                    double e_a0 = 0.0, e_d = 0.0;
-#pragma unroll 8
+                    double ea = 0.0, ed = 0.0, ec = 0.0, ee = 0.0;
+#pragma unroll 4
                     for (int t = ts + 1; t < ce; t++) {
                         if (t == cs) {
-                            e_a0 = a0;
-                            e_d = a1 - a0;
+                            ea = a0;
+                            ed = a1 - a0;
+                            ec = c0;
+                            ee = c1 - c0;
                         }
                         const double2 le = sm.le[ext[t] & 31];
                         const double f0 = lse_lut2<false>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
                         const double f1 = lse_lut2<false>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
+                        const double h0 = lse_lut2<false>(ks.lt00 + c0, ks.lt10 + c1, lut_addr) + le.x;
+                        const double h1 = lse_lut2<false>(ks.lt01 + c0, ks.lt11 + c1, lut_addr) + le.y;
                         a0 = f0;
                         a1 = f1;
+                        c0 = h0;
+                        c1 = h1;
                     }
-                    sm.f_inc[k] = a0 - e_a0;  // exact: both are multiples of the same ulp
-                    sm.f_dentry[k] = e_d;
-                    sm.f_dexit[k] = a1 - a0;
+                    sm.g_inc[0][k] = a0 - ea;  // exact: both are multiples of the same ulp
+                    sm.g_ea0[0][k] = ea;
+                    sm.g_den[0][k] = ed;
+                    sm.g_dex[0][k] = a1 - a0;
+                    sm.g_inc[1][k] = c0 - ec;
+                    sm.g_ea0[1][k] = ec;
+                    sm.g_den[1][k] = ee;
+                    sm.g_dex[1][k] = c1 - c0;
                 }
             }
         }
@@ -538,7 +569,8 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 }
                 const double lo = fmin(fabs(mn), fabs(mx)) * (1.0 - 1e-6), hi = fmax(fabs(mn), fabs(mx)) * (1.0 + 1e-6);
                 cross[q] = k == 0 || !(mn > 0.0 || mx < 0.0) || !(lo >= 1.0) ||
-                           (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20);
+                           (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20) ||
+                           ((g.tie_mask[1 + q] >> (((__double2hiint(lo) >> 20) & 0x7ff) - 1023)) & 1ull);
                 sm.cross_q[q][k] = cross[q] ? 1 : 0;
             }
             if (k == 0) {
@@ -660,11 +692,22 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             double A1 = A0 + dex;
             int nfb = 0;
             for (int kk = 1; kk < K; kk++) {
-                const bool ok = !g.force_seq_forward && !sm.cross_f[kk] &&
-                                __double_as_longlong(sm.f_dentry[kk]) == __double_as_longlong(dex);
-                if (ok) {
-                    A0 = A0 + sm.f_inc[kk];
-                    dex = sm.f_dexit[kk];
+                // a frame is the jar's trajectory iff it enters the chunk an EVEN number of ulps away from the true a0
+                // and with exactly the bits of d the previous chunk left with
+                int fr = -1;
+                if (!g.force_seq_forward && !sm.cross_f[kk]) {
+                    const double u = __hiloint2double((((__double2hiint(fabs(A0)) >> 20) & 0x7ff) - 52) << 20, 0);
+#pragma unroll
+                    for (int f = 0; f < 2; f++) {
+                        const double q = (sm.g_ea0[f][kk] - A0) / u;  // exact: a small integer
+                        if (fr < 0 && q == 2.0 * rint(0.5 * q) &&
+                            __double_as_longlong(sm.g_den[f][kk]) == __double_as_longlong(dex))
+                            fr = f;
+                    }
+                }
+                if (fr >= 0) {
+                    A0 = A0 + sm.g_inc[fr][kk];
+                    dex = sm.g_dex[fr][kk];
                     A1 = A0 + dex;
                 } else {
                     const int s = kk * C, e = min(n, s + C);

@@ -76,6 +76,7 @@ struct plaac_ctx {
     // records are byte-identical however a proteome is batched or sharded), -1 automatic threshold per batch, 0 off
     int64_t long_min = 4096;
     int long_warm = 256;       // forward warm-up of that path
+    unsigned long long long_tie[4] = {0, 0, 0, 0};  // binades with an exact rounding tie among the table constants
     std::string err;
     int last_slot = 0;
 };
@@ -310,11 +311,27 @@ void slot_free(Slot& s)
     s = Slot();
 }
 
+// Binades (bit b: running value in [2^b, 2^(b+1)), ulp u = 2^(b-52)) in which adding one of the constants is an exact
+// round-half-even tie: the constant's bits below u are exactly u/2, i.e. c * 2^(53-b) is an odd integer.  There the
+// shift argument of the long-sequence path does not hold (the rounding depends on the parity of the sum), so its
+// chunks in those binades are redone sequentially (long_kernel.cuh).
+unsigned long long tie_binades(const double* c, int n)
+{
+    unsigned long long m = 0;
+    for (int b = 0; b < 63; b++)
+        for (int i = 0; i < n; i++) {
+            if (!std::isfinite(c[i]) || c[i] == 0.0) continue;
+            const double y = std::ldexp(std::fabs(c[i]), 53 - b);
+            if (y < 9007199254740992.0 && y == std::floor(y) && std::fmod(y, 2.0) == 1.0) m |= 1ull << b;
+        }
+    return m;
+}
+
 // Fixed threshold of the long-sequence path for this ctx (0 = none): it needs every window to be far shorter than a
 // protein.
 int64_t effective_long_min(const plaac_ctx* ctx)
 {
-    if (ctx->long_min <= 0 || ctx->v2_nwr <= 0) return 0;
+    if (ctx->long_min <= 0 || ctx->v2_nwr <= 0 || ctx->variant == 1) return 0;  // the path belongs to the v2 kernel
     const int64_t maxoff = std::max<int64_t>(std::max(4 * ctx->ks.w + 2, ctx->ks.core_len), ctx->ks.mw_window);
     return std::max<int64_t>(std::max<int64_t>(ctx->long_min, 1024), 4 * maxoff);
 }
@@ -487,6 +504,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             la.errflag = (int*)s.errflag.p;
             la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
             la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
+            for (int i = 0; i < 4; i++) la.tie_mask[i] = getenv("PLAAC_LONG_TIES") ? ~0ull >> 1 : ctx->long_tie[i];
             la.warm = std::max(1, std::abs(ctx->long_warm));
             la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
             // on its own stream, launched first: its CTAs (one per long protein) take SMs while the persistent CTAs of
@@ -671,6 +689,16 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
             return bail(PLAAC_E_CUDA);
         }
     }
+    {
+        const plaac_params& P = ctx->params;
+        double vc[4 + 2 * PLAAC_NAA];
+        vc[0] = P.lt[0][0], vc[1] = P.lt[0][1], vc[2] = P.lt[1][0], vc[3] = P.lt[1][1];
+        for (int i = 0; i < PLAAC_NAA; i++) vc[4 + i] = P.le[0][i], vc[4 + PLAAC_NAA + i] = P.le[1][i];
+        ctx->long_tie[0] = tie_binades(vc, 4 + 2 * PLAAC_NAA);
+        ctx->long_tie[1] = tie_binades(P.llr, PLAAC_NAA);
+        ctx->long_tie[2] = tie_binades(P.le[0], PLAAC_NAA);
+        ctx->long_tie[3] = tie_binades(P.hydro2, PLAAC_NAA);
+    }
     ctx->res_plan = residue_v2_plan(ctx->ks);
     rc = residue_v2_setup(ctx->res_plan);
     if (rc == PLAAC_OK) rc = residue_setup(ctx->ks, ctx->ring_words);
@@ -826,7 +854,7 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         const int64_t base = offsets[start];
         int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0;
         int64_t long_min = per_res ? 0 : effective_long_min(ctx);
-        const bool long_auto = !per_res && ctx->long_min < 0 && ctx->v2_nwr > 0;
+        const bool long_auto = !per_res && ctx->long_min < 0 && ctx->v2_nwr > 0 && ctx->variant != 1;
         unsigned long long bins[3 * kLongBins];
         if (long_auto) memset(bins, 0, sizeof(bins));
         while (end < nprot && end - start < max_prot) {
