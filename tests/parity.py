@@ -67,7 +67,9 @@ def papa_tie_class_ok(P, codes, offsets, i, got_row, rtol=RTOL):
     twice-smoothed PAPA track.  On plateaus (poly-Q, perfect repeats >= 2*ww-1 long) the jar's own choice
     is decided by its rounding noise, so a different centre is accepted iff, in the ORACLE's tracks, it
     attains the maximum within tolerance and satisfies the same FoldIndex gate, and the four values
-    reported at the centre match the oracle's tracks at that centre."""
+    reported at the centre match the oracle's tracks at that centre.  The gate `fix2 < 0` (:4944) is itself a
+    threshold on a value that is legitimately ~0: a centre whose |fix2| is below the tolerance (1e-9 * scale) may
+    be gated either way (found by tests/test_gpu_fuzz.py: the jar accepted a centre with fix2 = -1.3e-16)."""
     from oracle import orc
 
     lo, hi = int(offsets[i]), int(offsets[i + 1])
@@ -79,13 +81,16 @@ def papa_tie_class_ok(P, codes, offsets, i, got_row, rtol=RTOL):
     if not (h <= k < n - h):
         return False
     px, fx = tr["papax2"], tr["fix2"]
+    gate_tol = rtol * SCALE["fix2"]
     with np.errstate(invalid="ignore"):
-        valid = np.zeros(n, bool)
-        valid[h:n - h] = True
-        valid &= (fx < 0) & ~np.isnan(px)
+        inrange = np.zeros(n, bool)
+        inrange[h:n - h] = True
+        inrange &= ~np.isnan(px)
+        valid = inrange & (fx < gate_tol)      # centres that may pass the gate
+        firm = inrange & (fx < -gate_tol)      # centres that certainly pass it
     if not valid[k]:
         return False
-    best = px[valid].max()
+    best = px[firm].max() if firm.any() else -np.inf
     if not (px[k] >= best - rtol * max(abs(best), SCALE["papa_prop"])):
         return False
     want = dict(papa_combo=px[k], papa_prop=px[k], papa_fi=fx[k], papa_llr=tr["plaac"][k], papa_llr2=tr["plaacx2"][k])
@@ -95,8 +100,11 @@ def papa_tie_class_ok(P, codes, offsets, i, got_row, rtol=RTOL):
 def compare_with_tie_classes(P, codes, offsets, got, ref, int_fields, dbl_fields, rtol=RTOL):
     """compare_summaries + the PAPA tie-class rule.  Returns (mismatches, n_tie_class_rows)."""
     idx = np.nonzero(got["papa_center"] != ref["papa_center"])[0]
-    ties = [int(i) for i in idx if ref["papa_center"][i] >= 0 and got["papa_center"][i] >= 0
-            and papa_tie_class_ok(P, codes, offsets, int(i), got[i], rtol)]
+    ties = [int(i) for i in idx if got["papa_center"][i] >= 0 and papa_tie_class_ok(P, codes, offsets, int(i), got[i], rtol)]
+    # the other direction of the gate: the jar accepted a centre whose fix2 is ~0 and the candidate found none at all
+    for i in idx:
+        if got["papa_center"][i] < 0 and ref["papa_center"][i] >= 0 and abs(ref["papa_fi"][i]) <= rtol * SCALE["fix2"]:
+            ties.append(int(i))
     if ties:
         got = got.copy()
         for f in PAPA_FIELDS:

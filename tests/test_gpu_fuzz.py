@@ -9,8 +9,12 @@ import plaac_b200
 from oracle import orc
 from tests import parity, synth
 
+import os
+
 pytestmark = pytest.mark.gpu
 NT = 16
+N_SUMMARY = int(os.environ.get("PLAAC_FUZZ_N", "24"))   # PLAAC_FUZZ_N=400 for a soak run
+N_RESIDUE = max(6, N_SUMMARY // 4)
 
 
 def _random_case(seed):
@@ -55,7 +59,7 @@ def _random_case(seed):
     return kw, seqs, api
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(N_SUMMARY))
 def test_random_case_against_oracle(seed):
     kw, seqs, api = _random_case(seed)
     codes, offs = plaac_b200.pack(seqs)
@@ -85,7 +89,7 @@ def test_random_case_against_oracle(seed):
             assert parity.max_rel(got, ref, f) <= 1e-13, (seed, f, parity.max_rel(got, ref, f))
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(N_RESIDUE))
 def test_random_case_per_residue_against_oracle(seed):
     kw, seqs, api = _random_case(100 + seed)
     seqs = [s for s in seqs if len(s) <= 3000][:300]
