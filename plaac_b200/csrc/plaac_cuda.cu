@@ -32,7 +32,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-// One set of device work buffers; plaac_score() uses two of them to overlap copies with compute.
+// One set of device work buffers; plaac_score() cycles through kSlots of them to overlap copies with compute.
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count;
@@ -55,12 +55,17 @@ struct Slot {
 
 }  // namespace
 
+// plaac_score() pipelines its chunks over this many sets of device buffers: chunk i+1's and i+2's host->device copies are
+// queued while chunk i computes and copies back, so the copy engine never waits for the host (with two sets it did:
+// 0.7 ms per chunk, measured).
+constexpr int kSlots = 3;
+
 struct plaac_ctx {
     int device = 0;
     plaac_params params;
     KScalars ks;
     DeviceTables* d_tabs = nullptr;
-    Slot slot[2];
+    Slot slot[kSlots];
     int nwarps = 0, ring_words = 0;
     size_t smem_bytes = 0;
     int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
@@ -71,7 +76,7 @@ struct plaac_ctx {
     std::string v2_why;
     int sm_count = 0;
     plaac_stats stats;
-    int64_t chunk_res = (int64_t)128 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
+    int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
     // long-sequence path: > 0 fixed threshold (default: which path a protein takes does not depend on its batch, so
     // records are byte-identical however a proteome is batched or sharded), -1 automatic threshold per batch, 0 off
     int64_t long_min = 4096;
@@ -706,7 +711,7 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         ctx->err = "cudaFuncSetAttribute(per-residue kernels) failed";
         return bail(rc);
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kSlots; i++) {
         rc = slot_init(ctx, ctx->slot[i]);
         if (rc != PLAAC_OK) return bail(rc);
     }
@@ -718,7 +723,7 @@ void plaac_destroy(plaac_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (int i = 0; i < 2; i++) slot_free(ctx->slot[i]);
+    for (int i = 0; i < kSlots; i++) slot_free(ctx->slot[i]);
     if (ctx->d_tabs) cudaFree(ctx->d_tabs);
     delete ctx;
 }
@@ -792,7 +797,7 @@ int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
 {
     if (!ctx || !out) return fail(ctx, PLAAC_E_INVALID, "plaac_get_stats: NULL argument");
     ctx->stats.long_redone_chunks = 0;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kSlots; i++) {
         unsigned long long v = 0;
         if (ctx->slot[i].lg_cnt.p && cudaSetDevice(ctx->device) == cudaSuccess &&
             cudaMemcpy(&v, (char*)ctx->slot[i].lg_cnt.p + 16, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess)
@@ -835,12 +840,17 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
     if (!codes && offsets[nprot] != offsets[0]) return fail(ctx, PLAAC_E_INVALID, "NULL codes");
     CU(ctx, cudaSetDevice(ctx->device));
 
-    // Chunking: bounded device footprint, two slots so chunk i+1's H2D overlaps chunk i's kernels/D2H.
-    const int64_t max_res = per_res ? ctx->chunk_res_pr : ctx->chunk_res;
+    // Chunking: bounded device footprint; kSlots sets of buffers so the next chunks' H2D overlap this chunk's kernels and
+    // D2H.  Chunk sizes ramp up from max/8 and down again towards the end: the first chunk's copy and the last chunk's
+    // kernels + copy-back are the only parts of the pipeline nothing overlaps with.
+    const int64_t max_res_full = per_res ? ctx->chunk_res_pr : ctx->chunk_res;
+    const int64_t min_res = std::max<int64_t>(max_res_full / 8, 1 << 20);
+    const int64_t total_res = offsets[nprot] - offsets[0];
+    int64_t ramp = min_res;
     const int64_t max_prot = ctx->chunk_prot;
     int64_t start = 0;
     int which = 0;
-    bool pending[2] = {false, false};
+    bool pending[kSlots] = {};
     int rc = PLAAC_OK;
     auto drain = [&](int i) -> int {
         if (!pending[i]) return PLAAC_OK;
@@ -852,6 +862,9 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         // walk overlaps the previous chunk's copies and kernels).
         int64_t end = start;
         const int64_t base = offsets[start];
+        const int64_t remaining = total_res - (base - offsets[0]);
+        const int64_t max_res = std::min(max_res_full, std::max(min_res, std::min(ramp, remaining / 2)));
+        ramp = std::min(max_res_full, ramp * 2);
         int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0;
         int64_t long_min = per_res ? 0 : effective_long_min(ctx);
         const bool long_auto = !per_res && ctx->long_min < 0 && ctx->v2_nwr > 0 && ctx->variant != 1;
@@ -948,12 +961,13 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
                 if (hd[k]) CU(ctx, cudaMemcpyAsync(hd[k] + o, dd[k], N * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         }
         pending[which] = true;
-        which ^= 1;
+        which = (which + 1) % kSlots;
         start = end;
     }
-    int rc2 = drain(0);
-    int rc3 = drain(1);
-    if (rc == PLAAC_OK) rc = rc2 != PLAAC_OK ? rc2 : rc3;
+    for (int k = 0; k < kSlots; k++) {  // oldest chunk first
+        const int rcd = drain((which + k) % kSlots);
+        if (rc == PLAAC_OK) rc = rcd;
+    }
     return rc;
 }
 
