@@ -473,7 +473,7 @@ def measure_extras(scorer, dev, summaries, nprot):
         d_out = torch.zeros(160, dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
         res = {}
-        for tag, min_len in (("long_path_ms", 4096), ("bucketed_kernel_ms", 0)):
+        for tag, min_len in (("long_path_ms", 8192), ("bucketed_kernel_ms", 0)):
             scorer.set_long_path(min_len)
             ms = []
             for it in range(6):
@@ -481,7 +481,7 @@ def measure_extras(scorer, dev, summaries, nprot):
                 if it:
                     ms.append(scorer.stats().last_total_ms)
             res[tag] = sum(ms) / len(ms)
-        scorer.set_long_path(4096)
+        scorer.set_long_path(8192)
         res["residues_per_s_long_path"] = n / (res["long_path_ms"] * 1e-3)
         out["long_sequences"]["n%d" % n] = res
     out["long_sequences"]["note"] = ("whole device pipeline of one call (CUDA events inside the library), a single "

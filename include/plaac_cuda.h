@@ -222,8 +222,8 @@ int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
  * warm-started LUT forward chunks fix the absolute magnitudes, then both recurrences are re-run chunk-parallel in the
  * jar's own binade, where every rounding commutes with the chunk's shift, so the combined HMMall / HMMvit / Viterbi
  * path have the jar's bits.  The path is a latency device (a CTA per protein is less efficient per residue than the
- * bucketed kernel).  min_len > 0: fixed threshold (default 4096; raised to 1024 / four times the longest window if
- * smaller) -- which path a protein takes then does not depend on its batch, so records are byte-identical however a
+ * bucketed kernel).  min_len > 0: fixed threshold (default 8192, where a lane's sequential walk of the protein,
+ * ~1.4 ms, exceeds what a whole typical batch takes; raised to 1024 / four times the longest window if smaller) -- which path a protein takes then does not depend on its batch, so records are byte-identical however a
  * proteome is batched or sharded.  min_len = -1: automatic threshold per batch -- the smallest length, at least 1024
  * residues and at least ntotal/81600 + 220 (a lane's sequential walk of the protein must be a visible part of the
  * batch's time), that leaves no more long proteins than the GPU has SMs; best latency for small proteomes.

@@ -79,7 +79,7 @@ struct plaac_ctx {
     int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
     // long-sequence path: > 0 fixed threshold (default: which path a protein takes does not depend on its batch, so
     // records are byte-identical however a proteome is batched or sharded), -1 automatic threshold per batch, 0 off
-    int64_t long_min = 4096;
+    int64_t long_min = 8192;
     int long_warm = 256;       // forward warm-up of that path
     unsigned long long long_tie[4] = {0, 0, 0, 0};  // binades with an exact rounding tie among the table constants
     std::string err;

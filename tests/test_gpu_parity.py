@@ -121,7 +121,7 @@ def test_long_sequences(scorer):
         assert scorer.stats().long_proteins == before + 2
         _check(got, ref, "long sequences (bucketed kernel)")
     finally:
-        scorer.set_long_path(4096)
+        scorer.set_long_path(8192)
 
 
 def test_long_path_mixed_batch_thresholds_and_fallback():

@@ -88,8 +88,7 @@ def test_cuda_summary_against_the_jar(which):
     enc, kw, rows = jarvec.scenario(which.replace("_bucketed", ""))
     codes, offs = plaac_b200.pack([c for _, c in enc])
     sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
-    if bucketed:
-        sc.set_long_path(0)
+    sc.set_long_path(0 if bucketed else 4096)
     got = sc.score(codes, offs)
     if which.startswith("long"):
         assert sc.stats().long_proteins == (0 if bucketed else 2)
