@@ -1,3 +1,2 @@
-ncu --set full --clock-control none -k regex:k_pack -c 1 -o gpurun_out/r01_pack_full -f python bench.py --steps 1 --warmup 1 --proteins-per-gpu 4000000 --no-cpu-baseline --no-e2e --no-per-residue --no-extras > /dev/null 2>&1
-ncu -i gpurun_out/r01_pack_full.ncu-rep --page raw --csv > gpurun_out/r01_pack_full_raw.csv 2>/dev/null
-python profiles/summarise_ncu.py gpurun_out/r01_pack_full_raw.csv 1406000000
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for i in 1 2; do python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-per-residue --no-e2e --no-extras | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('value %.4g ms/step %.2f kernel_ms %.2f frac %.3f launches %d'%(d['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['roofline']['frac'],d['gpu_launches']))"; done

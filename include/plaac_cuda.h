@@ -223,13 +223,14 @@ int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
  * jar's own binade, where every rounding commutes with the chunk's shift, so the combined HMMall / HMMvit / Viterbi
  * path have the jar's bits.  The path is a latency device (a CTA per protein is less efficient per residue than the
  * bucketed kernel).  min_len > 0: fixed threshold (default 8192, where a lane's sequential walk of the protein,
- * ~1.4 ms, exceeds what a whole typical batch takes; raised to 1024 / four times the longest window if smaller) -- which path a protein takes then does not depend on its batch, so records are byte-identical however a
- * proteome is batched or sharded.  min_len = -1: automatic threshold per batch -- the smallest length, at least 1024
- * residues and at least ntotal/81600 + 220 (a lane's sequential walk of the protein must be a visible part of the
- * batch's time), that leaves no more long proteins than the GPU has SMs; best latency for small proteomes.
- * min_len = 0: path off.  warm: forward warm-up length, 0 keeps the current value (default 256); a negative value redoes
- * every forward chunk sequentially (testing).  Integer and reference-order columns are bit-identical on both paths; the
- * FoldIndex/PAPA window columns (running sums, restarted per chunk on the long path) agree to rounding (~1e-15). */
+ * ~1.4 ms, exceeds what a whole typical batch takes; raised to 1024 / four times the longest window if smaller).
+ * min_len = -1: automatic threshold per batch -- the smallest length, at least 1024 residues and at least
+ * ntotal/81600 + 220 (the walk must be a visible part of the batch's time), that leaves no more long proteins than the
+ * GPU has SMs; best latency for small proteomes (a yeast-sized set: 0.9 instead of 1.4 ms) at the price of one more
+ * host synchronisation per device-resident call.  min_len = 0: path off.  warm: forward warm-up length, 0 keeps the
+ * current value (default 256); a negative value redoes every forward chunk sequentially (testing).  Both paths give the
+ * same bytes in every column (the recurrences by the binade-frame argument, the window columns because their sums are
+ * exact on a 2^-41 grid), so records do not depend on the setting, the batching or the sharding. */
 int plaac_set_long_path(plaac_ctx *ctx, int64_t min_len, int warm);
 
 /* Kernel selection for testing: 0 = automatic (default), 1 = the reference-order anchor kernel (one fused

@@ -24,6 +24,10 @@ struct KScalars {
 // Per-code tables + LUT as uploaded once per ctx (global memory; kernels stage them in shared memory).
 struct DeviceTables {
     double le0[kTabN], le1[kTabN], lebg[kTabN], llr[kTabN], hyd[kTabN], pap[kTabN];
+    // hydropathy rounded to the 2^-k grid on which every window sum of up to (2w+2)^2 taps is exact (like pap): the
+    // sliding-window sums of the summary kernels are then exact, i.e. independent of the order and of where a running
+    // sum was (re)started; hyd stays exact for the sequential mean and the per-residue tracks
+    double hydw[kTabN];
     double lut[PLAAC_LUT_LEN + 3];
 };
 

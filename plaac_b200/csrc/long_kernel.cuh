@@ -70,7 +70,7 @@ struct LongArgs {
 struct LongShared {
     double2 lut2[PLAAC_LUT_LEN + 1];
     double2 le[32];
-    double llr[kTabN], hyd[kTabN], pap[kTabN];
+    double llr[kTabN], hyd[kTabN], pap[kTabN], hydw[kTabN];
     // per chunk
     double M[4][kLongMaxChunks];       // Viterbi transfer matrix: [0] 0->0, [1] 0->1, [2] 1->0, [3] 1->1
     double Sa[2][kLongMaxChunks];      // pass 1: approximate Viterbi scores at the chunk's last residue
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
         if (tid < kTabN) {
             sm.llr[tid] = T->llr[tid];
             sm.hyd[tid] = T->hyd[tid];
+            sm.hydw[tid] = T->hydw[tid];
             sm.pap[tid] = T->pap[tid];
         }
     }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     const uint32_t e0 = (t < n) ? ext[t] : (uint32_t)kPad;
                     const uint32_t e1 = (t - off1 >= t_start) ? ext[t - off1] : (uint32_t)kPad;
                     const uint32_t e2 = (t - off2 >= t_start) ? ext[t - off2] : (uint32_t)kPad;
-                    const double hy0 = sm.hyd[e0 & 63], hy1 = sm.hyd[e1 & 63], hy2 = sm.hyd[e2 & 63];
+                    const double hy0 = sm.hydw[e0 & 63], hy1 = sm.hydw[e1 & 63], hy2 = sm.hydw[e2 & 63];
                     const double pa0 = sm.pap[e0 & 63], pa1 = sm.pap[e1 & 63], pa2 = sm.pap[e2 & 63];
                     const int ch0 = (int)(int8_t)e0 >> 6, ch1 = (int)(int8_t)e1 >> 6, ch2 = (int)(int8_t)e2 >> 6;
                     SLh = (SLh + hy0) - hy1;

@@ -77,8 +77,8 @@ struct plaac_ctx {
     int sm_count = 0;
     plaac_stats stats;
     int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
-    // long-sequence path: > 0 fixed threshold (default: which path a protein takes does not depend on its batch, so
-    // records are byte-identical however a proteome is batched or sharded), -1 automatic threshold per batch, 0 off
+    // long-sequence path: > 0 fixed threshold (default 8192), -1 automatic threshold per batch, 0 off.  Both paths give
+    // the same bytes for every column, so the choice never shows in the results.
     int64_t long_min = 8192;
     int long_warm = 256;       // forward warm-up of that path
     unsigned long long long_tie[4] = {0, 0, 0, 0};  // binades with an exact rounding tie among the table constants
@@ -238,12 +238,12 @@ int setup_scalars(plaac_ctx* ctx)
 // of up to (2w+1)^2 of them is exactly representable: all those double additions are then exact.
 // Grid error <= 2^-41 for the default windows (values ~0.1 => ~5e-12 relative).  Not applied when the
 // grid would be coarser than 2^-38 (huge windows) or a table entry is not finite.
-double papa_grid(const plaac_params& P, int w)
+double sum_grid(const double* tab, int w)
 {
     double maxabs = 0;
     for (int c = 0; c < PLAAC_NAA; c++) {
-        if (!std::isfinite(P.papa_lod[c])) return 0.0;
-        maxabs = std::max(maxabs, std::fabs(P.papa_lod[c]));
+        if (!std::isfinite(tab[c])) return 0.0;
+        maxabs = std::max(maxabs, std::fabs(tab[c]));
     }
     if (maxabs == 0) return 0.0;
     const double taps = (2.0 * w + 2.0) * (2.0 * w + 2.0);
@@ -257,7 +257,11 @@ double papa_grid(const plaac_params& P, int w)
 void fill_tables(const plaac_params& P, DeviceTables& T, int w)
 {
     memset(&T, 0, sizeof(T));
-    const double grid = papa_grid(P, w);
+    const double grid = sum_grid(P.papa_lod, w);
+    // The hydropathy window sums get the same treatment (grid 2^-41 for PLAAC's tables: 2e-13 relative to a window
+    // mean): the summary kernels' FoldIndex columns then do not depend on how a running sum was started, so the
+    // bucketed kernel and the chunked long-sequence path give the same bits.
+    const double gridh = sum_grid(P.hydro2, w);
     for (int e = 0; e < kTabN; e++) {
         const int c = e & 31;
         if (c >= PLAAC_NAA) continue;  // pad and unused codes: all zero
@@ -266,6 +270,7 @@ void fill_tables(const plaac_params& P, DeviceTables& T, int w)
         T.lebg[e] = P.le0[c];
         T.llr[e] = P.llr[c];
         T.hyd[e] = P.hydro2[c];
+        T.hydw[e] = gridh > 0 ? std::nearbyint(P.hydro2[c] / gridh) * gridh : P.hydro2[c];
         double pl = P.papa_lod[c];
         if (grid > 0) pl = std::nearbyint(pl / grid) * grid;
         T.pap[e] = (e & kPapaMaskBit) ? 0.0 : pl;

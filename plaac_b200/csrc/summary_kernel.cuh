@@ -17,7 +17,7 @@ namespace plaac {
 
 struct SummarySmem {
     double lut[PLAAC_LUT_LEN + 3];
-    double le0[kTabN], le1[kTabN], lebg[kTabN], llr[kTabN], hyd[kTabN], pap[kTabN];
+    double le0[kTabN], le1[kTabN], lebg[kTabN], llr[kTabN], hyd[kTabN], pap[kTabN], hydw[kTabN];
     double rcp[kTabN * 4];  // 1/cnt for cnt in [0, 255]; only used when 2w+1 <= 255
 };
 
@@ -111,6 +111,7 @@ k_score_summary(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs
         S.lebg[i] = tabs->lebg[i];
         S.llr[i] = tabs->llr[i];
         S.hyd[i] = tabs->hyd[i];
+        S.hydw[i] = tabs->hydw[i];
         S.pap[i] = tabs->pap[i];
     }
     for (int i = tid; i < kTabN * 4; i += blockDim.x) S.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
@@ -244,13 +245,13 @@ k_score_summary(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs
 
         // ---------------- sliding windows ----------------
         {
-            const double hy1 = S.hyd[c1], hy2 = S.hyd[c2];
+            const double hy0w = S.hydw[c0], hy1 = S.hydw[c1], hy2 = S.hydw[c2];  // window sums: exact on the grid
             const double lr1 = S.llr[c1], lr2 = S.llr[c2];
             const double pa0 = S.pap[e0 & 63], pa1 = S.pap[e1 & 63], pa2 = S.pap[e2 & 63];
             const int ch0 = code_charge(ks.charge_plus, ks.charge_minus, c0);
             const int ch1 = code_charge(ks.charge_plus, ks.charge_minus, c1);
             const int ch2 = code_charge(ks.charge_plus, ks.charge_minus, c2);
-            SLh = (SLh + hy0) - hy1;
+            SLh = (SLh + hy0w) - hy1;
             SLl = (SLl + lr0) - lr1;
             SLp = (SLp + pa0) - pa1;
             SLc += ch0 - ch1;

@@ -31,13 +31,14 @@ namespace plaac {
 constexpr int kV2MaxThreads = 768;
 
 // Byte offsets from an 8 KB-aligned shared-memory base.
-constexpr uint32_t kOffHydB = 0;         // double [64 ext codes][16 lane copies]
+constexpr uint32_t kOffHydB = 0;         // double [64 ext codes][16 lane copies]: hydropathy on the exact-sum grid (windows)
 constexpr uint32_t kOffPapB = 8192;      // double [64][16]
 constexpr uint32_t kOffLlrB = 16384;     // double [64][16]   (tail loops only)
 constexpr uint32_t kOffLeA = 24576;      // double2 [32 codes][8 lane copies]  {le0, le1}
 constexpr uint32_t kOffLlrA = 28672;     // double [32][16]
 constexpr uint32_t kOffLut2 = 32768;     // double2 [4002]  {lut[d], lut[d+1]}
-constexpr uint32_t kV2FixedBytes = kOffLut2 + (PLAAC_LUT_LEN + 1) * 16;
+constexpr uint32_t kOffHydX = kOffLut2 + (PLAAC_LUT_LEN + 1) * 16;  // double [64][16]: exact hydropathy (sequential mean)
+constexpr uint32_t kV2FixedBytes = kOffHydX + 8192;
 constexpr uint32_t kV2AlignSlack = 8192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -409,7 +410,7 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         const double hy1 = lds_f64(hb | k1), pa1 = lds_f64_off<kOffPapB>(hb | k1);
         const double hy2 = lds_f64(hb | k2), pa2 = lds_f64_off<kOffPapB>(hb | k2);
         if (FAST || t < n) {
-            sh = sh + hy0;  // mean() :1584, sequential
+            sh = sh + lds_f64_off<kOffHydX>(hb | k0);  // mean() :1584, sequential, exact table values
             csum += ch0;
         }
         // window sums of the zero-padded sequence: lead centre p = t-w, lag centre p-(2w+1)
@@ -595,8 +596,10 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
         double* hy = reinterpret_cast<double*>(sm + kOffHydB);
         double* pa = reinterpret_cast<double*>(sm + kOffPapB);
         double* lb = reinterpret_cast<double*>(sm + kOffLlrB);
+        double* hx = reinterpret_cast<double*>(sm + kOffHydX);
         for (int i = tid; i < kTabN * 16; i += blockDim.x) {
-            hy[i] = T->hyd[i >> 4];
+            hx[i] = T->hyd[i >> 4];
+            hy[i] = T->hydw[i >> 4];
             pa[i] = T->pap[i >> 4];
             lb[i] = T->llr[i >> 4];
         }
