@@ -74,7 +74,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -84,7 +84,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: rows from here on belong to the region that starts now."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -94,7 +98,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:last]:
             parts = [x.strip() for x in r.split(",")]
             if len(parts) < 8:
                 continue
@@ -259,11 +263,12 @@ def main():
         scorer.score_device(codes.data_ptr(), offsets.data_ptr(), nprot, ntotal, summaries.data_ptr(), sync=True)
 
     # ---- device-resident timing -------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs ~0.1 s to start streaming: started before the warm-up, read for the timed region only
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    m0 = sampler.mark()
     l0 = scorer.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     score_ms = []
@@ -275,7 +280,8 @@ def main():
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    m1 = sampler.mark()
+    clocks = sampler.stop(m0, max(m1, m0 + 1))
     launches = scorer.stats().kernel_launches - l0
     dev_ms = ev0.elapsed_time(ev1)
     t_rank = torch.tensor([dev_ms / 1e3, float(ntotal), wall], dtype=torch.float64, device=dev)
