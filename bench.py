@@ -492,6 +492,7 @@ def measure_extras(scorer, dev, summaries, nprot):
         out["long_sequences"]["n%d" % n] = res
     out["long_sequences"]["note"] = ("whole device pipeline of one call (CUDA events inside the library), a single "
                                      "protein on the GPU; both paths give the same 160-byte record bit for bit")
+    out["fasta_ingest"] = measure_ingest(scorer, dev)
     order = torch.empty(nprot, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     ts = []
@@ -504,6 +505,61 @@ def measure_extras(scorer, dev, summaries, nprot):
                       "note": "plaac_rank_device: COREscore desc, LLR desc, no-CORE rows last (web/lib/server.rb:222-229); "
                               "wall clock around the call (it ends with a stream synchronise)"}
     return out
+
+
+def measure_ingest(scorer, dev):
+    """Row N2: raw FASTA text (60-column lines, '>' names) already in HBM -> residue codes, offsets, name spans and the
+    22-bin background counts (plaac_ingest_fasta_device).  Text of 300 k synthetic proteins (~130 MB)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import plaac_b200
+
+    rng = np.random.default_rng(7)
+    nrec = 300000
+    lens = np.clip(np.rint(rng.lognormal(LN_MEDIAN, SIGMA, nrec)), MIN_LEN, MAX_LEN).astype(np.int64)
+    ntot = int(lens.sum())
+    bg = np.array(BG_SCER) / sum(BG_SCER)
+    letters = np.frombuffer(b"XACDEFGHIKLMNPQRSTVWY*", dtype=np.uint8)
+    res = letters[rng.choice(22, size=ntot, p=bg)]
+    # text layout: ">p<i>\n" then the sequence in lines of 60
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    parts = []
+    for i in range(nrec):
+        parts.append(b">p%d\n" % i)
+        s = res[starts[i]:starts[i + 1]]
+        nl = (len(s) + 59) // 60
+        buf = np.full(len(s) + nl, 10, dtype=np.uint8)
+        idx = np.arange(len(s))
+        buf[idx + idx // 60] = s
+        parts.append(buf.tobytes())
+    text = b"".join(parts)
+    nbytes = len(text)
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).to(dev)
+    d_codes = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_offs = torch.empty(nrec + 2, dtype=torch.int64, device=dev)
+    d_npos = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
+    d_nlen = torch.empty(nrec + 1, dtype=torch.int32, device=dev)
+    d_flags = torch.zeros(nrec + 8, dtype=torch.uint8, device=dev)
+    d_bg = torch.zeros(22, dtype=torch.int64, device=dev)
+    idx = plaac_b200.capi.FastaIndex()
+    L = plaac_b200.lib()
+    torch.cuda.synchronize()
+    ts = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        rc = L.plaac_ingest_fasta_device(scorer._h, d_text.data_ptr(), nbytes, d_codes.data_ptr(), d_offs.data_ptr(),
+                                         d_npos.data_ptr(), d_nlen.data_ptr(), d_flags.data_ptr(), nrec + 1, C.byref(idx),
+                                         d_bg.data_ptr())
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+        assert rc == 0 and idx.nrec == nrec and idx.nres == ntot, (rc, idx.nrec, idx.nres)
+    t = min(ts[1:])
+    return {"text_bytes": nbytes, "records": nrec, "residues": ntot, "ms": t * 1e3, "text_gb_per_s": nbytes / t / 1e9,
+            "note": "plaac_ingest_fasta_device (5 kernels + background histogram), text resident in HBM; wall clock around "
+                    "the call, which ends with a stream synchronise"}
 
 
 class C_double:
