@@ -514,7 +514,11 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             la.errflag = (int*)s.errflag.p;
             la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
             la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
-            for (int i = 0; i < 4; i++) la.tie_mask[i] = getenv("PLAAC_LONG_TIES") ? ~0ull >> 1 : ctx->long_tie[i];
+            // PLAAC_LONG_TIES (testing): "1" treats every binade as a tie binade (everything redone sequentially), "0"
+            // ignores the masks (shows what they are for)
+            const char* ties_env = getenv("PLAAC_LONG_TIES");
+            for (int i = 0; i < 4; i++)
+                la.tie_mask[i] = !ties_env ? ctx->long_tie[i] : (ties_env[0] == '0' ? 0ull : ~0ull >> 1);
             la.warm = std::max(1, std::abs(ctx->long_warm));
             la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
             // on its own stream, launched first: its CTAs (one per long protein) take SMs while the persistent CTAs of

@@ -418,3 +418,45 @@ def test_long_path_automatic_threshold():
     sc.score(big, boffs)
     assert sc.stats().long_proteins == 0
     sc.close()
+
+
+def test_long_path_with_exact_tie_constants():
+    """Table constants that are exact round-half-even ties in the binades a long protein walks through (bits below
+    the ulp exactly 1000...0): there a sum's rounding depends on its parity, the shift argument of the long-sequence
+    path does not hold, and plaac_create must route those binades to the sequential redo (tie_binades).  The oracle
+    does the same arithmetic sequentially.  (With PLAAC_LONG_TIES=0, which ignores the masks, this test fails.)"""
+    rng = np.random.default_rng(99)
+    bg = synth.BG_SCER / synth.BG_SCER.sum()
+    prd = synth.PRD_28 / synth.PRD_28.sum()
+    seqs = []
+    for n in (9000, 20000):
+        s = rng.choice(22, size=n, p=bg).astype(np.uint8)
+        for frac in (0.2, 0.6):
+            st = int(n * frac)
+            s[st:st + 180] = rng.choice(22, size=180, p=prd)
+        seqs.append(s)
+    codes, offs = plaac_b200.pack(seqs)
+    P = plaac_b200.default_params()
+    Q = orc.make_params()
+    # binade [8192, 16384): ulp 2^-39, tie = an odd multiple of 2^-40; binade [16384, 32768): odd multiple of 2^-39
+    ties = {10: -(2.0 + 3 * 2.0 ** -40),   # leucine, frequent: background and hmm0 emission, forward and Viterbi
+            16: -(3.0 + 5 * 2.0 ** -39)}   # serine
+    for code, v in ties.items():
+        P.le[0][code] = v
+        P.le0[code] = v
+        Q.hmm1.le[0][code] = v
+        Q.hmm0.le[0][code] = v
+        Q.hmm0.le[1][code] = v
+    P.llr[12] = 1.5 + 2.0 ** -40           # asparagine: the psum[] of the LLR search
+    Q.llr[12] = P.llr[12]
+    P.hydro2[1] = 0.25 + 2.0 ** -43        # alanine: the hydropathy sum (magnitudes 2^11..2^13 -> ulp 2^-41..2^-39)
+    Q.hydro2[1] = P.hydro2[1]
+    ref = orc.score_batch(Q, codes, offs)
+    for min_len in (4096, 0):
+        sc = plaac_b200.Scorer(P)
+        sc.set_long_path(min_len)
+        got = sc.score(codes, offs)
+        st = sc.stats()
+        sc.close()
+        assert st.long_proteins == (2 if min_len else 0)
+        _check(got, ref, f"tie constants, long_min={min_len}")
