@@ -501,7 +501,21 @@ def measure_extras(scorer, dev, summaries, nprot):
         ncore = scorer.rank_device(summaries.data_ptr(), nprot, order.data_ptr())
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
-    out["ranking"] = {"records": nprot, "with_core": ncore, "ms": min(ts) * 1e3,
+    # the order is checked where it lies: COREscore desc, then LLR desc, then input index asc; no-CORE rows last
+    rec = summaries.view(torch.float64).view(nprot, 20)   # 160 B = 20 x 8 B; doubles start at byte 56: llr, core_score
+    idx = order.long()
+    cs, ll = rec[idx, 8], rec[idx, 7]
+
+    def in_order(p, s, i):
+        a, b = slice(0, -1), slice(1, None)
+        return bool(((p[a] > p[b]) | ((p[a] == p[b]) & ((s[a] > s[b]) | ((s[a] == s[b]) & (i[a] < i[b]))))).all())
+
+    ok = (not bool(torch.isnan(cs[:ncore]).any())) and bool(torch.isnan(cs[ncore:]).all())
+    ok = ok and in_order(cs[:ncore], ll[:ncore], idx[:ncore])
+    ok = ok and in_order(torch.zeros_like(ll[ncore:]), ll[ncore:], idx[ncore:])
+    ok = ok and bool((torch.sort(idx).values == torch.arange(nprot, device=dev)).all())
+    del rec, idx, cs, ll
+    out["ranking"] = {"records": nprot, "with_core": ncore, "ms": min(ts) * 1e3, "order_verified": ok,
                       "note": "plaac_rank_device: COREscore desc, LLR desc, no-CORE rows last (web/lib/server.rb:222-229); "
                               "wall clock around the call (it ends with a stream synchronise)"}
     return out
