@@ -948,6 +948,8 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
             dres.post_prd = d + 9 * N;
         }
         if (nres > 0) CU(ctx, cudaMemcpyAsync(s.codes.p, codes + base, (size_t)nres, cudaMemcpyHostToDevice, s.stream));
+        // k_pack reads whole aligned 16-byte blocks and masks what lies beyond a protein: keep the slack defined
+        CU(ctx, cudaMemsetAsync((char*)s.codes.p + nres, 0, 64, s.stream));
         CU(ctx, cudaMemcpyAsync(s.offsets.p, offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
         rc = run_batch(ctx, s, (const uint8_t*)s.codes.p, (const int64_t*)s.offsets.p, base, np, nres,
                        summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base, slots_bound,
