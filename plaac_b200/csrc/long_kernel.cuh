@@ -256,32 +256,13 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     a0 = 0.0;
                     a1 = -INFINITY;
                 }
-#pragma unroll 8
-                for (int t = t0; t < ce; t++) {
-                    const double2 le = sm.le[ext[t] & 31];
-                    const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
-                    const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
-                    const bool pA0 = vA10 > vA00, pA1 = vA11 > vA01;
-                    a0 = (pA0 ? vA10 : vA00) + le.x;
-                    a1 = (pA1 ? vA11 : vA01) + le.y;
-                    b0 = fmax(vB00, vB10) + le.x;
-                    b1 = fmax(vB01, vB11) + le.y;
-                    if (k == 0) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
-                }
-                sm.M[0][k] = a0;
-                sm.M[1][k] = a1;
-                sm.M[2][k] = b0;
-                sm.M[3][k] = b1;
-            }
-            // ---- chunk-local sums of the three sequential-sum columns with their running extremes, charge sum, Q/N window
-            {
+                // fused with the chunk-local sums of the three sequential-sum columns (running extremes for the binade
+                // test), the charge sum and the Q/N window: independent dependency chains in one loop
                 double q0 = 0, q1 = 0, q2 = 0, mn0 = 0, mn1 = 0, mn2 = 0, mx0 = 0, mx1 = 0, mx2 = 0;
                 int cq = 0;
                 int qn = 0, mbest = -1, mstop = -1;
                 for (int t = max(0, cs - mw); t < cs; t++) qn += (int)((ks.qn_mask >> (ext[t] & 31)) & 1u);
-#pragma unroll 8
-                for (int t = cs; t < ce; t++) {
-                    const uint32_t e = ext[t];
+                auto stats = [&](int t, uint32_t e) {
                     q0 = q0 + sm.llr[e & 31];
                     q1 = q1 + sm.le[e & 31].x;
                     q2 = q2 + sm.hyd[e & 63];
@@ -296,7 +277,26 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                         mbest = qn;
                         mstop = t;
                     }
+                };
+                if (k == 0) stats(0, ext[0]);
+#pragma unroll 4
+                for (int t = t0; t < ce; t++) {
+                    const uint32_t e = ext[t];
+                    const double2 le = sm.le[e & 31];
+                    const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
+                    const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
+                    const bool pA0 = vA10 > vA00, pA1 = vA11 > vA01;
+                    a0 = (pA0 ? vA10 : vA00) + le.x;
+                    a1 = (pA1 ? vA11 : vA01) + le.y;
+                    b0 = fmax(vB00, vB10) + le.x;
+                    b1 = fmax(vB01, vB11) + le.y;
+                    if (k == 0) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
+                    stats(t, e);
                 }
+                sm.M[0][k] = a0;
+                sm.M[1][k] = a1;
+                sm.M[2][k] = b0;
+                sm.M[3][k] = b1;
                 sm.q_sum[0][k] = q0, sm.q_min[0][k] = mn0, sm.q_max[0][k] = mx0;
                 sm.q_sum[1][k] = q1, sm.q_min[1][k] = mn1, sm.q_max[1][k] = mx1;
                 sm.q_sum[2][k] = q2, sm.q_min[2][k] = mn2, sm.q_max[2][k] = mx2;
@@ -483,26 +483,55 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20) ||
                                    ((g.tie_mask[0] >> (((__double2hiint(lo) >> 20) & 0x7ff) - 1023)) & 1ull);
                 sm.cross_v[k] = cross ? 1 : 0;
-                if (!cross) {
-                    const double R = sm.Sa[0][k - 1];
-                    double a0 = R, a1 = -INFINITY, b0 = -INFINITY, b1 = R;
-#pragma unroll 8
-                    for (int t = cs; t < ce; t++) {
-                        const double2 le = sm.le[ext[t] & 31];
-                        const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
-                        const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
-                        const bool pA0 = vA10 > vA00, pA1 = vA11 > vA01, pB0 = vB10 > vB00, pB1 = vB11 > vB01;
-                        a0 = (pA0 ? vA10 : vA00) + le.x;
-                        a1 = (pA1 ? vA11 : vA01) + le.y;
-                        b0 = (pB0 ? vB10 : vB00) + le.x;
-                        b1 = (pB1 ? vB11 : vB01) + le.y;
-                        tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
+                // One loop over the chunk for the Viterbi frames, the psum[] LLR search and the two plain sums, each in its
+                // own binade frame: independent dependency chains that hide each other's latency.  Everything is
+                // computed whether or not its crossing flag is set (the combine step ignores flagged results); only the
+                // traceback bytes of a flagged chunk are left to the sequential redo.
+                const double R = sm.Sa[0][k - 1];
+                double a0 = R, a1 = -INFINITY, b0 = -INFINITY, b1 = R;
+                double lagsum = 0;
+                for (int t = cs - c; t < cs; t++) lagsum += sm.llr[ext[t] & 31];
+                double lag = sm.q_abs[0][k] - lagsum;  // approximate psum before residue cs-c: fixes the frame
+                double lead = lag;
+                for (int t = cs - c; t < cs; t++) lead = lead + sm.llr[ext[t] & 31];
+                const double lead0 = lead;
+                double best = -INFINITY, mid = lead;
+                int stop = -1;
+                const double x10 = sm.q_abs[1][k], x20 = sm.q_abs[2][k];
+                double x1 = x10, x2 = x20;
+#pragma unroll 4
+                for (int t = cs; t < ce; t++) {
+                    const uint32_t e = ext[t];
+                    const double2 le = sm.le[e & 31];
+                    const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
+                    const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
+                    const bool pA0 = vA10 > vA00, pA1 = vA11 > vA01, pB0 = vB10 > vB00, pB1 = vB11 > vB01;
+                    a0 = (pA0 ? vA10 : vA00) + le.x;
+                    a1 = (pA1 ? vA11 : vA01) + le.y;
+                    b0 = (pB0 ? vB10 : vB00) + le.x;
+                    b1 = (pB1 ? vB11 : vB01) + le.y;
+                    if (!cross) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
+                    lead = lead + sm.llr[e & 31];
+                    lag = lag + sm.llr[ext[t - c] & 31];
+                    const double d = lead - lag;  // exact, and the jar's number
+                    if (d > best) {
+                        best = d;
+                        stop = t;
                     }
-                    sm.M[0][k] = a0;  // values at the chunk's last residue had the chunk been entered in state 0 with score R
-                    sm.M[1][k] = a1;
-                    sm.M[2][k] = b0;  // ... in state 1 with score R
-                    sm.M[3][k] = b1;
+                    if (t == ce - c - 1) mid = lead;
+                    x1 = x1 + le.x;
+                    x2 = x2 + sm.hyd[e & 63];
                 }
+                sm.M[0][k] = a0;  // values at the chunk's last residue had the chunk been entered in state 0 with score R
+                sm.M[1][k] = a1;
+                sm.M[2][k] = b0;  // ... in state 1 with score R
+                sm.M[3][k] = b1;
+                sm.q_inc[0][k] = lead - lead0;
+                sm.q_mid[k] = mid - lead0;
+                sm.q_best[k] = best;
+                sm.q_stop[k] = stop;
+                sm.q_inc[1][k] = x1 - x10;
+                sm.q_inc[2][k] = x2 - x20;
             }
             {
                 const double lo = fabs(sm.A_cs[k]) - 64.0;
@@ -598,44 +627,6 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 sm.q_inc[0][0] = ps, sm.q_mid[0] = mid, sm.q_best[0] = best, sm.q_stop[0] = stop;
                 sm.q_inc[1][0] = s0;
                 sm.q_inc[2][0] = shy;
-            } else {
-                if (!cross[0]) {
-                    double lagsum = 0;
-                    for (int t = cs - c; t < cs; t++) lagsum += sm.llr[ext[t] & 31];
-                    double lag = sm.q_abs[0][k] - lagsum;  // approximate psum before residue cs-c: fixes the frame
-                    double lead = lag;
-                    for (int t = cs - c; t < cs; t++) lead = lead + sm.llr[ext[t] & 31];
-                    const double lead0 = lead;
-                    double best = -INFINITY, mid = lead;
-                    int stop = -1;
-#pragma unroll 8
-                    for (int t = cs; t < ce; t++) {
-                        lead = lead + sm.llr[ext[t] & 31];
-                        lag = lag + sm.llr[ext[t - c] & 31];
-                        const double d = lead - lag;  // exact, and the jar's number
-                        if (d > best) {
-                            best = d;
-                            stop = t;
-                        }
-                        if (t == ce - c - 1) mid = lead;
-                    }
-                    sm.q_inc[0][k] = lead - lead0;
-                    sm.q_mid[k] = mid - lead0;
-                    sm.q_best[k] = best;
-                    sm.q_stop[k] = stop;
-                }
-                if (!cross[1]) {
-                    const double x0 = sm.q_abs[1][k];
-                    double x = x0;
-                    for (int t = cs; t < ce; t++) x = x + sm.le[ext[t] & 31].x;
-                    sm.q_inc[1][k] = x - x0;
-                }
-                if (!cross[2]) {
-                    const double x0 = sm.q_abs[2][k];
-                    double x = x0;
-                    for (int t = cs; t < ce; t++) x = x + sm.hyd[ext[t] & 63];
-                    sm.q_inc[2][k] = x - x0;
-                }
             }
         }
         long_chunk_bar();
