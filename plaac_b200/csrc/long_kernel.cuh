@@ -41,6 +41,30 @@ constexpr int kLongChunkWarps = 12;
 constexpr int kLongMaxChunks = kLongChunkWarps * 32;
 constexpr int kLongMinChunk = 256;
 constexpr int kLongPadTail = 128;  // ext bytes past the end are pad codes
+constexpr int kLongChunkMajorMin = 49152;  // from here on the chunk lanes read a chunk-major copy (LongArgs::extT)
+
+// Chunk geometry of one long protein: C residues per chunk (a multiple of 32 that holds a whole CORE / MW window), K
+// chunks (<= kLongMaxChunks), Kp = row pitch of the chunk-major copies (room for the chunk after the last one).
+__host__ __device__ inline void long_geometry(int64_t n, int c, int mw, int* C, int* K, int* Kp)
+{
+    int64_t cc = (n + kLongMaxChunks - 1) / kLongMaxChunks;
+    cc = (cc + 31) & ~(int64_t)31;
+    if (cc < kLongMinChunk) cc = kLongMinChunk;
+    const int64_t wmin = (((c > mw ? c : mw) + 32) + 31) & ~(int64_t)31;
+    if (cc < wmin) cc = wmin;
+    const int64_t kk = (n + cc - 1) / cc;
+    *C = (int)cc;
+    *K = (int)kk;
+    *Kp = (int)(((kk + 1) + 31) & ~(int64_t)31);
+}
+// Scratch bytes per array (ext, chunk-major ext, chunk-major traceback) of one long protein.
+__host__ __device__ inline int64_t long_scratch_need(int64_t n, int c, int mw)
+{
+    int C, K, Kp;
+    long_geometry(n, c, mw, &C, &K, &Kp);
+    const int64_t a = n + kLongPadTail, b = (int64_t)C * Kp;
+    return ((a > b ? a : b) + 127) & ~(int64_t)127;
+}
 
 struct LongArgs {
     const uint8_t* codes;
@@ -52,7 +76,12 @@ struct LongArgs {
     const DeviceTables* tabs;
     plaac_summary* out;
     uint8_t* ext;   // ext code per residue (same byte layout as the bucketed stream)
-    uint8_t* tb;    // 4 traceback bits per residue: variant A (P0, P1), variant B (P0, P1)
+    uint8_t* extT;  // the same, chunk-major: [position in chunk][chunk], so the 32 chunk lanes of a warp read 32
+                    // consecutive bytes per step (one sector) instead of 32 different lines.  Used from cm_min
+                    // residues on: with few chunk lanes the L1 hits of the protein-major copy are the faster choice
+                    // (measured: 100 k residues 1.72 -> 1.46 ms chunk-major, 35 k residues 0.93 -> 0.99 ms)
+    uint8_t* tb;    // 4 traceback bits per residue, same layout as the copy the lanes read: variant A (P0, P1), variant B (P0, P1)
+    int cm_min;     // proteins of at least this many residues use the chunk-major layout
     long long* dbg_clocks;       // optional: phase time stamps of the CTA with blockIdx 0 (16 slots)
     unsigned long long* redone;  // statistics: forward chunks redone sequentially because d had not coalesced
     uint32_t* vit;  // Viterbi bits, one word per 32 residues
@@ -99,15 +128,16 @@ struct LongShared {
 
 // Proteins of at least long_min residues are scored by k_long_score; the bucketed path sees them as empty.
 __global__ void __launch_bounds__(256)
-k_long_select(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_min, int32_t* __restrict__ list,
-              int64_t* __restrict__ scratch_off, unsigned long long* __restrict__ counters /* [0] count, [1] scratch cursor */)
+k_long_select(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_min, int c, int mw,
+              int32_t* __restrict__ list, int64_t* __restrict__ scratch_off,
+              unsigned long long* __restrict__ counters /* [0] count, [1] scratch cursor */)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nprot) return;
     const int64_t len = offsets[i + 1] - offsets[i];
     if (len < long_min) return;
     const unsigned long long slot = atomicAdd(&counters[0], 1ull);
-    const unsigned long long need = (unsigned long long)((len + kLongPadTail + 127) & ~(int64_t)127);
+    const unsigned long long need = (unsigned long long)long_scratch_need(len, c, mw);
     list[slot] = (int32_t)i;
     scratch_off[slot] = (int64_t)atomicAdd(&counters[1], need);
 }
@@ -134,7 +164,7 @@ inline int64_t long_edge(int b) { return b < 60 ? 1024 + 256 * (int64_t)b : (int
 
 // per bin: [b] proteins, [kLongBins + b] scratch bytes, [2 * kLongBins + b] longest member
 __global__ void __launch_bounds__(256)
-k_long_levels(const int64_t* __restrict__ offsets, int64_t nprot, unsigned long long* __restrict__ bins)
+k_long_levels(const int64_t* __restrict__ offsets, int64_t nprot, int c, int mw, unsigned long long* __restrict__ bins)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nprot) return;
@@ -142,7 +172,7 @@ k_long_levels(const int64_t* __restrict__ offsets, int64_t nprot, unsigned long 
     const int b = long_bin(len);
     if (b < 0) return;
     atomicAdd(&bins[b], 1ull);
-    atomicAdd(&bins[kLongBins + b], (unsigned long long)((len + kLongPadTail + 127) & ~(int64_t)127));
+    atomicAdd(&bins[kLongBins + b], (unsigned long long)long_scratch_need(len, c, mw));
     atomicMax(&bins[2 * kLongBins + b], (unsigned long long)len);
 }
 
@@ -173,7 +203,8 @@ __device__ __forceinline__ MP2 mp_shfl_up(const MP2& a, int d)
         if (g.dbg_clocks && tid == 0 && blockIdx.x == 0) g.dbg_clocks[i] = clock64(); \
     } while (0)
 
-__global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
+template <bool CM>
+__device__ __forceinline__ void long_score_body(const LongArgs& g)
 {
     extern __shared__ __align__(16) unsigned char long_smem[];
     LongShared& sm = *reinterpret_cast<LongShared*>(long_smem);
@@ -184,9 +215,16 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     const int n = (int)(g.offsets[prot + 1] - g.offsets[prot]);
     const uint8_t* src = g.codes + (g.offsets[prot] - g.off_base);
     uint8_t* __restrict__ ext = g.ext + so;
-    uint8_t* __restrict__ tb = g.tb + so;
+    uint8_t* __restrict__ extT = g.extT + so;
+    uint8_t* __restrict__ tbT = g.tb + so;
     uint32_t* __restrict__ vit = g.vit + (so >> 5);
     const int c = ks.core_len, w = ks.w, mw = ks.mw_window;
+    int C, K, Kp;
+    long_geometry(n, c, mw, &C, &K, &Kp);
+    // layout the chunk lanes walk (CM: chunk-major copies, else the protein-major ones): byte of residue rel of chunk kk
+    // at rel * sR + kk * sK
+    constexpr bool cm = CM;
+    const size_t sR = cm ? (size_t)Kp : 1, sK = cm ? 1 : (size_t)C;
 
     // ---- tables
     {
@@ -207,6 +245,10 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     // ---- phase 0: ext codes (k_pack's byte layout: code | PAPA proline mask << 5 | charge class << 6)
     {
         int bad = 0;
+        if (cm) {
+            for (int i = tid; i < C * Kp; i += kLongThreads) extT[i] = (uint8_t)kPad;
+            __syncthreads();
+        }
         for (int i = tid; i < n; i += kLongThreads) {
             uint32_t cd = src[i];
             if (cd > 21u) {
@@ -221,6 +263,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             else if ((ks.charge_minus >> cd) & 1u)
                 e |= 0xc0u;
             ext[i] = (uint8_t)e;
+            if (cm) extT[(size_t)(i % C) * Kp + i / C] = (uint8_t)e;
         }
         for (int i = n + tid; i < n + kLongPadTail; i += kLongThreads) ext[i] = (uint8_t)kPad;
         if (bad) atomicOr(g.errflag, 1);
@@ -228,10 +271,6 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
     __syncthreads();
 
     LONG_STAMP(0);
-    // chunk geometry: C is a multiple of 32, K <= kLongMaxChunks chunks
-    int C = (n + kLongMaxChunks - 1) / kLongMaxChunks;
-    C = max(max(kLongMinChunk, (C + 31) & ~31), ((max(c, mw) + 32) + 31) & ~31);  // a chunk holds a whole CORE / MW window
-    const int K = (n + C - 1) / C;
     const uint32_t lut_addr = smem_u32(&sm.lut2[0]);
 
     const int warm = max(1, min(g.warm, C));
@@ -239,6 +278,20 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
         const int k = tid;
         const bool live = k < K;
         const int cs = k * C, ce = min(n, cs + C);
+        // residue t through the strided copy: t lies in this lane's chunk or in a neighbour (halos, lags <= C)
+        auto xt = [&](int t) -> uint32_t {
+            if constexpr (!CM) return ext[t];
+            int rel = t - cs, kk = k;
+            if (rel < 0) {
+                rel += C;
+                kk--;
+            } else if (rel >= C) {
+                rel -= C;
+                kk++;
+            }
+            return extT[(size_t)rel * Kp + kk];
+        };
+        uint8_t* const tbk = tbT + (size_t)k * sK;  // traceback byte of residue t of this chunk: tbk[(t - cs) * sR]
         // ================= pass 1: chunk-local frame =================
         if (live) {
             // ---- Viterbi: the chunk's 2x2 max-plus transfer matrix (first chunk: the true chain, with its traceback)
@@ -246,11 +299,11 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 double a0, a1, b0 = -INFINITY, b1 = 0.0;
                 int t0 = cs;
                 if (k == 0) {
-                    const double2 le = sm.le[ext[0] & 31];
+                    const double2 le = sm.le[xt(0) & 31];
                     a0 = ks.li0 + le.x;
                     a1 = ks.li1 + le.y;
                     b1 = -INFINITY;
-                    tb[0] = 0;
+                    tbk[0] = 0;
                     t0 = 1;
                 } else {
                     a0 = 0.0;
@@ -261,7 +314,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 double q0 = 0, q1 = 0, q2 = 0, mn0 = 0, mn1 = 0, mn2 = 0, mx0 = 0, mx1 = 0, mx2 = 0;
                 int cq = 0;
                 int qn = 0, mbest = -1, mstop = -1;
-                for (int t = max(0, cs - mw); t < cs; t++) qn += (int)((ks.qn_mask >> (ext[t] & 31)) & 1u);
+                for (int t = max(0, cs - mw); t < cs; t++) qn += (int)((ks.qn_mask >> (xt(t) & 31)) & 1u);
                 auto stats = [&](int t, uint32_t e) {
                     q0 = q0 + sm.llr[e & 31];
                     q1 = q1 + sm.le[e & 31].x;
@@ -272,16 +325,16 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     cq += (int)(int8_t)e >> 6;
                     // Q/N window :764-771: first strict maximum of the count in [t-mw+1, t] (n >= mw here)
                     qn += (int)((ks.qn_mask >> (e & 31)) & 1u);
-                    if (t >= mw) qn -= (int)((ks.qn_mask >> (ext[t - mw] & 31)) & 1u);
+                    if (t >= mw) qn -= (int)((ks.qn_mask >> (xt(t - mw) & 31)) & 1u);
                     if (t >= mw - 1 && qn > mbest) {
                         mbest = qn;
                         mstop = t;
                     }
                 };
-                if (k == 0) stats(0, ext[0]);
+                if (k == 0) stats(0, xt(0));
 #pragma unroll 4
                 for (int t = t0; t < ce; t++) {
-                    const uint32_t e = ext[t];
+                    const uint32_t e = xt(t);
                     const double2 le = sm.le[e & 31];
                     const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
                     const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
@@ -290,7 +343,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     a1 = (pA1 ? vA11 : vA01) + le.y;
                     b0 = fmax(vB00, vB10) + le.x;
                     b1 = fmax(vB01, vB11) + le.y;
-                    if (k == 0) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
+                    if (k == 0) tbk[(size_t)(t - cs) * sR] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
                     stats(t, e);
                 }
                 sm.M[0][k] = a0;
@@ -308,13 +361,13 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
             {
                 const int ts = (k == 0) ? 0 : max(0, cs - warm);
                 const int tmid = ce - warm;  // where the next chunk's warm-up starts
-                const double2 le0 = sm.le[ext[ts] & 31];
+                const double2 le0 = sm.le[xt(ts) & 31];
                 double a0 = ks.li0 + le0.x, a1 = ks.li1 + le0.y;
                 double e_a0 = 0.0, m_a0 = a0;
 #pragma unroll 8
                 for (int t = ts + 1; t < ce; t++) {
                     if (t == cs) e_a0 = a0;
-                    const double2 le = sm.le[ext[t] & 31];
+                    const double2 le = sm.le[xt(t) & 31];
                     const double f0 = lse_lut2<false>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
                     const double f1 = lse_lut2<false>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
                     a0 = f0;
@@ -342,9 +395,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 bool all = true;
 #pragma unroll 8
                 for (int t = t_start; t <= t_last; t++) {
-                    const uint32_t e0 = (t < n) ? ext[t] : (uint32_t)kPad;
-                    const uint32_t e1 = (t - off1 >= t_start) ? ext[t - off1] : (uint32_t)kPad;
-                    const uint32_t e2 = (t - off2 >= t_start) ? ext[t - off2] : (uint32_t)kPad;
+                    const uint32_t e0 = (t < n) ? xt(t) : (uint32_t)kPad;
+                    const uint32_t e1 = (t - off1 >= t_start) ? xt(t - off1) : (uint32_t)kPad;
+                    const uint32_t e2 = (t - off2 >= t_start) ? xt(t - off2) : (uint32_t)kPad;
                     const double hy0 = sm.hydw[e0 & 63], hy1 = sm.hydw[e1 & 63], hy2 = sm.hydw[e2 & 63];
                     const double pa0 = sm.pap[e0 & 63], pa1 = sm.pap[e1 & 63], pa2 = sm.pap[e2 & 63];
                     const int ch0 = (int)(int8_t)e0 >> 6, ch1 = (int)(int8_t)e1 >> 6, ch2 = (int)(int8_t)e2 >> 6;
@@ -490,10 +543,10 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 const double R = sm.Sa[0][k - 1];
                 double a0 = R, a1 = -INFINITY, b0 = -INFINITY, b1 = R;
                 double lagsum = 0;
-                for (int t = cs - c; t < cs; t++) lagsum += sm.llr[ext[t] & 31];
+                for (int t = cs - c; t < cs; t++) lagsum += sm.llr[xt(t) & 31];
                 double lag = sm.q_abs[0][k] - lagsum;  // approximate psum before residue cs-c: fixes the frame
                 double lead = lag;
-                for (int t = cs - c; t < cs; t++) lead = lead + sm.llr[ext[t] & 31];
+                for (int t = cs - c; t < cs; t++) lead = lead + sm.llr[xt(t) & 31];
                 const double lead0 = lead;
                 double best = -INFINITY, mid = lead;
                 int stop = -1;
@@ -501,7 +554,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 double x1 = x10, x2 = x20;
 #pragma unroll 4
                 for (int t = cs; t < ce; t++) {
-                    const uint32_t e = ext[t];
+                    const uint32_t e = xt(t);
                     const double2 le = sm.le[e & 31];
                     const double vA00 = ks.lt00 + a0, vA10 = ks.lt10 + a1, vA01 = ks.lt01 + a0, vA11 = ks.lt11 + a1;
                     const double vB00 = ks.lt00 + b0, vB10 = ks.lt10 + b1, vB01 = ks.lt01 + b0, vB11 = ks.lt11 + b1;
@@ -510,9 +563,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     a1 = (pA1 ? vA11 : vA01) + le.y;
                     b0 = (pB0 ? vB10 : vB00) + le.x;
                     b1 = (pB1 ? vB11 : vB01) + le.y;
-                    if (!cross) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
+                    if (!cross) tbk[(size_t)(t - cs) * sR] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
                     lead = lead + sm.llr[e & 31];
-                    lag = lag + sm.llr[ext[t - c] & 31];
+                    lag = lag + sm.llr[xt(t - c) & 31];
                     const double d = lead - lag;  // exact, and the jar's number
                     if (d > best) {
                         best = d;
@@ -544,7 +597,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     // interpolation term is a tie about once per 2^15 additions at these magnitudes).  The combine
                     // step takes the frame of the right parity.
                     const int ts = max(0, cs - warm);
-                    const double2 le0 = sm.le[ext[ts] & 31];
+                    const double2 le0 = sm.le[xt(ts) & 31];
                     double a0 = ks.li0 + le0.x, a1 = ks.li1 + le0.y;
                     double c0 = a0, c1 = a1;
                     if (ts > 0) {
@@ -564,7 +617,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                             ec = c0;
                             ee = c1 - c0;
                         }
-                        const double2 le = sm.le[ext[t] & 31];
+                        const double2 le = sm.le[xt(t) & 31];
                         const double f0 = lse_lut2<false>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
                         const double f1 = lse_lut2<false>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
                         const double h0 = lse_lut2<false>(ks.lt00 + c0, ks.lt10 + c1, lut_addr) + le.x;
@@ -610,9 +663,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 double s0 = 0, shy = 0;
 #pragma unroll 8
                 for (int t = 0; t < ce; t++) {
-                    const uint32_t e = ext[t];
+                    const uint32_t e = xt(t);
                     ps = ps + sm.llr[e & 31];
-                    if (t >= c) psl = psl + sm.llr[ext[t - c] & 31];
+                    if (t >= c) psl = psl + sm.llr[xt(t - c) & 31];
                     if (t >= c - 1) {
                         const double d = ps - psl;
                         if (t == c - 1 || d > best) {
@@ -645,7 +698,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                         const bool p0 = v10 > v00, p1 = v11 > v01;
                         S0 = (p0 ? v10 : v00) + le.x;
                         S1 = (p1 ? v11 : v01) + le.y;
-                        tb[t] = (uint8_t)((int)p0 | ((int)p1 << 1));
+                        tbT[(size_t)(t - s) * sR + (size_t)kk * sK] = (uint8_t)((int)p0 | ((int)p1 << 1));
                     }
                 } else {
                     const double R = sm.Sa[0][kk - 1];
@@ -667,7 +720,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                 sm.endstate[kk] = (unsigned char)e;
                 if (sm.cross_v[kk]) {
                     const int s = kk * C, en = min(n, s + C);
-                    for (int t = en - 1; t >= s; t--) e = (tb[t] >> e) & 1;
+                    for (int t = en - 1; t >= s; t--) e = (tbT[(size_t)(t - s) * sR + (size_t)kk * sK] >> e) & 1;
                     sm.variant[kk] = 0;
                 } else {
                     const int v = (sm.choice[kk] >> e) & 1;
@@ -849,7 +902,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
                     vit[t >> 5] = word;
                     word = 0;
                 }
-                v = (tb[t] >> (sh + v)) & 1;
+                v = (tbk[(size_t)(t - cs) * sR] >> (sh + v)) & 1;
             }
             sm.v_all[k] = closed ? 0 : 1;
             sm.v_pre[k] = cur;
@@ -994,6 +1047,16 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
         r->prd_end = prd_e;
         r->prd_score = prd_sc;
     }
+}
+
+__global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
+{
+    // one instantiation per layout: the choice is per protein (per CTA), the strides are compile-time constants
+    const int32_t prot = g.list[blockIdx.x];
+    if (g.offsets[prot + 1] - g.offsets[prot] >= g.cm_min)
+        long_score_body<true>(g);
+    else
+        long_score_body<false>(g);
 }
 
 }  // namespace plaac

@@ -42,7 +42,7 @@ struct Slot {
     DevBuf ing_agg, ing_cnt, ing_base, ing_misc;                 // FASTA ingest scratch
     DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
     DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
-    DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_tb, lg_vit;                             // long-sequence path
+    DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_extT, lg_tb, lg_vit;                             // long-sequence path
     unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues, or 3 x kLongBins bins
     DevBuf lg_bins;
     cudaStream_t aux1 = nullptr, aux2 = nullptr;
@@ -308,7 +308,7 @@ void slot_free(Slot& s)
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
-                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_tb, &s.lg_vit, &s.lg_bins})
+                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins})
         release(*b);
     if (s.h_long) cudaFreeHost(s.h_long);
     if (s.h_total) cudaFreeHost(s.h_total);
@@ -402,7 +402,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         // automatic threshold with device-resident offsets: bin the lengths, let the host choose
         if ((rc = ensure(ctx, s.lg_bins, 3 * kLongBins * sizeof(unsigned long long)))) return rc;
         CU(ctx, cudaMemsetAsync(s.lg_bins.p, 0, 3 * kLongBins * sizeof(unsigned long long), st));
-        k_long_levels<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, (unsigned long long*)s.lg_bins.p);
+        k_long_levels<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, ctx->ks.core_len, ctx->ks.mw_window,
+                                                                      (unsigned long long*)s.lg_bins.p);
         ctx->stats.kernel_launches += 1;
         CU(ctx, cudaMemcpyAsync(s.h_long, s.lg_bins.p, 3 * kLongBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaStreamSynchronize(st));
@@ -420,7 +421,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         if ((rc = ensure(ctx, s.lg_off, sizeof(int64_t) * (size_t)cap))) return rc;
         if ((rc = ensure(ctx, s.lg_cnt, 32 + 16 * 8))) return rc;  // [0] count, [1] scratch cursor, [2] redone chunks (cumulative)
         CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 16, st));
-        k_long_select<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, long_min, (int32_t*)s.lg_list.p,
+        k_long_select<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, long_min, ctx->ks.core_len,
+                                                                      ctx->ks.mw_window, (int32_t*)s.lg_list.p,
                                                                       (int64_t*)s.lg_off.p, (unsigned long long*)s.lg_cnt.p);
         ctx->stats.kernel_launches += 1;
         if (nlong_known >= 0) {
@@ -497,6 +499,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     if (d_summaries && use_v2) {
         if (use_long && nlong > 0) {
             if ((rc = ensure(ctx, s.lg_ext, (size_t)long_scratch + 256))) return rc;
+            if ((rc = ensure(ctx, s.lg_extT, (size_t)long_scratch + 256))) return rc;
             if ((rc = ensure(ctx, s.lg_tb, (size_t)long_scratch + 256))) return rc;
             if ((rc = ensure(ctx, s.lg_vit, (size_t)long_scratch / 8 + 256))) return rc;
             LongArgs la;
@@ -509,6 +512,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             la.tabs = ctx->d_tabs;
             la.out = d_summaries;
             la.ext = (uint8_t*)s.lg_ext.p;
+            la.extT = (uint8_t*)s.lg_extT.p;
+            la.cm_min = getenv("PLAAC_LONG_CM_MIN") ? atoi(getenv("PLAAC_LONG_CM_MIN")) : kLongChunkMajorMin;
             la.tb = (uint8_t*)s.lg_tb.p;
             la.vit = (uint32_t*)s.lg_vit.p;
             la.errflag = (int*)s.errflag.p;
@@ -894,12 +899,12 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
                 // decided after the walk (choose_long_threshold)
                 const int b = long_bin(len);
                 bins[b]++;
-                bins[kLongBins + b] += (unsigned long long)((len + kLongPadTail + 127) & ~(int64_t)127);
+                bins[kLongBins + b] += (unsigned long long)long_scratch_need(len, ctx->ks.core_len, ctx->ks.mw_window);
                 bins[2 * kLongBins + b] = std::max<unsigned long long>(bins[2 * kLongBins + b], (unsigned long long)len);
             } else if (long_min > 0 && len >= long_min) {
                 // scored by the long-sequence path; the bucketed stream sees an empty protein
                 nlp++;
-                lp_scratch += (len + kLongPadTail + 127) & ~(int64_t)127;
+                lp_scratch += long_scratch_need(len, ctx->ks.core_len, ctx->ks.mw_window);
             } else {
                 lmax = std::max(lmax, len);
                 nlong += len >= kHistBins;

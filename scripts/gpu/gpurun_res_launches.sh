@@ -1,4 +1,4 @@
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 --csv --log-file gpurun_out/res_launches.csv python gpurun_res_prof.py > gpurun_out/res_prof.log 2>&1
+PYTHONPATH=. ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 --csv --log-file gpurun_out/res_launches.csv python scripts/gpu/gpurun_res_prof.py > gpurun_out/res_prof.log 2>&1
 python - <<'PY'
 import csv,collections
 rows=[r for r in csv.reader(open('gpurun_out/res_launches.csv')) if len(r)>10]

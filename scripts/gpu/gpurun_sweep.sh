@@ -4,7 +4,7 @@ cp plaac_b200/csrc/summary_kernel_v2.cuh /tmp/orig.cuh
 for T in 768 640; do
   cp /tmp/orig.cuh plaac_b200/csrc/summary_kernel_v2.cuh
   sed -i "s/^constexpr int kV2MaxThreads = [0-9]*;/constexpr int kV2MaxThreads = $T;/" plaac_b200/csrc/summary_kernel_v2.cuh
-  python gpurun_tb_patch.py
+  PYTHONPATH=. python scripts/gpu/gpurun_tb_patch.py
   python plaac_b200/build.py -f -v 2>&1 | grep -A3 "k_score_summary_v2" | grep "Used"
   echo "threads=$T tb-patch"; $B | python -c "$P"
 done

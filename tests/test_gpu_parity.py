@@ -181,6 +181,32 @@ def test_long_path_mixed_batch_thresholds_and_fallback():
     sc.close()
 
 
+def test_long_path_both_scratch_layouts(monkeypatch):
+    """k_long_score walks a protein-major copy of the residues below 49 152 residues and a chunk-major one above
+    (LongArgs::extT): force each layout on proteins of both sizes; records must be the same bytes, and right."""
+    rng = np.random.default_rng(4242)
+    bg = synth.BG_SCER / synth.BG_SCER.sum()
+    prd = synth.PRD_28 / synth.PRD_28.sum()
+    seqs = []
+    for n in (8192, 9001, 24577, 49151, 49152, 60001):
+        s = rng.choice(22, size=n, p=bg).astype(np.uint8)
+        for st in (n // 7, n // 2, n - 150):
+            s[st:st + 150] = rng.choice(22, size=150, p=prd)
+        seqs.append(s)
+    codes, offs = plaac_b200.pack(seqs)
+    ref = orc.score_batch(orc.make_params(), codes, offs, nthreads=NT)
+    recs = {}
+    for cm_min in ("0", "49152", "1000000"):
+        monkeypatch.setenv("PLAAC_LONG_CM_MIN", cm_min)
+        sc = plaac_b200.Scorer(device=0)
+        got = sc.score(codes, offs)
+        assert sc.stats().long_proteins == len(seqs)
+        sc.close()
+        _check(got, ref, f"long path, chunk-major from {cm_min}")
+        recs[cm_min] = got.tobytes()
+    assert recs["0"] == recs["49152"] == recs["1000000"]
+
+
 @pytest.mark.parametrize("kw", [dict(core_len=30), dict(core_len=100, ww1=21, ww2=21), dict(ww1=40, ww2=40),
                                 dict(adjust_prolines=False), dict(core_len=7, ww1=5, ww2=5), dict(ww1=1, ww2=1)])
 def test_other_parameters(kw):
