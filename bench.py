@@ -147,7 +147,7 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def time_oracle(nprot, nthreads, full_jar_work, repeats=1):
+def time_oracle(nprot, nthreads, full_jar_work, repeats=1, keep=None):
     from oracle import orc
 
     codes, offsets = cpu_sample(nprot, SEED)
@@ -155,10 +155,30 @@ def time_oracle(nprot, nthreads, full_jar_work, repeats=1):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        orc.score_batch(P, codes, offsets, full_jar_work=full_jar_work, nthreads=nthreads)
+        ref = orc.score_batch(P, codes, offsets, full_jar_work=full_jar_work, nthreads=nthreads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
+    if keep is not None:
+        keep.update(codes=codes, offsets=offsets, ref=ref)
     return int(offsets[-1]), best
+
+
+def check_sample_against_oracle(scorer, kept):
+    """The CPU sample the oracle has just scored, through the product path: the oracle as the checker."""
+    from oracle import orc
+    from tests import parity
+
+    got = scorer.score(kept["codes"], kept["offsets"])
+    ref = kept["ref"]
+    int_bad = int(sum(int((got[f] != ref[f]).sum()) for f in orc.INT_FIELDS if f != "papa_center"))
+    bad = parity.compare_summaries(got, ref, [f for f in orc.INT_FIELDS if f != "papa_center"], orc.DBL_FIELDS)
+    cen = int((got["papa_center"] != ref["papa_center"]).sum())
+    return {"proteins": int(len(ref)), "int_mismatches": int_bad, "papa_center_differs": cen,
+            "max_rel_err": {f: parity.max_rel(got, ref, f) for f in ("llr", "core_score", "hmm_all", "hmm_vit", "papa_combo")},
+            "ok": not bad or all(("papa" in b) for b in bad),
+            "mismatches": bad[:5],
+            "note": "GPU records of the CPU sample vs the oracle's: integers bit-exact, doubles within 1e-9 relative "
+                    "(tests/parity.py); a differing PAPA centre is the documented exact-tie class (DESIGN.md 3)"}
 
 
 def run_reference(args, rank, world):
@@ -362,8 +382,16 @@ def main():
                "note": "plaac_score() on pinned host buffers in every rank (each GPU on its own PCIe link); byte counts are "
                        "whole-job totals; wall clock between barriers, max over ranks"}
         # sanity: both paths produce the same records
-        same = bool((h_sum.view(torch.int32)[:40] == summaries.cpu().view(torch.int32)[:40]).all())
+        # (every byte of every record: the host call scores the shard in pipelined chunks, the device call in one
+        # piece, so this is the chunking-invariance property at the full bench size)
+        same = True
+        piece = 1 << 28
+        flat = summaries.view(torch.uint8).reshape(-1)
+        for lo in range(0, flat.numel(), piece):
+            hi = min(flat.numel(), lo + piece)
+            same = same and bool(torch.equal(h_sum[lo:hi].to(dev, non_blocking=False), flat[lo:hi]))
         e2e["matches_device_path"] = same
+        e2e["records_compared"] = int(nprot)
         del h_codes, h_offsets, h_sum
 
     # ---- config 2 side measurement: per-residue mode (rank 0, N=1 only) -----------------------------
@@ -385,12 +413,16 @@ def main():
         n1 = args.cpu_sample_proteins or 6000
         nres1, dt1 = time_oracle(n1, 1, 1)
         nall = args.cpu_sample_proteins or 3000 * nthreads
-        nresn, dtn = time_oracle(nall, nthreads, 1)
+        kept = {}
+        nresn, dtn = time_oracle(nall, nthreads, 1, keep=kept)
+        sample_parity = check_sample_against_oracle(scorer, kept)
+        del kept
         nresn2, dtn2 = time_oracle(nall, nthreads, 0)
         cpu = {"value": nresn / dtn, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": f"{nall} proteins / {nresn} residues of the same synthetic distribution",
                "single_thread_value": nres1 / dt1,
                "needed_work_only_value": nresn2 / dtn2,
+               "gpu_parity_on_sample": sample_parity,
                "note": "oracle/plaac_oracle.c (gcc -O2 -ffp-contract=off), a line-faithful port of plaac.java; "
                        "value includes the posterior passes the jar computes but never prints; "
                        "needed_work_only_value skips them; single_thread_value is the jar's execution model; "
