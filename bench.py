@@ -213,7 +213,7 @@ def run_reference(args, rank, world):
                                    f"JVM {'present' if java.returncode == 0 else 'absent'} (plaac.jar not runnable)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -225,8 +225,29 @@ def workload_config(args, world):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries the one JSON line and nothing else: keep a private handle on it and send everything any library
+    prints to fd 1 (NCCL's version banner, for one, at some NCCL_DEBUG settings) to stderr instead."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -354,7 +375,18 @@ def main():
 
     # ---- end to end through the public host-buffer call -------------------------------------------
     e2e = None
+    e2e_skip = None
     if not args.no_e2e:
+        # every rank pins its shard's codes, offsets and records in host memory: make sure the box has room
+        need = (ntotal + 8 * (nprot + 1) + 160 * nprot) * max(1, world)
+        try:
+            with open("/proc/meminfo") as f:
+                avail = next(int(x.split()[1]) * 1024 for x in f if x.startswith("MemAvailable"))
+        except Exception:
+            avail = None
+        if avail is not None and need * 1.25 > avail:
+            e2e_skip = f"host memory: {need / 1e9:.0f} GB of pinned buffers needed, {avail / 1e9:.0f} GB available"
+    if not args.no_e2e and e2e_skip is None:
         h_codes = torch.empty(ntotal, dtype=torch.uint8).pin_memory()
         h_offsets = torch.empty(nprot + 1, dtype=torch.int64).pin_memory()
         h_sum = torch.empty(nprot * 160, dtype=torch.uint8).pin_memory()
@@ -393,6 +425,8 @@ def main():
         e2e["matches_device_path"] = same
         e2e["records_compared"] = int(nprot)
         del h_codes, h_offsets, h_sum
+    elif e2e_skip is not None:
+        e2e = {"value": None, "unit": UNIT, "skipped": e2e_skip}
 
     # ---- config 2 side measurement: per-residue mode (rank 0, N=1 only) -----------------------------
     per_res = None
@@ -438,7 +472,7 @@ def main():
             "extras": extras,
             "timing": "CUDA events on the library stream around K steps, max over ranks; wall %.3f s" % wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     scorer.close()
     if world > 1:
         dist.destroy_process_group()
