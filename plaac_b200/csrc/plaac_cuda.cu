@@ -35,7 +35,7 @@ struct DevBuf {
 // One set of device work buffers; plaac_score() cycles through kSlots of them to overlap copies with compute.
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count;
+    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count, scan_tmp;
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
     DevBuf res_b0, res_b1, res_a0, res_a1, res_mapw, res_lpseq;  // per-residue scratch (bucketed layout)
@@ -303,7 +303,7 @@ int slot_init(plaac_ctx* ctx, Slot& s)
 
 void slot_free(Slot& s)
 {
-    for (DevBuf* b : {&s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
+    for (DevBuf* b : {&s.scan_tmp, &s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
                       &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
@@ -384,6 +384,26 @@ LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long*
 
 // Enqueue the whole device pipeline for one batch on slot s.  d_offsets are absolute; off_base is
 // subtracted to index d_codes.  Contains ONE stream synchronisation (the padded stream size).
+// Exclusive scan out[0..n] of n int32 values on stream st: one CTA for small inputs, tiled (3 launches) for large ones.
+int launch_scan(plaac_ctx* ctx, Slot& s, const int32_t* in, int64_t* out, int64_t n, cudaStream_t st)
+{
+    if (n <= 4 * kScanTile) {
+        k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>(in, out, n);
+        ctx->stats.kernel_launches += 1;
+        return PLAAC_OK;
+    }
+    const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+    int rc;
+    if ((rc = ensure(ctx, s.scan_tmp, sizeof(int64_t) * (size_t)(2 * ntiles + 2)))) return rc;
+    int64_t* tile_sum = (int64_t*)s.scan_tmp.p;
+    int64_t* tile_base = tile_sum + ntiles;
+    k_scan_tile_sums<int32_t><<<(unsigned)ntiles, 1024, 0, st>>>(in, n, tile_sum);
+    k_scan_exclusive<int64_t><<<1, 1024, 0, st>>>(tile_sum, tile_base, ntiles);
+    k_scan_tiles_apply<int32_t><<<(unsigned)ntiles, 1024, 0, st>>>(in, n, tile_base, ntiles, out);
+    ctx->stats.kernel_launches += 3;
+    return PLAAC_OK;
+}
+
 int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_offsets, int64_t off_base,
               int64_t nprot, int64_t ntotal, plaac_summary* d_summaries, const plaac_residue_out* d_res,
               int64_t res_base, int64_t slots_bound = -1, int64_t nlong_known = -1, int64_t long_scratch_known = -1,
@@ -447,8 +467,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     k_scatter<<<g_scat, kPrepThreads, kHistSmemBytes, st>>>(d_offsets, nprot, lm, (int64_t*)s.cursor.p, (int32_t*)s.order.p);
     const unsigned gb = (unsigned)((nbuckets * 32 + tb - 1) / tb);
     k_bucket_chunks<<<gb, tb, 0, st>>>(d_offsets, (const int32_t*)s.order.p, nprot, nbuckets, lm, (int32_t*)s.nchunks.p);
-    k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.nchunks.p, (int64_t*)s.chunk_base.p, nbuckets);
-    ctx->stats.kernel_launches += 5;
+    if ((rc = launch_scan(ctx, s, (const int32_t*)s.nchunks.p, (int64_t*)s.chunk_base.p, nbuckets, st))) return rc;
+    ctx->stats.kernel_launches += 4;
     CU(ctx, cudaMemcpyAsync(s.h_total, (int64_t*)s.chunk_base.p + nbuckets, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     int64_t slots = slots_bound;
     if (slots < 0) {
@@ -1263,11 +1283,11 @@ int rank_pass(plaac_ctx* ctx, Slot& s, int64_t n, int shift, int cur)
     cudaStream_t st = s.stream;
     k_rank_hist<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>((const uint64_t*)s.rk_keys[cur].p, n, shift,
                                                                   (int32_t*)s.rk_hist.p, ntiles);
-    k_scan_exclusive<int32_t><<<1, 1024, 0, st>>>((const int32_t*)s.rk_hist.p, (int64_t*)s.rk_offs.p, kRankDigits * ntiles);
+    if ((rc = launch_scan(ctx, s, (const int32_t*)s.rk_hist.p, (int64_t*)s.rk_offs.p, (int64_t)kRankDigits * ntiles, st))) return rc;
     k_rank_scatter<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>(
         (const uint64_t*)s.rk_keys[cur].p, (const int32_t*)s.rk_vals[cur].p, (uint64_t*)s.rk_keys[cur ^ 1].p,
         (int32_t*)s.rk_vals[cur ^ 1].p, n, shift, (const int64_t*)s.rk_offs.p, ntiles);
-    ctx->stats.kernel_launches += 3;
+    ctx->stats.kernel_launches += 2;
     CU(ctx, cudaGetLastError());
     return PLAAC_OK;
 }
