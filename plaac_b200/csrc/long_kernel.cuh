@@ -148,6 +148,25 @@ __device__ __forceinline__ void long_chunk_bar()
     asm volatile("bar.sync 1, %0;" ::"n"(kLongChunkWarps * 32) : "memory");
 }
 
+// The exact forward combine (the longest single-lane walk: it redoes the binade-crossing chunks sequentially, ~300 cycles per
+// residue) runs on warp kLongChunkWarps beside everything that does not need its result (the other combines, the
+// traceback, the CORE search).  Barrier 2: pass 2 is complete (chunk warps + that warp).  Barrier 3: the other combines
+// are complete (the chunk warps only arrive; the forward warp waits for hmm0's emission sum there).
+constexpr int kLongFwdWarp = kLongChunkWarps;
+__device__ __forceinline__ void long_pass2_bar()
+{
+    asm volatile("bar.sync 2, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
+}
+__device__ __forceinline__ void long_combined_arrive()
+{
+    __threadfence_block();
+    asm volatile("bar.arrive 3, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
+}
+__device__ __forceinline__ void long_combined_wait()
+{
+    asm volatile("bar.sync 3, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
+}
+
 // Automatic threshold: length bins from 1024 up (256-residue steps to 16384, then powers of two); the host picks the
 // smallest bin edge that leaves at most one wave of long proteins (plaac_cuda.cu: choose_long_threshold).
 constexpr int kLongBins = 78;
@@ -202,6 +221,11 @@ __device__ __forceinline__ MP2 mp_shfl_up(const MP2& a, int d)
     do {                                                                           \
         if (g.dbg_clocks && tid == 0 && blockIdx.x == 0) g.dbg_clocks[i] = clock64(); \
     } while (0)
+// the same from whichever single lane runs a walk (slots 9..14: ends of the single-lane combines)
+#define LONG_STAMP_LANE(i)                                                    \
+    do {                                                                      \
+        if (g.dbg_clocks && blockIdx.x == 0) g.dbg_clocks[i] = clock64();     \
+    } while (0)
 
 template <bool CM>
 __device__ __forceinline__ void long_score_body(const LongArgs& g)
@@ -249,21 +273,36 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             for (int i = tid; i < C * Kp; i += kLongThreads) extT[i] = (uint8_t)kPad;
             __syncthreads();
         }
-        for (int i = tid; i < n; i += kLongThreads) {
-            uint32_t cd = src[i];
-            if (cd > 21u) {
-                bad = 1;
-                cd = 0;
+        // eight residues per thread and trip, all loads issued before the first use (a single byte load per trip left
+        // the CTA waiting on DRAM latency: 0.1 ms of the 1.4 ms at 100 k residues)
+        constexpr int kU = 8;
+        for (int base = 0; base < n; base += kLongThreads * kU) {
+            uint32_t cd[kU], p1[kU], p2[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int i = base + u * kLongThreads + tid;
+                cd[u] = i < n ? (uint32_t)src[i] : 0u;
+                p1[u] = (i < n && i >= 1) ? (uint32_t)src[i - 1] : 0u;
+                p2[u] = (i < n && i >= 2) ? (uint32_t)src[i - 2] : 0u;
             }
-            uint32_t e = cd;
-            if (ks.adjust_prolines && cd == 13u && ((i >= 1 && src[i - 1] == 13) || (i >= 2 && src[i - 2] == 13)))
-                e |= (uint32_t)kPapaMaskBit;
-            if ((ks.charge_plus >> cd) & 1u)
-                e |= 0x40u;
-            else if ((ks.charge_minus >> cd) & 1u)
-                e |= 0xc0u;
-            ext[i] = (uint8_t)e;
-            if (cm) extT[(size_t)(i % C) * Kp + i / C] = (uint8_t)e;
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int i = base + u * kLongThreads + tid;
+                if (i >= n) continue;
+                uint32_t c0 = cd[u];
+                if (c0 > 21u) {
+                    bad = 1;
+                    c0 = 0;
+                }
+                uint32_t e = c0;
+                if (ks.adjust_prolines && c0 == 13u && (p1[u] == 13u || p2[u] == 13u)) e |= (uint32_t)kPapaMaskBit;
+                if ((ks.charge_plus >> c0) & 1u)
+                    e |= 0x40u;
+                else if ((ks.charge_minus >> c0) & 1u)
+                    e |= 0xc0u;
+                ext[i] = (uint8_t)e;
+                if (cm) extT[(size_t)(i % C) * Kp + i / C] = (uint8_t)e;
+            }
         }
         for (int i = n + tid; i < n + kLongPadTail; i += kLongThreads) ext[i] = (uint8_t)kPad;
         if (bad) atomicOr(g.errflag, 1);
@@ -682,7 +721,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                 sm.q_inc[2][0] = shy;
             }
         }
-        long_chunk_bar();
+        long_pass2_bar();
         LONG_STAMP(3);
         // ================= combine 2: exact, in chunk order =================
         if (wid == 0 && lane == 0) {
@@ -691,6 +730,10 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             for (int kk = 1; kk < K; kk++) {
                 const int s = kk * C, e = min(n, s + C);
                 if (sm.cross_v[kk]) {
+                    // redone from the exact values; f0/f1 = state at the last residue of the previous chunk if the
+                    // state at t is 0/1 (the composition of the traceback maps, so the walk back below needs no
+                    // second pass over the chunk: its dependent loads of the just-written bytes cost more than the redo)
+                    int f0 = 0, f1 = 1;
 #pragma unroll 8
                     for (int t = s; t < e; t++) {
                         const double2 le = sm.le[ext[t] & 31];
@@ -699,7 +742,11 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                         S0 = (p0 ? v10 : v00) + le.x;
                         S1 = (p1 ? v11 : v01) + le.y;
                         tbT[(size_t)(t - s) * sR + (size_t)kk * sK] = (uint8_t)((int)p0 | ((int)p1 << 1));
+                        const int n0 = p0 ? f1 : f0, n1 = p1 ? f1 : f0;
+                        f0 = n0;
+                        f1 = n1;
                     }
+                    sm.choice[kk] = (unsigned char)(f0 | (f1 << 1));
                 } else {
                     const double R = sm.Sa[0][kk - 1];
                     const double d0 = S0 - R, d1 = S1 - R;  // exact shifts
@@ -718,58 +765,13 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             int e = vlast;
             for (int kk = K - 1; kk >= 1; kk--) {
                 sm.endstate[kk] = (unsigned char)e;
-                if (sm.cross_v[kk]) {
-                    const int s = kk * C, en = min(n, s + C);
-                    for (int t = en - 1; t >= s; t--) e = (tbT[(size_t)(t - s) * sR + (size_t)kk * sK] >> e) & 1;
-                    sm.variant[kk] = 0;
-                } else {
-                    const int v = (sm.choice[kk] >> e) & 1;
-                    sm.variant[kk] = (unsigned char)v;
-                    e = v;  // state at the last residue of the previous chunk
-                }
+                const int v = (sm.choice[kk] >> e) & 1;
+                sm.variant[kk] = sm.cross_v[kk] ? 0 : (unsigned char)v;  // redone chunks hold the exact bits as variant A
+                e = v;  // state at the last residue of the previous chunk
             }
             sm.endstate[0] = (unsigned char)e;
             sm.variant[0] = 0;
-        } else if (wid == 1 && lane == 0) {
-            // forward: the chunk's trajectory is the jar's iff it enters the chunk with the bits of d the previous
-            // chunk left with; then its increment is added exactly.  Otherwise the chunk is redone from the exact values.
-            double A0 = sm.f_inc[0], dex = sm.f_dexit[0];
-            double A1 = A0 + dex;
-            int nfb = 0;
-            for (int kk = 1; kk < K; kk++) {
-                // a frame is the jar's trajectory iff it enters the chunk an EVEN number of ulps away from the true a0
-                // and with exactly the bits of d the previous chunk left with
-                int fr = -1;
-                if (!g.force_seq_forward && !sm.cross_f[kk]) {
-                    const double u = __hiloint2double((((__double2hiint(fabs(A0)) >> 20) & 0x7ff) - 52) << 20, 0);
-#pragma unroll
-                    for (int f = 0; f < 2; f++) {
-                        const double q = (sm.g_ea0[f][kk] - A0) / u;  // exact: a small integer
-                        if (fr < 0 && q == 2.0 * rint(0.5 * q) &&
-                            __double_as_longlong(sm.g_den[f][kk]) == __double_as_longlong(dex))
-                            fr = f;
-                    }
-                }
-                if (fr >= 0) {
-                    A0 = A0 + sm.g_inc[fr][kk];
-                    dex = sm.g_dex[fr][kk];
-                    A1 = A0 + dex;
-                } else {
-                    const int s = kk * C, e = min(n, s + C);
-#pragma unroll 8
-                    for (int t = s; t < e; t++) {
-                        const double2 le = sm.le[ext[t] & 31];
-                        const double f0 = lse_lut2<false>(ks.lt00 + A0, ks.lt10 + A1, lut_addr) + le.x;
-                        const double f1 = lse_lut2<false>(ks.lt01 + A0, ks.lt11 + A1, lut_addr) + le.y;
-                        A0 = f0;
-                        A1 = f1;
-                    }
-                    dex = A1 - A0;
-                    nfb += sm.cross_f[kk] ? 0 : 1;
-                }
-            }
-            sm.fwd_redone = nfb;
-            sm.lmarg = lse_lut2<false>(A0 + ks.lf0, A1 + ks.lf1, lut_addr);
+            LONG_STAMP_LANE(9);
         } else if (wid == 3 && lane == 0) {
             // LLR window search: chunk maxima in order (first strict maximum), crossing chunks redone from exact values
             double P = sm.q_inc[0][0], Pl = sm.q_mid[0];
@@ -809,6 +811,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             }
             sm.llr_best = best;
             sm.llr_stop = stop;
+            LONG_STAMP_LANE(10);
         } else if (wid == 4 && lane < 2) {
             // hmm0's emission sum (lane 0) and the hydropathy sum (lane 1)
             const int q = 1 + lane;
@@ -828,6 +831,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                 sm.sum0 = x;
             else
                 sm.sh = x;
+            LONG_STAMP_LANE(12 + lane);
         } else if (wid == 5 && lane == 0) {
             int best = sm.m_best[0], stop = sm.m_stop[0], cq = sm.c_sum[0];
             for (int kk = 1; kk < K; kk++) {
@@ -877,6 +881,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         sm.pVfi = vfib;
         }
         long_chunk_bar();
+        long_combined_arrive();
         LONG_STAMP(4);
         // ---- traceback of every chunk in parallel (:3110-3113) + run statistics for longestrun (:1787-1804)
         if (live) {
@@ -909,12 +914,62 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             sm.v_suf[k] = closed ? suf : cur;
             sm.v_max[k] = inmax;
         }
-    }
-    __syncthreads();
+        long_chunk_bar();
+    } else if (wid == kLongFwdWarp) {
+        long_pass2_bar();
+        if (lane == 0) {
+            // forward: the chunk's trajectory is the jar's iff it enters the chunk with the bits of d the previous
+            // chunk left with; then its increment is added exactly.  Otherwise the chunk is redone from the exact values.
+            double A0 = sm.f_inc[0], dex = sm.f_dexit[0];
+            double A1 = A0 + dex;
+            int nfb = 0;
+            for (int kk = 1; kk < K; kk++) {
+                // a frame is the jar's trajectory iff it enters the chunk an EVEN number of ulps away from the true a0
+                // and with exactly the bits of d the previous chunk left with
+                int fr = -1;
+                if (!g.force_seq_forward && !sm.cross_f[kk]) {
+                    const double u = __hiloint2double((((__double2hiint(fabs(A0)) >> 20) & 0x7ff) - 52) << 20, 0);
+#pragma unroll
+                    for (int f = 0; f < 2; f++) {
+                        const double q = (sm.g_ea0[f][kk] - A0) / u;  // exact: a small integer
+                        if (fr < 0 && q == 2.0 * rint(0.5 * q) &&
+                            __double_as_longlong(sm.g_den[f][kk]) == __double_as_longlong(dex))
+                            fr = f;
+                    }
+                }
+                if (fr >= 0) {
+                    A0 = A0 + sm.g_inc[fr][kk];
+                    dex = sm.g_dex[fr][kk];
+                    A1 = A0 + dex;
+                } else {
+                    const int s = kk * C, e = min(n, s + C);
+#pragma unroll 8
+                    for (int t = s; t < e; t++) {
+                        const double2 le = sm.le[ext[t] & 31];
+                        const double f0 = lse_lut2<false>(ks.lt00 + A0, ks.lt10 + A1, lut_addr) + le.x;
+                        const double f1 = lse_lut2<false>(ks.lt01 + A0, ks.lt11 + A1, lut_addr) + le.y;
+                        A0 = f0;
+                        A1 = f1;
+                    }
+                    dex = A1 - A0;
+                    nfb += sm.cross_f[kk] ? 0 : 1;
+                }
+            }
+            sm.fwd_redone = nfb;
+            sm.lmarg = lse_lut2<false>(A0 + ks.lf0, A1 + ks.lf1, lut_addr);
+            LONG_STAMP_LANE(11);
+        }
+        long_combined_wait();
+        if (lane == 0) {
+            g.out[prot].hmm_all = sm.lmarg - sm.sum0;
+            if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
+        }
+        return;
+    } else
+        return;
     LONG_STAMP(6);
 
     if (tid != 0) return;
-    if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
     plaac_summary* r = g.out + prot;
     r->prot_len = n;
     r->mw_score = sm.mw_best;
@@ -923,7 +978,6 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
     r->llr = sm.llr_best;
     r->llr_start = sm.llr_stop - c + 1;
     r->llr_end = sm.llr_stop;
-    r->hmm_all = sm.lmarg - sm.sum0;
     r->hmm_vit = sm.lvit - sm.sum0;
     const double mh = (1.0 * sm.sh) / (double)n;
     const double mc = (1.0 * (double)sm.csum) / (double)n;

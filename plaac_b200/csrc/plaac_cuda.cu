@@ -841,7 +841,7 @@ int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
         long long ck[16];
         if (cudaMemcpy(ck, (char*)ctx->slot[0].lg_cnt.p + 32, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
             std::fprintf(stderr, "long-path clocks (cycles since kernel start):");
-            for (int i = 1; i <= 8; i++) std::fprintf(stderr, " %lld", ck[i] ? ck[i] - ck[0] : 0LL);
+            for (int i = 1; i <= 13; i++) std::fprintf(stderr, " %lld", ck[i] ? ck[i] - ck[0] : 0LL);
             std::fprintf(stderr, "\n");
         }
     }

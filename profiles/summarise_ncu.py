@@ -41,8 +41,8 @@ def main():
         res = float(sys.argv[2])
         inst = float(v[h.index("smsp__inst_executed.sum")].replace(",", ""))
         ratio = float(v[h.index("smsp__thread_inst_executed_per_inst_executed.ratio")])
-        rd = float(v[h.index("dram__bytes_read.sum")]) * {"Gbyte": 1e9, "Mbyte": 1e6, "byte": 1}[u[h.index("dram__bytes_read.sum")]]
-        wr = float(v[h.index("dram__bytes_write.sum")]) * {"Gbyte": 1e9, "Mbyte": 1e6, "byte": 1}[u[h.index("dram__bytes_write.sum")]]
+        rd = float(v[h.index("dram__bytes_read.sum")]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u[h.index("dram__bytes_read.sum")]]
+        wr = float(v[h.index("dram__bytes_write.sum")]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u[h.index("dram__bytes_write.sum")]]
         print(f"residues per launch {res:.0f}")
         print(f"thread-instructions per residue {inst * ratio / res:.1f}")
         print(f"DRAM bytes per residue {(rd + wr) / res:.2f}  (read {rd / res:.2f}, write {wr / res:.2f})")

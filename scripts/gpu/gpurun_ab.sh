@@ -16,6 +16,7 @@ for lengths in [(100000,), (80000,), (65000,), (50000,), (35000,), (9000,)]:
     print(lengths, min(ts), sorted(ts)[len(ts) // 2], flush=True)
     sc.close()
 PY
-for v in 49152 0 1000000; do echo "== cm_min $v"; PLAAC_LONG_CM_MIN=$v PYTHONPATH=. python /tmp/ab.py; done
+for v in 49152; do echo "== cm_min $v"; PLAAC_LONG_CM_MIN=$v PYTHONPATH=. python /tmp/ab.py; done
 python -m pytest tests/test_gpu_parity.py tests/test_jar_vectors.py tests/test_gpu_fuzz.py -m gpu -x -q -k "long or random_case_against or tie" 2>&1 | tail -4
 PLAAC_LONG_CM_MIN=0 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -x -q -k "long or random_case_against or tie" 2>&1 | tail -4
+PLAAC_LONG_TIES=1 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "long_sequences or mixed_batch" 2>&1 | tail -2
