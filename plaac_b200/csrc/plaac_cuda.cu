@@ -208,6 +208,7 @@ int setup_scalars(plaac_ctx* ctx)
         const size_t fixed2 = (size_t)kV2FixedBytes + kV2AlignSlack;
         if (fixed2 + 2 * per_warp <= limit) {
             int nwr = (int)std::min<size_t>(kV2MaxThreads / 64, (limit - fixed2) / (2 * per_warp));
+            if (const char* e = getenv("PLAAC_V2_WARP_PAIRS")) nwr = std::max(1, std::min(nwr, atoi(e)));  // experiments
             ctx->v2_nwr = nwr;
             ctx->v2_smem_bytes = fixed2 + per_warp * 2 * nwr;
         } else

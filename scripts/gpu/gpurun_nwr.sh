@@ -1,0 +1,3 @@
+for n in 12 11 10 8; do
+PLAAC_V2_WARP_PAIRS=$n python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-per-residue --no-extras | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$n', 'value %.4g ms/step %.2f kernel_ms %.2f frac %.3f'%(d['value'],d['ms_per_step'],d['roofline']['kernel_ms'],d['roofline']['frac']))"
+done
