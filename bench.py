@@ -387,9 +387,11 @@ def main():
         if avail is not None and need * 1.25 > avail:
             e2e_skip = f"host memory: {need / 1e9:.0f} GB of pinned buffers needed, {avail / 1e9:.0f} GB available"
     if not args.no_e2e and e2e_skip is None:
-        h_codes = torch.empty(ntotal, dtype=torch.uint8).pin_memory()
-        h_offsets = torch.empty(nprot + 1, dtype=torch.int64).pin_memory()
-        h_sum = torch.empty(nprot * 160, dtype=torch.uint8).pin_memory()
+        # host buffers from the library's own allocator (plaac_host_alloc: page-locked), as a host program would hold them
+        pb_codes = plaac_b200.PinnedBuffer(ntotal, np.uint8)
+        pb_offsets = plaac_b200.PinnedBuffer(nprot + 1, np.int64)
+        pb_sum = plaac_b200.PinnedBuffer(nprot * 160, np.uint8)
+        h_codes, h_offsets, h_sum = (torch.from_numpy(b.array) for b in (pb_codes, pb_offsets, pb_sum))
         h_codes.copy_(codes[:ntotal])
         h_offsets.copy_(offsets)
         torch.cuda.synchronize()
@@ -411,7 +413,7 @@ def main():
         e2e = {"value": res_total * args.steps / float(tt[0]), "unit": UNIT,
                "h2d_bytes_per_step": int(res_total + 8 * (nprot + 1) * world), "d2h_bytes_per_step": int(160 * nprot * world),
                "ms_per_step": float(tt[0]) / args.steps * 1e3,
-               "note": "plaac_score() on pinned host buffers in every rank (each GPU on its own PCIe link); byte counts are "
+               "note": "plaac_score() on host buffers from plaac_host_alloc (page-locked) in every rank (each GPU on its own PCIe link); byte counts are "
                        "whole-job totals; wall clock between barriers, max over ranks"}
         # sanity: both paths produce the same records
         # (every byte of every record: the host call scores the shard in pipelined chunks, the device call in one
@@ -425,6 +427,8 @@ def main():
         e2e["matches_device_path"] = same
         e2e["records_compared"] = int(nprot)
         del h_codes, h_offsets, h_sum
+        for b in (pb_codes, pb_offsets, pb_sum):
+            b.close()
     elif e2e_skip is not None:
         e2e = {"value": None, "unit": UNIT, "skipped": e2e_skip}
 

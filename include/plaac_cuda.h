@@ -126,6 +126,21 @@ const char *plaac_last_error(const plaac_ctx *ctx);
 int plaac_score(plaac_ctx *ctx, const uint8_t *codes, const int64_t *offsets, int64_t nprot,
                 plaac_summary *summaries, const plaac_residue_out *per_res);
 
+/* Page-locked host memory for the buffers handed to plaac_score / plaac_score_multi / plaac_ingest_fasta.  The
+ * reference has no counterpart (its arrays live on the Java heap, plaac.java:755-948); a host that keeps the batch in
+ * ordinary pageable memory still gets correct results, but the driver then stages every copy and the chunk pipeline of
+ * plaac_score runs at a fraction of the PCIe rate.  Usable before any ctx exists; errors are
+ * reported like plaac_create's (plaac_last_error(NULL)).
+ *   plaac_host_alloc     new pinned block (flags: 0, or PLAAC_HOST_WRITE_COMBINED for blocks the host only writes
+ *                        sequentially, e.g. codes: not cached on the CPU side, slow to read back);
+ *   plaac_host_register  pins memory the host already owns (a Java FFM MemorySegment, a malloc'd block); pinning costs
+ *                        about as much as one pass over the memory, so register buffers that are reused. */
+#define PLAAC_HOST_WRITE_COMBINED 1
+int plaac_host_alloc(void **out, size_t bytes, int flags);
+int plaac_host_free(void *p);
+int plaac_host_register(void *p, size_t bytes);
+int plaac_host_unregister(void *p);
+
 /* Same with DEVICE buffers already resident on ctx's GPU (offsets[0] must be 0,
  * ntotal = offsets[nprot]).  Work is enqueued on the ctx stream; call
  * plaac_sync() (or synchronise plaac_stream()) before reading the outputs. */

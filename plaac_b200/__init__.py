@@ -6,5 +6,5 @@ and bench.py; it has no CPU fallback and raises if the CUDA library is missing.
 """
 from .capi import (  # noqa: F401
     LIB_PATH, PlaacError, Params, Summary, SUMMARY_DTYPE, Scorer, default_params, encode, lib, pack,
-    RESIDUE_F64, RESIDUE_U8, MultiScorer, shard_plan,
+    RESIDUE_F64, RESIDUE_U8, MultiScorer, shard_plan, PinnedBuffer, host_register, host_unregister,
 )

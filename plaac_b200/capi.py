@@ -100,6 +100,10 @@ def lib():
         L.plaac_params_init.argtypes = [C.POINTER(Params), dbl, vp, vp, i32, i32, i32, i32, i32, vp]
         L.plaac_encode_host.restype = None
         L.plaac_encode_host.argtypes = [vp, i64, vp]
+        for nm, at in (("plaac_host_alloc", [C.POINTER(vp), C.c_size_t, C.c_int]), ("plaac_host_free", [vp]),
+                       ("plaac_host_register", [vp, C.c_size_t]), ("plaac_host_unregister", [vp])):
+            getattr(L, nm).restype = C.c_int
+            getattr(L, nm).argtypes = at
         L.plaac_set_chunk.restype = C.c_int
         L.plaac_set_chunk.argtypes = [vp, i64, i64]
         L.plaac_set_long_path.restype = C.c_int
@@ -176,6 +180,51 @@ def pack(seqs):
     np.cumsum(lens, out=offsets[1:])
     codes = np.concatenate(seqs).astype(np.uint8) if len(seqs) and offsets[-1] > 0 else np.zeros(0, np.uint8)
     return np.ascontiguousarray(codes), offsets
+
+
+class PinnedBuffer:
+    """Page-locked host memory from plaac_host_alloc as a numpy array (`.array`); freed by close() / the context
+    manager / garbage collection.  Hand `.array` (or slices of it) to Scorer.score()."""
+
+    def __init__(self, shape, dtype=np.uint8, write_combined=False):
+        self.dtype = np.dtype(dtype)
+        self.shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        rc = lib().plaac_host_alloc(C.byref(p), nbytes, 1 if write_combined else 0)
+        if rc != 0:
+            raise PlaacError(rc, lib().plaac_last_error(None).decode())
+        self.ptr = p.value
+        self.nbytes = nbytes
+        raw = (C.c_uint8 * max(1, nbytes)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=nbytes // self.dtype.itemsize).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().plaac_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def host_register(arr: np.ndarray):
+    """Pins the memory of an existing contiguous numpy array (plaac_host_register); undo with host_unregister."""
+    rc = lib().plaac_host_register(arr.ctypes.data, arr.nbytes)
+    if rc != 0:
+        raise PlaacError(rc, lib().plaac_last_error(None).decode())
+
+
+def host_unregister(arr: np.ndarray):
+    rc = lib().plaac_host_unregister(arr.ctypes.data)
+    if rc != 0:
+        raise PlaacError(rc, lib().plaac_last_error(None).decode())
 
 
 class Scorer:

@@ -664,6 +664,56 @@ int plaac_device_count(void)
     return n;
 }
 
+int plaac_host_alloc(void** out, size_t bytes, int flags)
+{
+    if (!out) return fail(nullptr, PLAAC_E_INVALID, "plaac_host_alloc: NULL argument");
+    *out = nullptr;
+    if (flags & ~PLAAC_HOST_WRITE_COMBINED) return fail(nullptr, PLAAC_E_INVALID, "plaac_host_alloc: unknown flags %d", flags);
+    const unsigned f = cudaHostAllocPortable | ((flags & PLAAC_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0u);
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, f);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? PLAAC_E_NOMEM : PLAAC_E_CUDA, "cudaHostAlloc(%zu bytes): %s", bytes,
+                    cudaGetErrorString(e));
+    }
+    return PLAAC_OK;
+}
+
+int plaac_host_free(void* p)
+{
+    if (!p) return PLAAC_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, PLAAC_E_INVALID, "cudaFreeHost: %s", cudaGetErrorString(e));
+    }
+    return PLAAC_OK;
+}
+
+int plaac_host_register(void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return fail(nullptr, PLAAC_E_INVALID, "plaac_host_register: empty range");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? PLAAC_E_NOMEM : PLAAC_E_INVALID, "cudaHostRegister(%zu bytes): %s",
+                    bytes, cudaGetErrorString(e));
+    }
+    return PLAAC_OK;
+}
+
+int plaac_host_unregister(void* p)
+{
+    if (!p) return PLAAC_OK;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, PLAAC_E_INVALID, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return PLAAC_OK;
+}
+
 int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
 {
     if (!out || !params) return fail(nullptr, PLAAC_E_INVALID, "plaac_create: NULL argument");

@@ -51,6 +51,11 @@ public final class Plaac {
         private static final MethodHandle SCORE =
             fn("plaac_score", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
 
+        // int plaac_host_alloc(void **out, size_t bytes, int flags); int plaac_host_free(void *p)
+        private static final MethodHandle HOST_ALLOC =
+            fn("plaac_host_alloc", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_INT));
+        private static final MethodHandle HOST_FREE = fn("plaac_host_free", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+
         static final long SUMMARY_BYTES = 160;   // plaac_summary: 14 x int32, 13 x double
         // plaac_params: 8 x int32, then lt[2][2] li[2] lf[2] le[2][22] le0 llr papa_lod hydro2 charge (22 each) fi_cc[3]
         // big_neg ln2 loglut[4001]
@@ -103,14 +108,30 @@ public final class Plaac {
             return m.reinterpret(512).getString(0);
         }
 
+        /** Page-locked native memory (plaac_host_alloc), released with the arena: plaac_score overlaps the copies of a
+         *  batch with its compute only when the batch lies in pinned memory (pageable memory is staged by the driver). */
+        static MemorySegment pinned(long bytes, Arena a) throws Throwable {
+            long n = Math.max(1L, bytes);
+            MemorySegment out = a.allocate(ADDRESS);
+            int rc = (int) HOST_ALLOC.invokeExact(out, n, 0);
+            if (rc != 0) throw new IllegalStateException("plaac_host_alloc failed (" + rc + "): " + lastError(MemorySegment.NULL));
+            return out.get(ADDRESS, 0).reinterpret(n, a, seg -> {
+                try {
+                    int ignored = (int) HOST_FREE.invokeExact(seg);
+                } catch (Throwable t) {
+                    throw new IllegalStateException(t);
+                }
+            });
+        }
+
         /** Summary records of one batch (record i at i * 160). */
         MemorySegment score(Batch b, Arena a) throws Throwable {
             int nprot = b.names.size();
-            MemorySegment codes = a.allocate(Math.max(1, b.ncodes));
+            MemorySegment codes = pinned(b.ncodes, a);
             MemorySegment.copy(b.codes, 0, codes, JAVA_BYTE, 0, b.ncodes);
-            MemorySegment offs = a.allocate(8L * (nprot + 1), 8);
+            MemorySegment offs = pinned(8L * (nprot + 1), a);
             for (int i = 0; i <= nprot; i++) offs.setAtIndex(JAVA_LONG, i, b.offsets.get(i));
-            MemorySegment sum = a.allocate(SUMMARY_BYTES * nprot, 8);
+            MemorySegment sum = pinned(SUMMARY_BYTES * nprot, a);
             int rc = (int) SCORE.invokeExact(ctx, codes, offs, (long) nprot, sum, MemorySegment.NULL);
             if (rc != 0) throw new IllegalStateException("plaac_score failed (" + rc + "): " + lastError(ctx));
             return sum;

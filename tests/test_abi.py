@@ -64,3 +64,8 @@ def test_no_gpu_fails_loudly():
     with pytest.raises(plaac_b200.PlaacError) as e:
         plaac_b200.Scorer()
     assert e.value.code == -5
+    # the pinned-memory helpers report an error too (no crash, no silent pageable fallback)
+    with pytest.raises(plaac_b200.PlaacError):
+        plaac_b200.PinnedBuffer(1024)
+    with pytest.raises(plaac_b200.PlaacError):
+        plaac_b200.host_register(np.zeros(4096, np.uint8))

@@ -275,6 +275,30 @@ def test_invalid_inputs_are_reported(scorer):
     assert got["prot_len"][0] == 3
 
 
+def test_pinned_host_buffers(scorer):
+    """plaac_host_alloc (plain and write-combined) and plaac_host_register: same records as from pageable memory."""
+    codes, offs = synth.proteome(3000, seed=11)
+    n = len(offs) - 1
+    ref = scorer.score(codes, offs)
+    with plaac_b200.PinnedBuffer(len(codes), np.uint8, write_combined=True) as pc, \
+            plaac_b200.PinnedBuffer(len(offs), np.int64) as po, \
+            plaac_b200.PinnedBuffer(n, plaac_b200.SUMMARY_DTYPE) as ps:
+        pc.array[:] = codes
+        po.array[:] = offs
+        scorer.score_ptr(pc.ptr, po.ptr, n, ps.ptr)
+        assert ps.array.tobytes() == ref.tobytes()
+    c2 = codes.copy()
+    plaac_b200.host_register(c2)
+    try:
+        assert scorer.score(c2, offs).tobytes() == ref.tobytes()
+    finally:
+        plaac_b200.host_unregister(c2)
+    with pytest.raises(plaac_b200.PlaacError):
+        plaac_b200.host_unregister(np.zeros(64, np.uint8))  # never registered
+    with pytest.raises(plaac_b200.PlaacError):
+        plaac_b200.host_register(np.zeros(0, np.uint8))
+
+
 def test_device_resident_api_and_stats(scorer):
     import torch
 
