@@ -3,6 +3,8 @@
 Runs web/bin/plaac.jar's `plaac.main` under tests/golden/minijvm.py (this image has no JVM) on
   * cli/example/four_classic_prions.fasta of the reference (summary table and `-p all` per-residue table), and
   * a synthetic FASTA of edge cases (written by this script, embedded in the fixture),
+  * two long proteins (chunked long-sequence path) and eight proteins of human composition scored with
+    `-B bg_freqs_HUMAN.txt -a 0.5` (config 3's background blend),
 and stores every value the jar passed to System.out.format()/print() at full precision.
 
     python tests/golden/make_jar_vectors.py        # needs /root/reference; writes tests/golden/jar_vectors.json.gz
@@ -151,6 +153,31 @@ def long_fasta():
     return "\n".join(lines) + "\n"
 
 
+def human_fasta():
+    """Config 3's parameter path: proteins of human background composition (half of them with a Q/N-rich segment),
+    scored with `-B bg_freqs_HUMAN.txt -a 0.5` (read_aa_params + the alpha blend of main :449-500)."""
+    rng = np.random.default_rng(20261019)
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    bg = np.array([float(ln.split()[0]) for ln in open(os.path.join(HERE, "bg_freqs_HUMAN.txt"))][1:21])
+    bg /= bg.sum()
+    prd = np.array([0.04865, 0.00219, 0.01638, 0.00783, 0.02537, 0.07603, 0.0181, 0.02018, 0.01641, 0.02639, 0.02975,
+                    0.25885, 0.05126, 0.15178, 0.025, 0.10988, 0.03841, 0.01972, 0.00157, 0.05624])
+    prd /= prd.sum()
+
+    def rnd(n, p):
+        return "".join(rng.choice(list(aa), n, p=p))
+
+    lines = []
+    for k, n in enumerate((90, 150, 233, 310, 415, 520, 640, 800)):
+        sq = rnd(n, bg)
+        if k % 2:
+            st, m = n // 3, min(100, n - n // 3)
+            sq = sq[:st] + rnd(m, prd) + sq[st + m:]
+        lines.append(f">hs{k}_{n}")
+        lines += [sq[j:j + 60] for j in range(0, len(sq), 60)]
+    return "\n".join(lines) + "\n"
+
+
 def main():
     out = {"generator": "tests/golden/make_jar_vectors.py (reference bytecode web/bin/plaac.jar under minijvm.py)",
            "jar_manifest": "Created-By: 1.7.0_55"}
@@ -189,6 +216,20 @@ def main():
     out["long_summary"] = rows
     out["long_params"] = params
     print("long summary:", len(rows), "rows,", steps, "bytecodes")
+    os.unlink(path)
+    txt = human_fasta()
+    with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+        f.write(txt)
+        path = f.name
+    bgfile = "/root/reference/web/bg_freqs/bg_freqs_HUMAN.txt"
+    assert open(bgfile).read() == open(os.path.join(HERE, "bg_freqs_HUMAN.txt")).read()  # the committed copy is the reference's
+    ev, steps = run_main(["-i", path, "-B", bgfile, "-a", "0.5"])
+    rows, params = parse_summary(ev)
+    out["human_fasta"] = txt
+    out["human_args"] = ["-B", "bg_freqs_HUMAN.txt", "-a", "0.5"]
+    out["human_summary"] = rows
+    out["human_params"] = params
+    print("human (-B, alpha 0.5) summary:", len(rows), "rows,", steps, "bytecodes")
     os.unlink(path)
     import gzip
 

@@ -91,6 +91,13 @@ def scenario(which):
         text, kw, rows = J["prions_fasta"], {}, J["prions_residue"]
     elif which == "edge_residue":
         text, kw, rows = J["edge_fasta"], dict(alpha=0.5, core_len=40, ww1=21, ww2=21), J["edge_residue"]
+    elif which == "human_summary":
+        # -B file: read_aa_params (plaac.java:1923-1941) takes the first number of each of the 22 lines
+        bgf = np.array([float(ln.split()[0]) for ln in open(os.path.join(HERE, "golden", "bg_freqs_HUMAN.txt"))][:22])
+        recs = jar_reader(J["human_fasta"])
+        enc = [(n, orc.encode(s)) for n, s in recs if s]
+        assert len(enc) == len(J["human_summary"])
+        return enc, dict(alpha=0.5, bg_counts=bgf), J["human_summary"]
     else:
         raise KeyError(which)
     recs = jar_reader(text)

@@ -11,7 +11,7 @@ from oracle import orc
 from tests import jarvec, parity
 
 
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary", "human_summary"])
 def test_oracle_summary_is_bit_identical_to_the_jar(which):
     enc, kw, rows = jarvec.scenario(which)
     codes, offs = orc.pack([c for _, c in enc])
@@ -67,7 +67,7 @@ def test_parameter_block_matches_the_jar():
     J = jarvec.load()
     from tests.test_host_cli import java_fmt
 
-    for tag, sc in (("prions_params", "prions_summary"), ("edge_params", "edge_summary")):
+    for tag, sc in (("prions_params", "prions_summary"), ("edge_params", "edge_summary"), ("human_params", "human_summary")):
         _, kw, _ = jarvec.scenario(sc)
         P = orc.make_params(**kw)
         for key, vec in (("fg_used", P.fg), ("bg_scer", P.bgscer), ("bg_input", P.bgthis), ("bg_used", P.bg), ("plaac_llr", P.llr),
@@ -77,7 +77,7 @@ def test_parameter_block_matches_the_jar():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary", "long_summary_bucketed"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary", "long_summary_bucketed", "human_summary"])
 def test_cuda_summary_against_the_jar(which):
     """long_summary: 4 500 and 9 000 residues, scored by the chunked long-sequence path (scan of max-plus chunk
     matrices, warm-started forward chunks, binade-frame second pass) and, `_bucketed`, by the bucketed kernel:
