@@ -50,6 +50,8 @@ typedef struct plaac_params {
     int32_t ww1;             /* -w FoldIndex window, :318 (41) */
     int32_t ww2;             /* -W PAPA window, :319 (41) */
     int32_t ww3;             /* PLAAC-LLR smoothing window, :320,:355 (= ww2) */
+                             /* (ww1, ww2, ww3 are independent as in the jar; settings whose half-widths differ take
+                                tap-by-tap kernels in the jar's operation order instead of the streaming ones) */
     int32_t adjust_prolines; /* :328 (1) */
     int32_t mw_window;       /* :767 (80) */
     int32_t reserved[2];

@@ -21,6 +21,7 @@
 #include "summary_kernel.cuh"
 #include "summary_kernel_v2.cuh"
 #include "long_kernel.cuh"
+#include "generic_windows.cuh"
 
 using namespace plaac;
 
@@ -36,7 +37,7 @@ struct DevBuf {
 // One set of device work buffers; plaac_score() cycles through kSlots of them to overlap copies with compute.
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count, scan_tmp;
+    DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count, scan_tmp, gen_f64;
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
     DevBuf res_b0, res_b1, res_a0, res_a1, res_mapw, res_lpseq;  // per-residue scratch (bucketed layout)
@@ -83,6 +84,7 @@ struct plaac_ctx {
     int variant = 0;           // 0 auto, 1 = v1 (reference-order anchor), 2 = v2
     std::string v2_why;
     int sm_count = 0;
+    bool generic_windows = false;  // ww1, ww2, ww3 with different half-widths: generic_windows.cuh
     plaac_stats stats;
     int64_t chunk_res = (int64_t)256 << 20, chunk_res_pr = (int64_t)32 << 20, chunk_prot = (int64_t)4 << 20;
     // long-sequence path: > 0 fixed threshold (default 8192), -1 automatic threshold per batch, 0 off.  Both paths give
@@ -160,14 +162,14 @@ int setup_scalars(plaac_ctx* ctx)
     if (P.core_len < 1) return fail(ctx, PLAAC_E_INVALID, "core_len must be >= 1 (got %d)", P.core_len);
     if (P.ww1 < 1 || P.ww2 < 1 || P.ww3 < 1) return fail(ctx, PLAAC_E_INVALID, "window sizes must be >= 1");
     if (P.mw_window < 1) return fail(ctx, PLAAC_E_INVALID, "mw_window must be >= 1");
-    if (P.ww1 / 2 != P.ww2 / 2 || P.ww1 / 2 != P.ww3 / 2 || (P.ww1 - 1) / 2 != (P.ww2 - 1) / 2)
-        return fail(ctx, PLAAC_E_UNSUPPORTED,
-                    "ww1=%d ww2=%d ww3=%d: the streaming kernels need equal half-widths (ww/2 and (ww-1)/2)", P.ww1,
-                    P.ww2, P.ww3);
+    // The streaming kernels carry one half-width.  Window sizes with different half-widths (-w and -W of the jar are
+    // independent) take the tap-by-tap kernels of generic_windows.cuh for everything that depends on the windows; the
+    // streaming kernels then run with ww1 for all three (their window columns are overwritten).
+    ctx->generic_windows = P.ww1 / 2 != P.ww2 / 2 || P.ww1 / 2 != P.ww3 / 2 || (P.ww1 - 1) / 2 != (P.ww2 - 1) / 2;
     k.core_len = P.core_len;
     k.w = P.ww1 / 2;
     k.h_fi = (P.ww1 - 1) / 2;
-    k.h_papa = (P.ww2 - 1) / 2;
+    k.h_papa = ctx->generic_windows ? (P.ww1 - 1) / 2 : (P.ww2 - 1) / 2;
     k.mw_window = P.mw_window;
     k.adjust_prolines = P.adjust_prolines ? 1 : 0;
     k.charge_plus = k.charge_minus = 0;
@@ -312,7 +314,7 @@ int slot_init(plaac_ctx* ctx, Slot& s)
 
 void slot_free(Slot& s)
 {
-    for (DevBuf* b : {&s.scan_tmp, &s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
+    for (DevBuf* b : {&s.gen_f64, &s.scan_tmp, &s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
                       &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
@@ -641,6 +643,61 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         } else
             rc = launch_residue(ctx->ks, ctx->d_tabs, bv, *d_res, res_base, ctx->sm_count, st, &ctx->stats.kernel_launches);
         if (rc != PLAAC_OK) return fail(ctx, rc, "per-residue kernels failed to launch");
+    }
+    if (ctx->generic_windows) {
+        // everything that depends on the windows, tap by tap in the jar's order (generic_windows.cuh): into the caller's
+        // per-residue arrays if there are any, else into scratch; then the window columns of the records
+        GenArgs ga;
+        ga.codes = d_codes;
+        ga.offsets = d_offsets;
+        ga.code_base = off_base;
+        ga.nprot = nprot;
+        ga.ww1 = ctx->params.ww1;
+        ga.ww2 = ctx->params.ww2;
+        ga.ww3 = ctx->params.ww3;
+        ga.adjust_prolines = ctx->params.adjust_prolines ? 1 : 0;
+        ga.cc0 = ctx->params.fi_cc[0];
+        ga.cc1 = ctx->params.fi_cc[1];
+        ga.cc2 = ctx->params.fi_cc[2];
+        for (int c = 0; c < PLAAC_NAA; c++) {
+            ga.t.hyd[c] = ctx->params.hydro2[c];
+            ga.t.chg[c] = ctx->params.charge[c];
+            ga.t.llr[c] = ctx->params.llr[c];
+            ga.t.pap[c] = ctx->params.papa_lod[c];
+        }
+        const bool own = d_res && d_res->charge && d_res->hydro && d_res->fi && d_res->plaac && d_res->papa && d_res->fix2 &&
+                         d_res->plaacx2 && d_res->papax2;
+        if (own) {
+            ga.out_base = res_base;
+            ga.hydro = d_res->hydro, ga.charge = d_res->charge, ga.fi = d_res->fi, ga.plaac = d_res->plaac;
+            ga.papa = d_res->papa, ga.fix2 = d_res->fix2, ga.plaacx2 = d_res->plaacx2, ga.papax2 = d_res->papax2;
+        } else {
+            const size_t N = (size_t)std::max<int64_t>(ntotal, 1);
+            if ((rc = ensure(ctx, s.gen_f64, sizeof(double) * 8 * N))) return rc;
+            double* d = (double*)s.gen_f64.p;
+            ga.out_base = off_base;
+            ga.hydro = d, ga.charge = d + N, ga.fi = d + 2 * N, ga.plaac = d + 3 * N;
+            ga.papa = d + 4 * N, ga.fix2 = d + 5 * N, ga.plaacx2 = d + 6 * N, ga.papax2 = d + 7 * N;
+        }
+        ga.out = d_summaries;
+        const unsigned gw = (unsigned)std::min<int64_t>((nprot + 3) / 4, (int64_t)ctx->sm_count * 64);
+        k_gen_pass1<<<gw, 128, 0, st>>>(ga);
+        k_gen_pass2<<<gw, 128, 0, st>>>(ga);
+        ctx->stats.kernel_launches += 2;
+        if (d_summaries) {
+            k_gen_report<<<(unsigned)std::min<int64_t>((nprot + 127) / 128, (int64_t)ctx->sm_count * 16), 128, 0, st>>>(ga);
+            ctx->stats.kernel_launches += 1;
+        }
+        if (d_res && !own) {
+            // a caller that asked for some of the tracks only: hand those over from the scratch copy
+            double* const dst[8] = {d_res->hydro, d_res->charge, d_res->fi, d_res->plaac, d_res->papa, d_res->fix2,
+                                    d_res->plaacx2, d_res->papax2};
+            const double* const src[8] = {ga.hydro, ga.charge, ga.fi, ga.plaac, ga.papa, ga.fix2, ga.plaacx2, ga.papax2};
+            for (int k = 0; k < 8; k++)
+                if (dst[k] && ntotal > 0)
+                    CU(ctx, cudaMemcpyAsync(dst[k] + (off_base - res_base), src[k], sizeof(double) * (size_t)ntotal,
+                                            cudaMemcpyDeviceToDevice, st));
+        }
     }
     CU(ctx, cudaEventRecord(s.ev_d, st));
     CU(ctx, cudaGetLastError());
@@ -994,7 +1051,8 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
     // Chunking: bounded device footprint; kSlots sets of buffers so the next chunks' H2D overlap this chunk's kernels and
     // D2H.  Chunk sizes ramp up from max/8 and down again towards the end: the first chunk's copy and the last chunk's
     // kernels + copy-back are the only parts of the pipeline nothing overlaps with.
-    const int64_t max_res_full = per_res ? ctx->chunk_res_pr : ctx->chunk_res;
+    // (different half-widths of the windows: 64 bytes of track scratch per residue, so summary mode chunks like per-residue mode)
+    const int64_t max_res_full = (per_res || ctx->generic_windows) ? std::min(ctx->chunk_res_pr, ctx->chunk_res) : ctx->chunk_res;
     const int64_t min_res = std::max<int64_t>(max_res_full / 8, 1 << 20);
     const int64_t total_res = offsets[nprot] - offsets[0];
     int64_t ramp = min_res;

@@ -205,6 +205,18 @@ def main():
     out["edge_residue_args"] = ["-a", "0.5", "-c", "40", "-w", "21", "-W", "21"]
     out["edge_residue"] = [p for p in parse_residue(ev)]
     print("edge per-residue:", len(out["edge_residue"]), "proteins,", steps, "bytecodes")
+    # -w and -W with different half-widths (FoldIndex window 31, PAPA/LLR windows 51): the windows of disorderreport are
+    # independent in the jar (:4875-4903)
+    ev, steps = run_main(["-i", path, "-a", "0", "-c", "30", "-w", "31", "-W", "51"])
+    rows, params = parse_summary(ev)
+    out["edge_alt_args"] = ["-a", "0", "-c", "30", "-w", "31", "-W", "51"]
+    out["edge_alt_summary"] = rows
+    out["edge_alt_params"] = params
+    print("edge summary, -w 31 -W 51:", len(rows), "rows,", steps, "bytecodes")
+    ev, steps = run_main(["-i", path, "-a", "0", "-p", "all", "-w", "52", "-W", "9"])
+    out["edge_alt_residue_args"] = ["-a", "0", "-w", "52", "-W", "9"]
+    out["edge_alt_residue"] = [p for p in parse_residue(ev)]
+    print("edge per-residue, -w 52 -W 9:", len(out["edge_alt_residue"]), "proteins,", steps, "bytecodes")
     os.unlink(path)
     txt = long_fasta()
     with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:

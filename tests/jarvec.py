@@ -91,6 +91,10 @@ def scenario(which):
         text, kw, rows = J["prions_fasta"], {}, J["prions_residue"]
     elif which == "edge_residue":
         text, kw, rows = J["edge_fasta"], dict(alpha=0.5, core_len=40, ww1=21, ww2=21), J["edge_residue"]
+    elif which == "edge_alt_summary":
+        text, kw, rows = J["edge_fasta"], dict(alpha=0.0, core_len=30, ww1=31, ww2=51), J["edge_alt_summary"]
+    elif which == "edge_alt_residue":
+        text, kw, rows = J["edge_fasta"], dict(alpha=0.0, ww1=52, ww2=9), J["edge_alt_residue"]
     elif which == "human_summary":
         # -B file: read_aa_params (plaac.java:1923-1941) takes the first number of each of the 22 lines
         bgf = np.array([float(ln.split()[0]) for ln in open(os.path.join(HERE, "golden", "bg_freqs_HUMAN.txt"))][:22])

@@ -208,7 +208,10 @@ def test_long_path_both_scratch_layouts(monkeypatch):
 
 
 @pytest.mark.parametrize("kw", [dict(core_len=30), dict(core_len=100, ww1=21, ww2=21), dict(ww1=40, ww2=40),
-                                dict(adjust_prolines=False), dict(core_len=7, ww1=5, ww2=5), dict(ww1=1, ww2=1)])
+                                dict(adjust_prolines=False), dict(core_len=7, ww1=5, ww2=5), dict(ww1=1, ww2=1),
+                                # -w and -W with different half-widths: the tap-by-tap kernels of generic_windows.cuh
+                                dict(ww1=31, ww2=51), dict(ww1=52, ww2=9, core_len=30), dict(ww1=41, ww2=40),
+                                dict(ww1=3, ww2=120, adjust_prolines=False)])
 def test_other_parameters(kw):
     codes, offs = synth.proteome(1500, seed=11, median=200.0)
     e, eo = synth.edge_cases()
@@ -268,8 +271,10 @@ def test_invalid_inputs_are_reported(scorer):
         scorer.score(np.array([1, 2, 3], np.uint8), np.array([0, 2, 1], np.int64))
     assert e.value.code == -1
     with pytest.raises(plaac_b200.PlaacError) as e:
-        plaac_b200.Scorer(plaac_b200.default_params(ww1=41, ww2=21))
-    assert e.value.code == -3
+        plaac_b200.Scorer(plaac_b200.default_params(ww1=0, ww2=21))
+    assert e.value.code == -1
+    # -w / -W with different half-widths used to be PLAAC_E_UNSUPPORTED: now scored (generic_windows.cuh)
+    plaac_b200.Scorer(plaac_b200.default_params(ww1=41, ww2=21)).close()
     # the ctx still works afterwards
     got = scorer.score(np.array([1, 2, 3], np.uint8), np.array([0, 3], np.int64))
     assert got["prot_len"][0] == 3
@@ -391,6 +396,28 @@ def test_per_residue_edge_cases_and_chunking():
     _check_residue(got, ref, "edge cases per-residue")
 
 
+@pytest.mark.parametrize("kw", [dict(ww1=31, ww2=51), dict(ww1=52, ww2=9, alpha=0.5)])
+def test_per_residue_windows_with_different_half_widths(kw):
+    """-w / -W independent (generic_windows.cuh): per-residue tracks and the summary records of the same call, host API
+    in several chunks and device-resident API."""
+    codes, offs = synth.proteome(700, seed=31, median=180.0)
+    e, eo = synth.edge_cases()
+    codes, offs = np.concatenate([codes, e]), np.concatenate([offs, eo[1:] + offs[-1]])
+    P = orc.make_params(**kw)
+    ref_s = orc.score_batch(P, codes, offs, nthreads=NT)
+    ref_r = orc.residue_batch(P, codes, offs)
+    sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    sc.set_chunk(40000, 300)
+    got_s, got_r = sc.score(codes, offs, per_residue=True)
+    sc.close()
+    _check(got_s, ref_s, f"summary beside per-residue {kw}", P, codes, offs, max_ties=6)
+    _check_residue(got_r, ref_r, f"per-residue {kw}")
+    # the window tracks are evaluated tap by tap in the jar's order: the same bits as the oracle's
+    for k in ("hydro", "charge", "fi", "plaac", "papa", "fix2", "plaacx2", "papax2"):
+        a, b = got_r[k], ref_r[k]
+        assert ((a == b) | (np.isnan(a) & np.isnan(b))).all(), k
+
+
 def test_per_residue_long_and_other_params():
     codes, offs = synth.long_proteins(lengths=(35000,))
     kw = dict(core_len=30, ww1=21, ww2=21, alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS)
@@ -403,7 +430,8 @@ def test_per_residue_long_and_other_params():
 
 @pytest.mark.parametrize("kw", [dict(core_len=100, ww1=21, ww2=21), dict(core_len=7, ww1=5, ww2=5),
                                 dict(core_len=30, ww1=40, ww2=40, adjust_prolines=False),
-                                dict(alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS), dict(core_len=250, ww1=61, ww2=61)])
+                                dict(alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS), dict(core_len=250, ww1=61, ww2=61),
+                                dict(ww1=31, ww2=51)])
 def test_long_path_other_parameters(kw):
     """The chunked long-sequence path with other window / core sizes and a blended background: chunk geometry
     (a chunk holds a whole CORE / MW window), halo widths and the binade-frame passes all depend on them."""

@@ -11,7 +11,7 @@ from oracle import orc
 from tests import jarvec, parity
 
 
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary", "human_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "edge_alt_summary", "long_summary", "human_summary"])
 def test_oracle_summary_is_bit_identical_to_the_jar(which):
     enc, kw, rows = jarvec.scenario(which)
     codes, offs = orc.pack([c for _, c in enc])
@@ -40,10 +40,11 @@ def test_oracle_summary_is_bit_identical_to_the_jar(which):
         else:
             want = ["-"] * 4
         assert [row["COREaa"], row["STARTaa"], row["ENDaa"], row["PRDaa"]] == want, name
-        assert row["PAPAaa"] == sub(r["papa_center"] - 20, r["papa_center"] + 20), name
+        hw = kw.get("ww2", 41) // 2  # :944 submatrix(aa, papamaxcenter - ww2/2, papamaxcenter + ww2/2)
+        assert row["PAPAaa"] == sub(r["papa_center"] - hw, r["papa_center"] + hw), name
 
 
-@pytest.mark.parametrize("which", ["prions_residue", "edge_residue"])
+@pytest.mark.parametrize("which", ["prions_residue", "edge_residue", "edge_alt_residue"])
 def test_oracle_per_residue_is_bit_identical_to_the_jar(which):
     enc, kw, prots = jarvec.scenario(which)
     P = orc.make_params(**kw)
@@ -67,7 +68,8 @@ def test_parameter_block_matches_the_jar():
     J = jarvec.load()
     from tests.test_host_cli import java_fmt
 
-    for tag, sc in (("prions_params", "prions_summary"), ("edge_params", "edge_summary"), ("human_params", "human_summary")):
+    for tag, sc in (("prions_params", "prions_summary"), ("edge_params", "edge_summary"), ("human_params", "human_summary"),
+                    ("edge_alt_params", "edge_alt_summary")):
         _, kw, _ = jarvec.scenario(sc)
         P = orc.make_params(**kw)
         for key, vec in (("fg_used", P.fg), ("bg_scer", P.bgscer), ("bg_input", P.bgthis), ("bg_used", P.bg), ("plaac_llr", P.llr),
@@ -77,7 +79,7 @@ def test_parameter_block_matches_the_jar():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "long_summary", "long_summary_bucketed", "human_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "edge_alt_summary", "long_summary", "long_summary_bucketed", "human_summary"])
 def test_cuda_summary_against_the_jar(which):
     """long_summary: 4 500 and 9 000 residues, scored by the chunked long-sequence path (scan of max-plus chunk
     matrices, warm-started forward chunks, binade-frame second pass) and, `_bucketed`, by the bucketed kernel:
@@ -114,7 +116,7 @@ def test_cuda_summary_against_the_jar(which):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["prions_residue", "edge_residue"])
+@pytest.mark.parametrize("which", ["prions_residue", "edge_residue", "edge_alt_residue"])
 def test_cuda_per_residue_against_the_jar(which):
     import plaac_b200
 
