@@ -166,10 +166,17 @@ int setup_scalars(plaac_ctx* ctx)
     // independent) take the tap-by-tap kernels of generic_windows.cuh for everything that depends on the windows; the
     // streaming kernels then run with ww1 for all three (their window columns are overwritten).
     ctx->generic_windows = P.ww1 / 2 != P.ww2 / 2 || P.ww1 / 2 != P.ww3 / 2 || (P.ww1 - 1) / 2 != (P.ww2 - 1) / 2;
+    // ... and so do windows whose look-back (4w + 2 residues) would crowd the residue rings out of shared memory; the
+    // streaming kernels then run with the default window
+    int ww_stream = P.ww1;
+    if (4 * (P.ww1 / 2) + 2 > 512) {
+        ctx->generic_windows = true;
+        ww_stream = 41;
+    }
     k.core_len = P.core_len;
-    k.w = P.ww1 / 2;
-    k.h_fi = (P.ww1 - 1) / 2;
-    k.h_papa = ctx->generic_windows ? (P.ww1 - 1) / 2 : (P.ww2 - 1) / 2;
+    k.w = ww_stream / 2;
+    k.h_fi = (ww_stream - 1) / 2;
+    k.h_papa = ctx->generic_windows ? (ww_stream - 1) / 2 : (P.ww2 - 1) / 2;
     k.mw_window = P.mw_window;
     k.adjust_prolines = P.adjust_prolines ? 1 : 0;
     k.charge_plus = k.charge_minus = 0;

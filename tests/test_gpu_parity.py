@@ -211,7 +211,9 @@ def test_long_path_both_scratch_layouts(monkeypatch):
                                 dict(adjust_prolines=False), dict(core_len=7, ww1=5, ww2=5), dict(ww1=1, ww2=1),
                                 # -w and -W with different half-widths: the tap-by-tap kernels of generic_windows.cuh
                                 dict(ww1=31, ww2=51), dict(ww1=52, ww2=9, core_len=30), dict(ww1=41, ww2=40),
-                                dict(ww1=3, ww2=120, adjust_prolines=False)])
+                                dict(ww1=3, ww2=120, adjust_prolines=False),
+                                # windows longer than most proteins (look-back beyond the residue rings)
+                                dict(ww1=601, ww2=601), dict(ww1=2000, ww2=41, core_len=90)])
 def test_other_parameters(kw):
     codes, offs = synth.proteome(1500, seed=11, median=200.0)
     e, eo = synth.edge_cases()
