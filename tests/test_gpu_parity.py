@@ -213,7 +213,9 @@ def test_long_path_both_scratch_layouts(monkeypatch):
                                 dict(ww1=31, ww2=51), dict(ww1=52, ww2=9, core_len=30), dict(ww1=41, ww2=40),
                                 dict(ww1=3, ww2=120, adjust_prolines=False),
                                 # windows longer than most proteins (look-back beyond the residue rings)
-                                dict(ww1=601, ww2=601), dict(ww1=2000, ww2=41, core_len=90)])
+                                dict(ww1=601, ww2=601), dict(ww1=2000, ww2=41, core_len=90),
+                                # a core length beyond the throughput kernel's rings: reference-order anchor kernel
+                                dict(core_len=1500)])
 def test_other_parameters(kw):
     codes, offs = synth.proteome(1500, seed=11, median=200.0)
     e, eo = synth.edge_cases()
