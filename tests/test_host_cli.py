@@ -267,6 +267,37 @@ def test_per_residue_table_end_to_end(cli, tmp_path, golden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which,args", [("edge_residue", ["-a", "0.5", "-c", "40", "-w", "21", "-W", "21"]),
+                                        ("edge_alt_residue", ["-a", "0", "-w", "52", "-W", "9"])])
+def test_per_residue_table_equals_the_jars_own_output(cli, tmp_path, which, args):
+    """`-p all` on the edge-case FASTA against what plaac.jar's bytecode printed for the same command line: ORDER, name,
+    position, residue, VIT, MAP and the ten numeric columns (%.4f / %.8f through java.util.Formatter's rule)."""
+    from tests import jarvec
+
+    J = jarvec.load()
+    fa = tmp_path / "edge.fa"
+    fa.write_text(J["edge_fasta"])
+    r = run(cli, "-i", str(fa), "-s", "-p", "all", *args)
+    assert r.returncode == 0, r.stderr
+    body = [l for l in r.stdout.rstrip("\n").split("\n")[1:] if not l.startswith("#")]
+    prots = J[which]
+    assert len(body) == sum(len(p["aa"]) for p in prots)
+    pos = 0
+    for pr in prots:
+        for t in range(len(pr["aa"])):
+            got = body[pos].split("\t")
+            want = [pr["order"], pr["name"], str(t + 1), pr["aa"][t], str(pr["vit"][t]), str(pr["map"][t])]
+            for k, d in (("CHARGE", 4), ("HYDRO", 4), ("FI", 8), ("PLAAC", 4), ("PAPA", 8), ("FIx2", 8), ("PLAACx2", 4),
+                         ("PAPAx2", 8)):
+                want.append(java_fmt(jarvec.val(pr[k][t]), d))
+            want += [java_fmt(jarvec.val(v), 4) for v in pr["post"][t]]
+            assert len(got) == len(want) == 16
+            for g, w in zip(got, want):
+                assert _cells_match(g, w), (pr["name"], t, got, want)
+            pos += 1
+
+
+@pytest.mark.gpu
 def test_gpu_ingest_path_prints_the_same_table(cli, tmp_path, golden):
     """--gpu-ingest (FASTA parsed, encoded and scored on the GPU, in record-aligned pieces) == the host reader path,
     including name trimming at piece boundaries."""
