@@ -242,6 +242,13 @@ def main():
     out["human_summary"] = rows
     out["human_params"] = params
     print("human (-B, alpha 0.5) summary:", len(rows), "rows,", steps, "bytecodes")
+    # -F: main :388 reads the -B file name for the foreground too (a bug of the jar); the host keeps it behind --compat-F
+    ev, steps = run_main(["-i", path, "-B", bgfile, "-F", "/nonexistent/ignored_by_the_jar.txt", "-a", "0.5"])
+    rows, params = parse_summary(ev)
+    out["human_F_args"] = ["-B", "bg_freqs_HUMAN.txt", "-F", "ignored_by_the_jar.txt", "-a", "0.5"]
+    out["human_F_summary"] = rows
+    out["human_F_params"] = params
+    print("human with -F (the jar reads the -B file):", len(rows), "rows,", steps, "bytecodes")
     os.unlink(path)
     import gzip
 

@@ -109,6 +109,22 @@ def test_parameter_block_and_column_docs(cli, tmp_path):
         assert hdr and hdr[0].split("\t") == open(os.path.join(GOLD, "column_names.txt")).read().split()
 
 
+def test_parameter_block_equals_the_jars_with_B_and_F(cli, tmp_path):
+    """`-B file -a 0.5` and the jar's -F behaviour (main :388 reads the -B file for the foreground; --compat-F):
+    the six `## ...` vectors the binary prints are the ones the jar's bytecode printed."""
+    from tests import jarvec
+
+    J = jarvec.load()
+    fa = tmp_path / "h.fa"
+    fa.write_text(J["human_fasta"])
+    bgf = os.path.join(GOLD, "bg_freqs_HUMAN.txt")
+    for tag, extra in (("human_params", []), ("human_F_params", ["-F", str(tmp_path / "ignored.txt"), "--compat-F"])):
+        r = run(cli, "-i", str(fa), "-B", bgf, "-a", "0.5", *extra)
+        got = {l[3:l.index(":")]: l for l in r.stdout.split("\n") if l.startswith("## ") and ": {" in l}
+        for key, want in J[tag].items():
+            assert got[key] == want, (tag, key)
+
+
 # ------------------------------------------------------------------------------------------------- end to end (GPU)
 def _expected_summary_row(P, name, aa, s, corelen, ww2):
     names = orc.AANAMES
