@@ -23,7 +23,13 @@
 #include <fstream>
 #include <map>
 #include <string>
+#include <string_view>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "plaac_cuda.h"
 
@@ -114,16 +120,47 @@ std::string jdouble(double x)
 // '>' line is skipped; the name is everything after '>' (trimmed only when found by hasmorefastas).
 class FastaReader {
 public:
-    explicit FastaReader(const std::string& path) : in_(path, std::ios::binary)
+    // The file is mapped and scanned in memory: one get() per character through an ifstream made the reader the slowest
+    // part of the program (the jar reads the input twice -- background counts, then scoring -- and so does this host).
+    explicit FastaReader(const std::string& path)
     {
-        good_ = in_.good();
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd >= 0 && ::fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+            good_ = true;
+            size_ = (size_t)st.st_size;
+            if (size_ > 0) {
+                void* m = ::mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m == MAP_FAILED)
+                    good_ = false;
+                else {
+                    data_ = (const char*)m;
+                    ::madvise(m, size_, MADV_SEQUENTIAL);
+                }
+            }
+        } else if (fd >= 0) {
+            // not a regular file (a pipe, /dev/stdin): read it through
+            good_ = true;
+            char tmp[1 << 16];
+            ssize_t k;
+            while ((k = ::read(fd, tmp, sizeof(tmp))) > 0) own_.append(tmp, (size_t)k);
+            data_ = own_.data();
+            size_ = own_.size();
+        }
+        if (fd >= 0) ::close(fd);
         if (!good_) std::printf("# Couldn't open %s\n", path.c_str());
     }
+    ~FastaReader()
+    {
+        if (data_ && own_.empty() && size_ > 0) ::munmap((void*)data_, size_);
+    }
+    FastaReader(const FastaReader&) = delete;
+    FastaReader& operator=(const FastaReader&) = delete;
     bool hasmore()
     {
         if (!good_) return false;
         if (ondeck_) return true;
-        std::string line;
+        std::string_view line;
         while (readline(line)) {
             if (!line.empty() && line[0] == '>') {
                 name_ = trim(line).substr(1);
@@ -138,7 +175,7 @@ public:
     void next(std::string& seq)
     {
         seq.clear();
-        std::string line;
+        std::string_view line;
         while (readline(line)) {
             if (line.empty()) {
                 ondeck_ = false;
@@ -146,35 +183,38 @@ public:
             }
             if (line[0] == '>') {
                 ondeck_ = true;
-                name_ = line.substr(1);
+                name_.assign(line.substr(1));
                 return;
             }
-            seq += line;
+            seq.append(line);
         }
         ondeck_ = false;
     }
 
 private:
-    static std::string trim(const std::string& s)
+    static std::string trim(std::string_view s)
     {
         size_t a = 0, b = s.size();
         while (a < b && (unsigned char)s[a] <= ' ') a++;  // String.trim(): code points <= U+0020
         while (b > a && (unsigned char)s[b - 1] <= ' ') b--;
-        return s.substr(a, b - a);
+        return std::string(s.substr(a, b - a));
     }
-    bool readline(std::string& line)
+    // BufferedReader.readLine: a line ends with \n, \r or \r\n; the last line may end with the file
+    bool readline(std::string_view& line)
     {
-        line.clear();
-        int c = in_.get();
-        if (c == EOF) return false;
-        while (c != EOF && c != '\n' && c != '\r') {
-            line.push_back((char)c);
-            c = in_.get();
-        }
-        if (c == '\r' && in_.peek() == '\n') in_.get();
+        if (pos_ >= size_) return false;
+        const char* b = data_ + pos_;
+        const char* e = data_ + size_;
+        const char* p = b;
+        while (p < e && *p != '\n' && *p != '\r') p++;
+        line = std::string_view(b, (size_t)(p - b));
+        if (p < e) p += (*p == '\r' && p + 1 < e && p[1] == '\n') ? 2 : 1;
+        pos_ = (size_t)(p - data_);
         return true;
     }
-    std::ifstream in_;
+    const char* data_ = nullptr;
+    size_t size_ = 0, pos_ = 0;
+    std::string own_;
     bool good_ = false, ondeck_ = false;
     std::string name_;
 };
