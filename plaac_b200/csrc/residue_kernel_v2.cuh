@@ -515,19 +515,54 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
                 }
             }
             __syncwarp();
-            // 1. per-residue values, zero outside the protein (pad code: all tables are 0)
-            for (int e = lane; e < NXe; e += 32) {
-                const uint32_t cd = Cd[e + 2];
-                double pp = tab_p[cd];
-                // PAPA proline rule (:2652-2655): the second proline of PP / PxP is not scored
-                if (ks.adjust_prolines && cd == 13u && (Cd[e + 1] == 13 || Cd[e] == 13)) pp = 0.0;
-                Xh[e] = tab_h[cd];
-                Xl[e] = tab_l[cd];
-                Xp[e] = pp;
-                Xc[e] = (int)((ks.charge_plus >> cd) & 1u) - (int)((ks.charge_minus >> cd) & 1u);
+            // 1. per-residue values (zero outside the protein: all tables are 0 for the pad code) and their prefix sums in
+            // one go: lane l owns the run [l*per_x, l*per_x + per_x), adds its values up as it looks them up and stores the
+            // running sums (same association as a scan of stored values: run sums, warp scan of the run totals, offsets)
+            {
+                const int lo = lane * per_x, hi = min(lo + per_x, NXe);
+                double ra = 0, rb = 0, rc = 0;
+                int rd = 0;
+                for (int e = lo; e < hi; e++) {
+                    const uint32_t cd = Cd[e + 2];
+                    double pp = tab_p[cd];
+                    // PAPA proline rule (:2652-2655): the second proline of PP / PxP is not scored
+                    if (ks.adjust_prolines && cd == 13u && (Cd[e + 1] == 13 || Cd[e] == 13)) pp = 0.0;
+                    ra = ra + tab_h[cd];
+                    rb = rb + tab_l[cd];
+                    rc = rc + pp;
+                    rd = rd + ((int)((ks.charge_plus >> cd) & 1u) - (int)((ks.charge_minus >> cd) & 1u));
+                    Xh[e] = ra;
+                    Xl[e] = rb;
+                    Xp[e] = rc;
+                    Xc[e] = rd;
+                }
+                double ia = ra, ib = rb, ic = rc;
+                int id = rd;
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const double oa = __shfl_up_sync(0xffffffffu, ia, sft), ob = __shfl_up_sync(0xffffffffu, ib, sft);
+                    const double oc = __shfl_up_sync(0xffffffffu, ic, sft);
+                    const int od = __shfl_up_sync(0xffffffffu, id, sft);
+                    if (lane >= sft) {
+                        ia = ia + oa;
+                        ib = ib + ob;
+                        ic = ic + oc;
+                        id = id + od;
+                    }
+                }
+                const double ea = __shfl_up_sync(0xffffffffu, ia, 1), eb = __shfl_up_sync(0xffffffffu, ib, 1);
+                const double ec = __shfl_up_sync(0xffffffffu, ic, 1);
+                const int ed = __shfl_up_sync(0xffffffffu, id, 1);
+                if (lane > 0) {
+                    for (int e = lo; e < hi; e++) {
+                        Xh[e] = Xh[e] + ea;
+                        Xl[e] = Xl[e] + eb;
+                        Xp[e] = Xp[e] + ec;
+                        Xc[e] = Xc[e] + ed;
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            warp_scan4_inplace(Xh, Xl, Xp, Xc, NXe, per_x, lane);
             // 2. pass-1 window sums for centres t0-w .. t0+T+w-1 and the five pass-1 tracks.  S*[idx] replaces X*[idx]:
             // a window needs X*[idx+2w] (not yet overwritten: chunks ascend) and X*[idx-1], which is the own-position
             // value of the lane below (shuffle; lane 0 takes lane 31's value of the previous chunk).
