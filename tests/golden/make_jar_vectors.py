@@ -249,6 +249,17 @@ def main():
     out["human_F_summary"] = rows
     out["human_F_params"] = params
     print("human with -F (the jar reads the -B file):", len(rows), "rows,", steps, "bytecodes")
+    # -b: background counted from another FASTA (computeaafreq + isvalidprotein :1655-1739 on the edge-case file)
+    with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+        f.write(edge_fasta())
+        bpath = f.name
+    ev, steps = run_main(["-i", path, "-b", bpath, "-a", "0.3"])
+    rows, params = parse_summary(ev)
+    out["human_b_args"] = ["-b", "<edge_fasta>", "-a", "0.3"]
+    out["human_b_summary"] = rows
+    out["human_b_params"] = params
+    print("human with -b edge.fa -a 0.3:", len(rows), "rows,", steps, "bytecodes")
+    os.unlink(bpath)
     os.unlink(path)
     import gzip
 

@@ -95,6 +95,11 @@ def scenario(which):
         text, kw, rows = J["edge_fasta"], dict(alpha=0.0, core_len=30, ww1=31, ww2=51), J["edge_alt_summary"]
     elif which == "edge_alt_residue":
         text, kw, rows = J["edge_fasta"], dict(alpha=0.0, ww1=52, ww2=9), J["edge_alt_residue"]
+    elif which == "human_b_summary":
+        recs = jar_reader(J["human_fasta"])
+        enc = [(n, orc.encode(s)) for n, s in recs if s]
+        assert len(enc) == len(J[which])
+        return enc, dict(alpha=0.3, bg_counts=background_counts(jar_reader(J["edge_fasta"]))), J[which]
     elif which in ("human_summary", "human_F_summary"):
         # -B file: read_aa_params (plaac.java:1923-1941) takes the first number of each of the 22 lines
         bgf = np.array([float(ln.split()[0]) for ln in open(os.path.join(HERE, "golden", "bg_freqs_HUMAN.txt"))][:22])

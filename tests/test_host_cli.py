@@ -118,8 +118,12 @@ def test_parameter_block_equals_the_jars_with_B_and_F(cli, tmp_path):
     fa = tmp_path / "h.fa"
     fa.write_text(J["human_fasta"])
     bgf = os.path.join(GOLD, "bg_freqs_HUMAN.txt")
-    for tag, extra in (("human_params", []), ("human_F_params", ["-F", str(tmp_path / "ignored.txt"), "--compat-F"])):
-        r = run(cli, "-i", str(fa), "-B", bgf, "-a", "0.5", *extra)
+    edge = tmp_path / "edge.fa"
+    edge.write_text(J["edge_fasta"])
+    for tag, args in (("human_params", ["-B", bgf, "-a", "0.5"]),
+                      ("human_F_params", ["-B", bgf, "-a", "0.5", "-F", str(tmp_path / "ignored.txt"), "--compat-F"]),
+                      ("human_b_params", ["-b", str(edge), "-a", "0.3"])):  # background counted from another FASTA
+        r = run(cli, "-i", str(fa), *args)
         got = {l[3:l.index(":")]: l for l in r.stdout.split("\n") if l.startswith("## ") and ": {" in l}
         for key, want in J[tag].items():
             assert got[key] == want, (tag, key)

@@ -11,7 +11,7 @@ from oracle import orc
 from tests import jarvec, parity
 
 
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "edge_alt_summary", "long_summary", "human_summary", "human_F_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "edge_alt_summary", "long_summary", "human_summary", "human_F_summary", "human_b_summary"])
 def test_oracle_summary_is_bit_identical_to_the_jar(which):
     enc, kw, rows = jarvec.scenario(which)
     codes, offs = orc.pack([c for _, c in enc])
@@ -69,7 +69,8 @@ def test_parameter_block_matches_the_jar():
     from tests.test_host_cli import java_fmt
 
     for tag, sc in (("prions_params", "prions_summary"), ("edge_params", "edge_summary"), ("human_params", "human_summary"),
-                    ("edge_alt_params", "edge_alt_summary"), ("human_F_params", "human_F_summary")):
+                    ("edge_alt_params", "edge_alt_summary"), ("human_F_params", "human_F_summary"),
+                    ("human_b_params", "human_b_summary")):
         _, kw, _ = jarvec.scenario(sc)
         P = orc.make_params(**kw)
         for key, vec in (("fg_used", P.fg), ("bg_scer", P.bgscer), ("bg_input", P.bgthis), ("bg_used", P.bg), ("plaac_llr", P.llr),
