@@ -80,7 +80,8 @@ def test_parameter_block_matches_the_jar():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "edge_alt_summary", "long_summary", "long_summary_bucketed", "human_summary"])
+@pytest.mark.parametrize("which", ["prions_summary", "edge_summary", "edge_alt_summary", "long_summary", "long_summary_bucketed",
+                                   "human_summary", "human_F_summary", "human_b_summary"])
 def test_cuda_summary_against_the_jar(which):
     """long_summary: 4 500 and 9 000 residues, scored by the chunked long-sequence path (scan of max-plus chunk
     matrices, warm-started forward chunks, binade-frame second pass) and, `_bucketed`, by the bucketed kernel:
