@@ -756,7 +756,12 @@ void par_memcpy(void* dst, const void* src, size_t n)
     const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
     for (size_t t = 1; t < nt; t++) {
         const size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
-        if (hi > lo) th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+        if (hi <= lo) continue;
+        try {
+            th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+        } catch (...) {  // no thread to be had: this slice on the calling thread (nothing may throw across the C ABI)
+            memcpy((char*)dst + lo, (const char*)src + lo, hi - lo);
+        }
     }
     memcpy(dst, src, std::min(n, per));
     for (auto& t : th) t.join();
@@ -1260,7 +1265,7 @@ int plaac_score_multi(plaac_ctx* const* ctxs, int nctx, const uint8_t* codes, co
     for (int k = 0; k < nctx; k++) {
         const int64_t lo = bounds[k], hi = bounds[k + 1];
         if (hi <= lo) continue;
-        threads.emplace_back([=, &rcs]() {
+        auto shard = [=, &rcs]() {
             plaac_residue_out shifted;
             const plaac_residue_out* pr = nullptr;
             if (per_res) {
@@ -1276,7 +1281,12 @@ int plaac_score_multi(plaac_ctx* const* ctxs, int nctx, const uint8_t* codes, co
                 pr = &shifted;
             }
             rcs[k] = plaac_score(ctxs[k], codes, offsets + lo, hi - lo, summaries ? summaries + lo : nullptr, pr);
-        });
+        };
+        try {
+            threads.emplace_back(shard);
+        } catch (...) {  // no thread to be had: this shard on the calling thread (nothing may throw across the C ABI)
+            shard();
+        }
     }
     for (auto& t : threads) t.join();
     for (int k = 0; k < nctx; k++)
