@@ -255,9 +255,7 @@ def main():
         run_reference(args, rank, world)
         return
 
-    # NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO; stdout carries the one JSON line only
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # (NCCL_DEBUG is left as the launcher set it: whatever NCCL prints on fd 1 goes to stderr, see claim_stdout)
     import numpy as np
     import torch
     import torch.distributed as dist

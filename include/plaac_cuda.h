@@ -151,6 +151,50 @@ int plaac_score_device(plaac_ctx *ctx, const uint8_t *d_codes, const int64_t *d_
 int plaac_sync(plaac_ctx *ctx);
 void *plaac_stream(plaac_ctx *ctx); /* cudaStream_t of the ctx */
 
+/* ---- transport-lean batch call -----------------------------------------------------------------------------
+ * Same scoring as plaac_score() with fewer bytes on the host link, which is what bounds the host-buffer call
+ * (DESIGN.md section 7).  The reference has no counterpart: its arrays never leave the Java heap (plaac.java:755-948).
+ *
+ *   IN   residues as radix-22 words: 7 residue codes per uint32, word = c0 + 22*c1 + ... + 22^6*c6 (22^7 < 2^32),
+ *        i.e. 4/7 = 0.571 byte per residue instead of 1; the batch's residues are concatenated WITHOUT regard to
+ *        protein boundaries (residue r of the batch is digit r%7 of word r/7; unused digits of the last word are 0);
+ *        int32 lengths instead of int64 offsets.
+ *   OUT  optionally not the whole table but its head in the order the reference's consumer gives it
+ *        (web/lib/server.rb:222-229, "TODO: move this sorting into the java"): every protein with a CORE, or the top K
+ *        rows, best first, each with the index of its protein in the batch. */
+#define PLAAC_PACK_PER_WORD 7
+/* number of uint32 words that hold nres residues: ceil(nres / 7) */
+int64_t plaac_packed_words(int64_t nres);
+/* codes (0..21, one byte each; larger bytes are packed as X and the call returns PLAAC_E_INVALID after packing
+ * everything) -> words.  nthreads <= 0: all host threads.  Pure host code (no GPU, no ctx). */
+int plaac_pack_host(const uint8_t *codes, int64_t nres, uint32_t *words, int nthreads);
+/* FASTA letters -> words in one pass: aatoint (plaac.java:1508-1534) fused with the packing. */
+int plaac_pack_chars_host(const char *chars, int64_t nres, uint32_t *words, int nthreads);
+/* words -> codes for residues [first, first + count) of the packed batch (the host needs residues again for the
+ * string columns COREaa .. PAPAaa, plaac.java:915-944). */
+int plaac_unpack_host(const uint32_t *words, int64_t first, int64_t count, uint8_t *codes);
+
+#define PLAAC_HITS_CORE 1 /* every protein with a CORE (COREscore not NaN), ranked */
+#define PLAAC_HITS_TOPK 2 /* the first `capacity` rows of the ranking of the whole batch */
+typedef struct plaac_hits {
+    int32_t mode;           /* in: PLAAC_HITS_CORE or PLAAC_HITS_TOPK */
+    int32_t rank_flags;     /* in: as plaac_rank_device (0) */
+    int64_t capacity;       /* in: rows `records` and `index` can hold */
+    plaac_summary *records; /* out: `count` rows, best first (COREscore desc, LLR desc, input order) */
+    int32_t *index;         /* out: index of each row's protein in the batch */
+    int64_t count;          /* out: rows written = min(capacity, rows the mode selects) */
+    int64_t n_core;         /* out: proteins of the batch with a CORE (may exceed capacity) */
+} plaac_hits;
+
+/* words/lengths as above, nres = sum of lengths (checked).  summaries: nprot records in input order, or NULL when only
+ * hits are wanted; hits: NULL or the compact output (at least one of the two).  per_res as in plaac_score (element
+ * index = residue index in the batch).  HOST buffers, pinned or not, chunked and pipelined exactly like plaac_score;
+ * records are bit-identical to plaac_score's.  nprot < 2^31 when hits are requested. */
+int plaac_score_packed(plaac_ctx *ctx, const uint32_t *words, const int32_t *lengths, int64_t nprot, int64_t nres,
+                       plaac_summary *summaries, const plaac_residue_out *per_res, plaac_hits *hits);
+/* The same compact output for the one-byte codes of plaac_score(). */
+int plaac_score_hits(plaac_ctx *ctx, const uint8_t *codes, const int64_t *offsets, int64_t nprot, plaac_hits *hits);
+
 /* ---- multi-GPU: proteins are independent, so the batch is cut into contiguous,
  * residue-balanced shards, one per ctx (each ctx on its own GPU), scored concurrently by one host thread per
  * ctx, each writing its records / per-residue rows straight into the caller's arrays at the input position.
@@ -164,6 +208,11 @@ int plaac_shard_plan(const int64_t *offsets, int64_t nprot, int nshards, int64_t
  * (its text is on that shard's ctx); all shards are always joined before returning. */
 int plaac_score_multi(plaac_ctx *const *ctxs, int nctx, const uint8_t *codes, const int64_t *offsets, int64_t nprot,
                       plaac_summary *summaries, const plaac_residue_out *per_res);
+
+/* The transport-lean form of plaac_score_multi (see plaac_score_packed): shards are cut on the lengths, a shard may
+ * start in the middle of a word; the shards' ranked lists are merged on the host into `hits`. */
+int plaac_score_multi_packed(plaac_ctx *const *ctxs, int nctx, const uint32_t *words, const int32_t *lengths, int64_t nprot,
+                             int64_t nres, plaac_summary *summaries, const plaac_residue_out *per_res, plaac_hits *hits);
 
 /* ---- GPU FASTA ingest and background counts --------------------------------
  * Replaces fastareader (plaac.java:4302-4375) + string2aa (:1764-1769) + the terminal '*' strip (:758) for a whole

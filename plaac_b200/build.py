@@ -40,7 +40,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB,
                os.path.join(CSRC, "plaac_cuda.cu"), os.path.join(CSRC, "bench_utils.cu"),
-               os.path.join(CSRC, "host_params.cpp")]
+               os.path.join(CSRC, "host_params.cpp"), os.path.join(CSRC, "host_pack.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

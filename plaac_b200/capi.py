@@ -69,6 +69,14 @@ class FastaIndex(C.Structure):
 
 
 RANK_WEB_QUIRKS = 1
+HITS_CORE, HITS_TOPK = 1, 2
+PACK_PER_WORD = 7
+
+
+class Hits(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("rank_flags", C.c_int32), ("capacity", C.c_int64), ("records", C.c_void_p),
+                ("index", C.c_void_p), ("count", C.c_int64), ("n_core", C.c_int64)]
+
 
 _lib = None
 
@@ -128,6 +136,20 @@ def lib():
         L.plaac_rank_device.argtypes = [vp, vp, i64, C.c_int, vp, C.POINTER(i64)]
         L.plaac_gather_device.restype = C.c_int
         L.plaac_gather_device.argtypes = [vp, vp, vp, i64, vp]
+        L.plaac_packed_words.restype = i64
+        L.plaac_packed_words.argtypes = [i64]
+        L.plaac_pack_host.restype = C.c_int
+        L.plaac_pack_host.argtypes = [vp, i64, vp, C.c_int]
+        L.plaac_pack_chars_host.restype = C.c_int
+        L.plaac_pack_chars_host.argtypes = [vp, i64, vp, C.c_int]
+        L.plaac_unpack_host.restype = C.c_int
+        L.plaac_unpack_host.argtypes = [vp, i64, i64, vp]
+        L.plaac_score_packed.restype = C.c_int
+        L.plaac_score_packed.argtypes = [vp, vp, vp, i64, i64, vp, C.POINTER(ResidueOut), C.POINTER(Hits)]
+        L.plaac_score_multi_packed.restype = C.c_int
+        L.plaac_score_multi_packed.argtypes = [C.POINTER(vp), C.c_int, vp, vp, i64, i64, vp, C.POINTER(ResidueOut), C.POINTER(Hits)]
+        L.plaac_score_hits.restype = C.c_int
+        L.plaac_score_hits.argtypes = [vp, vp, vp, i64, C.POINTER(Hits)]
         L.plaac_bench_synth_lengths.restype = C.c_int
         L.plaac_bench_synth_lengths.argtypes = [vp, C.c_uint64, i64, i64, dbl, dbl, i32, i32, vp]
         L.plaac_bench_synth_residues.restype = C.c_int
@@ -180,6 +202,37 @@ def pack(seqs):
     np.cumsum(lens, out=offsets[1:])
     codes = np.concatenate(seqs).astype(np.uint8) if len(seqs) and offsets[-1] > 0 else np.zeros(0, np.uint8)
     return np.ascontiguousarray(codes), offsets
+
+
+def pack_words(codes: np.ndarray, nthreads: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+    """plaac_pack_host: one-byte codes -> radix-22 words (7 residues per uint32) for Scorer.score_packed()."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    nw = int(lib().plaac_packed_words(len(codes)))
+    words = out if out is not None else np.zeros(nw, dtype=np.uint32)
+    assert words.dtype == np.uint32 and len(words) >= nw
+    rc = lib().plaac_pack_host(codes.ctypes.data if len(codes) else None, len(codes), words.ctypes.data if nw else None, nthreads)
+    if rc != 0:
+        raise PlaacError(rc, "plaac_pack_host: residue code > 21")
+    return words
+
+
+def pack_chars(text: bytes, nthreads: int = 0) -> np.ndarray:
+    """plaac_pack_chars_host: FASTA letters -> radix-22 words (aatoint fused with the packing)."""
+    buf = np.frombuffer(text, dtype=np.uint8)
+    words = np.zeros(int(lib().plaac_packed_words(len(buf))), dtype=np.uint32)
+    rc = lib().plaac_pack_chars_host(buf.ctypes.data if len(buf) else None, len(buf), words.ctypes.data if len(words) else None, nthreads)
+    if rc != 0:
+        raise PlaacError(rc, "plaac_pack_chars_host failed")
+    return words
+
+
+def unpack_words(words: np.ndarray, first: int, count: int) -> np.ndarray:
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    out = np.zeros(count, dtype=np.uint8)
+    rc = lib().plaac_unpack_host(words.ctypes.data if len(words) else None, first, count, out.ctypes.data if count else None)
+    if rc != 0:
+        raise PlaacError(rc, "plaac_unpack_host failed")
+    return out
 
 
 class PinnedBuffer:
@@ -271,6 +324,52 @@ class Scorer:
         if per_residue:
             return out, res
         return out
+
+    def _hits(self, mode, capacity, records=True):
+        cap = max(int(capacity), 0)
+        rec = np.zeros(cap, dtype=SUMMARY_DTYPE) if records else None
+        idx = np.zeros(cap, dtype=np.int32)
+        h = Hits(mode=mode, rank_flags=0, capacity=cap, records=rec.ctypes.data if records and cap else None,
+                 index=idx.ctypes.data if cap else None, count=0, n_core=0)
+        return h, rec, idx
+
+    def score_packed(self, words: np.ndarray, lengths: np.ndarray, nres: int | None = None, summaries: bool = True,
+                     per_residue: bool = False, hits: str | None = None, capacity: int | None = None):
+        """plaac_score_packed: radix-22 words + int32 lengths in; the table and / or its ranked head out.
+        hits: None, "core" (every protein with a CORE, ranked) or "topk" (first `capacity` rows of the ranking).
+        Returns summaries (or None) [, residue dict] [, dict(records, index, n_core)] in that order."""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        nprot = len(lengths)
+        if nres is None:
+            nres = int(lengths.astype(np.int64).sum())
+        out = np.zeros(nprot, dtype=SUMMARY_DTYPE) if summaries else None
+        res, ro = None, None
+        if per_residue:
+            res = {n: np.zeros(nres, dtype=np.uint8) for n in RESIDUE_U8}
+            res.update({n: np.zeros(nres, dtype=np.float64) for n in RESIDUE_F64})
+            ro = C.byref(ResidueOut(**{n: a.ctypes.data for n, a in res.items()}))
+        h = rec = idx = None
+        if hits is not None:
+            h, rec, idx = self._hits(HITS_CORE if hits == "core" else HITS_TOPK, nprot if capacity is None else capacity)
+        self._check(lib().plaac_score_packed(self._h, words.ctypes.data if len(words) else None, lengths.ctypes.data if nprot else None,
+                                             nprot, nres, out.ctypes.data if out is not None and nprot else None, ro,
+                                             C.byref(h) if h is not None else None))
+        ret = [out]
+        if per_residue:
+            ret.append(res)
+        if h is not None:
+            ret.append({"records": rec[:h.count], "index": idx[:h.count], "n_core": int(h.n_core)})
+        return ret[0] if len(ret) == 1 else tuple(ret)
+
+    def score_hits(self, codes: np.ndarray, offsets: np.ndarray, hits: str = "core", capacity: int | None = None):
+        """plaac_score_hits: one-byte codes in, ranked compact output only."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        nprot = len(offsets) - 1
+        h, rec, idx = self._hits(HITS_CORE if hits == "core" else HITS_TOPK, nprot if capacity is None else capacity)
+        self._check(lib().plaac_score_hits(self._h, codes.ctypes.data, offsets.ctypes.data, nprot, C.byref(h)))
+        return {"records": rec[:h.count], "index": idx[:h.count], "n_core": int(h.n_core)}
 
     def score_ptr(self, codes_ptr: int, offsets_ptr: int, nprot: int, summaries_ptr: int):
         """Raw host pointers (e.g. pinned torch tensors)."""
@@ -403,3 +502,32 @@ class MultiScorer:
             msgs = [lib().plaac_last_error(s._h).decode() for s in self.scorers]
             raise PlaacError(rc, "; ".join(m for m in msgs if m) or lib().plaac_last_error(None).decode())
         return (out, res) if per_residue else out
+
+    def score_packed(self, words: np.ndarray, lengths: np.ndarray, per_residue: bool = False, hits: str | None = None,
+                     capacity: int | None = None):
+        """plaac_score_multi_packed: (summaries[, residue dict][, hits dict])."""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        nprot = len(lengths)
+        nres = int(lengths.astype(np.int64).sum())
+        out = np.zeros(nprot, dtype=SUMMARY_DTYPE)
+        res, ro = None, None
+        if per_residue:
+            res = {n: np.zeros(nres, dtype=np.uint8) for n in RESIDUE_U8}
+            res.update({n: np.zeros(nres, dtype=np.float64) for n in RESIDUE_F64})
+            ro = C.byref(ResidueOut(**{n: a.ctypes.data for n, a in res.items()}))
+        h = rec = idx = None
+        if hits is not None:
+            h, rec, idx = self.scorers[0]._hits(HITS_CORE if hits == "core" else HITS_TOPK, nprot if capacity is None else capacity)
+        handles = (C.c_void_p * len(self.scorers))(*[s._h for s in self.scorers])
+        rc = lib().plaac_score_multi_packed(handles, len(self.scorers), words.ctypes.data, lengths.ctypes.data, nprot, nres,
+                                            out.ctypes.data, ro, C.byref(h) if h is not None else None)
+        if rc != 0:
+            msgs = [lib().plaac_last_error(s._h).decode() for s in self.scorers]
+            raise PlaacError(rc, "; ".join(m for m in msgs if m) or lib().plaac_last_error(None).decode())
+        ret = [out]
+        if per_residue:
+            ret.append(res)
+        if h is not None:
+            ret.append({"records": rec[:h.count], "index": idx[:h.count], "n_core": int(h.n_core)})
+        return ret[0] if len(ret) == 1 else tuple(ret)

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -21,6 +23,7 @@
 #include "summary_kernel.cuh"
 #include "summary_kernel_v2.cuh"
 #include "long_kernel.cuh"
+#include "lean.cuh"
 #include "generic_windows.cuh"
 
 using namespace plaac;
@@ -39,6 +42,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf hist, cursor, order, nchunks, chunk_base, stream_buf, tbw, slot_bucket, errflag, core_list, core_count, scan_tmp, gen_f64;
     DevBuf codes, offsets, summaries;  // staging for the host-buffer API
+    DevBuf words, lengths;             // ... of its packed form (plaac_score_packed)
+    DevBuf hit_flag, hit_pos;          // compact ranked output (plaac_hits)
     DevBuf res_u8, res_f64;            // per-residue staging for the host-buffer API
     DevBuf res_b0, res_b1, res_a0, res_a1, res_mapw, res_lpseq;  // per-residue scratch (bucketed layout)
     DevBuf ing_agg, ing_cnt, ing_base, ing_misc;                 // FASTA ingest scratch
@@ -75,6 +80,7 @@ struct plaac_ctx {
     KScalars ks;
     DeviceTables* d_tabs = nullptr;
     Slot slot[kSlots];
+    DevBuf all_summaries;      // records of a whole host-buffer call, kept on the device for the compact ranked output
     int nwarps = 0, ring_words = 0;
     size_t smem_bytes = 0;
     int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
@@ -112,6 +118,27 @@ int fail(plaac_ctx* ctx, int code, const char* fmt, ...)
     return code;
 }
 
+// Function-try-block handler of every extern "C" entry point: nothing may throw across the C ABI (include/plaac_cuda.h).
+int api_caught(plaac_ctx* ctx, const char* fn) noexcept
+{
+    int code = PLAAC_E_INVALID;
+    char what[200] = "unknown C++ exception";
+    try {
+        throw;
+    } catch (const std::bad_alloc&) {
+        code = PLAAC_E_NOMEM;
+        snprintf(what, sizeof(what), "out of host memory");
+    } catch (const std::exception& e) {
+        snprintf(what, sizeof(what), "%s", e.what());
+    } catch (...) {
+    }
+    try {
+        return fail(ctx, code, "%s: %s", fn, what);
+    } catch (...) {
+        return code;
+    }
+}
+
 #define CU(ctx, call)                                                                                      \
     do {                                                                                                   \
         cudaError_t e__ = (call);                                                                          \
@@ -119,6 +146,12 @@ int fail(plaac_ctx* ctx, int code, const char* fmt, ...)
             return fail(ctx, e__ == cudaErrorMemoryAllocation ? PLAAC_E_NOMEM : PLAAC_E_CUDA, "%s: %s", #call, \
                         cudaGetErrorString(e__));                                                          \
     } while (0)
+
+int cu_rc(plaac_ctx* ctx, cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return PLAAC_OK;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? PLAAC_E_NOMEM : PLAAC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
 
 int ensure(plaac_ctx* ctx, DevBuf& b, size_t bytes)
 {
@@ -322,7 +355,7 @@ int slot_init(plaac_ctx* ctx, Slot& s)
 void slot_free(Slot& s)
 {
     for (DevBuf* b : {&s.gen_f64, &s.scan_tmp, &s.hist, &s.cursor, &s.order, &s.nchunks, &s.chunk_base, &s.stream_buf, &s.tbw, &s.slot_bucket, &s.errflag,
-                      &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.res_u8, &s.res_f64, &s.res_b0,
+                      &s.core_list, &s.core_count, &s.codes, &s.offsets, &s.summaries, &s.words, &s.lengths, &s.hit_flag, &s.hit_pos, &s.res_u8, &s.res_f64, &s.res_b0,
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
@@ -778,7 +811,7 @@ int finish_slot(plaac_ctx* ctx, Slot& s)
     ctx->stats.last_padded_slots = *s.h_total * 32;
     if (*s.h_err) {
         cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream);
-        return fail(ctx, PLAAC_E_INVALID, "input contains residue codes > 21 (treated as X)");
+        return fail(ctx, PLAAC_E_INVALID, "input contains residue codes > 21 or packed words >= 22^7 (treated as X)");
     }
     return PLAAC_OK;
 }
@@ -788,7 +821,7 @@ int finish_slot(plaac_ctx* ctx, Slot& s)
 extern "C" {
 
 int plaac_device_count(void)
-{
+try {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) {
@@ -797,10 +830,12 @@ int plaac_device_count(void)
         return 0;
     }
     return n;
+} catch (...) {
+    return api_caught(nullptr, "plaac_device_count");
 }
 
 int plaac_host_alloc(void** out, size_t bytes, int flags)
-{
+try {
     if (!out) return fail(nullptr, PLAAC_E_INVALID, "plaac_host_alloc: NULL argument");
     *out = nullptr;
     if (flags & ~PLAAC_HOST_WRITE_COMBINED) return fail(nullptr, PLAAC_E_INVALID, "plaac_host_alloc: unknown flags %d", flags);
@@ -813,10 +848,12 @@ int plaac_host_alloc(void** out, size_t bytes, int flags)
                     cudaGetErrorString(e));
     }
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(nullptr, "plaac_host_alloc");
 }
 
 int plaac_host_free(void* p)
-{
+try {
     if (!p) return PLAAC_OK;
     const cudaError_t e = cudaFreeHost(p);
     if (e != cudaSuccess) {
@@ -824,10 +861,12 @@ int plaac_host_free(void* p)
         return fail(nullptr, PLAAC_E_INVALID, "cudaFreeHost: %s", cudaGetErrorString(e));
     }
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(nullptr, "plaac_host_free");
 }
 
 int plaac_host_register(void* p, size_t bytes)
-{
+try {
     if (!p || bytes == 0) return fail(nullptr, PLAAC_E_INVALID, "plaac_host_register: empty range");
     const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
     if (e != cudaSuccess) {
@@ -836,10 +875,12 @@ int plaac_host_register(void* p, size_t bytes)
                     bytes, cudaGetErrorString(e));
     }
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(nullptr, "plaac_host_register");
 }
 
 int plaac_host_unregister(void* p)
-{
+try {
     if (!p) return PLAAC_OK;
     const cudaError_t e = cudaHostUnregister(p);
     if (e != cudaSuccess) {
@@ -847,10 +888,12 @@ int plaac_host_unregister(void* p)
         return fail(nullptr, PLAAC_E_INVALID, "cudaHostUnregister: %s", cudaGetErrorString(e));
     }
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(nullptr, "plaac_host_unregister");
 }
 
 int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
-{
+try {
     if (!out || !params) return fail(nullptr, PLAAC_E_INVALID, "plaac_create: NULL argument");
     *out = nullptr;
     int ndev = plaac_device_count();
@@ -861,7 +904,12 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
     if (prop.major != 10)
         return fail(nullptr, PLAAC_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
-    plaac_ctx* ctx = new plaac_ctx();
+    // (owned here until the very end: an exception on the way -- std::string, the table block -- must not leak the ctx)
+    struct CtxGuard {
+        plaac_ctx* p;
+        ~CtxGuard() { if (p) plaac_destroy(p); }
+    } guard{new plaac_ctx()};
+    plaac_ctx* ctx = guard.p;
     ctx->device = device;
     ctx->params = *params;
     ctx->sm_count = prop.multiProcessorCount;
@@ -869,49 +917,42 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
     int rc = setup_scalars(ctx);
     if (rc != PLAAC_OK) {
         g_last_error = ctx->err;
-        delete ctx;
         return rc;
     }
     auto bail = [&](int code) {
         g_last_error = ctx->err;
-        plaac_destroy(ctx);
         return code;
     };
     if (cudaSetDevice(device) != cudaSuccess) {
         ctx->err = "cudaSetDevice failed";
         return bail(PLAAC_E_CUDA);
     }
-    DeviceTables* h = new DeviceTables();
-    fill_tables(ctx->params, *h, ctx->ks.w);
-    cudaError_t e = cudaMalloc((void**)&ctx->d_tabs, sizeof(DeviceTables));
-    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tabs, h, sizeof(DeviceTables), cudaMemcpyHostToDevice);
-    delete h;
-    if (e != cudaSuccess) {
-        ctx->err = std::string("table upload: ") + cudaGetErrorString(e);
-        return bail(PLAAC_E_CUDA);
-    }
-    e = cudaFuncSetAttribute(k_long_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LongShared));
-    if (e != cudaSuccess) {
-        ctx->err = std::string("cudaFuncSetAttribute(k_long_score): ") + cudaGetErrorString(e);
-        return bail(PLAAC_E_CUDA);
-    }
-    e = cudaFuncSetAttribute(k_score_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes);
-    if (e != cudaSuccess) {
-        ctx->err = std::string("cudaFuncSetAttribute(k_score_summary): ") + cudaGetErrorString(e);
-        return bail(PLAAC_E_CUDA);
-    }
-    if (ctx->v2_nwr > 0) {
-        e = cudaFuncSetAttribute(k_score_summary_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->v2_smem_bytes);
+    {
+        std::unique_ptr<DeviceTables> h(new DeviceTables());
+        fill_tables(ctx->params, *h, ctx->ks.w);
+        cudaError_t e = cudaMalloc((void**)&ctx->d_tabs, sizeof(DeviceTables));
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tabs, h.get(), sizeof(DeviceTables), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
-            ctx->err = std::string("cudaFuncSetAttribute(k_score_summary_v2): ") + cudaGetErrorString(e);
+            ctx->err = std::string("table upload: ") + cudaGetErrorString(e);
             return bail(PLAAC_E_CUDA);
         }
     }
-    for (const void* fn : {(const void*)k_len_hist, (const void*)k_scatter}) {
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes);
-        if (e != cudaSuccess) {
-            ctx->err = std::string("cudaFuncSetAttribute(prep kernels): ") + cudaGetErrorString(e);
-            return bail(PLAAC_E_CUDA);
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION on the device, shared by every ctx of
+    // the process: it is raised once to the device's opt-in maximum, never to this ctx's own sizes (a ctx created later
+    // with a smaller ring would otherwise lower the limit under an earlier ctx's launches).
+    {
+        const int optin = (int)prop.sharedMemPerBlockOptin;
+        if ((size_t)optin < std::max<size_t>(std::max(ctx->smem_bytes, ctx->v2_smem_bytes), sizeof(LongShared))) {
+            ctx->err = "device offers less opt-in shared memory per block than the kernels need";
+            return bail(PLAAC_E_UNSUPPORTED);
+        }
+        for (const void* fn : {(const void*)k_long_score, (const void*)k_score_summary, (const void*)k_score_summary_v2,
+                               (const void*)k_len_hist, (const void*)k_scatter}) {
+            const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e);
+                return bail(PLAAC_E_CUDA);
+            }
         }
     }
     {
@@ -925,7 +966,7 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         ctx->long_tie[3] = tie_binades(P.hydro2, PLAAC_NAA);
     }
     ctx->res_plan = residue_v2_plan(ctx->ks);
-    rc = residue_v2_setup(ctx->res_plan);
+    rc = residue_v2_setup(ctx->res_plan, (int)prop.sharedMemPerBlockOptin);
     if (rc == PLAAC_OK) rc = residue_setup(ctx->ks, ctx->ring_words);
     if (rc != PLAAC_OK) {
         ctx->err = "cudaFuncSetAttribute(per-residue kernels) failed";
@@ -935,8 +976,11 @@ int plaac_create(plaac_ctx** out, int device, const plaac_params* params)
         rc = slot_init(ctx, ctx->slot[i]);
         if (rc != PLAAC_OK) return bail(rc);
     }
+    guard.p = nullptr;
     *out = ctx;
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(nullptr, "plaac_create");
 }
 
 void plaac_destroy(plaac_ctx* ctx)
@@ -944,6 +988,7 @@ void plaac_destroy(plaac_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (int i = 0; i < kSlots; i++) slot_free(ctx->slot[i]);
+    release(ctx->all_summaries);
     if (ctx->d_tabs) cudaFree(ctx->d_tabs);
     delete ctx;
 }
@@ -955,7 +1000,7 @@ const char* plaac_last_error(const plaac_ctx* ctx)
 
 int plaac_score_device(plaac_ctx* ctx, const uint8_t* d_codes, const int64_t* d_offsets, int64_t nprot, int64_t ntotal,
                        plaac_summary* d_summaries, const plaac_residue_out* d_per_res)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_device: NULL ctx");
     if (nprot < 0 || ntotal < 0) return fail(ctx, PLAAC_E_INVALID, "negative size");
     if (nprot == 0) return PLAAC_OK;
@@ -964,10 +1009,12 @@ int plaac_score_device(plaac_ctx* ctx, const uint8_t* d_codes, const int64_t* d_
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->last_slot = 0;
     return run_batch(ctx, ctx->slot[0], d_codes, d_offsets, 0, nprot, ntotal, d_summaries, d_per_res, 0);
+} catch (...) {
+    return api_caught(ctx, "plaac_score_device");
 }
 
 int plaac_sync(plaac_ctx* ctx)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_sync: NULL ctx");
     CU(ctx, cudaSetDevice(ctx->device));
     Slot& s = ctx->slot[0];
@@ -978,6 +1025,8 @@ int plaac_sync(plaac_ctx* ctx)
         if (cudaEventElapsedTime(&ms, s.ev_b, s.ev_c) == cudaSuccess) ctx->stats.last_score_ms = ms;
     }
     return rc;
+} catch (...) {
+    return api_caught(ctx, "plaac_sync");
 }
 
 void* plaac_stream(plaac_ctx* ctx)
@@ -986,35 +1035,41 @@ void* plaac_stream(plaac_ctx* ctx)
 }
 
 int plaac_set_chunk(plaac_ctx* ctx, int64_t max_residues, int64_t max_proteins)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_chunk: NULL ctx");
     if (max_residues < 0 || max_proteins < 0) return fail(ctx, PLAAC_E_INVALID, "negative chunk size");
     if (max_residues > 0) ctx->chunk_res = ctx->chunk_res_pr = max_residues;
     if (max_proteins > 0) ctx->chunk_prot = std::min<int64_t>(max_proteins, 0x7fffffff);
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_set_chunk");
 }
 
 int plaac_set_long_path(plaac_ctx* ctx, int64_t min_len, int warm)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_long_path: NULL ctx");
     if (min_len < -1) return fail(ctx, PLAAC_E_INVALID, "min_len must be -1 (automatic), 0 (off) or a length");
     ctx->long_min = min_len;
     if (warm != 0) ctx->long_warm = warm;
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_set_long_path");
 }
 
 int plaac_set_kernel_variant(plaac_ctx* ctx, int variant)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_kernel_variant: NULL ctx");
     if (variant < 0 || variant > 2) return fail(ctx, PLAAC_E_INVALID, "variant must be 0, 1 or 2");
     if (variant == 2 && ctx->v2_nwr <= 0)
         return fail(ctx, PLAAC_E_UNSUPPORTED, "v2 kernel unavailable for these parameters: %s", ctx->v2_why.c_str());
     ctx->variant = variant;
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_set_kernel_variant");
 }
 
 int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
-{
+try {
     if (!ctx || !out) return fail(ctx, PLAAC_E_INVALID, "plaac_get_stats: NULL argument");
     ctx->stats.long_redone_chunks = 0;
     for (int i = 0; i < kSlots; i++) {
@@ -1033,6 +1088,8 @@ int plaac_get_stats(plaac_ctx* ctx, plaac_stats* out)
     }
     *out = ctx->stats;
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_get_stats");
 }
 
 void plaac_encode_host(const char* chars, int64_t n, uint8_t* codes)
@@ -1049,16 +1106,238 @@ void plaac_encode_host(const char* chars, int64_t n, uint8_t* codes)
     for (int64_t i = 0; i < n; i++) codes[i] = lut[(unsigned char)chars[i]];
 }
 
-int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int64_t nprot, plaac_summary* summaries,
-                const plaac_residue_out* per_res)
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ ranking (N4)
+namespace {
+
+// One stable radix pass over the first n rows of buffer pair `cur`; the result lands in pair cur ^ 1.
+template <bool SPLIT>
+int rank_pass(plaac_ctx* ctx, Slot& s, int64_t n, int shift, int cur)
 {
-    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score: NULL ctx");
-    if (nprot < 0) return fail(ctx, PLAAC_E_INVALID, "negative nprot");
+    const int64_t ntiles = (n + kRankTile - 1) / kRankTile;
+    int rc;
+    if ((rc = ensure(ctx, s.rk_hist, sizeof(int32_t) * (size_t)(kRankDigits * ntiles)))) return rc;
+    if ((rc = ensure(ctx, s.rk_offs, sizeof(int64_t) * (size_t)(kRankDigits * ntiles + 1)))) return rc;
+    cudaStream_t st = s.stream;
+    k_rank_hist<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>((const uint64_t*)s.rk_keys[cur].p, n, shift,
+                                                                  (int32_t*)s.rk_hist.p, ntiles);
+    if ((rc = launch_scan(ctx, s, (const int32_t*)s.rk_hist.p, (int64_t*)s.rk_offs.p, (int64_t)kRankDigits * ntiles, st))) return rc;
+    k_rank_scatter<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>(
+        (const uint64_t*)s.rk_keys[cur].p, (const int32_t*)s.rk_vals[cur].p, (uint64_t*)s.rk_keys[cur ^ 1].p,
+        (int32_t*)s.rk_vals[cur ^ 1].p, n, shift, (const int64_t*)s.rk_offs.p, ntiles);
+    ctx->stats.kernel_launches += 2;
+    CU(ctx, cudaGetLastError());
+    return PLAAC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plaac_rank_device(plaac_ctx* ctx, const plaac_summary* d_summaries, int64_t nprot, int flags, int32_t* d_order,
+                      int64_t* n_core)
+try {
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank_device: NULL ctx");
+    if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
+    if (n_core) *n_core = 0;
     if (nprot == 0) return PLAAC_OK;
-    if (!offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
-    if (!summaries && !per_res) return fail(ctx, PLAAC_E_INVALID, "no output requested");
-    if (!codes && offsets[nprot] != offsets[0]) return fail(ctx, PLAAC_E_INVALID, "NULL codes");
+    if (!d_summaries || !d_order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
     CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    int rc;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = ensure(ctx, s.rk_keys[k], sizeof(uint64_t) * (size_t)nprot))) return rc;
+        if ((rc = ensure(ctx, s.rk_vals[k], sizeof(int32_t) * (size_t)nprot))) return rc;
+    }
+    const unsigned gk = (unsigned)((nprot + 255) / 256);
+    int cur = 0;
+    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 0, (flags & PLAAC_RANK_WEB_QUIRKS) ? 1 : 0, (uint64_t*)s.rk_keys[cur].p,
+                                    (int32_t*)s.rk_vals[cur].p);
+    ctx->stats.kernel_launches += 1;
+    for (int shift = 0; shift < 64; shift += 8) {
+        if ((rc = rank_pass<false>(ctx, s, nprot, shift, cur))) return rc;
+        cur ^= 1;
+    }
+    // CORE proteins first (stable), then order them by COREscore
+    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 1, 0, (uint64_t*)s.rk_keys[cur].p, (int32_t*)s.rk_vals[cur].p);
+    ctx->stats.kernel_launches += 1;
+    if ((rc = rank_pass<true>(ctx, s, nprot, 0, cur))) return rc;
+    cur ^= 1;
+    const int64_t ntiles = (nprot + kRankTile - 1) / kRankTile;
+    int64_t ncore = 0;  // rows with digit 0 = output base of (digit 1, tile 0)
+    CU(ctx, cudaMemcpyAsync(&ncore, (const int64_t*)s.rk_offs.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    if (ncore > 1) {
+        // the tail (no CORE) must stay where it is: park it in d_order before the two buffers start to alternate
+        const int tail_src = cur;
+        if (nprot > ncore)
+            CU(ctx, cudaMemcpyAsync(d_order + ncore, (const int32_t*)s.rk_vals[tail_src].p + ncore,
+                                    sizeof(int32_t) * (size_t)(nprot - ncore), cudaMemcpyDeviceToDevice, st));
+        for (int shift = 0; shift < 64; shift += 8) {
+            if ((rc = rank_pass<false>(ctx, s, ncore, shift, cur))) return rc;
+            cur ^= 1;
+        }
+        CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)ncore, cudaMemcpyDeviceToDevice, st));
+    } else {
+        CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)nprot, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    if (n_core) *n_core = ncore;
+    return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_rank_device");
+}
+
+int plaac_gather_device(plaac_ctx* ctx, const plaac_summary* d_summaries, const int32_t* d_order, int64_t count,
+                        plaac_summary* d_out)
+try {
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_gather_device: NULL ctx");
+    if (count < 0) return fail(ctx, PLAAC_E_INVALID, "negative count");
+    if (count == 0) return PLAAC_OK;
+    if (!d_summaries || !d_order || !d_out) return fail(ctx, PLAAC_E_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int64_t threads = count * (int64_t)(sizeof(plaac_summary) / 8);
+    k_rank_gather<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->slot[0].stream>>>(d_summaries, d_order, count, d_out);
+    ctx->stats.kernel_launches += 1;
+    CU(ctx, cudaGetLastError());
+    return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_gather_device");
+}
+
+int plaac_rank(plaac_ctx* ctx, const plaac_summary* summaries, int64_t nprot, int flags, int32_t* order, int64_t* n_core)
+try {
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank: NULL ctx");
+    if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
+    if (n_core) *n_core = 0;
+    if (nprot == 0) return PLAAC_OK;
+    if (!summaries || !order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot& s = ctx->slot[0];
+    int rc;
+    if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * (size_t)nprot))) return rc;
+    if ((rc = ensure(ctx, s.rk_order, sizeof(int32_t) * (size_t)nprot))) return rc;
+    CU(ctx, cudaMemcpyAsync(s.summaries.p, summaries, sizeof(plaac_summary) * (size_t)nprot, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = plaac_rank_device(ctx, (const plaac_summary*)s.summaries.p, nprot, flags, (int32_t*)s.rk_order.p, n_core))) return rc;
+    CU(ctx, cudaMemcpy(order, s.rk_order.p, sizeof(int32_t) * (size_t)nprot, cudaMemcpyDeviceToHost));
+    return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_rank");
+}
+
+}  // extern "C"
+
+namespace {
+
+// What the host-buffer calls are given: one-byte codes + int64 offsets (plaac_score), or radix-22 words + int32
+// lengths (plaac_score_packed).
+struct HostInput {
+    const uint8_t* codes = nullptr;
+    const int64_t* offsets = nullptr;
+    const uint32_t* words = nullptr;
+    const int32_t* lengths = nullptr;
+    int64_t nres = 0;  // packed input: the caller's total (checked against the lengths)
+    int64_t pos0 = 0;  // packed input: residue index, counted from digit 0 of words[0], of the first protein (a shard of a
+                       // larger batch starts in the middle of a word)
+    bool packed() const { return words != nullptr || lengths != nullptr; }
+};
+
+// Compact ranked output of a whole host-buffer call: the records of every chunk were kept in ctx->all_summaries.
+int finish_hits(plaac_ctx* ctx, int64_t nprot, plaac_hits* hits)
+{
+    Slot& s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    const plaac_summary* all = (const plaac_summary*)ctx->all_summaries.p;
+    int rc;
+    hits->count = hits->n_core = 0;
+    const int64_t cap = std::max<int64_t>(hits->capacity, 0);
+    if ((rc = ensure(ctx, s.rk_order, sizeof(int32_t) * (size_t)nprot))) return rc;
+    int32_t* d_order = (int32_t*)s.rk_order.p;
+    int64_t count = 0;
+    if (hits->mode == PLAAC_HITS_TOPK) {
+        int64_t ncore = 0;
+        if ((rc = plaac_rank_device(ctx, all, nprot, hits->rank_flags, d_order, &ncore))) return rc;
+        hits->n_core = ncore;
+        count = std::min(cap, nprot);
+    } else {
+        // rows with a CORE only: flag -> scan -> stable compaction, then the two stable LSD sorts of rank.cuh on those rows
+        if ((rc = ensure(ctx, s.hit_flag, sizeof(int32_t) * (size_t)nprot))) return rc;
+        if ((rc = ensure(ctx, s.hit_pos, sizeof(int64_t) * (size_t)(nprot + 1)))) return rc;
+        const unsigned gn = (unsigned)((nprot + 255) / 256);
+        k_hits_flag<<<gn, 256, 0, st>>>(all, nprot, (int32_t*)s.hit_flag.p);
+        if ((rc = launch_scan(ctx, s, (const int32_t*)s.hit_flag.p, (int64_t*)s.hit_pos.p, nprot, st))) return rc;
+        int64_t ncore = 0;
+        CU(ctx, cudaMemcpyAsync(&ncore, (const int64_t*)s.hit_pos.p + nprot, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        ctx->stats.kernel_launches += 1;
+        hits->n_core = ncore;
+        count = std::min(cap, ncore);
+        if (ncore > 0) {
+            for (int k = 0; k < 2; k++) {
+                if ((rc = ensure(ctx, s.rk_keys[k], sizeof(uint64_t) * (size_t)ncore))) return rc;
+                if ((rc = ensure(ctx, s.rk_vals[k], sizeof(int32_t) * (size_t)ncore))) return rc;
+            }
+            int cur = 0;
+            k_hits_compact<<<gn, 256, 0, st>>>((const int32_t*)s.hit_flag.p, (const int64_t*)s.hit_pos.p, nprot,
+                                               (int32_t*)s.rk_vals[cur].p);
+            ctx->stats.kernel_launches += 1;
+            const unsigned gc = (unsigned)((ncore + 255) / 256);
+            for (int field = 0; field < 2; field++) {
+                k_hits_keys<<<gc, 256, 0, st>>>(all, (const int32_t*)s.rk_vals[cur].p, ncore, field,
+                                                (hits->rank_flags & PLAAC_RANK_WEB_QUIRKS) ? 1 : 0, (uint64_t*)s.rk_keys[cur].p);
+                ctx->stats.kernel_launches += 1;
+                for (int shift = 0; shift < 64; shift += 8) {
+                    if ((rc = rank_pass<false>(ctx, s, ncore, shift, cur))) return rc;
+                    cur ^= 1;
+                }
+            }
+            CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)ncore, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    hits->count = count;
+    if (count > 0) {
+        if (!hits->records && !hits->index) return fail(ctx, PLAAC_E_INVALID, "plaac_hits: no output array");
+        if (hits->records) {
+            if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * (size_t)count))) return rc;
+            if ((rc = plaac_gather_device(ctx, all, d_order, count, (plaac_summary*)s.summaries.p))) return rc;
+            CU(ctx, cudaMemcpyAsync(hits->records, s.summaries.p, sizeof(plaac_summary) * (size_t)count, cudaMemcpyDeviceToHost, st));
+        }
+        if (hits->index)
+            CU(ctx, cudaMemcpyAsync(hits->index, d_order, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    return PLAAC_OK;
+}
+
+int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary* summaries, const plaac_residue_out* per_res,
+               plaac_hits* hits)
+{
+    if (nprot < 0) return fail(ctx, PLAAC_E_INVALID, "negative nprot");
+    if (hits) {
+        hits->count = hits->n_core = 0;
+        if (hits->mode != PLAAC_HITS_CORE && hits->mode != PLAAC_HITS_TOPK) return fail(ctx, PLAAC_E_INVALID, "plaac_hits.mode must be PLAAC_HITS_CORE or PLAAC_HITS_TOPK");
+        if (hits->capacity < 0) return fail(ctx, PLAAC_E_INVALID, "plaac_hits.capacity is negative");
+        if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins with compact output");
+    }
+    if (nprot == 0) {
+        if (in.packed() && in.nres != 0) return fail(ctx, PLAAC_E_INVALID, "nres does not equal the sum of the lengths");
+        return PLAAC_OK;
+    }
+    const bool packed = in.packed();
+    if (packed) {
+        if (!in.lengths) return fail(ctx, PLAAC_E_INVALID, "NULL lengths");
+        if (in.nres < 0 || (in.nres > 0 && !in.words)) return fail(ctx, PLAAC_E_INVALID, "NULL words / negative nres");
+    } else {
+        if (!in.offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
+        if (!in.codes && in.offsets[nprot] != in.offsets[0]) return fail(ctx, PLAAC_E_INVALID, "NULL codes");
+    }
+    if (!summaries && !per_res && !hits) return fail(ctx, PLAAC_E_INVALID, "no output requested");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const bool want_rec = summaries || hits;  // the device computes records
+    int rc = PLAAC_OK;
+    if (hits && (rc = ensure(ctx, ctx->all_summaries, sizeof(plaac_summary) * (size_t)nprot))) return rc;
 
     // Chunking: bounded device footprint; kSlots sets of buffers so the next chunks' H2D overlap this chunk's kernels and
     // D2H.  Chunk sizes ramp up from max/8 and down again towards the end: the first chunk's copy and the last chunk's
@@ -1066,48 +1345,55 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
     // (different half-widths of the windows: 64 bytes of track scratch per residue, so summary mode chunks like per-residue mode)
     const int64_t max_res_full = (per_res || ctx->generic_windows) ? std::min(ctx->chunk_res_pr, ctx->chunk_res) : ctx->chunk_res;
     const int64_t min_res = std::max<int64_t>(max_res_full / 8, 1 << 20);
-    const int64_t total_res = offsets[nprot] - offsets[0];
+    const int64_t first_off = packed ? 0 : in.offsets[0];
+    const int64_t total_res = packed ? in.nres : in.offsets[nprot] - first_off;
     int64_t ramp = min_res;
     const int64_t max_prot = ctx->chunk_prot;
     int64_t start = 0;
+    const int64_t pos0 = packed ? in.pos0 : 0;
+    int64_t pos = pos0;  // residue index of protein `start` (packed: counted from digit 0 of words[0])
     int which = 0;
     bool pending[kSlots] = {};
-    int rc = PLAAC_OK;
     // Pageable caller buffers (a Java heap array behind JNI, a std::vector): the driver would stage every copy
     // synchronously (measured 568 instead of 94 ms for the 4.4 G-residue shard).  The codes and the records then go
     // through pinned staging buffers of the slot, filled / emptied by a multi-threaded memcpy that overlaps the copies
     // and kernels of the other slots.
-    const bool stage_codes = total_res > 0 && !host_is_pinned(codes + offsets[0]);
+    const void* in_main = packed ? (const void*)in.words : (const void*)(in.codes + first_off);
+    const bool stage_in = total_res > 0 && !host_is_pinned(in_main);
     const bool stage_sum = summaries && !host_is_pinned(summaries);
     auto drain = [&](int i) -> int {
         if (!pending[i]) return PLAAC_OK;
         pending[i] = false;
         return finish_slot(ctx, ctx->slot[i]);
     };
+    // Inside the chunk loop a CUDA error may not return at once: copies into the caller's buffers may be in flight on
+    // other slots, and the header promises "blocks until done".  Errors break out to the drain loop below.
+#define CUB(call)                                  \
+    if ((rc = cu_rc(ctx, (call), #call)) != PLAAC_OK) break
     while (start < nprot && rc == PLAAC_OK) {
-        // Cut the next chunk; validate it and collect what bounds its padded size while walking its offsets (the
+        // Cut the next chunk; validate it and collect what bounds its padded size while walking its lengths (the
         // walk overlaps the previous chunk's copies and kernels).
         int64_t end = start;
-        const int64_t base = offsets[start];
-        const int64_t remaining = total_res - (base - offsets[0]);
+        const int64_t remaining = total_res - (pos - pos0);
         const int64_t max_res = std::min(max_res_full, std::max(min_res, std::min(ramp, remaining / 2)));
         ramp = std::min(max_res_full, ramp * 2);
-        int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0;
+        int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0, nres = 0;
         int64_t long_min = per_res ? 0 : effective_long_min(ctx);
         const bool long_auto = !per_res && ctx->long_min < 0 && ctx->v2_nwr > 0 && ctx->variant != 1;
         unsigned long long bins[3 * kLongBins];
         if (long_auto) memset(bins, 0, sizeof(bins));
         while (end < nprot && end - start < max_prot) {
-            const int64_t len = offsets[end + 1] - offsets[end];
+            const int64_t len = packed ? (int64_t)in.lengths[end] : in.offsets[end + 1] - in.offsets[end];
             if (len < 0) {
-                rc = fail(ctx, PLAAC_E_INVALID, "offsets not monotone at protein %lld", (long long)end);
+                rc = fail(ctx, PLAAC_E_INVALID, packed ? "negative length at protein %lld" : "offsets not monotone at protein %lld",
+                          (long long)end);
                 break;
             }
             if (len > 0x7fffff00LL) {
                 rc = fail(ctx, PLAAC_E_INVALID, "protein %lld longer than 2^31", (long long)end);
                 break;
             }
-            if (end != start && offsets[end + 1] - base > max_res) break;
+            if (end != start && nres + len > max_res) break;
             if (long_auto && len >= 1024) {
                 // decided after the walk (choose_long_threshold)
                 const int b = long_bin(len);
@@ -1122,11 +1408,15 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
                 lmax = std::max(lmax, len);
                 nlong += len >= kHistBins;
             }
+            nres += len;
             end++;
         }
         if (rc != PLAAC_OK) break;
+        if (packed && (pos - pos0) + nres > in.nres) {
+            rc = fail(ctx, PLAAC_E_INVALID, "the lengths add up to more than nres = %lld residues", (long long)in.nres);
+            break;
+        }
         const int64_t np = end - start;
-        const int64_t nres = offsets[end] - base;
         int64_t long_thr = per_res ? 0 : (long_auto ? 0 : long_min);
         if (long_auto) {
             const LongChoice lc = choose_long_threshold(ctx, bins, nres);
@@ -1143,17 +1433,33 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
         Slot& s = ctx->slot[which];
         if ((rc = drain(which))) break;
         s.out_dst = nullptr;  // (a call that failed half-way may have left one behind)
+        // packed input: words [w0, w1) hold the chunk; its first residue is digit `skip` of word w0
+        const int64_t w0 = packed ? pos / PLAAC_PACK_PER_WORD : 0;
+        const int64_t w1 = packed ? (pos + nres + PLAAC_PACK_PER_WORD - 1) / PLAAC_PACK_PER_WORD : 0;
+        const int skip = packed ? (int)(pos - w0 * PLAAC_PACK_PER_WORD) : 0;
+        const int64_t nwords = w1 - w0;
         {
             // k_pack reads whole aligned 16-byte blocks and masks what lies beyond a protein: keep the slack behind the
             // residues defined.  Zeroed once per (re)allocation, not per chunk: a memset between the two H2D copies of a
             // chunk sends the second one to the back of the copy engine's queue, behind the next chunk's codes
             // (measured: 94 -> 136 ms end to end for the 4.4 G-residue shard).
             const size_t cap0 = s.codes.cap;
-            if ((rc = ensure(ctx, s.codes, (size_t)nres + 64))) break;
-            if (s.codes.cap != cap0) CU(ctx, cudaMemsetAsync(s.codes.p, 0, s.codes.cap, s.stream));
+            const size_t need = packed ? (size_t)((nwords + kUnpackTileWords) / kUnpackTileWords) * kUnpackTileBytes + 64 : (size_t)nres + 64;
+            if ((rc = ensure(ctx, s.codes, need))) break;
+            if (s.codes.cap != cap0) CUB(cudaMemsetAsync(s.codes.p, 0, s.codes.cap, s.stream));
         }
         if ((rc = ensure(ctx, s.offsets, sizeof(int64_t) * (np + 1)))) break;
-        if (summaries && (rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * np))) break;
+        if (packed) {
+            if ((rc = ensure(ctx, s.words, sizeof(uint32_t) * (size_t)(nwords + 4)))) break;
+            if ((rc = ensure(ctx, s.lengths, sizeof(int32_t) * (size_t)np))) break;
+        }
+        plaac_summary* d_sum = nullptr;
+        if (hits)
+            d_sum = (plaac_summary*)ctx->all_summaries.p + start;
+        else if (summaries) {
+            if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * np))) break;
+            d_sum = (plaac_summary*)s.summaries.p;
+        }
         plaac_residue_out dres;
         if (per_res) {
             if ((rc = ensure(ctx, s.res_u8, (size_t)2 * (nres + 16)))) break;
@@ -1174,48 +1480,142 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
             dres.post_bg = d + 8 * N;
             dres.post_prd = d + 9 * N;
         }
-        const uint8_t* src_codes = codes + base;
-        if (stage_codes && nres > 0) {
-            if ((rc = ensure_host(ctx, s.h_stage_codes, s.h_stage_codes_cap, (size_t)nres))) break;
-            par_memcpy(s.h_stage_codes, codes + base, (size_t)nres);
-            src_codes = (const uint8_t*)s.h_stage_codes;
+        const void* src_main = packed ? (const void*)(in.words + w0) : (const void*)(in.codes + first_off + pos);
+        const size_t main_bytes = packed ? sizeof(uint32_t) * (size_t)nwords : (size_t)nres;
+        if (stage_in && main_bytes > 0) {
+            if ((rc = ensure_host(ctx, s.h_stage_codes, s.h_stage_codes_cap, main_bytes))) break;
+            par_memcpy(s.h_stage_codes, src_main, main_bytes);
+            src_main = s.h_stage_codes;
         }
         if (stage_sum && (rc = ensure_host(ctx, s.h_stage_sum, s.h_stage_sum_cap, sizeof(plaac_summary) * (size_t)np))) break;
-        if (nres > 0) CU(ctx, cudaMemcpyAsync(s.codes.p, src_codes, (size_t)nres, cudaMemcpyHostToDevice, s.stream));
-        CU(ctx, cudaMemcpyAsync(s.offsets.p, offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
-        rc = run_batch(ctx, s, (const uint8_t*)s.codes.p, (const int64_t*)s.offsets.p, base, np, nres,
-                       summaries ? (plaac_summary*)s.summaries.p : nullptr, per_res ? &dres : nullptr, base, slots_bound,
-                       nlp, lp_scratch, long_thr);
+        const uint8_t* d_codes = (const uint8_t*)s.codes.p;
+        int64_t off_base = first_off + pos;  // offsets[] of the chunk are relative to this residue index
+        if (packed) {
+            if (main_bytes > 0) CUB(cudaMemcpyAsync(s.words.p, src_main, main_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUB(cudaMemcpyAsync(s.lengths.p, in.lengths + start, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, s.stream));
+            if (nwords > 0) {
+                const int64_t ntiles = (nwords + kUnpackTileWords - 1) / kUnpackTileWords;
+                const unsigned g = (unsigned)std::min<int64_t>((ntiles + 7) / 8, (int64_t)ctx->sm_count * 8);
+                k_unpack22<<<g, kUnpackThreads, 0, s.stream>>>((const uint32_t*)s.words.p, nwords, (uint8_t*)s.codes.p, (int*)s.errflag.p);
+                ctx->stats.kernel_launches += 1;
+            }
+            // offsets of the chunk = exclusive scan of its lengths, counted from the chunk's first residue
+            if ((rc = launch_scan(ctx, s, (const int32_t*)s.lengths.p, (int64_t*)s.offsets.p, np, s.stream))) break;
+            d_codes += skip;
+            off_base = 0;
+        } else {
+            if (nres > 0) CUB(cudaMemcpyAsync(s.codes.p, src_main, (size_t)nres, cudaMemcpyHostToDevice, s.stream));
+            CUB(cudaMemcpyAsync(s.offsets.p, in.offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
+        }
+        rc = run_batch(ctx, s, d_codes, (const int64_t*)s.offsets.p, off_base, np, nres, want_rec ? d_sum : nullptr,
+                       per_res ? &dres : nullptr, off_base, slots_bound, nlp, lp_scratch, long_thr);
         if (rc) break;
+        if (summaries && hits) {
+            CUB(cudaMemcpyAsync(stage_sum ? (plaac_summary*)s.h_stage_sum : summaries + start, d_sum, sizeof(plaac_summary) * np,
+                                cudaMemcpyDeviceToHost, s.stream));
+        } else if (summaries) {
+            CUB(cudaMemcpyAsync(stage_sum ? (plaac_summary*)s.h_stage_sum : summaries + start, s.summaries.p,
+                                sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));
+        }
         if (summaries && stage_sum) {
-            CU(ctx, cudaMemcpyAsync(s.h_stage_sum, s.summaries.p, sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));
             s.out_dst = summaries + start;
             s.out_bytes = sizeof(plaac_summary) * (size_t)np;
-        } else if (summaries)
-            CU(ctx, cudaMemcpyAsync(summaries + start, s.summaries.p, sizeof(plaac_summary) * np, cudaMemcpyDeviceToHost, s.stream));
+        }
         if (per_res && nres > 0) {
-            const int64_t o = base - offsets[0];
+            const int64_t o = pos - pos0;
             const size_t N = (size_t)nres;
             uint8_t* hu[2] = {per_res->vit, per_res->map};
             const uint8_t* du[2] = {dres.vit, dres.map};
             for (int k = 0; k < 2; k++)
-                if (hu[k]) CU(ctx, cudaMemcpyAsync(hu[k] + o, du[k], N, cudaMemcpyDeviceToHost, s.stream));
+                if (hu[k] && rc == PLAAC_OK)
+                    rc = cu_rc(ctx, cudaMemcpyAsync(hu[k] + o, du[k], N, cudaMemcpyDeviceToHost, s.stream), "cudaMemcpyAsync(per-residue bytes)");
             double* hd[10] = {per_res->charge, per_res->hydro,   per_res->fi,     per_res->plaac,   per_res->papa,
                               per_res->fix2,   per_res->plaacx2, per_res->papax2, per_res->post_bg, per_res->post_prd};
             const double* dd[10] = {dres.charge, dres.hydro,   dres.fi,     dres.plaac,   dres.papa,
                                     dres.fix2,   dres.plaacx2, dres.papax2, dres.post_bg, dres.post_prd};
             for (int k = 0; k < 10; k++)
-                if (hd[k]) CU(ctx, cudaMemcpyAsync(hd[k] + o, dd[k], N * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+                if (hd[k] && rc == PLAAC_OK)
+                    rc = cu_rc(ctx, cudaMemcpyAsync(hd[k] + o, dd[k], N * sizeof(double), cudaMemcpyDeviceToHost, s.stream),
+                               "cudaMemcpyAsync(per-residue doubles)");
         }
-        pending[which] = true;
+        pending[which] = true;  // (set even if a copy failed to enqueue: the drain below must still wait for this slot)
+        if (rc) break;
         which = (which + 1) % kSlots;
         start = end;
+        pos += nres;
     }
     for (int k = 0; k < kSlots; k++) {  // oldest chunk first
         const int rcd = drain((which + k) % kSlots);
         if (rc == PLAAC_OK) rc = rcd;
     }
+#undef CUB
+    if (rc == PLAAC_OK && packed && pos - pos0 != in.nres)
+        rc = fail(ctx, PLAAC_E_INVALID, "the lengths add up to %lld residues, nres is %lld", (long long)(pos - pos0), (long long)in.nres);
+    if (rc != PLAAC_OK) {
+        // leave nothing behind that a later plaac_sync() could copy into this call's (by then stale) buffers
+        const std::string keep = ctx->err;
+        for (int k = 0; k < kSlots; k++) {
+            cudaStreamSynchronize(ctx->slot[k].stream);
+            ctx->slot[k].out_dst = nullptr;
+        }
+        cudaGetLastError();
+        ctx->err = keep;
+    }
+    if (hits && (rc == PLAAC_OK || (rc == PLAAC_E_INVALID && start >= nprot))) {
+        // (invalid residue codes are reported after the batch, with every record computed: the compact output too)
+        const std::string keep = ctx->err;
+        const int rch = finish_hits(ctx, nprot, hits);
+        if (rch != PLAAC_OK)
+            rc = rch;
+        else
+            ctx->err = keep;
+    }
     return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int64_t nprot, plaac_summary* summaries,
+                const plaac_residue_out* per_res)
+try {
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score: NULL ctx");
+    HostInput in;
+    in.codes = codes;
+    in.offsets = offsets;
+    if (nprot > 0 && !offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
+    if (nprot > 0 && !summaries && !per_res) return fail(ctx, PLAAC_E_INVALID, "no output requested");
+    return score_host(ctx, in, nprot, summaries, per_res, nullptr);
+} catch (...) {
+    return api_caught(ctx, "plaac_score");
+}
+
+int plaac_score_hits(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, int64_t nprot, plaac_hits* hits)
+try {
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_hits: NULL ctx");
+    if (!hits) return fail(ctx, PLAAC_E_INVALID, "plaac_score_hits: NULL hits");
+    HostInput in;
+    in.codes = codes;
+    in.offsets = offsets;
+    if (nprot > 0 && !offsets) return fail(ctx, PLAAC_E_INVALID, "NULL offsets");
+    return score_host(ctx, in, nprot, nullptr, nullptr, hits);
+} catch (...) {
+    return api_caught(ctx, "plaac_score_hits");
+}
+
+int plaac_score_packed(plaac_ctx* ctx, const uint32_t* words, const int32_t* lengths, int64_t nprot, int64_t nres,
+                       plaac_summary* summaries, const plaac_residue_out* per_res, plaac_hits* hits)
+try {
+    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_packed: NULL ctx");
+    HostInput in;
+    in.words = words;
+    in.lengths = lengths;
+    in.nres = nres;
+    if (nprot > 0 && !lengths) return fail(ctx, PLAAC_E_INVALID, "NULL lengths");
+    return score_host(ctx, in, nprot, summaries, per_res, hits);
+} catch (...) {
+    return api_caught(ctx, "plaac_score_packed");
 }
 
 }  // extern "C"
@@ -1226,7 +1626,7 @@ int plaac_score(plaac_ctx* ctx, const uint8_t* codes, const int64_t* offsets, in
 extern "C" {
 
 int plaac_shard_plan(const int64_t* offsets, int64_t nprot, int nshards, int64_t* bounds)
-{
+try {
     if (!offsets || !bounds || nprot < 0 || nshards < 1) return PLAAC_E_INVALID;
     constexpr int64_t kPerProtein = 64;  // per-record overhead in residue equivalents
     const int64_t base = offsets[0];
@@ -1247,11 +1647,13 @@ int plaac_shard_plan(const int64_t* offsets, int64_t nprot, int nshards, int64_t
     }
     bounds[nshards] = nprot;
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(nullptr, "plaac_shard_plan");
 }
 
 int plaac_score_multi(plaac_ctx* const* ctxs, int nctx, const uint8_t* codes, const int64_t* offsets, int64_t nprot,
                       plaac_summary* summaries, const plaac_residue_out* per_res)
-{
+try {
     if (!ctxs || nctx < 1) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi: no contexts");
     for (int k = 0; k < nctx; k++)
         if (!ctxs[k]) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi: NULL ctx %d", k);
@@ -1292,6 +1694,152 @@ int plaac_score_multi(plaac_ctx* const* ctxs, int nctx, const uint8_t* codes, co
     for (int k = 0; k < nctx; k++)
         if (rcs[k] != PLAAC_OK) return rcs[k];
     return PLAAC_OK;
+} catch (...) {
+    return api_caught((ctxs && nctx > 0 ? ctxs[0] : nullptr), "plaac_score_multi");
+}
+
+// Is row a of the web order before row b?  (COREscore desc, LLR desc, rows without a CORE last, then input order:
+// rank.cuh's keys compared on the host, for merging the shards' ranked lists.)
+static bool hit_before(const plaac_summary& a, int64_t ia, const plaac_summary& b, int64_t ib, int web_quirks)
+{
+    auto key = [](double v) -> uint64_t {
+        if (v != v) return ~0ull;
+        uint64_t u;
+        memcpy(&u, &v, 8);
+        const uint64_t asc = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+        return ~asc;
+    };
+    const uint64_t ca = key(a.core_score), cb = key(b.core_score);
+    if (ca != cb) return ca < cb;
+    double la = a.llr, lb = b.llr;
+    if (web_quirks) {
+        if (std::isinf(la)) la = 0.0;
+        if (std::isinf(lb)) lb = 0.0;
+    }
+    const uint64_t ka = key(la), kb = key(lb);
+    if (ka != kb) return ka < kb;
+    return ia < ib;
+}
+
+int plaac_score_multi_packed(plaac_ctx* const* ctxs, int nctx, const uint32_t* words, const int32_t* lengths, int64_t nprot,
+                             int64_t nres, plaac_summary* summaries, const plaac_residue_out* per_res, plaac_hits* hits)
+try {
+    if (!ctxs || nctx < 1) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi_packed: no contexts");
+    for (int k = 0; k < nctx; k++)
+        if (!ctxs[k]) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi_packed: NULL ctx %d", k);
+    if (nctx == 1) return plaac_score_packed(ctxs[0], words, lengths, nprot, nres, summaries, per_res, hits);
+    if (nprot < 0 || (nprot > 0 && !lengths)) return fail(ctxs[0], PLAAC_E_INVALID, "plaac_score_multi_packed: bad lengths/nprot");
+    if (hits) {
+        hits->count = hits->n_core = 0;
+        if (hits->capacity < 0 || nprot > 0x7fffffff) return fail(ctxs[0], PLAAC_E_INVALID, "plaac_hits: bad capacity / too many proteins");
+    }
+    if (nprot == 0) return nres == 0 ? PLAAC_OK : fail(ctxs[0], PLAAC_E_INVALID, "nres does not equal the sum of the lengths");
+    // shard bounds balanced on residues + 64 per protein (as plaac_shard_plan): one pass over the lengths
+    std::vector<int64_t> bounds((size_t)nctx + 1, nprot), rpos((size_t)nctx + 1, 0);
+    {
+        constexpr int64_t kPerProtein = 64;
+        int64_t tot = 0;
+        for (int64_t i = 0; i < nprot; i++) {
+            if (lengths[i] < 0) return fail(ctxs[0], PLAAC_E_INVALID, "negative length at protein %lld", (long long)i);
+            tot += lengths[i];
+        }
+        if (tot != nres) return fail(ctxs[0], PLAAC_E_INVALID, "the lengths add up to %lld residues, nres is %lld", (long long)tot, (long long)nres);
+        const int64_t total = tot + kPerProtein * nprot;
+        bounds[0] = 0;
+        int k = 1;
+        int64_t cost = 0, r = 0;
+        for (int64_t i = 0; i < nprot && k < nctx; i++) {
+            while (k < nctx && cost >= (int64_t)(((__int128)total * k) / nctx)) {
+                bounds[k] = i;
+                rpos[k] = r;
+                k++;
+            }
+            cost += lengths[i] + kPerProtein;
+            r += lengths[i];
+        }
+        for (; k < nctx; k++) bounds[k] = nprot, rpos[k] = nres;
+        bounds[nctx] = nprot;
+        rpos[nctx] = nres;
+    }
+    std::vector<int> rcs((size_t)nctx, PLAAC_OK);
+    std::vector<plaac_hits> sh_hits((size_t)nctx);
+    std::vector<std::vector<plaac_summary>> sh_rec((size_t)nctx);
+    std::vector<std::vector<int32_t>> sh_idx((size_t)nctx);
+    std::vector<std::thread> threads;
+    for (int k = 0; k < nctx; k++) {
+        const int64_t lo = bounds[k], hi = bounds[k + 1];
+        if (hi <= lo) continue;
+        if (hits) {
+            const int64_t cap = std::min<int64_t>(hits->capacity, hi - lo);
+            sh_rec[k].resize((size_t)cap);
+            sh_idx[k].resize((size_t)cap);
+            sh_hits[k] = *hits;
+            sh_hits[k].capacity = cap;
+            sh_hits[k].records = sh_rec[k].data();
+            sh_hits[k].index = sh_idx[k].data();
+        }
+        auto shard = [=, &rcs, &sh_hits]() {
+            plaac_residue_out shifted;
+            const plaac_residue_out* pr = nullptr;
+            if (per_res) {
+                const int64_t o = rpos[k];
+                shifted = *per_res;
+                uint8_t** u8s[2] = {&shifted.vit, &shifted.map};
+                for (auto p : u8s)
+                    if (*p) *p += o;
+                double** f64s[10] = {&shifted.charge, &shifted.hydro,   &shifted.fi,     &shifted.plaac,   &shifted.papa,
+                                     &shifted.fix2,   &shifted.plaacx2, &shifted.papax2, &shifted.post_bg, &shifted.post_prd};
+                for (auto p : f64s)
+                    if (*p) *p += o;
+                pr = &shifted;
+            }
+            HostInput in;
+            const int64_t w0 = rpos[k] / PLAAC_PACK_PER_WORD;
+            in.words = words + w0;
+            in.lengths = lengths + lo;
+            in.nres = rpos[k + 1] - rpos[k];
+            in.pos0 = rpos[k] - w0 * PLAAC_PACK_PER_WORD;
+            try {
+                rcs[k] = score_host(ctxs[k], in, hi - lo, summaries ? summaries + lo : nullptr, pr, hits ? &sh_hits[k] : nullptr);
+            } catch (...) {
+                rcs[k] = api_caught(ctxs[k], "plaac_score_multi_packed (shard)");
+            }
+        };
+        try {
+            threads.emplace_back(shard);
+        } catch (...) {  // no thread to be had: this shard on the calling thread (nothing may throw across the C ABI)
+            shard();
+        }
+    }
+    for (auto& t : threads) t.join();
+    for (int k = 0; k < nctx; k++)
+        if (rcs[k] != PLAAC_OK) return rcs[k];
+    if (hits) {
+        // k-way merge of the shards' ranked lists (each is the head of its shard's order, so the merged head is exact up
+        // to min over shards of what each returned: every shard returned min(capacity, its rows))
+        std::vector<int64_t> cur((size_t)nctx, 0);
+        int64_t out = 0;
+        for (int k = 0; k < nctx; k++) hits->n_core += bounds[k + 1] > bounds[k] ? sh_hits[k].n_core : 0;
+        while (out < hits->capacity) {
+            int best = -1;
+            for (int k = 0; k < nctx; k++) {
+                if (bounds[k + 1] <= bounds[k] || cur[k] >= sh_hits[k].count) continue;
+                if (best < 0 ||
+                    hit_before(sh_rec[k][(size_t)cur[k]], bounds[k] + sh_idx[k][(size_t)cur[k]], sh_rec[best][(size_t)cur[best]],
+                               bounds[best] + sh_idx[best][(size_t)cur[best]], hits->rank_flags & PLAAC_RANK_WEB_QUIRKS))
+                    best = k;
+            }
+            if (best < 0) break;
+            if (hits->records) hits->records[out] = sh_rec[best][(size_t)cur[best]];
+            if (hits->index) hits->index[out] = (int32_t)(bounds[best] + sh_idx[best][(size_t)cur[best]]);
+            cur[best]++;
+            out++;
+        }
+        hits->count = out;
+    }
+    return PLAAC_OK;
+} catch (...) {
+    return api_caught((ctxs && nctx > 0 ? ctxs[0] : nullptr), "plaac_score_multi_packed");
 }
 
 }  // extern "C"
@@ -1303,7 +1851,7 @@ extern "C" {
 int plaac_ingest_fasta_device(plaac_ctx* ctx, const char* d_text, int64_t nbytes, uint8_t* d_codes, int64_t* d_offsets,
                               int64_t* d_name_pos, int32_t* d_name_len, uint8_t* d_flags, int64_t max_rec,
                               plaac_fasta_index* index, uint64_t* d_bg_counts)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_ingest_fasta_device: NULL ctx");
     if (nbytes < 0 || max_rec < 0 || !index) return fail(ctx, PLAAC_E_INVALID, "bad size / NULL index");
     if (nbytes > 0 && (!d_text || !d_codes)) return fail(ctx, PLAAC_E_INVALID, "NULL text/codes");
@@ -1386,11 +1934,13 @@ int plaac_ingest_fasta_device(plaac_ctx* ctx, const char* d_text, int64_t nbytes
     CU(ctx, cudaStreamSynchronize(st));
     CU(ctx, cudaGetLastError());
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_ingest_fasta_device");
 }
 
 int plaac_ingest_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, uint8_t* codes, int64_t* offsets, int64_t* name_pos,
                        int32_t* name_len, uint8_t* flags, int64_t max_rec, plaac_fasta_index* index, double* bg_counts)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_ingest_fasta: NULL ctx");
     if (nbytes < 0 || max_rec < 0 || !index || !offsets) return fail(ctx, PLAAC_E_INVALID, "bad size / NULL argument");
     if (nbytes > 0 && (!text || !codes)) return fail(ctx, PLAAC_E_INVALID, "NULL text/codes");
@@ -1422,6 +1972,8 @@ int plaac_ingest_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, uint8_t
         for (int i = 0; i < PLAAC_NAA; i++) bg_counts[i] = (double)h[i];
     }
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_ingest_fasta");
 }
 
 }  // extern "C"
@@ -1430,7 +1982,7 @@ int plaac_ingest_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, uint8_t
 extern "C" int plaac_score_fasta(plaac_ctx* ctx, const char* text, int64_t nbytes, int64_t max_rec, plaac_summary* summaries,
                                  uint8_t* codes, int64_t* offsets, int64_t* name_pos, int32_t* name_len, uint8_t* flags,
                                  plaac_fasta_index* index, double* bg_counts)
-{
+try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_fasta: NULL ctx");
     if (nbytes < 0 || max_rec < 0 || !index || !offsets || !summaries) return fail(ctx, PLAAC_E_INVALID, "bad size / NULL argument");
     if (nbytes > 0 && !text) return fail(ctx, PLAAC_E_INVALID, "NULL text");
@@ -1476,120 +2028,8 @@ extern "C" int plaac_score_fasta(plaac_ctx* ctx, const char* text, int64_t nbyte
         for (int i = 0; i < PLAAC_NAA; i++) bg_counts[i] = (double)h[i];
     }
     return PLAAC_OK;
+} catch (...) {
+    return api_caught(ctx, "plaac_score_fasta");
 }
 
 
-// ------------------------------------------------------------------------------------------------ ranking (N4)
-namespace {
-
-// One stable radix pass over the first n rows of buffer pair `cur`; the result lands in pair cur ^ 1.
-template <bool SPLIT>
-int rank_pass(plaac_ctx* ctx, Slot& s, int64_t n, int shift, int cur)
-{
-    const int64_t ntiles = (n + kRankTile - 1) / kRankTile;
-    int rc;
-    if ((rc = ensure(ctx, s.rk_hist, sizeof(int32_t) * (size_t)(kRankDigits * ntiles)))) return rc;
-    if ((rc = ensure(ctx, s.rk_offs, sizeof(int64_t) * (size_t)(kRankDigits * ntiles + 1)))) return rc;
-    cudaStream_t st = s.stream;
-    k_rank_hist<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>((const uint64_t*)s.rk_keys[cur].p, n, shift,
-                                                                  (int32_t*)s.rk_hist.p, ntiles);
-    if ((rc = launch_scan(ctx, s, (const int32_t*)s.rk_hist.p, (int64_t*)s.rk_offs.p, (int64_t)kRankDigits * ntiles, st))) return rc;
-    k_rank_scatter<SPLIT><<<(unsigned)ntiles, kRankThreads, 0, st>>>(
-        (const uint64_t*)s.rk_keys[cur].p, (const int32_t*)s.rk_vals[cur].p, (uint64_t*)s.rk_keys[cur ^ 1].p,
-        (int32_t*)s.rk_vals[cur ^ 1].p, n, shift, (const int64_t*)s.rk_offs.p, ntiles);
-    ctx->stats.kernel_launches += 2;
-    CU(ctx, cudaGetLastError());
-    return PLAAC_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
-int plaac_rank_device(plaac_ctx* ctx, const plaac_summary* d_summaries, int64_t nprot, int flags, int32_t* d_order,
-                      int64_t* n_core)
-{
-    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank_device: NULL ctx");
-    if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
-    if (n_core) *n_core = 0;
-    if (nprot == 0) return PLAAC_OK;
-    if (!d_summaries || !d_order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
-    CU(ctx, cudaSetDevice(ctx->device));
-    Slot& s = ctx->slot[0];
-    cudaStream_t st = s.stream;
-    int rc;
-    for (int k = 0; k < 2; k++) {
-        if ((rc = ensure(ctx, s.rk_keys[k], sizeof(uint64_t) * (size_t)nprot))) return rc;
-        if ((rc = ensure(ctx, s.rk_vals[k], sizeof(int32_t) * (size_t)nprot))) return rc;
-    }
-    const unsigned gk = (unsigned)((nprot + 255) / 256);
-    int cur = 0;
-    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 0, (flags & PLAAC_RANK_WEB_QUIRKS) ? 1 : 0, (uint64_t*)s.rk_keys[cur].p,
-                                    (int32_t*)s.rk_vals[cur].p);
-    ctx->stats.kernel_launches += 1;
-    for (int shift = 0; shift < 64; shift += 8) {
-        if ((rc = rank_pass<false>(ctx, s, nprot, shift, cur))) return rc;
-        cur ^= 1;
-    }
-    // CORE proteins first (stable), then order them by COREscore
-    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 1, 0, (uint64_t*)s.rk_keys[cur].p, (int32_t*)s.rk_vals[cur].p);
-    ctx->stats.kernel_launches += 1;
-    if ((rc = rank_pass<true>(ctx, s, nprot, 0, cur))) return rc;
-    cur ^= 1;
-    const int64_t ntiles = (nprot + kRankTile - 1) / kRankTile;
-    int64_t ncore = 0;  // rows with digit 0 = output base of (digit 1, tile 0)
-    CU(ctx, cudaMemcpyAsync(&ncore, (const int64_t*)s.rk_offs.p + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(ctx, cudaStreamSynchronize(st));
-    if (ncore > 1) {
-        // the tail (no CORE) must stay where it is: park it in d_order before the two buffers start to alternate
-        const int tail_src = cur;
-        if (nprot > ncore)
-            CU(ctx, cudaMemcpyAsync(d_order + ncore, (const int32_t*)s.rk_vals[tail_src].p + ncore,
-                                    sizeof(int32_t) * (size_t)(nprot - ncore), cudaMemcpyDeviceToDevice, st));
-        for (int shift = 0; shift < 64; shift += 8) {
-            if ((rc = rank_pass<false>(ctx, s, ncore, shift, cur))) return rc;
-            cur ^= 1;
-        }
-        CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)ncore, cudaMemcpyDeviceToDevice, st));
-    } else {
-        CU(ctx, cudaMemcpyAsync(d_order, s.rk_vals[cur].p, sizeof(int32_t) * (size_t)nprot, cudaMemcpyDeviceToDevice, st));
-    }
-    CU(ctx, cudaStreamSynchronize(st));
-    if (n_core) *n_core = ncore;
-    return PLAAC_OK;
-}
-
-int plaac_gather_device(plaac_ctx* ctx, const plaac_summary* d_summaries, const int32_t* d_order, int64_t count,
-                        plaac_summary* d_out)
-{
-    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_gather_device: NULL ctx");
-    if (count < 0) return fail(ctx, PLAAC_E_INVALID, "negative count");
-    if (count == 0) return PLAAC_OK;
-    if (!d_summaries || !d_order || !d_out) return fail(ctx, PLAAC_E_INVALID, "NULL argument");
-    CU(ctx, cudaSetDevice(ctx->device));
-    const int64_t threads = count * (int64_t)(sizeof(plaac_summary) / 8);
-    k_rank_gather<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->slot[0].stream>>>(d_summaries, d_order, count, d_out);
-    ctx->stats.kernel_launches += 1;
-    CU(ctx, cudaGetLastError());
-    return PLAAC_OK;
-}
-
-int plaac_rank(plaac_ctx* ctx, const plaac_summary* summaries, int64_t nprot, int flags, int32_t* order, int64_t* n_core)
-{
-    if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank: NULL ctx");
-    if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
-    if (n_core) *n_core = 0;
-    if (nprot == 0) return PLAAC_OK;
-    if (!summaries || !order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
-    CU(ctx, cudaSetDevice(ctx->device));
-    Slot& s = ctx->slot[0];
-    int rc;
-    if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * (size_t)nprot))) return rc;
-    if ((rc = ensure(ctx, s.rk_order, sizeof(int32_t) * (size_t)nprot))) return rc;
-    CU(ctx, cudaMemcpyAsync(s.summaries.p, summaries, sizeof(plaac_summary) * (size_t)nprot, cudaMemcpyHostToDevice, s.stream));
-    if ((rc = plaac_rank_device(ctx, (const plaac_summary*)s.summaries.p, nprot, flags, (int32_t*)s.rk_order.p, n_core))) return rc;
-    CU(ctx, cudaMemcpy(order, s.rk_order.p, sizeof(int32_t) * (size_t)nprot, cudaMemcpyDeviceToHost));
-    return PLAAC_OK;
-}
-
-}  // extern "C"

@@ -680,12 +680,13 @@ inline ResidueV2Plan residue_v2_plan(const KScalars& ks)
     return P;
 }
 
-inline int residue_v2_setup(const ResidueV2Plan& P)
+// (the attribute belongs to the function, not to a ctx: raised once to the device's opt-in maximum, see plaac_create)
+inline int residue_v2_setup(const ResidueV2Plan& P, int optin_bytes)
 {
     if (!P.ok) return PLAAC_OK;
-    if (cudaFuncSetAttribute(k_res_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bwd_smem) != cudaSuccess) return PLAAC_E_CUDA;
-    if (cudaFuncSetAttribute(k_res_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.fwd_smem) != cudaSuccess) return PLAAC_E_CUDA;
-    if (cudaFuncSetAttribute(k_res_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.trk_smem) != cudaSuccess) return PLAAC_E_CUDA;
+    if ((size_t)optin_bytes < P.bwd_smem || (size_t)optin_bytes < P.fwd_smem || (size_t)optin_bytes < P.trk_smem) return PLAAC_E_UNSUPPORTED;
+    for (const void* fn : {(const void*)k_res_bwd, (const void*)k_res_fwd, (const void*)k_res_tracks})
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_bytes) != cudaSuccess) return PLAAC_E_CUDA;
     return PLAAC_OK;
 }
 

@@ -95,3 +95,51 @@ def test_multi_ctx_scoring_matches_single(golden):
     assert got_s.tobytes() == ref_s.tobytes() == got_only.tobytes()
     for k in ref_r:
         assert got_r[k].tobytes() == ref_r[k].tobytes(), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nctx", [2, 3])
+def test_multi_ctx_packed_with_merged_hits(nctx):
+    """plaac_score_multi_packed: shards start in the middle of a radix-22 word; the merged ranked hits equal the
+    single-ctx ones (which tests/test_lean.py checks against the web order)."""
+    ndev = plaac_b200.lib().plaac_device_count()
+    devices = [k % max(ndev, 1) for k in range(nctx)]
+    codes, offs = synth.proteome(3000, seed=14, median=250.0, prd_rate=0.2)
+    lengths = np.diff(offs).astype(np.int32)
+    words = plaac_b200.pack_words(codes)
+    one = plaac_b200.Scorer()
+    ref_s, ref_r = one.score(codes, offs, per_residue=True)
+    _, ref_h = one.score_packed(words, lengths, hits="core")
+    _, ref_t = one.score_packed(words, lengths, hits="topk", capacity=500)
+    one.close()
+    ms = plaac_b200.MultiScorer(devices=devices)
+    got_s, got_r, got_h = ms.score_packed(words, lengths, per_residue=True, hits="core")
+    _, got_t = ms.score_packed(words, lengths, hits="topk", capacity=500)
+    ms.close()
+    assert got_s.tobytes() == ref_s.tobytes()
+    for k in ref_r:
+        assert got_r[k].tobytes() == ref_r[k].tobytes(), k
+    assert got_h["n_core"] == ref_h["n_core"] > 100
+    assert np.array_equal(got_h["index"], ref_h["index"]) and got_h["records"].tobytes() == ref_h["records"].tobytes()
+    assert np.array_equal(got_t["index"], ref_t["index"]) and got_t["records"].tobytes() == ref_t["records"].tobytes()
+
+
+@pytest.mark.gpu
+def test_multi_ctx_on_distinct_devices():
+    """The single-process multi-GPU path (one ctx + host thread per GPU) on really different devices; skipped on a
+    one-GPU box, where test_multi_ctx_scoring_matches_single runs both ctxs on device 0."""
+    ndev = plaac_b200.lib().plaac_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (plaac_device_count() = %d)" % ndev)
+    codes, offs = synth.proteome(20000, seed=15, median=300.0)
+    lengths = np.diff(offs).astype(np.int32)
+    words = plaac_b200.pack_words(codes)
+    one = plaac_b200.Scorer(device=0)
+    ref = one.score(codes, offs)
+    one.close()
+    ms = plaac_b200.MultiScorer(devices=list(range(ndev)))
+    got = ms.score(codes, offs)
+    got_p, hits = ms.score_packed(words, lengths, hits="core")
+    ms.close()
+    assert got.tobytes() == ref.tobytes() == got_p.tobytes()
+    assert hits["n_core"] == int((~np.isnan(ref["core_score"])).sum())
