@@ -376,7 +376,7 @@ def main():
     e2e_skip = None
     if not args.no_e2e:
         # every rank pins its shard's codes, offsets and records in host memory: make sure the box has room
-        need = (ntotal + 8 * (nprot + 1) + 160 * nprot) * max(1, world)
+        need = (ntotal + 8 * (nprot + 1) + 160 * nprot + 4 * (ntotal // 7) + 4 * nprot + 21 * nprot) * max(1, world)
         try:
             with open("/proc/meminfo") as f:
                 avail = next(int(x.split()[1]) * 1024 for x in f if x.startswith("MemAvailable"))
@@ -385,48 +385,7 @@ def main():
         if avail is not None and need * 1.25 > avail:
             e2e_skip = f"host memory: {need / 1e9:.0f} GB of pinned buffers needed, {avail / 1e9:.0f} GB available"
     if not args.no_e2e and e2e_skip is None:
-        # host buffers from the library's own allocator (plaac_host_alloc: page-locked), as a host program would hold them
-        pb_codes = plaac_b200.PinnedBuffer(ntotal, np.uint8)
-        pb_offsets = plaac_b200.PinnedBuffer(nprot + 1, np.int64)
-        pb_sum = plaac_b200.PinnedBuffer(nprot * 160, np.uint8)
-        h_codes, h_offsets, h_sum = (torch.from_numpy(b.array) for b in (pb_codes, pb_offsets, pb_sum))
-        h_codes.copy_(codes[:ntotal])
-        h_offsets.copy_(offsets)
-        torch.cuda.synchronize()
-
-        def e2e_step():
-            scorer.score_ptr(h_codes.data_ptr(), h_offsets.data_ptr(), nprot, h_sum.data_ptr())
-
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": res_total * args.steps / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": int(res_total + 8 * (nprot + 1) * world), "d2h_bytes_per_step": int(160 * nprot * world),
-               "ms_per_step": float(tt[0]) / args.steps * 1e3,
-               "note": "plaac_score() on host buffers from plaac_host_alloc (page-locked) in every rank (each GPU on its own PCIe link); byte counts are "
-                       "whole-job totals; wall clock between barriers, max over ranks"}
-        # sanity: both paths produce the same records
-        # (every byte of every record: the host call scores the shard in pipelined chunks, the device call in one
-        # piece, so this is the chunking-invariance property at the full bench size)
-        same = True
-        piece = 1 << 28
-        flat = summaries.view(torch.uint8).reshape(-1)
-        for lo in range(0, flat.numel(), piece):
-            hi = min(flat.numel(), lo + piece)
-            same = same and bool(torch.equal(h_sum[lo:hi].to(dev, non_blocking=False), flat[lo:hi]))
-        e2e["matches_device_path"] = same
-        e2e["records_compared"] = int(nprot)
-        del h_codes, h_offsets, h_sum
-        for b in (pb_codes, pb_offsets, pb_sum):
-            b.close()
+        e2e = measure_e2e(args, scorer, dev, world, barrier, codes, offsets, summaries, nprot, ntotal, res_total)
     elif e2e_skip is not None:
         e2e = {"value": None, "unit": UNIT, "skipped": e2e_skip}
 
@@ -478,6 +437,122 @@ def main():
     scorer.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_e2e(args, scorer, dev, world, barrier, codes, offsets, summaries, nprot, ntotal, res_total):
+    """End to end through the public host-buffer calls, host buffers from plaac_host_alloc (page-locked), H2D of the inputs
+    and D2H of the results inside the timed region, wall clock between barriers, max over ranks.  Three transports of the
+    SAME scoring (records bit-identical, checked below):
+      packed_in_hits_out     plaac_score_packed: radix-22 words (4/7 B per residue) + int32 lengths in, the ranked records
+                             of the proteins with a CORE out (what the reference's consumer displays) -- the headline
+      packed_in_records_out  the same input, all 160-byte records out
+      bytes_in_records_out   plaac_score: 1 B per residue + int64 offsets in, all records out (round 1's figure)"""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import plaac_b200
+
+    L = plaac_b200.lib()
+    pb_codes = plaac_b200.PinnedBuffer(ntotal, np.uint8)
+    pb_offsets = plaac_b200.PinnedBuffer(nprot + 1, np.int64)
+    pb_sum = plaac_b200.PinnedBuffer(nprot * 160, np.uint8)
+    nwords = int(L.plaac_packed_words(ntotal))
+    pb_words = plaac_b200.PinnedBuffer(max(nwords, 1), np.uint32)
+    pb_len = plaac_b200.PinnedBuffer(nprot, np.int32)
+    cap = nprot // 8 + 1024          # the synthetic proteome has a CORE in ~5 % of its proteins
+    pb_hrec = plaac_b200.PinnedBuffer(cap * 160, np.uint8)
+    pb_hidx = plaac_b200.PinnedBuffer(cap, np.int32)
+    h_codes, h_offsets, h_sum = (torch.from_numpy(b.array) for b in (pb_codes, pb_offsets, pb_sum))
+    h_codes.copy_(codes[:ntotal])
+    h_offsets.copy_(offsets)
+    torch.cuda.synchronize()
+    pb_len.array[:] = np.diff(pb_offsets.array).astype(np.int32)
+    t0 = time.perf_counter()
+    plaac_b200.pack_words(pb_codes.array, out=pb_words.array)
+    pack_s = time.perf_counter() - t0
+    hits = plaac_b200.Hits(mode=plaac_b200.HITS_CORE, rank_flags=0, capacity=cap, records=pb_hrec.ptr, index=pb_hidx.ptr,
+                           count=0, n_core=0)
+
+    def run_bytes():
+        scorer.score_ptr(h_codes.data_ptr(), h_offsets.data_ptr(), nprot, h_sum.data_ptr())
+
+    def run_packed_records():
+        scorer._check(L.plaac_score_packed(scorer._h, pb_words.ptr, pb_len.ptr, nprot, ntotal, pb_sum.ptr, None, None))
+
+    def run_packed_hits():
+        scorer._check(L.plaac_score_packed(scorer._h, pb_words.ptr, pb_len.ptr, nprot, ntotal, None, None, C.byref(hits)))
+
+    flat = summaries.view(torch.uint8).reshape(-1)
+
+    def records_match():
+        # every byte of every record: the host calls score the shard in pipelined chunks, the device call in one piece
+        same = True
+        piece = 1 << 28
+        for lo in range(0, flat.numel(), piece):
+            hi = min(flat.numel(), lo + piece)
+            same = same and bool(torch.equal(h_sum[lo:hi].to(dev, non_blocking=False), flat[lo:hi]))
+        return same
+
+    def hits_match():
+        n = int(hits.count)
+        rec = summaries.view(torch.float64).view(nprot, 20)
+        ncore_dev = int((~torch.isnan(rec[:, 8])).sum().item())
+        idx = torch.from_numpy(pb_hidx.array[:n].copy()).to(dev).long()
+        got = torch.from_numpy(pb_hrec.array[:n * 160].copy()).to(dev)
+        want = summaries.view(torch.uint8).view(nprot, 160)[idx].reshape(-1)
+        cs, ll = rec[idx, 8], rec[idx, 7]
+        a, b = slice(0, -1), slice(1, None)
+        ordered = bool(((cs[a] > cs[b]) | ((cs[a] == cs[b]) & ((ll[a] > ll[b]) | ((ll[a] == ll[b]) & (idx[a] < idx[b]))))).all())
+        return {"n_core": int(hits.n_core), "returned": n, "n_core_device_path": ncore_dev,
+                "records_equal_device_path": bool(torch.equal(got, want)), "order_verified": ordered,
+                "complete": n == int(hits.n_core) == ncore_dev}
+
+    out = {}
+    for tag, fn in (("bytes_in_records_out", run_bytes), ("packed_in_records_out", run_packed_records),
+                    ("packed_in_hits_out", run_packed_hits)):
+        h_sum.zero_()
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if tag == "bytes_in_records_out":
+            h2d, d2h = ntotal + 8 * (nprot + 1), 160 * nprot
+        else:
+            h2d = 4 * nwords + 4 * nprot
+            d2h = 160 * nprot if tag == "packed_in_records_out" else 164 * int(hits.count)
+        bb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(bb, op=dist.ReduceOp.SUM)
+        v = {"value": res_total * args.steps / float(tt[0]), "unit": UNIT, "ms_per_step": float(tt[0]) / args.steps * 1e3,
+             "h2d_bytes_per_step": int(bb[0]), "d2h_bytes_per_step": int(bb[1])}
+        if tag == "packed_in_hits_out":
+            v["hits"] = hits_match()
+        else:
+            v["matches_device_path"] = records_match()
+            v["records_compared"] = int(nprot)
+        out[tag] = v
+    head = dict(out["packed_in_hits_out"])
+    head["call"] = "plaac_score_packed(words, lengths, hits=PLAAC_HITS_CORE)"
+    head["variants"] = {k: out[k] for k in ("packed_in_records_out", "bytes_in_records_out")}
+    head["host_pack_s"] = pack_s
+    head["note"] = ("host buffers from plaac_host_alloc (page-locked) in every rank (each GPU on its own PCIe link); byte "
+                    "counts are whole-job totals counted from the buffers copied; wall clock between barriers, max over "
+                    "ranks; packing the residues into radix-22 words is host preprocessing outside the timed region "
+                    "(host_pack_s, all host threads), like the FASTA->codes encoding of the one-byte call")
+    del h_codes, h_offsets, h_sum
+    for b in (pb_codes, pb_offsets, pb_sum, pb_words, pb_len, pb_hrec, pb_hidx):
+        b.close()
+    return head
 
 
 def measure_per_residue(L, scorer, dev, hbm_peak):

@@ -46,6 +46,19 @@ struct BatchView {
     int64_t long_min;         // proteins at least this long belong to the long-sequence path: empty for the bucketed one
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION on the device, shared by every ctx of the process:
+// it is raised once to everything the device allows (opt-in maximum minus the kernel's static shared memory), never to one
+// ctx's own sizes -- a ctx created later with smaller rings would otherwise lower the limit under an earlier ctx.
+inline cudaError_t raise_dynamic_smem_limit(const void* fn, int optin_bytes, size_t need_bytes)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, fn);
+    if (e != cudaSuccess) return e;
+    const long long room = (long long)optin_bytes - (long long)a.sharedSizeBytes;
+    if (room < (long long)need_bytes) return cudaErrorInvalidValue;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
+}
+
 // Length of a protein as the bucketed path sees it.
 __device__ __forceinline__ int64_t eff_len(int64_t len, int64_t long_min) { return len >= long_min ? 0 : len; }
 

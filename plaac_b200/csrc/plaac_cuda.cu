@@ -937,20 +937,19 @@ try {
             return bail(PLAAC_E_CUDA);
         }
     }
-    // cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION on the device, shared by every ctx of
-    // the process: it is raised once to the device's opt-in maximum, never to this ctx's own sizes (a ctx created later
-    // with a smaller ring would otherwise lower the limit under an earlier ctx's launches).
+    // (shared-memory limits are per function, not per ctx: common.cuh, raise_dynamic_smem_limit)
     {
         const int optin = (int)prop.sharedMemPerBlockOptin;
-        if ((size_t)optin < std::max<size_t>(std::max(ctx->smem_bytes, ctx->v2_smem_bytes), sizeof(LongShared))) {
-            ctx->err = "device offers less opt-in shared memory per block than the kernels need";
-            return bail(PLAAC_E_UNSUPPORTED);
-        }
-        for (const void* fn : {(const void*)k_long_score, (const void*)k_score_summary, (const void*)k_score_summary_v2,
-                               (const void*)k_len_hist, (const void*)k_scatter}) {
-            const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        const std::pair<const void*, size_t> fns[] = {{(const void*)k_long_score, sizeof(LongShared)},
+                                                      {(const void*)k_score_summary, ctx->smem_bytes},
+                                                      {(const void*)k_score_summary_v2, ctx->v2_smem_bytes},
+                                                      {(const void*)k_len_hist, kHistSmemBytes},
+                                                      {(const void*)k_scatter, kHistSmemBytes}};
+        for (const auto& f : fns) {
+            const cudaError_t e = raise_dynamic_smem_limit(f.first, optin, f.second);
             if (e != cudaSuccess) {
-                ctx->err = std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                ctx->err = std::string("shared-memory limit of a kernel: ") + cudaGetErrorString(e);
                 return bail(PLAAC_E_CUDA);
             }
         }

@@ -684,9 +684,9 @@ inline ResidueV2Plan residue_v2_plan(const KScalars& ks)
 inline int residue_v2_setup(const ResidueV2Plan& P, int optin_bytes)
 {
     if (!P.ok) return PLAAC_OK;
-    if ((size_t)optin_bytes < P.bwd_smem || (size_t)optin_bytes < P.fwd_smem || (size_t)optin_bytes < P.trk_smem) return PLAAC_E_UNSUPPORTED;
-    for (const void* fn : {(const void*)k_res_bwd, (const void*)k_res_fwd, (const void*)k_res_tracks})
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin_bytes) != cudaSuccess) return PLAAC_E_CUDA;
+    if (raise_dynamic_smem_limit((const void*)k_res_bwd, optin_bytes, P.bwd_smem) != cudaSuccess) return PLAAC_E_CUDA;
+    if (raise_dynamic_smem_limit((const void*)k_res_fwd, optin_bytes, P.fwd_smem) != cudaSuccess) return PLAAC_E_CUDA;
+    if (raise_dynamic_smem_limit((const void*)k_res_tracks, optin_bytes, P.trk_smem) != cudaSuccess) return PLAAC_E_CUDA;
     return PLAAC_OK;
 }
 
