@@ -178,7 +178,7 @@ int plaac_unpack_host(const uint32_t *words, int64_t first, int64_t count, uint8
 #define PLAAC_HITS_TOPK 2 /* the first `capacity` rows of the ranking of the whole batch */
 typedef struct plaac_hits {
     int32_t mode;           /* in: PLAAC_HITS_CORE or PLAAC_HITS_TOPK */
-    int32_t rank_flags;     /* in: as plaac_rank_device (0) */
+    int32_t rank_flags;     /* in: reserved, must be 0 */
     int64_t capacity;       /* in: rows `records` and `index` can hold */
     plaac_summary *records; /* out: `count` rows, best first (COREscore desc, LLR desc, input order) */
     int32_t *index;         /* out: index of each row's protein in the batch */
@@ -254,9 +254,9 @@ int plaac_score_fasta(plaac_ctx *ctx, const char *text, int64_t nbytes, int64_t 
  * order (the Ruby sort_by is unstable there, so any order of equal rows is one of its possible outputs).
  * order[k] = input index of the row ranked k; *n_core (may be NULL) = number of rows with a CORE, i.e. the head
  * order[0 .. n_core) is "every protein with a CORE, best first".  Values are compared at full precision (the web
- * compares the 3-decimal text).  flags: PLAAC_RANK_WEB_QUIRKS reproduces Ruby's "-Infinity".to_f == 0.0, which
- * ranks the LLR of proteins shorter than the core length as 0 instead of last. */
-#define PLAAC_RANK_WEB_QUIRKS 1
+ * compares the 3-decimal text).  A protein shorter than the core length has LLR = -Inf here and "NaN" in the printed
+ * table (inf2nan, plaac.java:904/1008), which server.rb:225 sorts last within its COREscore group -- exactly where
+ * -Inf sorts, so this IS the web order.  flags: reserved, must be 0. */
 int plaac_rank_device(plaac_ctx *ctx, const plaac_summary *d_summaries, int64_t nprot, int flags, int32_t *d_order,
                       int64_t *n_core);
 /* d_out[k] = d_summaries[d_order[k]] for k < count: ship the head of the ranking instead of 160 B x nprot.
@@ -300,8 +300,9 @@ int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
 int plaac_set_long_path(plaac_ctx *ctx, int64_t min_len, int warm);
 
 /* Kernel selection for testing: 0 = automatic (default), 1 = the reference-order anchor kernel (one fused
- * kernel, every recurrence in plaac.java's operation order, slower), 2 = the throughput kernel (needs
- * loglut[0] == ln2 and le0 == le[0], true for tables built as plaac.java builds them). */
+ * kernel, every recurrence in plaac.java's operation order, slower), 2 / 3 = the throughput kernels (role-split;
+ * 3 is 2 with fewer issue slots per residue and is what 0 selects; both need loglut[0] == ln2 and le0 == le[0],
+ * true for tables built as plaac.java builds them). */
 int plaac_set_kernel_variant(plaac_ctx *ctx, int variant);
 
 /* Accounting for benchmarks: kernels launched by this ctx so far, and the

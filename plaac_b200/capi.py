@@ -68,7 +68,6 @@ class FastaIndex(C.Structure):
     _fields_ = [("nrec", C.c_int64), ("nres", C.c_int64)]
 
 
-RANK_WEB_QUIRKS = 1
 HITS_CORE, HITS_TOPK = 1, 2
 PACK_PER_WORD = 7
 
@@ -414,18 +413,18 @@ class Scorer:
             out["bg_counts"] = bg
         return out
 
-    def rank(self, summaries: np.ndarray, web_quirks: bool = False):
+    def rank(self, summaries: np.ndarray):
         """plaac_rank: the web front end's order (web/lib/server.rb:222-229) -> (order int32[nprot], n_core)."""
         summaries = np.ascontiguousarray(summaries, dtype=SUMMARY_DTYPE)
         order = np.zeros(len(summaries), dtype=np.int32)
         ncore = C.c_int64(0)
-        self._check(lib().plaac_rank(self._h, summaries.ctypes.data, len(summaries), RANK_WEB_QUIRKS if web_quirks else 0,
+        self._check(lib().plaac_rank(self._h, summaries.ctypes.data, len(summaries), 0,
                                      order.ctypes.data, C.byref(ncore)))
         return order, int(ncore.value)
 
-    def rank_device(self, d_summaries_ptr: int, nprot: int, d_order_ptr: int, web_quirks: bool = False) -> int:
+    def rank_device(self, d_summaries_ptr: int, nprot: int, d_order_ptr: int) -> int:
         ncore = C.c_int64(0)
-        self._check(lib().plaac_rank_device(self._h, d_summaries_ptr, nprot, RANK_WEB_QUIRKS if web_quirks else 0,
+        self._check(lib().plaac_rank_device(self._h, d_summaries_ptr, nprot, 0,
                                             d_order_ptr, C.byref(ncore)))
         return int(ncore.value)
 

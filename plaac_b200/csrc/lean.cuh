@@ -82,15 +82,13 @@ k_hits_compact(const int32_t* __restrict__ flag, const int64_t* __restrict__ pos
 
 // keys of the rows listed in vals: field 0 LLR, field 1 COREscore (rank.cuh's order-preserving map)
 __global__ void __launch_bounds__(256)
-k_hits_keys(const plaac_summary* __restrict__ rec, const int32_t* __restrict__ vals, int64_t n, int field, int web_quirks,
+k_hits_keys(const plaac_summary* __restrict__ rec, const int32_t* __restrict__ vals, int64_t n, int field,
             uint64_t* __restrict__ keys)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const plaac_summary& r = rec[vals[i]];
-    double v = field ? r.core_score : r.llr;
-    if (!field && web_quirks && isinf(v)) v = 0.0;
-    keys[i] = rank_desc_key(v);
+    keys[i] = rank_desc_key(field ? r.core_score : r.llr);
 }
 
 }  // namespace plaac

@@ -22,6 +22,7 @@
 #include "residue_kernel_v2.cuh"
 #include "summary_kernel.cuh"
 #include "summary_kernel_v2.cuh"
+#include "summary_kernel_v3.cuh"
 #include "long_kernel.cuh"
 #include "lean.cuh"
 #include "generic_windows.cuh"
@@ -85,6 +86,8 @@ struct plaac_ctx {
     size_t smem_bytes = 0;
     int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
     size_t v2_smem_bytes = 0;
+    int v3_nwr = 0, v3_opt = 0, v3_mix = 0, v3_nt = 768;  // v3 kernel (same preconditions as v2): warps per role, option bits, role placement
+    size_t v3_smem_bytes = 0;
     int v2_always_in = 0;      // forward recurrence provably keeps |a-b| < 40 (no LUT range test needed)
     ResidueV2Plan res_plan;
     int variant = 0;           // 0 auto, 1 = v1 (reference-order anchor), 2 = v2
@@ -263,6 +266,29 @@ int setup_scalars(plaac_ctx* ctx)
             ctx->v2_smem_bytes = fixed2 + per_warp * 2 * nwr;
         } else
             ctx->v2_why = "ring does not fit beside the v2 tables";
+        // v3: same design, fewer issue slots per residue (summary_kernel_v3.cuh); on unless PLAAC_SUMMARY_KERNEL=2
+        ctx->v3_nwr = 0;
+        const size_t fixed3 = (size_t)kV2FixedBytes + kV2AlignSlack;
+        const char* ek = getenv("PLAAC_SUMMARY_KERNEL");
+        if (ctx->v2_nwr > 0 && fixed3 + 2 * per_warp <= limit && !(ek && atoi(ek) == 2)) {
+            int nwr = (int)std::min<size_t>(kV2MaxThreads / 64, (limit - fixed3) / (2 * per_warp));
+            if (const char* e = getenv("PLAAC_V2_WARP_PAIRS")) nwr = std::max(1, std::min(nwr, atoi(e)));
+            int opt = kV3DefaultOpt;
+            if (const char* e = getenv("PLAAC_V3_OPT")) opt = atoi(e);
+            // the packed Q/N window needs counts that fit a byte and the jar's Q/N code set
+            if (P.mw_window > 100 || k.qn_mask != ((1u << 12) | (1u << 14))) opt &= ~kV3SwarMw;
+            int nt = 768;
+            if (const char* e = getenv("PLAAC_V3_NT")) nt = atoi(e);
+            nwr = std::min(nwr, nt / 64);
+            if (v3_kernel(opt, nt)) {
+                ctx->v3_nt = nt;
+                ctx->v3_nwr = nwr;
+                ctx->v3_opt = opt;
+                ctx->v3_smem_bytes = fixed3 + per_warp * 2 * nwr;
+                // both roles on every scheduler partition: measured 1 % faster than one role per partition (round 2)
+                ctx->v3_mix = getenv("PLAAC_V3_MIX") ? atoi(getenv("PLAAC_V3_MIX")) : 1;
+            }
+        }
         // Range of d = a0 - a1 in the forward recurrence: alpha0/alpha1 is a Moebius image of the previous
         // ratio, so for t >= 1  d in [lt10 - lt11 + min(le0-le1), lt00 - lt01 + max(le0-le1)], and the two
         // log-sum-exp arguments differ by (lt0i - lt1i) + d.  If that is safely below 40 the LUT range test
@@ -469,7 +495,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     cudaStream_t st = s.stream;
     const int64_t nbuckets = (nprot + 31) / 32;
     int rc;
-    const bool use_v2 = ctx->variant == 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);
+    const bool use_v2 = ctx->variant >= 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);  // v2 or v3: the role-split kernels
     // Long-sequence path: summary mode of the throughput kernel only.
     CU(ctx, cudaEventRecord(s.ev_a, st));
     int64_t long_min = long_thr_known >= 0 ? long_thr_known : effective_long_min(ctx);
@@ -621,9 +647,21 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         g.core_count = (int32_t*)s.core_count.p;
         g.always_in = ctx->v2_always_in;
         g.work_counter = (unsigned long long*)((char*)s.core_count.p + 8);
+        const bool use_v3 = ctx->v3_nwr > 0 && ctx->variant != 2;
+        if (use_v3) {
+            const int full = 2 * ctx->ks.w + 1;
+            g.nwr = ctx->v3_nwr;
+            g.ks_wfull = (double)(full * full);
+            g.ks_cc2w = ctx->ks.cc2 * g.ks_wfull;
+            g.ks_cc2full = ctx->ks.cc2 * (double)full;
+            g.mix_roles = ctx->v3_mix;
+        }
         const int64_t nitems = 2 * nbuckets, wpc = 2 * g.nwr;
         const unsigned grid = (unsigned)std::min<int64_t>((nitems + wpc - 1) / wpc, ctx->sm_count);  // 1 CTA per SM
-        k_score_summary_v2<<<grid, g.nwr * 64, ctx->v2_smem_bytes, st>>>(g);
+        if (use_v3)
+            v3_kernel(ctx->v3_opt, ctx->v3_nt)<<<grid, g.nwr * 64, ctx->v3_smem_bytes, st>>>(g);
+        else
+            k_score_summary_v2<<<grid, g.nwr * 64, ctx->v2_smem_bytes, st>>>(g);
         // masked stretches can be jumped exactly when the masking constant is a negative integer (it is -1e6)
         const double bn = ctx->ks.big_neg;
         if (bn < 0 && bn == std::floor(bn) && bn >= -4194304.0)
@@ -945,7 +983,9 @@ try {
                                                       {(const void*)k_score_summary_v2, ctx->v2_smem_bytes},
                                                       {(const void*)k_len_hist, kHistSmemBytes},
                                                       {(const void*)k_scatter, kHistSmemBytes}};
-        for (const auto& f : fns) {
+        std::vector<std::pair<const void*, size_t>> all(std::begin(fns), std::end(fns));
+        if (ctx->v3_nwr > 0) all.push_back({(const void*)v3_kernel(ctx->v3_opt, ctx->v3_nt), ctx->v3_smem_bytes});
+        for (const auto& f : all) {
             const cudaError_t e = raise_dynamic_smem_limit(f.first, optin, f.second);
             if (e != cudaSuccess) {
                 cudaGetLastError();
@@ -1058,9 +1098,10 @@ try {
 int plaac_set_kernel_variant(plaac_ctx* ctx, int variant)
 try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_set_kernel_variant: NULL ctx");
-    if (variant < 0 || variant > 2) return fail(ctx, PLAAC_E_INVALID, "variant must be 0, 1 or 2");
-    if (variant == 2 && ctx->v2_nwr <= 0)
-        return fail(ctx, PLAAC_E_UNSUPPORTED, "v2 kernel unavailable for these parameters: %s", ctx->v2_why.c_str());
+    if (variant < 0 || variant > 3) return fail(ctx, PLAAC_E_INVALID, "variant must be 0, 1, 2 or 3");
+    if (variant >= 2 && ctx->v2_nwr <= 0)
+        return fail(ctx, PLAAC_E_UNSUPPORTED, "v2/v3 kernel unavailable for these parameters: %s", ctx->v2_why.c_str());
+    if (variant == 3 && ctx->v3_nwr <= 0) return fail(ctx, PLAAC_E_UNSUPPORTED, "v3 kernel switched off (PLAAC_SUMMARY_KERNEL=2)");
     ctx->variant = variant;
     return PLAAC_OK;
 } catch (...) {
@@ -1139,6 +1180,7 @@ int plaac_rank_device(plaac_ctx* ctx, const plaac_summary* d_summaries, int64_t 
 try {
     if (!ctx) return fail(nullptr, PLAAC_E_INVALID, "plaac_rank_device: NULL ctx");
     if (nprot < 0 || nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "nprot out of range");
+    if (flags != 0) return fail(ctx, PLAAC_E_INVALID, "flags are reserved and must be 0");
     if (n_core) *n_core = 0;
     if (nprot == 0) return PLAAC_OK;
     if (!d_summaries || !d_order) return fail(ctx, PLAAC_E_INVALID, "NULL summaries/order");
@@ -1152,7 +1194,7 @@ try {
     }
     const unsigned gk = (unsigned)((nprot + 255) / 256);
     int cur = 0;
-    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 0, (flags & PLAAC_RANK_WEB_QUIRKS) ? 1 : 0, (uint64_t*)s.rk_keys[cur].p,
+    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 0, (uint64_t*)s.rk_keys[cur].p,
                                     (int32_t*)s.rk_vals[cur].p);
     ctx->stats.kernel_launches += 1;
     for (int shift = 0; shift < 64; shift += 8) {
@@ -1160,7 +1202,7 @@ try {
         cur ^= 1;
     }
     // CORE proteins first (stable), then order them by COREscore
-    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 1, 0, (uint64_t*)s.rk_keys[cur].p, (int32_t*)s.rk_vals[cur].p);
+    k_rank_keys<<<gk, 256, 0, st>>>(d_summaries, nprot, 1, (uint64_t*)s.rk_keys[cur].p, (int32_t*)s.rk_vals[cur].p);
     ctx->stats.kernel_launches += 1;
     if ((rc = rank_pass<true>(ctx, s, nprot, 0, cur))) return rc;
     cur ^= 1;
@@ -1284,8 +1326,7 @@ int finish_hits(plaac_ctx* ctx, int64_t nprot, plaac_hits* hits)
             ctx->stats.kernel_launches += 1;
             const unsigned gc = (unsigned)((ncore + 255) / 256);
             for (int field = 0; field < 2; field++) {
-                k_hits_keys<<<gc, 256, 0, st>>>(all, (const int32_t*)s.rk_vals[cur].p, ncore, field,
-                                                (hits->rank_flags & PLAAC_RANK_WEB_QUIRKS) ? 1 : 0, (uint64_t*)s.rk_keys[cur].p);
+                k_hits_keys<<<gc, 256, 0, st>>>(all, (const int32_t*)s.rk_vals[cur].p, ncore, field, (uint64_t*)s.rk_keys[cur].p);
                 ctx->stats.kernel_launches += 1;
                 for (int shift = 0; shift < 64; shift += 8) {
                     if ((rc = rank_pass<false>(ctx, s, ncore, shift, cur))) return rc;
@@ -1318,6 +1359,7 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
         hits->count = hits->n_core = 0;
         if (hits->mode != PLAAC_HITS_CORE && hits->mode != PLAAC_HITS_TOPK) return fail(ctx, PLAAC_E_INVALID, "plaac_hits.mode must be PLAAC_HITS_CORE or PLAAC_HITS_TOPK");
         if (hits->capacity < 0) return fail(ctx, PLAAC_E_INVALID, "plaac_hits.capacity is negative");
+        if (hits->rank_flags != 0) return fail(ctx, PLAAC_E_INVALID, "plaac_hits.rank_flags is reserved and must be 0");
         if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins with compact output");
     }
     if (nprot == 0) {
@@ -1699,7 +1741,7 @@ try {
 
 // Is row a of the web order before row b?  (COREscore desc, LLR desc, rows without a CORE last, then input order:
 // rank.cuh's keys compared on the host, for merging the shards' ranked lists.)
-static bool hit_before(const plaac_summary& a, int64_t ia, const plaac_summary& b, int64_t ib, int web_quirks)
+static bool hit_before(const plaac_summary& a, int64_t ia, const plaac_summary& b, int64_t ib)
 {
     auto key = [](double v) -> uint64_t {
         if (v != v) return ~0ull;
@@ -1710,12 +1752,7 @@ static bool hit_before(const plaac_summary& a, int64_t ia, const plaac_summary& 
     };
     const uint64_t ca = key(a.core_score), cb = key(b.core_score);
     if (ca != cb) return ca < cb;
-    double la = a.llr, lb = b.llr;
-    if (web_quirks) {
-        if (std::isinf(la)) la = 0.0;
-        if (std::isinf(lb)) lb = 0.0;
-    }
-    const uint64_t ka = key(la), kb = key(lb);
+    const uint64_t ka = key(a.llr), kb = key(b.llr);
     if (ka != kb) return ka < kb;
     return ia < ib;
 }
@@ -1825,7 +1862,7 @@ try {
                 if (bounds[k + 1] <= bounds[k] || cur[k] >= sh_hits[k].count) continue;
                 if (best < 0 ||
                     hit_before(sh_rec[k][(size_t)cur[k]], bounds[k] + sh_idx[k][(size_t)cur[k]], sh_rec[best][(size_t)cur[best]],
-                               bounds[best] + sh_idx[best][(size_t)cur[best]], hits->rank_flags & PLAAC_RANK_WEB_QUIRKS))
+                               bounds[best] + sh_idx[best][(size_t)cur[best]]))
                     best = k;
             }
             if (best < 0) break;

@@ -30,18 +30,16 @@ __device__ __forceinline__ uint64_t rank_desc_key(double v)
     return ~asc;               // no finite or infinite double reaches ~0 (that would need u == all ones, a NaN)
 }
 
-// field 0: LLR (column 4), field 1: COREscore gathered through vals.  web_quirks: Ruby's "-Infinity".to_f is 0.0,
-// so the web order treats the LLR of proteins shorter than the core length as 0 (server.rb:224-226).
+// field 0: LLR (column 4), field 1: COREscore gathered through vals.  (LLR = -Inf, a protein shorter than the core
+// length, sorts last: the table prints it as NaN and server.rb:225 puts "NaN" last.)
 __global__ void __launch_bounds__(256)
-k_rank_keys(const plaac_summary* __restrict__ rec, int64_t n, int field, int web_quirks, uint64_t* __restrict__ keys,
+k_rank_keys(const plaac_summary* __restrict__ rec, int64_t n, int field, uint64_t* __restrict__ keys,
             int32_t* __restrict__ vals)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (field == 0) {
-        double v = rec[i].llr;
-        if (web_quirks && isinf(v)) v = 0.0;
-        keys[i] = rank_desc_key(v);
+        keys[i] = rank_desc_key(rec[i].llr);
         vals[i] = (int32_t)i;
     } else {
         keys[i] = rank_desc_key(rec[vals[i]].core_score);

@@ -1,123 +1,35 @@
-// Summary-mode scoring, throughput version ("v2").
+// Summary-mode scoring, throughput version "v3": the v2 kernel (summary_kernel_v2.cuh: one lane = one protein, one warp =
+// one length bucket, role A = the serial recurrences in reference operation order, role B = the sliding windows as exact
+// running sums; same shared-memory layout, same arithmetic, same bits in every column) with fewer issue slots per residue:
 //
-// One CTA = 2*NWR warps.  Warps 0..NWR-1 run role A, warps NWR..2*NWR-1 run role B, each on one length
-// bucket of 32 proteins (lane = protein), all lanes advancing the residue index t in lock step:
+//   * the Q/N window of the MW column (plaac.java:764-771) is counted four residues at a time in packed bytes (SWAR):
+//     flags, the window count after each residue and the "new maximum?" test for a whole word cost ~20 instructions
+//     instead of ~12 per residue; only a lane that does see a new maximum walks its four residues one by one;
+//   * traceback bits are collected per word in a nibble with predicated ORs and shifted into the bit planes once per word;
+//   * role B gets (2w+1)^2, cc2 * (2w+1)^2 and cc2 * (2w+1) as doubles from the host instead of re-converting them.
 //
-//   role A (the serial recurrences, REFERENCE OPERATION ORDER, bit-faithful to plaac.java):
-//     Viterbi max-plus recurrence + traceback bits   viterbidecodel :3077-3121
-//     LUT forward recurrence                          posteriorl :3349-3375, logeapeb :1024-1047
-//     hmm0's sequential log-emission sum              (= its Viterbi and marginal log-prob)
-//     sequential psum[] LLR window search             hss2 :1206-1257, call site :782-783
-//     MW Q/N window (exact integers)                  :764-771
-//     traceback -> Viterbi bits, longestrun           :3110-3113, :1787-1804
-//     proteins whose longest PrD run reaches the core length are appended to a list for k_core_search
-//   role B (sliding windows as running sums; |delta| ~1e-13, DESIGN.md "tolerances"):
-//     FoldIndex runs, means                           disorderreport :4866-5068
-//     PAPA centre search on the twice-smoothed tracks slidingaverage :2585-2662, :4941-4948
-//     the values reported at the PAPA centre (PAPAllr, PAPAllr2) are evaluated once per protein
-//
-// Shared-memory traffic is the scarce resource (one 128-byte wavefront per cycle per SM), so every
-// per-code table is replicated per bank group (conflict-free for any code pattern) and the 4001-entry
-// log-sum-exp LUT is stored as {lut[d], lut[d+1]} pairs (one 16-byte load per lookup).  Table bases are
-// aligned so that "base | code bits" forms the address in one LOP3.  Integer -> double conversions use the
-// 2^52 bit trick on the FP64 pipe instead of the slow XU conversion unit.
+// OPT is a compile-time bit set so that single steps can be measured against each other (PLAAC_V3_OPT).  Measured and
+// dropped (round 2, profiles/r02_v3_variants.json): a merged {le0, le1, llr} table entry (32-byte stride: two of the
+// eight lanes of a quarter warp always share a bank group, +10 %), the charge window sums on the FP64 pipe from a table
+// (three more shared-memory loads per residue, +3 %), a segmented word loop (a second copy of the generic body pushes
+// the executed code past the 32 KB instruction cache, +5 %).
 #pragma once
 #include <type_traits>
 
 #include "common.cuh"
+#include "summary_kernel_v2.cuh"
 
 namespace plaac {
 
-constexpr int kV2MaxThreads = 768;
+constexpr int kV3SwarMw = 1;    // SWAR Q/N window in role A's fast path (needs mw_window <= 100 and the Q/N code set {12, 14})
+constexpr int kV3NibbleTb = 2;  // traceback bits per word in a nibble
+constexpr int kV3Segments = 8;  // segmented word loop (measured slower; kept for the record)
 
-// Byte offsets from an 8 KB-aligned shared-memory base.
-constexpr uint32_t kOffHydB = 0;         // double [64 ext codes][16 lane copies]: hydropathy on the exact-sum grid (windows)
-constexpr uint32_t kOffPapB = 8192;      // double [64][16]
-constexpr uint32_t kOffLlrB = 16384;     // double [64][16]   (tail loops only)
-constexpr uint32_t kOffLeA = 24576;      // double2 [32 codes][8 lane copies]  {le0, le1}
-constexpr uint32_t kOffLlrA = 28672;     // double [32][16]
-constexpr uint32_t kOffLut2 = 32768;     // double2 [4002]  {lut[d], lut[d+1]}
-constexpr uint32_t kOffHydX = kOffLut2 + (PLAAC_LUT_LEN + 1) * 16;  // double [64][16]: exact hydropathy (sequential mean)
-constexpr uint32_t kV2FixedBytes = kOffHydX + 8192;
-constexpr uint32_t kV2AlignSlack = 8192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr)
-{
-    double v;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ double lds_f64_off(uint32_t addr)
-{
-    double v;
-    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-__device__ __forceinline__ double2 lds_v2f64(uint32_t addr)
-{
-    double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ double u2d(uint32_t v)
-{
-    // exact uint32 -> double on the FP64 pipe: 2^52 + v, minus 2^52
-    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
-}
-
-// logeapeb :1024-1047 for finite-or-(-Inf) arguments, given loglut[0] == ln 2 bit for bit (checked at
-// plaac_create): the a == b branch (a + ln2) then equals the interpolation at c = 0.  c = |a - b| is the
-// reference's (a - b) or (b - a) bit for bit; the larger argument is picked from the sign of a - b.
-template <bool ALWAYS_IN>
-__device__ __forceinline__ double lse_lut2(double a, double b, uint32_t lut_addr)
-{
-    const double d = a - b;
-    const double hi = (__double2hiint(d) < 0) ? b : a;  // a == b gives +0: hi = a
-    const double c = fabs(d);
-    const double x = 100.0 * c;
-    if (ALWAYS_IN) {
-        // plaac_create proved |a - b| < 40 for every reachable argument pair of the recurrence
-        // floor on the FP64 pipe: x + 2^52 rounded DOWN is 2^52 + floor(x) exactly (0 <= x < 2^51), its low word is
-        // the table index and subtracting 2^52 again gives floor(x) as a double -- no F2I, no separate int -> double
-        const double y = __dadd_rd(x, 4503599627370496.0);
-        const double2 l = lds_v2f64(lut_addr + (uint32_t)__double2loint(y) * 16u);
-        const double f1 = x - (y - 4503599627370496.0);
-        const double f0 = 1.0 - f1;
-        return hi + (f1 * l.y + f0 * l.x);
-    }
-    const bool in = c < 40.0;
-    const int dex = min(__double2int_rd(x), PLAAC_LUT_LEN - 1);  // x >= 0, NaN -> 0
-    const double2 l = lds_v2f64(lut_addr + (uint32_t)dex * 16u);
-    const double f1 = x - u2d((uint32_t)dex);  // 100*c - dex
-    const double f0 = 1.0 - f1;                // == (dex + 1) - 100*c exactly (both are exact differences)
-    const double r = hi + (f1 * l.y + f0 * l.x);
-    return in ? r : hi;
-}
-
-struct V2Args {
-    BatchView bv;
-    KScalars ks;
-    const DeviceTables* tabs;
-    plaac_summary* out;
-    int ring_words;       // per lane, power of two
-    int nwr;              // warps per role
-    int32_t* core_list;   // ranks needing the CORE search
-    int32_t* core_count;
-    int always_in;        // 1: |a-b| < 40 is guaranteed inside the forward recurrence (bound checked on the host)
-    unsigned long long* work_counter;  // zeroed before the launch
-    // v3 only: host-computed (double)(2w+1)^2, cc2 * that, cc2 * (2w+1); role placement
-    double ks_wfull, ks_cc2w, ks_cc2full;
-    int mix_roles;
-};
+// (shared-memory layout: v2's, kOff* / kV2FixedBytes / kV2AlignSlack)
 
 // ------------------------------------------------------------------------------------------------ role A
-__device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t* ring, int lane, int64_t b)
+template <int OPT>
+__device__ __forceinline__ void role_a3(const V2Args& g, uint32_t sbase, uint32_t* ring, int lane, int64_t b)
 {
     const KScalars& ks = g.ks;
     const BatchView& bv = g.bv;
@@ -147,6 +59,7 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     double ps = 0, psl = 0, llr_best = INFINITY;
     int llr_stop = -2;
     int qn = 0, mw_best = 0x7fffffff, mw_stop = -1;
+    uint32_t mwb1 = 0x80808080u;  // SWAR: (min(mw_best, 127) + 1) in every byte
     uint32_t acc0 = 0, acc1 = 0;  // traceback bit planes, newest residue at bit 31
 
     // lagged byte streams: position t - off, off = 4*a + b
@@ -163,7 +76,7 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
     const int wv_c1 = (c - 1) >> 2, wv_m1 = (mw - 1) >> 2;  // words holding the first complete LLR / MW window
 
     // one residue step; FAST: every lane has 0 < t < n-1 and t is not the first complete window of either search
-    auto step = [&](auto fast_tag, auto in_tag, int t, int i, uint32_t w0, uint32_t wc, uint32_t wm) {
+    auto step = [&](auto fast_tag, auto in_tag, int t, int i, uint32_t w0, uint32_t wc, uint32_t wm, uint32_t& nib0, uint32_t& nib1) {
         constexpr bool FAST = decltype(fast_tag)::value;
         constexpr bool AIN = decltype(in_tag)::value;
         // code bits 4:0 of byte i moved to address bits 11:7
@@ -173,8 +86,9 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
         const double lr0 = lds_f64(ll_base | k0);
         const double lrc = lds_f64(ll_base | kc);
         psl = psl + lrc;  // == psum[t-c+1]  (pad codes add +0.0)
-        qn += (int)((ks.qn_mask >> ((w0 >> (8 * i)) & 31u)) & 1u) - (int)((ks.qn_mask >> ((wm >> (8 * i)) & 31u)) & 1u);
-        uint32_t tb0u = 0, tb1u = 0;
+        if (!(FAST && (OPT & kV3SwarMw)))
+            qn += (int)((ks.qn_mask >> ((w0 >> (8 * i)) & 31u)) & 1u) - (int)((ks.qn_mask >> ((wm >> (8 * i)) & 31u)) & 1u);
+        bool tb0 = false, tb1 = false;
         if (FAST || t < n) {
             if (!FAST && t == 0) {
                 s0 = ks.li0 + le.x;
@@ -185,11 +99,10 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
             } else {
                 const double v00 = ks.lt00 + s0, v10 = ks.lt10 + s1;
                 const double v01 = ks.lt01 + s0, v11 = ks.lt11 + s1;
-                const bool tb0 = v10 > v00, tb1 = v11 > v01;
+                tb0 = v10 > v00;
+                tb1 = v11 > v01;
                 s0 = (tb0 ? v10 : v00) + le.x;
                 s1 = (tb1 ? v11 : v01) + le.y;
-                tb0u = tb0;
-                tb1u = tb1;
                 const double f0 = lse_lut2<AIN>(ks.lt00 + a0, ks.lt10 + a1, lut_addr) + le.x;
                 const double f1 = lse_lut2<AIN>(ks.lt01 + a0, ks.lt11 + a1, lut_addr) + le.y;
                 a0 = f0;
@@ -204,22 +117,35 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
                     llr_stop = t;
                 }
             }
-            if (FAST || t >= mw - 1) {
-                if ((!FAST && t == mw - 1) || qn > mw_best) {
+            if (!(FAST && (OPT & kV3SwarMw))) {
+                if (FAST || t >= mw - 1) {
+                    if ((!FAST && t == mw - 1) || qn > mw_best) {
+                        mw_best = qn;
+                        mw_stop = t;
+                    }
+                } else if (t == n - 1) {
                     mw_best = qn;
                     mw_stop = t;
                 }
-            } else if (t == n - 1) {
-                mw_best = qn;
-                mw_stop = t;
             }
         }
-        acc0 = __funnelshift_r(acc0, tb0u, 1);  // after 16 steps the bit of residue 16j+i sits at 16+i
-        acc1 = __funnelshift_r(acc1, tb1u, 1);
+        if (OPT & kV3NibbleTb) {
+            if (i == 0) {
+                nib0 = tb0 ? 1u : 0u;
+                nib1 = tb1 ? 1u : 0u;
+            } else {
+                if (tb0) nib0 |= 1u << i;
+                if (tb1) nib1 |= 1u << i;
+            }
+        } else {
+            acc0 = __funnelshift_r(acc0, tb0 ? 1u : 0u, 1);  // after 16 steps the bit of residue 16j+i sits at 16+i
+            acc1 = __funnelshift_r(acc1, tb1 ? 1u : 0u, 1);
+        }
     };
 
-#pragma unroll 1
-    for (int wv = 0; wv < nwords; wv++) {
+    // one word = 4 residues: ring traffic, the three byte streams, 4 steps, traceback word every fourth word
+    auto word = [&](auto fast_tag, int wv) {
+        constexpr bool FASTW = decltype(fast_tag)::value;
         if ((wv & 3) == 0) {
             const int j = wv >> 2;
             ring[((wv + 0) & rmask) * 32] = nxt.x;
@@ -237,22 +163,80 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
         lo_c = hi_c;
         lo_m = hi_m;
         const int tbase = wv * 4;
-        // warp-uniform; t = nmin-1 stays generic so the "whole protein is one MW window" case (n < mw) is seen there
-        if (wv != 0 && wv != wv_c1 && wv != wv_m1 && tbase + 3 < nmin - 1) {
+        uint32_t nib0 = 0, nib1 = 0;
+        if (FASTW) {
+            if (OPT & kV3SwarMw) {
+                // Q/N window four residues at a time.  A byte is Q or N iff (code & 0x1d) == 0x0c (codes 14, 12;
+                // the pad code 22 and the flag bits 7:5 of the ext byte drop out).  z: bit 7 of a byte = NOT Q/N.
+                const uint32_t z0 = (((w0 & 0x1d1d1d1du) ^ 0x0c0c0c0cu) + 0x7f7f7f7fu) >> 7;
+                const uint32_t zm = (((wm & 0x1d1d1d1du) ^ 0x0c0c0c0cu) + 0x7f7f7f7fu) >> 7;
+                // per byte 1 + isqn(entering) - isqn(leaving), in {0, 1, 2}; multiplying by 0x01010101 gives the
+                // inclusive prefix sums of the four bytes (<= 8: no carry between bytes)
+                const uint32_t D = (0x01010101u + (zm & 0x01010101u)) - (z0 & 0x01010101u);
+                const uint32_t P = D * 0x01010101u;
+                // window count after residue i in byte i: counts are >= 0 and <= mw <= 100, so no byte borrows
+                const uint32_t Q = ((uint32_t)qn * 0x01010101u + P) - 0x04030201u;
+                qn = (int)(Q >> 24);
+                // bit 7 of byte i: count_i > mw_best  (mwb1 = mw_best + 1 per byte, 128 while no window is complete)
+                if ((((Q | 0x80808080u) - mwb1) & 0x80808080u) != 0u) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int q = (int)((Q >> (8 * i)) & 0xffu);
+                        if (q > mw_best) {
+                            mw_best = q;
+                            mw_stop = tbase + i;
+                        }
+                    }
+                    mwb1 = (uint32_t)(mw_best + 1) * 0x01010101u;
+                }
+            }
             if (g.always_in) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) step(std::true_type{}, std::true_type{}, tbase + i, i, w0, wc, wm);
+                for (int i = 0; i < 4; i++) step(std::true_type{}, std::true_type{}, tbase + i, i, w0, wc, wm, nib0, nib1);
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; i++) step(std::true_type{}, std::false_type{}, tbase + i, i, w0, wc, wm);
+                for (int i = 0; i < 4; i++) step(std::true_type{}, std::false_type{}, tbase + i, i, w0, wc, wm, nib0, nib1);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) step(std::false_type{}, std::false_type{}, tbase + i, i, w0, wc, wm);
+            for (int i = 0; i < 4; i++) step(std::false_type{}, std::false_type{}, tbase + i, i, w0, wc, wm, nib0, nib1);
+            if (OPT & kV3SwarMw) mwb1 = (uint32_t)(min(mw_best, 127) + 1) * 0x01010101u;
+        }
+        if (OPT & kV3NibbleTb) {
+            acc0 = __funnelshift_r(acc0, nib0, 4);  // after 4 words the bit of residue 16j+i sits at 16+i
+            acc1 = __funnelshift_r(acc1, nib1, 4);
         }
         if ((wv & 3) == 3) {
             // low half: predecessor-of-state-0 bits of the slot's 16 residues, high half: predecessor-of-state-1 bits
             tbp[(size_t)(wv >> 2) * 32] = __byte_perm(acc0, acc1, 0x7632);
+        }
+    };
+
+    // fast words: wv != 0, not the word of the first complete LLR / MW window, and tbase + 3 < nmin - 1 (t = nmin-1 stays
+    // generic so the "whole protein is one MW window" case, n < mw, is seen there)
+    const int fast_end = nmin >= 5 ? (nmin - 1) >> 2 : 0;  // words wv < fast_end have 4*wv + 3 < nmin - 1
+    if (OPT & kV3Segments) {
+        int wv = 0;
+#pragma unroll 1
+        while (wv < nwords) {
+            if (wv == 0 || wv == wv_c1 || wv == wv_m1 || wv >= fast_end) {
+                word(std::false_type{}, wv);
+                wv++;
+                continue;
+            }
+            int stop = min(fast_end, nwords);
+            if (wv < wv_c1) stop = min(stop, wv_c1);
+            if (wv < wv_m1) stop = min(stop, wv_m1);
+#pragma unroll 1
+            for (; wv < stop; wv++) word(std::true_type{}, wv);
+        }
+    } else {
+#pragma unroll 1
+        for (int wv = 0; wv < nwords; wv++) {
+            if (wv != 0 && wv != wv_c1 && wv != wv_m1 && wv < fast_end)
+                word(std::true_type{}, wv);
+            else
+                word(std::false_type{}, wv);
         }
     }
 
@@ -345,7 +329,8 @@ __device__ __forceinline__ void role_a(const V2Args& g, uint32_t sbase, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------ role B
-__device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t* ring, int lane, int64_t b)
+template <int OPT>
+__device__ __forceinline__ void role_b3(const V2Args& g, uint32_t sbase, uint32_t* ring, int lane, int64_t b)
 {
     const KScalars& ks = g.ks;
     const BatchView& bv = g.bv;
@@ -368,7 +353,6 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
     const int a2o = off2 >> 2, s2o = 8 * (4 - (off2 & 3));
     const int full = 2 * w + 1;
     const int Wfull = full * full;
-    const double cc2full = ks.cc2 * (double)full;
 
     const uint32_t hb = sbase + kOffHydB + (uint32_t)(lane & 15) * 8u;
 
@@ -390,8 +374,9 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
     const int edge_hi = n - 1 - w;   // windows centred beyond this are clipped on the right
     int fi_run = 0, fi_numaa = 0, fi_maxrun = 0;  // fi_run: length of the open run of fi < 0 (snaps included)
     uint32_t lo1 = kPadW, lo2 = kPadW;
-    const double WfullD = (double)Wfull;
-    const double cc2W = ks.cc2 * WfullD;
+    // (host-computed: (double)(2w+1)^2, cc2 * that, cc2 * (2w+1); the compiler otherwise rematerialises the conversion
+    // inside the loop to save registers)
+    const double WfullD = g.ks_wfull, cc2W = g.ks_cc2w, cc2full = g.ks_cc2full;
     const double cc0 = ks.cc0, cc1 = ks.cc1;
 
     int nmin = (prot >= 0) ? n : 0x7fffffff;
@@ -406,31 +391,31 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         const uint32_t k0 = (i == 0 ? (w0 << 7) : (w0 >> (8 * i - 7))) & (63u << 7);
         const uint32_t k1 = (i == 0 ? (w1 << 7) : (w1 >> (8 * i - 7))) & (63u << 7);
         const uint32_t k2 = (i == 0 ? (w2 << 7) : (w2 >> (8 * i - 7))) & (63u << 7);
-        const int ch0 = (int)(w0 << (24 - 8 * i)) >> 30;
-        const int ch1 = (int)(w1 << (24 - 8 * i)) >> 30;
-        const int ch2 = (int)(w2 << (24 - 8 * i)) >> 30;
         const double hy0 = lds_f64(hb | k0), pa0 = lds_f64_off<kOffPapB>(hb | k0);
         const double hy1 = lds_f64(hb | k1), pa1 = lds_f64_off<kOffPapB>(hb | k1);
         const double hy2 = lds_f64(hb | k2), pa2 = lds_f64_off<kOffPapB>(hb | k2);
-        if (FAST || t < n) {
-            sh = sh + lds_f64_off<kOffHydX>(hb | k0);  // mean() :1584, sequential, exact table values
-            csum += ch0;
-        }
+        const int ch0 = (int)(w0 << (24 - 8 * i)) >> 30;
+        const int ch1 = (int)(w1 << (24 - 8 * i)) >> 30;
+        const int ch2 = (int)(w2 << (24 - 8 * i)) >> 30;
+        if (FAST || t < n) csum += ch0;
+        SLc += ch0 - ch1;
+        SGc += ch1 - ch2;
+        const int aSL = abs(SLc);
+        Tac += aSL - abs(SGc);
+        const double aSLd = u2d((uint32_t)aSL);
+        if (FAST || t < n) sh = sh + lds_f64_off<kOffHydX>(hb | k0);  // mean() :1584, sequential, exact table values
         // window sums of the zero-padded sequence: lead centre p = t-w, lag centre p-(2w+1)
         SLh = (SLh + hy0) - hy1;
         SGh = (SGh + hy1) - hy2;
         Th = (Th + SLh) - SGh;
         Dp = Dp + ((pa0 + pa2) - (pa1 + pa1));  // exact: PAPA log-odds live on a 2^-k grid
         Tp = Tp + Dp;
-        SLc += ch0 - ch1;
-        SGc += ch1 - ch2;
-        const int aSL = abs(SLc);
-        Tac += aSL - abs(SGc);
+        const double TacD = u2d((uint32_t)Tac);
         const int p = t - w;
         // FoldIndex run scan :5010-5059 over i in [halfw, n-halfw):
         // sign of fi[p] = cc0*hydro + cc1*|charge| + cc2, scaled by the tap count (> 0)
         if (FAST) {
-            const double fis = (cc0 * SLh + cc1 * u2d((uint32_t)aSL)) + cc2full;
+            const double fis = (cc0 * SLh + cc1 * aSLd) + cc2full;
             const bool neg = fis < 0;
             const int closed = (!neg && fi_run >= 5) ? fi_run : 0;
             fi_numaa += closed;
@@ -439,7 +424,7 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         } else if (p >= halfw && p < fi_hi) {
             double c2 = cc2full;
             if (p < w || p > edge_hi) c2 = ks.cc2 * u2d((uint32_t)(full - max(0, w - p) - max(0, p - edge_hi)));
-            const double fis = (cc0 * SLh + cc1 * u2d((uint32_t)aSL)) + c2;
+            const double fis = (cc0 * SLh + cc1 * aSLd) + c2;
             const bool neg = fis < 0;
             const bool last = (p == fi_hi - 1);
             // a run that starts at the first scanned position is snapped back to residue 0,
@@ -457,7 +442,7 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         // PAPA centre k = p - w: first strict maximum of Tp/W among centres with fix2 < 0 (:4941-4948)
         // Tp/Wd > Tb/Wb  <=>  Tp*Wb > Tb*Wd (both positive); products of grid units and small ints
         if (FAST) {
-            const double vfi = (cc0 * Th + cc1 * u2d((uint32_t)Tac)) + cc2W;
+            const double vfi = (cc0 * Th + cc1 * TacD) + cc2W;
             if ((pcen < 0 || Tp * Wb > Tb * WfullD) && vfi < 0) {
                 Tb = Tp;
                 Wb = WfullD;
@@ -472,7 +457,7 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
                     const int ml = 2 * w - k, mr = k - (edge_hi - w);
                     Wd = u2d((uint32_t)(Wfull - (ml > 0 ? (ml * (ml + 1)) >> 1 : 0) - (mr > 0 ? (mr * (mr + 1)) >> 1 : 0)));
                 }
-                const double vfi = (cc0 * Th + cc1 * u2d((uint32_t)Tac)) + ks.cc2 * Wd;
+                const double vfi = (cc0 * Th + cc1 * TacD) + ks.cc2 * Wd;
                 if ((pcen < 0 || Tp * Wb > Tb * Wd) && vfi < 0) {
                     Tb = Tp;
                     Wb = Wd;
@@ -485,8 +470,7 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
 
     uint4 nxt = make_uint4(kPadW, kPadW, kPadW, kPadW);
     if (nch > 0) nxt = sp[0];
-#pragma unroll 1
-    for (int wv = 0; wv < nwords; wv++) {
+    auto word = [&](auto fast_tag, int wv) {
         if ((wv & 3) == 0) {
             const int j = wv >> 2;
             ring[((wv + 0) & rmask) * 32] = nxt.x;
@@ -504,13 +488,28 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
         lo1 = hi1;
         lo2 = hi2;
         const int tbase = wv * 4;
-        // warp-uniform; t <= nmin-2 keeps the last scanned FoldIndex position (p = n-1-halfw) out of the fast path
-        if (tbase >= fast_lo && tbase + 3 < nmin - 1) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) step(std::true_type{}, tbase + i, i, w0, w1, w2);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) step(std::false_type{}, tbase + i, i, w0, w1, w2);
+        for (int i = 0; i < 4; i++) step(fast_tag, tbase + i, i, w0, w1, w2);
+    };
+    // fast words: tbase >= 4w and tbase + 3 < nmin - 1 (t <= nmin-2 keeps the last scanned FoldIndex position,
+    // p = n-1-halfw, out of the fast path)
+    const int fast_end = nmin >= 5 ? (nmin - 1) >> 2 : 0;
+    const int fast_begin = (fast_lo + 3) >> 2;
+    if (OPT & kV3Segments) {
+        int wv = 0;
+#pragma unroll 1
+        for (; wv < min(fast_begin, nwords); wv++) word(std::false_type{}, wv);
+#pragma unroll 1
+        for (; wv < min(fast_end, nwords); wv++) word(std::true_type{}, wv);
+#pragma unroll 1
+        for (; wv < nwords; wv++) word(std::false_type{}, wv);
+    } else {
+#pragma unroll 1
+        for (int wv = 0; wv < nwords; wv++) {
+            if (wv >= fast_begin && wv < fast_end)
+                word(std::true_type{}, wv);
+            else
+                word(std::false_type{}, wv);
         }
     }
 
@@ -577,7 +576,8 @@ __device__ __forceinline__ void role_b(const V2Args& g, uint32_t sbase, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
+template <int OPT, int NT>
+__global__ void __launch_bounds__(NT, 1) k_score_summary_v3(V2Args g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -612,16 +612,13 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
     constexpr uint32_t kPadW = 0x01010101u * kPad;
     __syncthreads();
 
-    // Persistent warps: work item = (bucket, role), handed out by one global counter in bucket order (longest
-    // buckets first, roles alternating), so every SM keeps all its warps busy with a balanced A/B mix until the
-    // queue is empty.  The first round is assigned statically to save one atomic round trip.
-    // A warp keeps ONE role while that role has buckets left (odd warps: role B), so the two warps a scheduler
-    // partition alternates between mostly run the same loop and the instruction caches hold one role per partition
-    // pair; each role has its own bucket counter and a warp whose role has run dry steals from the other one.
+    // Persistent warps, one role per warp while that role has buckets left (see k_score_summary_v2).  g.mix_roles:
+    // 0 = one role per scheduler partition (even warps A, odd warps B), 1 = both roles on every partition.
     const int64_t nb = g.bv.nbuckets;
-    int role = wid & 1;
+    int role = (g.mix_roles & 1) ? ((wid >> 2) & 1) : (wid & 1);
     const int64_t per_role = (int64_t)(blockDim.x >> 6);
-    int64_t item = (int64_t)blockIdx.x * per_role + (wid >> 1);
+    const int slot_in_role = (g.mix_roles & 1) ? (((wid >> 3) << 2) | (wid & 3)) : (wid >> 1);
+    int64_t item = (int64_t)blockIdx.x * per_role + slot_in_role;
     const int64_t first_dynamic = (int64_t)gridDim.x * per_role;
     int switched = 0;
     while (true) {
@@ -631,10 +628,12 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
             role ^= 1;
         } else {
             for (int i = 0; i < g.ring_words; i++) ring[i * 32] = kPadW;
-            if (role)
-                role_b(g, sbase, ring, lane, item);
-            else
-                role_a(g, sbase, ring, lane, item);
+            // (g.mix_roles bits 8/9: timing experiments that skip role B / role A; the records are then incomplete)
+            if (role) {
+                if (!(g.mix_roles & 256)) role_b3<OPT>(g, sbase, ring, lane, item);
+            } else {
+                if (!(g.mix_roles & 512)) role_a3<OPT>(g, sbase, ring, lane, item);
+            }
         }
         unsigned long long nx = 0;
         if (lane == 0) nx = atomicAdd(g.work_counter + role, 1ull);
@@ -642,209 +641,19 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) k_score_summary_v2(V2Args g)
     }
 }
 
-// ------------------------------------------------------------------------------------------------ CORE search
-// The -1e6-masked window search of plaac.java:816-833 (hss2 :1206-1257 in reference order: the masking
-// constant pollutes the sequential prefix sums, and the jar's COREscore/COREstart carry that pollution),
-// then the PrD expansion and PRDscore :851-873.  One lane per listed protein (about 5 % of all).
-__global__ void __launch_bounds__(128)
-k_core_search(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs, plaac_summary* __restrict__ out,
-              const int32_t* __restrict__ core_list, const int32_t* __restrict__ core_count)
+// The instantiations that exist (PLAAC_V3_OPT picks one for experiments).
+constexpr int kV3DefaultOpt = kV3SwarMw;
+using V3Kernel = void (*)(V2Args);
+// nt: threads per CTA the kernel is compiled for (768: 80 registers per thread)
+inline V3Kernel v3_kernel(int opt, int nt)
 {
-    __shared__ double llr_s[32][16];
-    for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) llr_s[i >> 4][i & 15] = tabs->llr[i >> 4];
-    __syncthreads();
-    const int total = *core_count;
-    const int c = ks.core_len;
-    const double big_neg = ks.big_neg;
-    const double* lt = &llr_s[0][threadIdx.x & 15];
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int32_t rank = core_list[2 * idx];
-        const int64_t b = rank >> 5;
-        const int lane = rank & 31;
-        const int32_t prot = bv.order[rank];
-        const int n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
-        const int64_t cb = bv.chunk_base[b];
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(bv.stream + cb * 32 + lane);
-        const uint32_t* vw = bv.tbw + cb * 32 + lane;
-        auto code_at = [&](int i) -> int { return sb[(size_t)(i >> 4) * 512 + (i & 15)] & 31; };
-        auto vit_at = [&](int i) -> int { return (vw[(size_t)(i >> 4) * 32] >> (i & 15)) & 1; };
-        double ps = 0.0, psl = 0.0, best = 0.0;
-        int bstop = c - 1;
-        // lead and lag cursors walk their own 16-residue slots
-        uint4 lead = make_uint4(0, 0, 0, 0), lag = lead;
-        uint32_t vlead = 0, vlag = 0;
-        for (int i = 0; i < n; i++) {
-            if ((i & 15) == 0) {
-                lead = *reinterpret_cast<const uint4*>(sb + (size_t)(i >> 4) * 512);
-                vlead = vw[(size_t)(i >> 4) * 32];
-            }
-            const int k = i - c;
-            if (k >= 0 && ((k & 15) == 0 || i == c)) {
-                lag = *reinterpret_cast<const uint4*>(sb + (size_t)(k >> 4) * 512);
-                vlag = vw[(size_t)(k >> 4) * 32];
-            }
-            const uint32_t lw = ((i & 12) == 0) ? lead.x : ((i & 12) == 4) ? lead.y : ((i & 12) == 8) ? lead.z : lead.w;
-            const int code = (lw >> ((i & 3) * 8)) & 31;
-            const double x = ((vlead >> (i & 15)) & 1) ? lt[code * 16] : big_neg;
-            ps = ps + x;
-            if (k >= 0) {
-                const uint32_t gw = ((k & 12) == 0) ? lag.x : ((k & 12) == 4) ? lag.y : ((k & 12) == 8) ? lag.z : lag.w;
-                const int codel = (gw >> ((k & 3) * 8)) & 31;
-                const double xl = ((vlag >> (k & 15)) & 1) ? lt[codel * 16] : big_neg;
-                psl = psl + xl;
-                const double d = ps - psl;
-                if (d > best) {
-                    best = d;
-                    bstop = i;
-                }
-            } else if (i == c - 1) {
-                best = ps;
-            }
-        }
-        if (best > big_neg / 2) {
-            const int s = bstop - c + 1, e = bstop;
-            int a0 = s, a1 = e;
-            while (a0 >= 0 && vit_at(a0) == 1) a0--;
-            a0++;
-            while (a1 < n && vit_at(a1) == 1) a1++;
-            a1--;
-            double sc = 0.0;
-            for (int kk = a0; kk <= a1; kk++) sc = sc + lt[code_at(kk) * 16];
-            plaac_summary* r = out + prot;
-            r->core_start = s;
-            r->core_end = e;
-            r->core_score = best;
-            r->prd_start = a0;
-            r->prd_end = a1;
-            r->prd_score = sc;
-        }
+    if (nt == 768) switch (opt) {
+        case 0: return k_score_summary_v3<0, 768>;
+        case 1: return k_score_summary_v3<1, 768>;
+        case 3: return k_score_summary_v3<3, 768>;
+        case 8: return k_score_summary_v3<8, 768>;
     }
-}
-
-// k masked residues add the masking constant B to the sequential prefix sum k times (hss2 :1230-1233 on the
-// masked sequence of :816-831).  For a negative INTEGER B (checked on the host) one such addition is exact
-// whenever the result stays inside the binade of ps: both operands are then multiples of the result's ulp.
-// So whole stretches are applied as one exact step and only the additions that cross into the next binade
-// (about one per power of two) are done one by one -- bit-identical to the jar's k rounded additions.
-__device__ __forceinline__ double masked_jump(double ps, int k, double B)
-{
-    const double aB = -B;
-    while (k > 0) {
-        double m = 0.0;
-        if (ps < 0.0) {
-            const double aps = -ps;
-            const int ebits = (__double2hiint(aps) >> 20) & 0x7ff;
-            const double lim = __hiloint2double((ebits + 1) << 20, 0);  // next power of two above |ps|
-            const double room = lim - aps;                             // exact (same binade)
-            m = floor(room / aB);
-            if (m * aB > room) m -= 1.0;                               // m * aB is an exact integer product
-        }
-        if (m >= 1.0) {
-            const double mm = fmin(m, (double)k);
-            ps = ps - mm * aB;  // exact
-            k -= (int)mm;
-        } else {
-            ps = ps + B;  // the rounded addition, as the reference does it
-            k -= 1;
-        }
-    }
-    return ps;
-}
-
-// Same search as k_core_search with the masked stretches jumped (needs big_neg to be a negative integer).
-// Only windows inside Viterbi runs can win (every other window is below big_neg/2 and a listed protein has a run
-// of at least c residues), so d = psum[i+1] - psum[i-c+1] is evaluated there only; the lagged prefix sum restarts
-// from the lead value at each run start and replays the same additions, so it has the jar's bits.
-__global__ void __launch_bounds__(128)
-k_core_search_jump(BatchView bv, KScalars ks, const DeviceTables* __restrict__ tabs, plaac_summary* __restrict__ out,
-                   const int32_t* __restrict__ core_list, const int32_t* __restrict__ core_count)
-{
-    __shared__ double llr_s[32][16];
-    for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) llr_s[i >> 4][i & 15] = tabs->llr[i >> 4];
-    __syncthreads();
-    const int total = *core_count;
-    const int c = ks.core_len;
-    const double big_neg = ks.big_neg;
-    const double* lt = &llr_s[0][threadIdx.x & 15];
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int32_t rank = core_list[2 * idx];
-        const uint32_t span = (uint32_t)core_list[2 * idx + 1];
-        const int64_t b = rank >> 5;
-        const int lane = rank & 31;
-        const int32_t prot = bv.order[rank];
-        const int n = (int)(bv.offsets[prot + 1] - bv.offsets[prot]);
-        const int64_t cb = bv.chunk_base[b];
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(bv.stream + cb * 32 + lane);
-        const uint32_t* vw = bv.tbw + cb * 32 + lane;
-        auto code_at = [&](int i) -> int { return sb[(size_t)(i >> 4) * 512 + (i & 15)] & 31; };
-        // One loop iteration = one Viterbi-1 residue (or one step to the next 16-residue word); masked residues
-        // cost nothing: the gap before a residue is applied as one jump.  PRDscore (:870-872, a sequential sum
-        // from the run start) and the PrD bounds (:861-866, the enclosing run) are carried along per run.
-        double ps = 0.0, lag = 0.0, best = -INFINITY, runsum = 0.0, prd_sc = 0.0;
-        int bstop = -1, run = 0, last = 0, run_start = 0, prd_s = -1, prd_e = -2;
-        bool hit = false;
-        const int nslots = min((n + 15) >> 4, (int)(span >> 16) + 1);  // nothing but masked residues beyond
-        int j = (int)(span & 0xffffu) - 1;                              // ... and before (one jump from residue 0)
-        uint32_t bits = 0, vnext = vw[(size_t)(j + 1) * 32];
-        uint4 cw = make_uint4(0, 0, 0, 0);
-        while (true) {
-            if (bits == 0) {
-                if (++j >= nslots) break;
-                const int nb = min(16, n - 16 * j);
-                bits = vnext & ((1u << nb) - 1u);
-                if (j + 1 < nslots) vnext = vw[(size_t)(j + 1) * 32];
-                if (bits) cw = *reinterpret_cast<const uint4*>(sb + (size_t)j * 512);
-                continue;
-            }
-            const int i = __ffs((int)bits) - 1;
-            bits &= bits - 1;
-            const int p = 16 * j + i;
-            if (p != last) {  // masked residues since the previous Viterbi-1 residue: the run (if any) ended
-                if (hit) {
-                    prd_s = run_start;
-                    prd_e = last - 1;
-                    prd_sc = runsum;
-                    hit = false;
-                }
-                ps = masked_jump(ps, p - last, big_neg);
-                run = 0;
-            }
-            if (run == 0) {
-                lag = ps;
-                run_start = p;
-                runsum = 0.0;
-            }
-            const uint32_t w = ((i & 12) == 0) ? cw.x : ((i & 12) == 4) ? cw.y : ((i & 12) == 8) ? cw.z : cw.w;
-            const double x = lt[((w >> ((i & 3) * 8)) & 31) * 16];
-            ps = ps + x;
-            runsum = runsum + x;
-            if (run >= c - 1) {
-                const double d = ps - lag;
-                if (d > best) {
-                    best = d;
-                    bstop = p;
-                    hit = true;
-                }
-                lag = lag + lt[code_at(p - c + 1) * 16];
-            }
-            run++;
-            last = p + 1;
-        }
-        if (hit) {
-            prd_s = run_start;
-            prd_e = last - 1;
-            prd_sc = runsum;
-        }
-        if (best > big_neg / 2) {
-            plaac_summary* r = out + prot;
-            r->core_start = bstop - c + 1;
-            r->core_end = bstop;
-            r->core_score = best;
-            r->prd_start = prd_s;
-            r->prd_end = prd_e;
-            r->prd_score = prd_sc;
-        }
-    }
+    return nullptr;
 }
 
 }  // namespace plaac

@@ -51,6 +51,24 @@ public final class Plaac {
         private static final MethodHandle SCORE =
             fn("plaac_score", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
 
+        // int plaac_score_multi(ctxs, nctx, codes, offsets, nprot, summaries, per_res): one ctx + host thread per GPU
+        private static final MethodHandle SCORE_MULTI = fn("plaac_score_multi",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
+        // transport-lean calls: radix-22 words (7 residues per int) + int lengths in, optional ranked hits out
+        private static final MethodHandle PACKED_WORDS = fn("plaac_packed_words", FunctionDescriptor.of(JAVA_LONG, JAVA_LONG));
+        private static final MethodHandle PACK_HOST =
+            fn("plaac_pack_host", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT));
+        private static final MethodHandle SCORE_PACKED = fn("plaac_score_packed",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+        private static final MethodHandle SCORE_MULTI_PACKED = fn("plaac_score_multi_packed",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+        // int plaac_rank(ctx, summaries, nprot, flags, order, n_core): the web front end's order (server.rb:222-229)
+        private static final MethodHandle RANK =
+            fn("plaac_rank", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS));
+        // int plaac_score_fasta(ctx, text, nbytes, max_rec, summaries, codes, offsets, name_pos, name_len, flags, index, bg_counts)
+        private static final MethodHandle SCORE_FASTA = fn("plaac_score_fasta", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS,
+            JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+
         // int plaac_host_alloc(void **out, size_t bytes, int flags); int plaac_host_free(void *p)
         private static final MethodHandle HOST_ALLOC =
             fn("plaac_host_alloc", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_INT));
@@ -135,6 +153,38 @@ public final class Plaac {
             int rc = (int) SCORE.invokeExact(ctx, codes, offs, (long) nprot, sum, MemorySegment.NULL);
             if (rc != 0) throw new IllegalStateException("plaac_score failed (" + rc + "): " + lastError(ctx));
             return sum;
+        }
+
+        /** Summary records of one batch scored on several GPUs at once (--gpus N): the batch goes over the host link as
+         *  radix-22 words (4/7 byte per residue) and int lengths, each ctx scores a residue-balanced contiguous shard
+         *  and writes its records at the input position (plaac_score_multi_packed; no collective, no gather copy). */
+        static MemorySegment scoreMulti(List<Cuda> ctxs, Batch b, Arena a) throws Throwable {
+            int nprot = b.names.size();
+            MemorySegment codes = a.allocate(Math.max(1, b.ncodes));
+            MemorySegment.copy(b.codes, 0, codes, JAVA_BYTE, 0, b.ncodes);
+            long nwords = (long) PACKED_WORDS.invokeExact((long) b.ncodes);
+            MemorySegment words = pinned(4L * Math.max(1, nwords), a);
+            int rc = (int) PACK_HOST.invokeExact(codes, (long) b.ncodes, words, 0);
+            if (rc != 0) throw new IllegalStateException("plaac_pack_host failed (" + rc + ")");
+            MemorySegment lens = pinned(4L * nprot, a);
+            for (int i = 0; i < nprot; i++) lens.setAtIndex(JAVA_INT, i, (int) (b.offsets.get(i + 1) - b.offsets.get(i)));
+            MemorySegment sum = pinned(SUMMARY_BYTES * nprot, a);
+            MemorySegment handles = a.allocate(ADDRESS.byteSize() * ctxs.size(), 8);
+            for (int k = 0; k < ctxs.size(); k++) handles.setAtIndex(ADDRESS, k, ctxs.get(k).ctx);
+            rc = (int) SCORE_MULTI_PACKED.invokeExact(handles, ctxs.size(), words, lens, (long) nprot, (long) b.ncodes, sum,
+                MemorySegment.NULL, MemorySegment.NULL);
+            if (rc != 0) throw new IllegalStateException("plaac_score_multi_packed failed (" + rc + "): " + lastError(ctxs.get(0).ctx));
+            return sum;
+        }
+
+        /** Row order of the reference's web front end (COREscore desc, LLR desc, rows without a CORE last): --rank. */
+        int[] rank(MemorySegment summaries, int nprot, Arena a) throws Throwable {
+            MemorySegment order = a.allocate(4L * Math.max(1, nprot), 4), ncore = a.allocate(8, 8);
+            int rc = (int) RANK.invokeExact(ctx, summaries, (long) nprot, 0, order, ncore);
+            if (rc != 0) throw new IllegalStateException("plaac_rank failed (" + rc + "): " + lastError(ctx));
+            int[] out = new int[nprot];
+            for (int i = 0; i < nprot; i++) out[i] = order.getAtIndex(JAVA_INT, i);
+            return out;
         }
 
         /** Per-residue arrays of one batch: 2 byte arrays (vit, map) and 10 double arrays, each ncodes long. */
@@ -407,11 +457,14 @@ public final class Plaac {
         + "PAPAx2\tHMM.background\tHMM.PrD-like";
 
     // ------------------------------------------------------------------------------------------ the two tables
-    static void printSummaryBatch(Cuda cuda, Batch b, Params p, PrintStream out) throws Throwable {
+    static void printSummaryBatch(List<Cuda> cudas, boolean ranked, Batch b, Params p, PrintStream out) throws Throwable {
         if (b.names.isEmpty()) return;
         try (Arena a = Arena.ofConfined()) {
-            MemorySegment s = cuda.score(b, a);
-            for (int i = 0; i < b.names.size(); i++) {
+            Cuda cuda = cudas.get(0);
+            MemorySegment s = cudas.size() > 1 ? Cuda.scoreMulti(cudas, b, a) : cuda.score(b, a);
+            int[] rowOrder = ranked ? cuda.rank(s, b.names.size(), a) : null;    // (ranking is per batch: use one batch)
+            for (int row = 0; row < b.names.size(); row++) {
+                int i = ranked ? rowOrder[row] : row;
                 long r = i * Cuda.SUMMARY_BYTES;
                 int[] I = new int[14];
                 for (int k = 0; k < 14; k++) I[k] = s.get(JAVA_INT, r + 4L * k);
@@ -467,13 +520,15 @@ public final class Plaac {
     public static void main(String[] argv) throws Throwable {
         String input = "", bgFasta = "", bgFreqFile = "", fgFreqFile = "", plotList = "";
         Params p = new Params();
-        boolean printDocs = false, printParams = true, compatF = false;
-        int device = 0;
+        boolean printDocs = false, printParams = true, compatF = false, ranked = false;
+        int device = 0, gpus = 1;
         long batchResidues = 256L << 20;
         List<String> args = new ArrayList<>();
         for (int i = 0; i < argv.length; i++) {          // options of this host start with "--"
             switch (argv[i]) {
                 case "--device" -> device = Integer.parseInt(argv[++i]);
+                case "--gpus" -> gpus = Integer.parseInt(argv[++i]);       // one ctx + host thread per GPU (summary table)
+                case "--rank" -> ranked = true;                            // rows in the web front end's order
                 case "--batch-mb" -> batchResidues = Long.parseLong(argv[++i]) << 20;
                 case "--compat-F" -> compatF = true;
                 default -> args.add(argv[i]);
@@ -539,7 +594,12 @@ public final class Plaac {
             System.err.println("Plaac: no CUDA device (" + Cuda.lastError(MemorySegment.NULL) + "); there is no CPU scoring path");
             System.exit(2);
         }
+        List<Cuda> cudas = new ArrayList<>();
+        gpus = Math.max(1, Math.min(gpus, Cuda.deviceCount() - device));
         try (Cuda cuda = new Cuda(device, p); Fasta f = new Fasta(input)) {
+            cudas.add(cuda);
+            for (int g = 1; g < gpus; g++) cudas.add(new Cuda(device + g, p));
+            if (ranked) batchResidues = Long.MAX_VALUE;   // one batch, so that the order is that of the whole table
             Batch b = new Batch();
             if (plotList.isEmpty()) {
                 if (printDocs) ColumnDocs.print(out);
@@ -551,9 +611,9 @@ public final class Plaac {
                     if (seq.endsWith("*")) seq = seq.substring(0, seq.length() - 1);
                     if (seq.isEmpty()) continue;
                     b.add(name, "", seq);
-                    if (b.ncodes >= batchResidues || b.names.size() >= (4 << 20)) printSummaryBatch(cuda, b, p, out);
+                    if (b.ncodes >= batchResidues || (!ranked && b.names.size() >= (4 << 20))) printSummaryBatch(cudas, ranked, b, p, out);
                 }
-                printSummaryBatch(cuda, b, p, out);
+                printSummaryBatch(cudas, ranked, b, p, out);
             } else {
                 boolean all = plotList.equals("all");
                 Map<String, String> synonym = new HashMap<>(), order = new HashMap<>();
@@ -585,6 +645,8 @@ public final class Plaac {
                 }
                 printResidueBatch(cuda, b, out);
             }
+        } finally {
+            for (int g = 1; g < cudas.size(); g++) cudas.get(g).close();
         }
     }
 

@@ -41,7 +41,7 @@ const char kAaNames[] = "XACDEFGHIKLMNPQRSTVWY*";  // plaac.java:26
 // java.util.Formatter %.<d>f takes the SHORTEST decimal digits that identify the double (the digits
 // Double.toString prints) and rounds THOSE half-up (sun.misc.FormattedFloatingDecimal.applyPrecision); C's printf
 // rounds the exact binary value half-even.  NaN -> "NaN", infinities -> "Infinity" / "-Infinity".
-std::string jfmt(double x, int d)
+std::string jfmt_exact(double x, int d)
 {
     if (std::isnan(x)) return "NaN";
     if (std::isinf(x)) return x > 0 ? "Infinity" : "-Infinity";
@@ -86,6 +86,43 @@ std::string jfmt(double x, int d)
         s.append(out, out.size() - d, d);
     }
     return s;
+}
+
+// Fast path of the same rule.  Rounding the shortest digits half-up differs from rounding the exact binary value only
+// when the shortest decimal form of x has exactly d+1 fractional digits and ends in 5 (a shorter form rounds to itself;
+// with a longer form no (d+1)-digit boundary can lie between x and its shortest form, or that boundary would BE the
+// shortest form).  Those x have x * 10^d within rounding noise of k + 0.5, so everything else goes through
+// std::to_chars(fixed, d), which rounds the exact value correctly; candidates near k + 0.5 take the exact routine.
+void put_fixed(std::string& out, double x, int d)
+{
+    static const double kPow10[] = {1, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9};
+    const double ax = std::fabs(x);
+    if (d >= 0 && d <= 9 && ax < 1e9) {  // (also false for NaN)
+        const double y = ax * kPow10[d];
+        const double f = y - std::floor(y);
+        // y < 2e12: the half ulp of x and the rounding of the product move y by < 4.4e-4 together, below the margin
+        if (y < 2e12 && std::fabs(f - 0.5) > 1e-3) {
+            char buf[48];
+            auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::fixed, d);
+            out.append(buf, (size_t)(r.ptr - buf));
+            return;
+        }
+    }
+    out += jfmt_exact(x, d);
+}
+
+std::string jfmt(double x, int d)
+{
+    std::string s;
+    put_fixed(s, x, d);
+    return s;
+}
+
+void put_int(std::string& out, long v)
+{
+    char buf[24];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    out.append(buf, (size_t)(r.ptr - buf));
 }
 
 // Double.toString for the alpha echo of plaac.java:505 (plain notation for 1e-3 <= |x| < 1e7, else d.dddE[-]x).
@@ -397,35 +434,49 @@ int die(const Scorers& S, int rc, const char* what)
     return 2;
 }
 
+// One row of the summary table (plaac.java:899-945) appended to `out`.
+void aa_sub_into(std::string& out, const uint8_t* aa, int m, int r1, int r2)
+{
+    if (m <= 0) return;
+    if (r1 < 0) r1 = 0;
+    if (r2 < r1) r2 = r1;
+    if (r1 >= m) r1 = m - 1;
+    if (r2 >= m) r2 = m - 1;
+    for (int i = r1; i <= r2; i++) out.push_back(kAaNames[aa[i]]);
+}
+
+void append_summary_row(const Options& o, std::string_view name, const plaac_summary& s, const uint8_t* aa, std::string& out)
+{
+    const int n = s.prot_len;
+    if (n < 1) return;  // :762
+    const int llrlen = s.llr_end - s.llr_start + 1;
+    const double llr = inf2nan(s.llr);
+    const int prdlen = s.prd_end - s.prd_start + 1;
+    out.append(name);
+    auto I = [&](long v) { out.push_back('\t'), put_int(out, v); };
+    auto F = [&](double v) { out.push_back('\t'), put_fixed(out, v, 3); };
+    I(s.mw_score), I(s.mw_start + 1), I(s.mw_end + 1), I(s.mw_end - s.mw_start + 1);
+    F(llr), I(s.llr_start + 1), I(s.llr_end + 1), I(llrlen), F(llr / (double)llrlen), I(s.vit_maxrun);
+    F(inf2nan(s.core_score)), I(s.core_start + 1), I(s.core_end + 1), I(s.core_end - s.core_start + 1);
+    F(s.prd_score), I(s.prd_start + 1), I(s.prd_end + 1), I(prdlen), I(n), F(s.hmm_all), F(s.hmm_vit);
+    if (prdlen >= o.corelength) {  // :915-931
+        out.push_back('\t'), aa_sub_into(out, aa, n, s.core_start, s.core_end);
+        out.push_back('\t'), aa_sub_into(out, aa, n, s.prd_start, s.prd_start + 14);
+        out.push_back('\t'), aa_sub_into(out, aa, n, s.prd_end - 14, s.prd_end);
+        out.push_back('\t'), aa_sub_into(out, aa, n, s.prd_start, s.prd_end);
+    } else
+        out += "\t-\t-\t-\t-";
+    I(s.fi_numaa), F(s.fi_meanhydro), F(s.fi_meancharge), F(s.fi_meancombo), I(s.fi_maxrun);
+    F(inf2nan(s.papa_combo)), F(s.papa_prop), F(s.papa_fi), F(s.papa_llr), F(s.papa_llr2), I(s.papa_center + 1);
+    out.push_back('\t'), aa_sub_into(out, aa, n, s.papa_center - o.ww2 / 2, s.papa_center + o.ww2 / 2);
+    out.push_back('\n');
+}
+
 void print_summary_row(const Options& o, const std::string& name, const plaac_summary& s, const uint8_t* aa, std::string& line)
 {
-    {
-        const int n = s.prot_len;
-        if (n < 1) return;  // :762
-        const int llrlen = s.llr_end - s.llr_start + 1;
-        const double llr = inf2nan(s.llr);
-        const int prdlen = s.prd_end - s.prd_start + 1;
-        line.clear();
-        line += name;
-        auto I = [&](long v) { line += "\t" + std::to_string(v); };
-        auto F = [&](double v) { line += "\t" + jfmt(v, 3); };
-        I(s.mw_score), I(s.mw_start + 1), I(s.mw_end + 1), I(s.mw_end - s.mw_start + 1);
-        F(llr), I(s.llr_start + 1), I(s.llr_end + 1), I(llrlen), F(llr / (double)llrlen), I(s.vit_maxrun);
-        F(inf2nan(s.core_score)), I(s.core_start + 1), I(s.core_end + 1), I(s.core_end - s.core_start + 1);
-        F(s.prd_score), I(s.prd_start + 1), I(s.prd_end + 1), I(prdlen), I(n), F(s.hmm_all), F(s.hmm_vit);
-        if (prdlen >= o.corelength) {  // :915-931
-            line += "\t" + aa_sub(aa, n, s.core_start, s.core_end);
-            line += "\t" + aa_sub(aa, n, s.prd_start, s.prd_start + 14);
-            line += "\t" + aa_sub(aa, n, s.prd_end - 14, s.prd_end);
-            line += "\t" + aa_sub(aa, n, s.prd_start, s.prd_end);
-        } else
-            line += "\t-\t-\t-\t-";
-        I(s.fi_numaa), F(s.fi_meanhydro), F(s.fi_meancharge), F(s.fi_meancombo), I(s.fi_maxrun);
-        F(inf2nan(s.papa_combo)), F(s.papa_prop), F(s.papa_fi), F(s.papa_llr), F(s.papa_llr2), I(s.papa_center + 1);
-        line += "\t" + aa_sub(aa, n, s.papa_center - o.ww2 / 2, s.papa_center + o.ww2 / 2);
-        line.push_back('\n');
-        std::fwrite(line.data(), 1, line.size(), stdout);
-    }
+    line.clear();
+    append_summary_row(o, name, s, aa, line);
+    std::fwrite(line.data(), 1, line.size(), stdout);
 }
 
 int score_summary_batch(const Options& o, Scorers& S, Batch& B)

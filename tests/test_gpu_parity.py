@@ -347,6 +347,23 @@ def test_throughput_kernel_against_reference_order_anchor_at_scale():
         assert parity.close(rb[f][same_cen], ra[f][same_cen], parity.SCALE[f]).all(), f
 
 
+def test_throughput_kernels_v2_and_v3_give_the_same_bytes():
+    """Variant 3 (default: packed Q/N window counting, roles mixed over the scheduler partitions) is variant 2's
+    arithmetic with fewer instructions: every byte of every record is the same, also with a long core / wide MW window
+    where the packed counting is switched off."""
+    codes, offs = synth.proteome(150_000, seed=78, median=290.0, sigma=0.62)
+    for params in (None, plaac_b200.default_params(core_len=100, ww1=61, ww2=61)):
+        a = plaac_b200.Scorer(params)
+        a.set_kernel_variant(2)
+        b = plaac_b200.Scorer(params)
+        b.set_kernel_variant(3)
+        c = plaac_b200.Scorer(params)
+        ra, rb, rc = a.score(codes, offs), b.score(codes, offs), c.score(codes, offs)
+        for s in (a, b, c):
+            s.close()
+        assert ra.tobytes() == rb.tobytes() == rc.tobytes()
+
+
 # ----------------------------------------------------------------------------- per-residue mode (config 2)
 def _check_residue(got, ref, what=""):
     for k in orc.RESIDUE_U8:

@@ -56,3 +56,48 @@ def test_java_column_docs_and_headers():
     names = open(os.path.join(ROOT, "tests", "golden", "column_names.txt")).read().split()
     hdr = "".join(re.findall(r'"((?:[^"\\]|\\.)*)"', re.search(r"SUMMARY_HEADER = (.*?);", java, flags=re.S).group(1)))
     assert hdr.replace("\\t", "\t").split("\t") == names
+
+
+def _c_prototypes():
+    txt = open(os.path.join(ROOT, "include", "plaac_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int64_t|int|void|const char \*|void \*)\s*(plaac_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        protos[name] = (ret, [] if args in ("", "void") else [a.strip() for a in args.split(",")])
+    return protos
+
+
+def _ffm_layout(ctype):
+    """C parameter / return type -> the java.lang.foreign layout that binds it."""
+    t = ctype.strip()
+    if "*" in t:
+        return "ADDRESS"
+    base = t.split()[0] if t.split()[0] != "const" else t.split()[1]
+    return {"int": "JAVA_INT", "int32_t": "JAVA_INT", "int64_t": "JAVA_LONG", "size_t": "JAVA_LONG", "double": "JAVA_DOUBLE",
+            "void": None}[base]
+
+
+def test_java_downcall_descriptors_match_the_header():
+    """Every fn("plaac_x", FunctionDescriptor...) of the Java host against the prototype in include/plaac_cuda.h:
+    arity and the layout of every argument and of the result.  The multi-GPU, packed, ranking and FASTA entry points
+    must be among them (the Java host bound plaac_score and the allocator only)."""
+    java = open(os.path.join(JAVA, "Plaac.java")).read()
+    protos = _c_prototypes()
+    bound = {}
+    for m in re.finditer(r'fn\("(plaac_\w+)",\s*FunctionDescriptor\.(of|ofVoid)\((.*?)\)\);', java, flags=re.S):
+        layouts = [x.strip() for x in " ".join(m.group(3).split()).split(",") if x.strip()]
+        bound[m.group(1)] = (m.group(2), layouts)
+    for need in ("plaac_score", "plaac_score_multi", "plaac_score_packed", "plaac_score_multi_packed", "plaac_pack_host",
+                 "plaac_packed_words", "plaac_rank", "plaac_score_fasta", "plaac_host_alloc", "plaac_create"):
+        assert need in bound, need
+    for name, (kind, layouts) in bound.items():
+        ret, args = protos[name]
+        want_ret = _ffm_layout(ret)
+        if kind == "ofVoid":
+            assert want_ret is None, name
+            got_args = layouts
+        else:
+            assert layouts[0] == want_ret, (name, layouts[0], want_ret)
+            got_args = layouts[1:]
+        assert got_args == [_ffm_layout(a) for a in args], (name, got_args, args)

@@ -9,12 +9,12 @@ from tests import synth
 pytestmark = pytest.mark.gpu
 
 
-def web_order(rec, web_quirks=False):
-    """The Ruby comparator on full-precision values, made total with the input index."""
+def web_order(rec):
+    """The Ruby comparator on full-precision values, made total with the input index.  The jar prints the LLR of a
+    protein shorter than the core length (-Inf) as NaN (inf2nan, plaac.java:904), and server.rb:225 sorts "NaN" last
+    within a COREscore group -- where -Inf sorts too."""
     core = rec["core_score"].astype(np.float64)
     llr = rec["llr"].astype(np.float64).copy()
-    if web_quirks:
-        llr[np.isinf(llr)] = 0.0  # "-Infinity".to_f == 0.0
     nan_core = np.isnan(core)
     k_core = np.where(nan_core, 0.0, -core)   # "NaN".to_f == 0.0 -> key -0.0; all NaN rows compare equal here
     idx = np.arange(len(rec))
@@ -33,12 +33,11 @@ def scorer():
 def test_rank_matches_web_order(scorer, nprot, seed):
     codes, offs = synth.proteome(nprot, seed, prd_rate=0.2, min_len=16)
     rec = scorer.score(codes, offs)
-    for quirks in (False, True):
-        order, ncore = scorer.rank(rec, web_quirks=quirks)
-        assert ncore == int(np.count_nonzero(~np.isnan(rec["core_score"])))
-        assert sorted(order.tolist()) == list(range(nprot))
-        assert order.tolist() == web_order(rec, quirks).tolist()
-        assert not np.isnan(rec["core_score"][order[:ncore]]).any()
+    order, ncore = scorer.rank(rec)
+    assert ncore == int(np.count_nonzero(~np.isnan(rec["core_score"])))
+    assert sorted(order.tolist()) == list(range(nprot))
+    assert order.tolist() == web_order(rec).tolist()
+    assert not np.isnan(rec["core_score"][order[:ncore]]).any()
 
 
 def test_rank_ties_keep_input_order_and_short_proteins(scorer):
@@ -50,11 +49,9 @@ def test_rank_ties_keep_input_order_and_short_proteins(scorer):
     codes, offs = plaac_b200.pack(seqs)
     rec = scorer.score(codes, offs)
     assert np.isinf(rec["llr"]).sum() == 4
-    for quirks in (False, True):
-        order, ncore = scorer.rank(rec, web_quirks=quirks)
-        assert order.tolist() == web_order(rec, quirks).tolist()
     plain, _ = scorer.rank(rec)
-    assert set(plain[-4:].tolist()) == set(range(450, 454))  # -Inf LLR last unless the web quirk is asked for
+    assert plain.tolist() == web_order(rec).tolist()
+    assert set(plain[-4:].tolist()) == set(range(450, 454))  # -Inf LLR (printed NaN) last, as the web sorts it
 
 
 def test_rank_device_and_gather(scorer):
