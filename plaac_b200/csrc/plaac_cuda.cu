@@ -82,6 +82,10 @@ struct plaac_ctx {
     DeviceTables* d_tabs = nullptr;
     Slot slot[kSlots];
     DevBuf all_summaries;      // records of a whole host-buffer call, kept on the device for the compact ranked output
+    // pageable <-> device copies of the FASTA calls: two pinned staging buffers, filled / emptied by a multi-threaded memcpy
+    void* stage_buf[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_pending[2] = {false, false};
     int nwarps = 0, ring_words = 0;
     size_t smem_bytes = 0;
     int v2_nwr = 0;            // warps per role of the v2 kernel (0 = v2 unavailable for these params)
@@ -838,6 +842,83 @@ void par_memcpy(void* dst, const void* src, size_t n)
     for (auto& t : th) t.join();
 }
 
+// Copies between PAGEABLE host memory and the device.  cudaMemcpy from pageable memory goes through the driver's own
+// staging at a few GB/s; here chunks go through two pinned staging buffers of the ctx, filled / emptied by a
+// multi-threaded memcpy while the other buffer's DMA runs (~20 GB/s).  Pinned caller memory is copied directly.
+constexpr size_t kStageChunk = (size_t)32 << 20;
+
+int stage_ready(plaac_ctx* ctx)
+{
+    for (int b = 0; b < 2; b++) {
+        if (!ctx->stage_buf[b]) {
+            const cudaError_t e = cudaHostAlloc(&ctx->stage_buf[b], kStageChunk, cudaHostAllocDefault);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ctx->stage_buf[b] = nullptr;
+                return fail(ctx, PLAAC_E_NOMEM, "cudaHostAlloc(staging): %s", cudaGetErrorString(e));
+            }
+        }
+        if (!ctx->stage_ev[b]) CU(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+    }
+    return PLAAC_OK;
+}
+
+// Returns when every byte of h_src has been read (the DMAs may still be in flight on st).
+int h2d_any(plaac_ctx* ctx, void* d_dst, const void* h_src, size_t n, cudaStream_t st)
+{
+    if (n == 0) return PLAAC_OK;
+    if (n < ((size_t)1 << 20) || host_is_pinned(h_src)) {
+        CU(ctx, cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, st));
+        return PLAAC_OK;
+    }
+    int rc = stage_ready(ctx);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int i = 0; off < n; i++) {
+        const int b = i & 1;
+        const size_t len = std::min(kStageChunk, n - off);
+        if (ctx->stage_pending[b]) CU(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
+        par_memcpy(ctx->stage_buf[b], (const char*)h_src + off, len);
+        CU(ctx, cudaMemcpyAsync((char*)d_dst + off, ctx->stage_buf[b], len, cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaEventRecord(ctx->stage_ev[b], st));
+        ctx->stage_pending[b] = true;
+        off += len;
+    }
+    return PLAAC_OK;
+}
+
+// Returns when h_dst holds the data (pinned h_dst: when the copy is enqueued on st, as cudaMemcpyAsync).
+int d2h_any(plaac_ctx* ctx, void* h_dst, const void* d_src, size_t n, cudaStream_t st)
+{
+    if (n == 0) return PLAAC_OK;
+    if (n < ((size_t)1 << 20) || host_is_pinned(h_dst)) {
+        CU(ctx, cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, st));
+        return PLAAC_OK;
+    }
+    int rc = stage_ready(ctx);
+    if (rc) return rc;
+    const size_t nchunks = (n + kStageChunk - 1) / kStageChunk;
+    auto enqueue = [&](size_t i) -> int {
+        const int b = (int)(i & 1);
+        const size_t off = i * kStageChunk, len = std::min(kStageChunk, n - off);
+        if (ctx->stage_pending[b]) CU(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
+        CU(ctx, cudaMemcpyAsync(ctx->stage_buf[b], (const char*)d_src + off, len, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaEventRecord(ctx->stage_ev[b], st));
+        ctx->stage_pending[b] = true;
+        return PLAAC_OK;
+    };
+    if ((rc = enqueue(0))) return rc;
+    for (size_t i = 0; i < nchunks; i++) {
+        if (i + 1 < nchunks && (rc = enqueue(i + 1))) return rc;  // (its buffer was emptied one iteration ago)
+        const int b = (int)(i & 1);
+        const size_t off = i * kStageChunk, len = std::min(kStageChunk, n - off);
+        CU(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
+        ctx->stage_pending[b] = false;
+        par_memcpy((char*)h_dst + off, ctx->stage_buf[b], len);
+    }
+    return PLAAC_OK;
+}
+
 int finish_slot(plaac_ctx* ctx, Slot& s)
 {
     CU(ctx, cudaMemcpyAsync(s.h_err, s.errflag.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
@@ -1028,6 +1109,10 @@ void plaac_destroy(plaac_ctx* ctx)
     cudaSetDevice(ctx->device);
     for (int i = 0; i < kSlots; i++) slot_free(ctx->slot[i]);
     release(ctx->all_summaries);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->stage_buf[b]) cudaFreeHost(ctx->stage_buf[b]);
+        if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
+    }
     if (ctx->d_tabs) cudaFree(ctx->d_tabs);
     delete ctx;
 }
@@ -2033,7 +2118,7 @@ try {
     if ((rc = ensure(ctx, s.ing_nlen, sizeof(int32_t) * cap))) return rc;
     if ((rc = ensure(ctx, s.ing_flags, cap + 8))) return rc;
     if ((rc = ensure(ctx, s.ing_hist, sizeof(uint64_t) * PLAAC_NAA))) return rc;
-    if (nbytes > 0) CU(ctx, cudaMemcpyAsync(s.ing_text.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, s.stream));
+    if ((rc = h2d_any(ctx, s.ing_text.p, text, (size_t)nbytes, s.stream))) return rc;
     rc = plaac_ingest_fasta_device(ctx, (const char*)s.ing_text.p, nbytes, (uint8_t*)s.ing_codes.p, (int64_t*)s.ing_offsets.p,
                                    (int64_t*)s.ing_npos.p, (int32_t*)s.ing_nlen.p, (uint8_t*)s.ing_flags.p, max_rec, index,
                                    bg_counts ? (uint64_t*)s.ing_hist.p : nullptr);
@@ -2044,14 +2129,14 @@ try {
         rc = plaac_score_device(ctx, (const uint8_t*)s.ing_codes.p, (const int64_t*)s.ing_offsets.p, (int64_t)nrec, index->nres,
                                 (plaac_summary*)s.summaries.p, nullptr);
         if (rc != PLAAC_OK) return rc;
-        // the index arrays travel back while the scoring kernels run
+        // the index arrays travel back while the scoring kernels run (pageable destinations through the staging buffers)
         cudaStream_t cp = s.aux1;
-        if (codes && index->nres > 0) CU(ctx, cudaMemcpyAsync(codes, s.ing_codes.p, (size_t)index->nres, cudaMemcpyDeviceToHost, cp));
-        CU(ctx, cudaMemcpyAsync(offsets, s.ing_offsets.p, sizeof(int64_t) * (nrec + 1), cudaMemcpyDeviceToHost, cp));
-        if (name_pos) CU(ctx, cudaMemcpyAsync(name_pos, s.ing_npos.p, sizeof(int64_t) * nrec, cudaMemcpyDeviceToHost, cp));
-        if (name_len) CU(ctx, cudaMemcpyAsync(name_len, s.ing_nlen.p, sizeof(int32_t) * nrec, cudaMemcpyDeviceToHost, cp));
-        if (flags) CU(ctx, cudaMemcpyAsync(flags, s.ing_flags.p, nrec, cudaMemcpyDeviceToHost, cp));
-        CU(ctx, cudaMemcpyAsync(summaries, s.summaries.p, sizeof(plaac_summary) * nrec, cudaMemcpyDeviceToHost, s.stream));
+        if (codes && (rc = d2h_any(ctx, codes, s.ing_codes.p, (size_t)index->nres, cp))) return rc;
+        if ((rc = d2h_any(ctx, offsets, s.ing_offsets.p, sizeof(int64_t) * (nrec + 1), cp))) return rc;
+        if (name_pos && (rc = d2h_any(ctx, name_pos, s.ing_npos.p, sizeof(int64_t) * nrec, cp))) return rc;
+        if (name_len && (rc = d2h_any(ctx, name_len, s.ing_nlen.p, sizeof(int32_t) * nrec, cp))) return rc;
+        if (flags && (rc = d2h_any(ctx, flags, s.ing_flags.p, nrec, cp))) return rc;
+        if ((rc = d2h_any(ctx, summaries, s.summaries.p, sizeof(plaac_summary) * nrec, s.stream))) return rc;
         rc = plaac_sync(ctx);
         CU(ctx, cudaStreamSynchronize(cp));
         if (rc != PLAAC_OK) return rc;

@@ -615,9 +615,10 @@ __global__ void __launch_bounds__(NT, 1) k_score_summary_v3(V2Args g)
     // Persistent warps, one role per warp while that role has buckets left (see k_score_summary_v2).  g.mix_roles:
     // 0 = one role per scheduler partition (even warps A, odd warps B), 1 = both roles on every partition.
     const int64_t nb = g.bv.nbuckets;
-    int role = (g.mix_roles & 1) ? ((wid >> 2) & 1) : (wid & 1);
+    // mixed: warps 2k and 2k+1 still take different roles, and the roles alternate along every partition (wid & 3)
+    int role = (g.mix_roles & 1) ? (((wid >> 2) ^ wid) & 1) : (wid & 1);
     const int64_t per_role = (int64_t)(blockDim.x >> 6);
-    const int slot_in_role = (g.mix_roles & 1) ? (((wid >> 3) << 2) | (wid & 3)) : (wid >> 1);
+    const int slot_in_role = wid >> 1;
     int64_t item = (int64_t)blockIdx.x * per_role + slot_in_role;
     const int64_t first_dynamic = (int64_t)gridDim.x * per_role;
     int switched = 0;

@@ -13,20 +13,26 @@
 //                   rows last; web/lib/server.rb:222-229), computed on the GPU (plaac_rank); --rank-core prints only the
 //                   rows with a CORE.  A file that fits one batch (--batch-mb) is ranked as a whole.
 //   --gpu-ingest    parse the FASTA on the GPU as well (plaac_score_fasta): the file goes to the device as raw bytes in
-//                   record-aligned pieces of --batch-mb; summary table only, one GPU
+//                   record-aligned pieces of --batch-mb, pieces round-robin over --gpus, rows formatted on all host
+//                   threads; summary table only.  The default for regular files of at least 1 MB; --host-reader forces
+//                   the reader of this program instead
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -389,7 +395,7 @@ struct Options {
     int gpus = 1, device = 0;
     int64_t batch_res = (int64_t)256 << 20;
     bool compat_F = false;
-    bool gpu_ingest = false;
+    bool gpu_ingest = false, host_reader = false;
     bool rank = false, rank_core_only = false;
 };
 
@@ -506,104 +512,297 @@ int score_summary_batch(const Options& o, Scorers& S, Batch& B)
     return 0;
 }
 
-// --gpu-ingest: the file is cut into pieces that end right before a '>' line; each piece is parsed, encoded and scored
-// on the GPU (plaac_score_fasta).  The jar trims a record name only when the reader found it after an empty line or
-// at the file start (:4362); for the first record of a later piece that context lies in the previous piece, so the
-// host re-derives it from the piece's last lines.
-int score_fasta_gpu(const Options& o, Scorers& S, bool count_only, double* bg_total)
+// ---------------------------------------------------------------------------------------------- file-to-table fast path
+// The whole file is mapped once and cut into pieces that end right before a '>' line; every piece goes to the GPU as
+// raw bytes and is parsed, encoded, counted (background) and scored there (plaac_score_fasta: reader semantics of
+// fastareader :4302-4375, tested against the host reader).  The host only cuts, formats the rows on all its threads
+// into one buffer per piece, and writes.  Pieces go round-robin to the GPUs of --gpus.
+// The jar trims a record name only when the reader found it after an empty line or at the file start (:4362); for the
+// first record of a later piece that context lies in the text before the piece, which is looked at directly.
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    bool good = false, mapped = false;
+    std::string own;
+    explicit MappedFile(const std::string& path)
+    {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd >= 0 && ::fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+            good = true;
+            size = (size_t)st.st_size;
+            if (size > 0) {
+                void* m = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+                if (m == MAP_FAILED)
+                    good = false;
+                else {
+                    data = (const char*)m;
+                    mapped = true;
+                }
+            }
+        } else if (fd >= 0) {  // a pipe, /dev/stdin: read it through
+            good = true;
+            char tmp[1 << 16];
+            ssize_t k;
+            while ((k = ::read(fd, tmp, sizeof(tmp))) > 0) own.append(tmp, (size_t)k);
+            data = own.data();
+            size = own.size();
+        }
+        if (fd >= 0) ::close(fd);
+    }
+    ~MappedFile()
+    {
+        if (mapped) ::munmap((void*)data, size);
+    }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+};
+
+// PLAAC_CLI_TIMING=1: phase times on stderr
+struct Phase {
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + ts.tv_nsec * 1e-9;
+    }
+    static bool on()
+    {
+        static const bool v = getenv("PLAAC_CLI_TIMING") != nullptr;
+        return v;
+    }
+    static void mark(const char* what)
+    {
+        static double t0 = now(), last = t0;
+        if (!on()) return;
+        const double t = now();
+        std::fprintf(stderr, "[plaac %8.3f s  +%7.3f] %s\n", t - t0, t - last, what);
+        last = t;
+    }
+};
+
+int host_threads()
 {
-    std::ifstream in(o.inputfile, std::ios::binary);
-    if (!in.good()) {
-        std::printf("# Couldn't open %s\n", o.inputfile.c_str());
+    cpu_set_t set;
+    int n = 0;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(n, 64));
+}
+
+// f(tid, lo, hi) over [0, n) cut into one contiguous range per thread
+template <class F>
+void parallel_ranges(size_t n, int nthreads, F f)
+{
+    nthreads = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthreads, n));
+    std::vector<std::thread> th;
+    const size_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 1; t < nthreads; t++) {
+        const size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+        if (hi > lo) th.emplace_back([=] { f(t, lo, hi); });
+    }
+    f(0, 0, std::min(n, per));
+    for (auto& t : th) t.join();
+}
+
+// Is the record that starts at text[pos] (a '>' at a line start) found by nextfasta in the jar, i.e. does the latest
+// header-or-empty line before it open a record?  Then its name is printed untrimmed.
+bool opened_by_previous_record(const char* text, size_t pos)
+{
+    size_t e = pos;  // a line start: the text before it ends with a line terminator
+    while (e > 0) {
+        size_t le = e;  // end of the previous line without its terminator (\n, \r or \r\n as BufferedReader.readLine sees them)
+        if (text[le - 1] == '\n') {
+            le--;
+            if (le > 0 && text[le - 1] == '\r') le--;
+        } else if (text[le - 1] == '\r')
+            le--;
+        size_t ls = le;
+        while (ls > 0 && text[ls - 1] != '\n' && text[ls - 1] != '\r') ls--;
+        if (ls == le) return false;        // an empty line: the reader is between records
+        if (text[ls] == '>') return true;  // a header line: the record it opened is still open
+        e = ls;
+    }
+    return false;  // file start: hasmorefastas finds the first record (trimmed)
+}
+
+struct PieceBuffers {  // reused from piece to piece (never zero-filled)
+    size_t cap_rec = 0, cap_bytes = 0;
+    std::unique_ptr<plaac_summary[]> sum;
+    std::unique_ptr<uint8_t[]> codes, flags;
+    std::unique_ptr<int64_t[]> offsets, npos;
+    std::unique_ptr<int32_t[]> nlen, order;
+    void reserve(size_t nrec, size_t nbytes)
+    {
+        if (nrec > cap_rec) {
+            cap_rec = nrec + nrec / 8 + 16;
+            sum.reset(new plaac_summary[cap_rec]);
+            flags.reset(new uint8_t[cap_rec + 16]);
+            offsets.reset(new int64_t[cap_rec + 1]);
+            npos.reset(new int64_t[cap_rec]);
+            nlen.reset(new int32_t[cap_rec]);
+            order.reset(new int32_t[cap_rec]);
+        }
+        if (nbytes > cap_bytes) {
+            cap_bytes = nbytes + nbytes / 8 + 64;
+            codes.reset(new uint8_t[cap_bytes]);
+        }
+    }
+};
+
+struct PieceResult {
+    std::vector<std::string> parts;  // the rows, one string per formatting thread, in order
+    double bg[PLAAC_NAA] = {0};
+    int rc = 0;
+    int64_t nrec = 0, nshow = 0;
+    bool ranked = false;
+};
+
+// GPU stage of one piece [lo, hi) of the text on ctx: parse + score (+ rank) on the GPU; results in B.
+void piece_gpu(const Options& o, plaac_ctx* ctx, const char* text, size_t lo, size_t hi, bool count_only, int nthreads,
+               PieceBuffers& B, PieceResult& R)
+{
+    const size_t nbytes = hi - lo;
+    // upper bound of the record count: '>' characters (counted on all threads; memchr runs at memory speed)
+    std::vector<size_t> part((size_t)nthreads, 0);
+    parallel_ranges(nbytes, nthreads, [&](int t, size_t a, size_t b) {
+        size_t c = 0;
+        const char* p = text + lo + a;
+        const char* e = text + lo + b;
+        while (p < e && (p = (const char*)memchr(p, '>', (size_t)(e - p)))) c++, p++;
+        part[(size_t)t] = c;
+    });
+    size_t maxrec = 1;
+    for (size_t c : part) maxrec += c;
+    B.reserve(maxrec, nbytes + 16);
+    memset(B.flags.get(), 0, maxrec + 8);
+    plaac_fasta_index idx;
+    R.rc = plaac_score_fasta(ctx, text + lo, (int64_t)nbytes, (int64_t)maxrec, B.sum.get(), B.codes.get(), B.offsets.get(),
+                             B.npos.get(), B.nlen.get(), B.flags.get(), &idx, R.bg);
+    Phase::mark("piece: plaac_score_fasta");
+    if (R.rc != PLAAC_OK || count_only) return;
+    R.nrec = R.nshow = idx.nrec;
+    if (o.rank && idx.nrec > 0) {
+        int64_t ncore = 0;
+        R.rc = plaac_rank(ctx, B.sum.get(), idx.nrec, 0, B.order.get(), &ncore);
+        if (R.rc != PLAAC_OK) return;
+        R.ranked = true;
+        if (o.rank_core_only) R.nshow = ncore;
+    }
+}
+
+// Host stage: the rows of the piece, formatted on `nthreads` threads.
+void piece_format(const Options& o, const char* text, size_t lo, int nthreads, const PieceBuffers& B, PieceResult& R)
+{
+    if (R.rc != PLAAC_OK || R.nshow <= 0) return;
+    const int32_t* order = R.ranked ? B.order.get() : nullptr;
+    const bool first_untrimmed = lo > 0 && opened_by_previous_record(text, lo);
+    R.parts.assign((size_t)nthreads, std::string());
+    parallel_ranges((size_t)R.nshow, nthreads, [&](int t, size_t a, size_t b) {
+        std::string& s = R.parts[(size_t)t];
+        s.reserve((b - a) * 320);
+        for (size_t k = a; k < b; k++) {
+            const size_t r = order ? (size_t)order[k] : k;
+            std::string_view name(text + lo + (size_t)B.npos[r], (size_t)B.nlen[r]);
+            bool trim = (B.flags[r] & 1) != 0;
+            if (r == 0 && first_untrimmed) trim = false;  // found by nextfasta in the jar: untrimmed
+            if (trim)
+                while (!name.empty() && (unsigned char)name.back() <= ' ') name.remove_suffix(1);
+            append_summary_row(o, name, B.sum[r], B.codes.get() + B.offsets[r], s);
+        }
+    });
+    Phase::mark("piece: rows formatted");
+}
+
+// Piece boundaries: every piece ends right before a '>' that starts a line (or at the end of the text).
+std::vector<size_t> cut_pieces(const char* text, size_t size, size_t piece)
+{
+    std::vector<size_t> cuts{0};
+    size_t start = 0;
+    while (start < size) {
+        size_t want = start + piece;
+        if (want >= size) {
+            cuts.push_back(size);
+            break;
+        }
+        // last record start in (start, want]; if there is none, the first one after want
+        size_t cut = 0;
+        for (size_t k = want; k > start + 1; k--)
+            if (text[k] == '>' && (text[k - 1] == '\n' || text[k - 1] == '\r')) {
+                cut = k;
+                break;
+            }
+        if (cut == 0) {
+            cut = size;
+            const char* p = text + want;
+            const char* e = text + size;
+            while (p < e && (p = (const char*)memchr(p, '>', (size_t)(e - p)))) {
+                if (p[-1] == '\n' || p[-1] == '\r') {
+                    cut = (size_t)(p - text);
+                    break;
+                }
+                p++;
+            }
+        }
+        cuts.push_back(cut);
+        start = cut;
+    }
+    if (cuts.size() == 1) cuts.push_back(size);
+    return cuts;
+}
+
+// Runs all pieces.  count_only: background counts only (bg_total).  sink(rows of one formatting thread) is called in
+// output order from the calling thread.  One GPU: the GPU stage of piece k+1 runs on a second host thread while this
+// thread formats and hands over piece k.  Several GPUs: piece k on ctx k % G, one host thread per ctx.
+template <class Sink>
+int score_fasta_gpu(const Options& o, Scorers& S, const MappedFile& F, bool count_only, double* bg_total, Sink sink)
+{
+    const std::vector<size_t> cuts = cut_pieces(F.data, F.size, (size_t)std::max<int64_t>(o.batch_res, 1 << 20));
+    const size_t npieces = cuts.size() - 1;
+    const int G = (int)S.ctx.size();
+    const int nthreads = std::max(1, host_threads() / std::max(1, std::min<int>(G, (int)npieces)));
+    auto hand_over = [&](PieceResult& R) -> int {
+        if (R.rc != PLAAC_OK) return die(S, R.rc, "plaac_score_fasta");
+        if (bg_total)
+            for (int i = 0; i < PLAAC_NAA; i++) bg_total[i] += R.bg[i];
+        if (!count_only)
+            for (auto& p : R.parts) sink(p);
+        return 0;
+    };
+    if (G <= 1 || npieces <= 1) {
+        PieceBuffers B[2];
+        PieceResult R[2];
+        piece_gpu(o, S.ctx[0], F.data, cuts[0], cuts[1], count_only, nthreads, B[0], R[0]);
+        for (size_t k = 0; k < npieces; k++) {
+            const int cur = (int)(k & 1), nxt = cur ^ 1;
+            std::thread ahead;
+            if (k + 1 < npieces && R[cur].rc == PLAAC_OK) {
+                R[nxt] = PieceResult();
+                ahead = std::thread([&, k, nxt] {
+                    piece_gpu(o, S.ctx[0], F.data, cuts[k + 1], cuts[k + 2], count_only, nthreads, B[nxt], R[nxt]);
+                });
+            }
+            if (!count_only) piece_format(o, F.data, cuts[k], nthreads, B[cur], R[cur]);
+            const int rc = hand_over(R[cur]);
+            if (ahead.joinable()) ahead.join();
+            if (rc) return rc;
+        }
         return 0;
     }
-    const size_t piece = (size_t)std::max<int64_t>(o.batch_res, 1 << 20);
-    std::string buf, carry;
-    std::vector<plaac_summary> sum;
-    std::vector<uint8_t> codes, flags;
-    std::vector<int64_t> offsets, npos;
-    std::vector<int32_t> nlen;
-    std::string line, name;
-    bool prev_open = false;  // the previous piece ended inside a record (its last marker line was a header)
-    bool first = true;
-    while (true) {
-        buf = carry;
-        carry.clear();
-        const size_t old = buf.size();
-        buf.resize(old + piece);
-        in.read(&buf[old], (std::streamsize)piece);
-        buf.resize(old + (size_t)in.gcount());
-        const bool eof = in.gcount() < (std::streamsize)piece;
-        if (buf.empty()) break;
-        size_t cut = buf.size();
-        if (!eof) {
-            // last line start that begins with '>' (not at 0): cut there
-            size_t k = buf.size();
-            cut = 0;
-            while (k > 1) {
-                k--;
-                if (buf[k] == '>' && (buf[k - 1] == '\n' || buf[k - 1] == '\r')) {
-                    cut = k;
-                    break;
-                }
+    std::vector<PieceResult> res(npieces);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+        th.emplace_back([&, g] {
+            PieceBuffers B;
+            for (size_t k = (size_t)g; k < npieces; k += (size_t)G) {
+                piece_gpu(o, S.ctx[(size_t)g], F.data, cuts[k], cuts[k + 1], count_only, nthreads, B, res[k]);
+                if (!count_only) piece_format(o, F.data, cuts[k], nthreads, B, res[k]);
             }
-            if (cut == 0) {  // no record boundary inside: keep reading into the same piece
-                carry.swap(buf);
-                continue;
-            }
-            carry.assign(buf, cut, std::string::npos);
-            buf.resize(cut);
-        }
-        size_t maxrec = 1;
-        for (char c : buf) maxrec += c == '>';
-        sum.resize(maxrec);
-        codes.resize(buf.size() + 16);
-        offsets.resize(maxrec + 1);
-        npos.resize(maxrec);
-        nlen.resize(maxrec);
-        flags.assign(maxrec + 8, 0);
-        plaac_fasta_index idx;
-        double bg[PLAAC_NAA];
-        const int rc = plaac_score_fasta(S.ctx[0], buf.data(), (int64_t)buf.size(), (int64_t)maxrec, sum.data(), codes.data(),
-                                         offsets.data(), npos.data(), nlen.data(), flags.data(), &idx, bg);
-        if (rc != PLAAC_OK) return die(S, rc, "plaac_score_fasta");
-        if (bg_total)
-            for (int i = 0; i < PLAAC_NAA; i++) bg_total[i] += bg[i];
-        if (!count_only) {
-            for (int64_t r = 0; r < idx.nrec; r++) {
-                name.assign(buf, (size_t)npos[(size_t)r], (size_t)nlen[(size_t)r]);
-                bool trim = (flags[(size_t)r] & 1) != 0;
-                if (r == 0 && !first && prev_open) trim = false;  // found by nextfasta in the jar: untrimmed
-                if (trim)
-                    while (!name.empty() && (unsigned char)name.back() <= ' ') name.pop_back();
-                print_summary_row(o, name, sum[(size_t)r], codes.data() + offsets[(size_t)r], line);
-            }
-        }
-        // state at the end of this piece: walk back over its last lines to the latest header-or-empty line
-        {
-            prev_open = false;
-            size_t e = buf.size();
-            while (e > 0) {
-                size_t ls = e;  // start of the line that ends at e
-                if (ls > 0 && buf[ls - 1] == '\n') ls--;
-                if (ls > 0 && buf[ls - 1] == '\r') ls--;
-                const size_t line_end = ls;
-                while (ls > 0 && buf[ls - 1] != '\n' && buf[ls - 1] != '\r') ls--;
-                if (line_end == ls) {  // empty line
-                    if (e == buf.size() && line_end == e) {  // no terminator at all: e is just the end of the buffer
-                        if (ls == 0) break;
-                    } else
-                        break;
-                } else if (buf[ls] == '>') {
-                    prev_open = true;
-                    break;
-                }
-                e = ls;
-            }
-            if (idx.nrec == 0 && !first) prev_open = prev_open;  // a piece without records cannot open one
-        }
-        first = false;
-        if (eof) break;
+        });
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < npieces; k++) {
+        const int rc = hand_over(res[k]);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -683,7 +882,9 @@ void usage()
     std::puts("  -d               print documentation of the output columns");
     std::puts("  -s               skip the run-time parameter block");
     std::puts("  -p list.txt|all  per-residue table for the listed proteins (one name per line) or for all");
-    std::puts("  --gpus N, --device D, --batch-mb M, --compat-F, --rank, --rank-core, --gpu-ingest   (this host only)");
+    std::puts("  --gpus N, --device D, --batch-mb M, --rank, --rank-core, --gpu-ingest, --host-reader   (this host only)");
+    std::puts("  --compat-F       -F reads the -B file, as plaac.jar does (plaac.java:388); without it -F reads its own file,");
+    std::puts("                   so the parameter block and every score differ from the jar's for the same command line");
 }
 
 }  // namespace
@@ -715,6 +916,8 @@ int main(int argc, char** argv)
             o.rank = o.rank_core_only = true;
         else if (a == "--gpu-ingest")
             o.gpu_ingest = true;
+        else if (a == "--host-reader")
+            o.host_reader = true;
         else if (a == "--format-check") {
             // test hook: lines "decimals value" on stdin -> the Java-formatted value on stdout
             int d;
@@ -753,20 +956,32 @@ int main(int argc, char** argv)
     }
     o.ww3 = o.ww2;  // :355
 
+    // The file-to-table fast path (GPU ingest) is the default for regular input files of at least 1 MB in summary mode;
+    // --host-reader forces the reader of this program, --gpu-ingest the GPU one.
+    bool fast = false;
+    if (o.plotlist.empty() && !o.inputfile.empty() && !o.host_reader) {
+        struct stat st;
+        fast = o.gpu_ingest || (::stat(o.inputfile.c_str(), &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= (1 << 20));
+    }
+    o.gpu_ingest = fast;
+    const bool input_bg = o.bgfreqfile.empty() && o.bgfile.empty() && !o.inputfile.empty();  // :382-384
+
     // background counts :374-384
     double bgf[PLAAC_NAA] = {0};
     if (!o.bgfreqfile.empty())
         read_aa_params(o.bgfreqfile, bgf);
     else if (!o.bgfile.empty())
         bg_counts_from_fasta(o.bgfile, bgf);
-    else if (!o.inputfile.empty())
-        bg_counts_from_fasta(o.inputfile, bgf);
+    else if (!o.inputfile.empty() && !fast)
+        bg_counts_from_fasta(o.inputfile, bgf);  // (fast path: counted on the GPU, below)
     double fgfile[PLAAC_NAA];
     const double* fg = nullptr;
     if (!o.fgfreqfile.empty()) {
         // plaac.java:388 reads bgfreqfile here (a bug); --compat-F reproduces it
         read_aa_params(o.compat_F ? o.bgfreqfile : o.fgfreqfile, fgfile);
         fg = fgfile;
+        if (!o.compat_F)
+            std::puts("# note: -F read from the -F file; plaac.jar reads the -B file here (plaac.java:388), --compat-F does the same");
     }
     if ((!o.bgfile.empty() || !o.bgfreqfile.empty()) && o.inputfile.empty()) {  // :393-403
         print_aa_params(bgf);
@@ -783,24 +998,36 @@ int main(int argc, char** argv)
 
     plaac_params P;
     double info[4][PLAAC_NAA];
-    int rc = plaac_params_init(&P, o.alpha, bgf, fg, o.corelength, o.ww1, o.ww2, o.ww3, o.adjustprolines ? 1 : 0, &info[0][0]);
-    if (rc != PLAAC_OK) {
-        std::fprintf(stderr, "plaac: plaac_params_init failed (%d)\n", rc);
-        return 2;
-    }
-    if (o.printparameters) {  // :503-514
-        std::puts("############################ parameters at run-time ####################################");
-        std::printf("## alpha=%s; corelength=%d; ww1=%d; ww2=%d; ww3=%d; adjustprolines=%s;\n", jdouble(o.alpha).c_str(),
-                    o.corelength, o.ww1, o.ww2, o.ww3, o.adjustprolines ? "true" : "false");
-        std::printf("## fg_used: {%s}\n", aaparams2string(info[0]).c_str());
-        std::printf("## bg_scer: {%s}\n", aaparams2string(info[1]).c_str());
-        std::printf("## bg_input: {%s}\n", aaparams2string(info[2]).c_str());
-        std::printf("## bg_used: {%s}\n", aaparams2string(info[3]).c_str());
-        std::printf("## plaac_llr: {%s}\n", aaparams2string(P.llr).c_str());
-        std::printf("## papa_lods: {%s}\n", aaparams2string(P.papa_lod).c_str());
-        std::puts("#######################################################################################");
-    }
-    if (!o.hmmdotfile.empty()) std::puts("# -h (GraphViz export of the HMM) is not part of this host; ignored");
+    int rc = 0;
+    auto make_params = [&]() -> int {
+        rc = plaac_params_init(&P, o.alpha, bgf, fg, o.corelength, o.ww1, o.ww2, o.ww3, o.adjustprolines ? 1 : 0, &info[0][0]);
+        if (rc != PLAAC_OK) std::fprintf(stderr, "plaac: plaac_params_init failed (%d)\n", rc);
+        return rc;
+    };
+    auto print_preamble = [&]() {
+        if (o.printparameters) {  // :503-514
+            std::puts("############################ parameters at run-time ####################################");
+            std::printf("## alpha=%s; corelength=%d; ww1=%d; ww2=%d; ww3=%d; adjustprolines=%s;\n", jdouble(o.alpha).c_str(),
+                        o.corelength, o.ww1, o.ww2, o.ww3, o.adjustprolines ? "true" : "false");
+            std::printf("## fg_used: {%s}\n", aaparams2string(info[0]).c_str());
+            std::printf("## bg_scer: {%s}\n", aaparams2string(info[1]).c_str());
+            std::printf("## bg_input: {%s}\n", aaparams2string(info[2]).c_str());
+            std::printf("## bg_used: {%s}\n", aaparams2string(info[3]).c_str());
+            std::printf("## plaac_llr: {%s}\n", aaparams2string(P.llr).c_str());
+            std::printf("## papa_lods: {%s}\n", aaparams2string(P.papa_lod).c_str());
+            std::puts("#######################################################################################");
+        }
+        if (!o.hmmdotfile.empty()) std::puts("# -h (GraphViz export of the HMM) is not part of this host; ignored");
+    };
+    auto print_table_head = [&]() {
+        if (o.printheaders) {  // :661-711
+            std::puts("############################ Description of output columns ############################");
+            for (const char* d : kColumnDocs) std::printf("## %s\n", d);
+            std::puts("#######################################################################################");
+        }
+        std::puts(kSummaryHeader);
+        std::fflush(stdout);
+    };
 
     Scorers S;
     auto open_devices = [&]() -> int {
@@ -820,20 +1047,69 @@ int main(int argc, char** argv)
             }
             S.ctx.push_back(c);
         }
+        Phase::mark("devices open");
         return 0;
     };
+    auto close_devices = [&]() {
+        for (auto c : S.ctx) plaac_destroy(c);
+        S.ctx.clear();
+    };
+
+    if (fast) {
+        Phase::mark("start");
+        MappedFile F(o.inputfile);
+        Phase::mark("file mapped");
+        if (!F.good) {
+            // the jar prints the message once per attempt to open the file (background pass, scoring pass)
+            if (input_bg) std::printf("# Couldn't open %s\n", o.inputfile.c_str());
+            if (make_params()) return 2;
+            print_preamble();
+            print_table_head();
+            std::printf("# Couldn't open %s\n", o.inputfile.c_str());
+            return 0;
+        }
+        auto to_stdout = [](const std::string& rows) { std::fwrite(rows.data(), 1, rows.size(), stdout); };
+        if (input_bg && o.alpha < 1) {
+            // the tables depend on the input's own composition: count first (GPU, provisional tables), then score
+            if (make_params()) return 2;
+            if ((rc = open_devices())) return rc;
+            if ((rc = score_fasta_gpu(o, S, F, true, bgf, to_stdout))) return rc;
+            close_devices();
+        }
+        if (input_bg && !(o.alpha < 1)) {
+            // alpha = 1: the input's composition only feeds the "## bg_input" line of the preamble, which is printed before
+            // the table.  One pass: score with the (composition-independent) tables, hold the rows, print the preamble
+            // with the counts that pass produced, then the rows.
+            if (make_params()) return 2;
+            if ((rc = open_devices())) return rc;
+            std::vector<std::string> held;
+            rc = score_fasta_gpu(o, S, F, false, bgf, [&](std::string& rows) { held.push_back(std::move(rows)); });
+            if (rc) return rc;
+            if (make_params()) return 2;  // same tables, bg_input filled in
+            print_preamble();
+            print_table_head();
+            for (const auto& h : held) std::fwrite(h.data(), 1, h.size(), stdout);
+            std::fflush(stdout);
+            Phase::mark("rows written");
+            return 0;
+        }
+        if (make_params()) return 2;
+        print_preamble();
+        print_table_head();
+        if ((rc = open_devices())) return rc;
+        rc = score_fasta_gpu(o, S, F, false, nullptr, to_stdout);
+        std::fflush(stdout);
+        Phase::mark("rows written");
+        return rc;
+    }
+
+    if (make_params()) return 2;
+    print_preamble();
     Batch B;
     std::string seq, name;
     if (o.plotlist.empty()) {
-        if (o.printheaders) {  // :661-711
-            std::puts("############################ Description of output columns ############################");
-            for (const char* d : kColumnDocs) std::printf("## %s\n", d);
-            std::puts("#######################################################################################");
-        }
-        std::puts(kSummaryHeader);
-        std::fflush(stdout);
+        print_table_head();
         if ((rc = open_devices())) return rc;
-        if (o.gpu_ingest) return score_fasta_gpu(o, S, false, nullptr);
         FastaReader fr(o.inputfile);
         while (fr.hasmore()) {
             name = fr.name();
