@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-sample-proteins", type=int, default=0, help="0 = sized automatically")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi-ctx", action="store_true",
+                    help="skip the single-process multi-GPU side measurement (plaac_score_multi_packed, N > 1 only)")
     ap.add_argument("--no-per-residue", action="store_true", help="skip the config-2 (per-residue mode) side measurement")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the config-5 (long sequences) and ranking side measurements")
@@ -389,6 +391,11 @@ def main():
     elif e2e_skip is not None:
         e2e = {"value": None, "unit": UNIT, "skipped": e2e_skip}
 
+    # ---- the single-process multi-GPU path (rank 0 drives all N GPUs; the other ranks idle at a host barrier) --------
+    multi_ctx = None
+    if world > 1 and not args.no_e2e and not args.no_multi_ctx:
+        multi_ctx = measure_multi_ctx(args, L, dev, rank, world, nprot)
+
     # ---- config 2 side measurement: per-residue mode (rank 0, N=1 only) -----------------------------
     per_res = None
     if rank == 0 and world == 1 and not args.no_per_residue:
@@ -429,7 +436,7 @@ def main():
             "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "residues_per_gpu": ntotal, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "per_residue_mode": per_res,
+            "roofline": roofline, "e2e": e2e, "multi_ctx_e2e": multi_ctx, "cpu_baseline": cpu, "per_residue_mode": per_res,
             "extras": extras,
             "timing": "CUDA events on the library stream around K steps, max over ranks; wall %.3f s" % wall,
         }
@@ -553,6 +560,93 @@ def measure_e2e(args, scorer, dev, world, barrier, codes, offsets, summaries, np
     for b in (pb_codes, pb_offsets, pb_sum, pb_words, pb_len, pb_hrec, pb_hidx):
         b.close()
     return head
+
+
+def measure_multi_ctx(args, L, dev, rank, world, nprot):
+    """The product's multi-GPU path for a host that drives several GPUs from ONE process (a Java or C++ host): rank 0
+    holds the shards of all `world` ranks as one batch in page-locked memory (radix-22 words + int32 lengths) and calls
+    plaac_score_multi_packed with one ctx per GPU (one host thread each, residue-balanced shards, ranked CORE hits merged on
+    the host).  The other ranks wait at a gloo (host) barrier so that their GPUs are idle.  Wall clock around K calls."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import plaac_b200
+
+    host_group = dist.new_group(backend="gloo")
+    dist.barrier(group=host_group)
+    out = None
+    if rank == 0:
+        steps = max(2, min(args.steps, 5))
+        bg = np.array(BG_SCER, dtype=np.float64)
+        prd = np.array(PRD_28, dtype=np.float64)
+        ntot_prot = nprot * world
+        pb_len = plaac_b200.PinnedBuffer(ntot_prot, np.int32)
+        # shard sizes first (lengths are cheap to generate), then one pinned word buffer for the whole batch
+        shard_res = []
+        for r in range(world):
+            lens = torch.empty(nprot, dtype=torch.int64, device=dev)
+            L.plaac_bench_synth_lengths(None, SEED, r * nprot, nprot, LN_MEDIAN, SIGMA, MIN_LEN, MAX_LEN, lens.data_ptr())
+            pb_len.array[r * nprot:(r + 1) * nprot] = lens.to(torch.int32).cpu().numpy()
+            shard_res.append(int(lens.sum().item()))
+            del lens
+        nres = int(sum(shard_res))
+        nwords = int(L.plaac_packed_words(nres))
+        pb_words = plaac_b200.PinnedBuffer(nwords, np.uint32)
+        pb_tmp = plaac_b200.PinnedBuffer(max(shard_res), np.uint8)
+        pos = 0
+        t0 = time.perf_counter()
+        for r in range(world):
+            lens = torch.from_numpy(pb_len.array[r * nprot:(r + 1) * nprot].astype(np.int64)).to(dev)
+            offs = torch.zeros(nprot + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lens, 0, out=offs[1:])
+            codes = torch.empty(shard_res[r] + 64, dtype=torch.uint8, device=dev)
+            L.plaac_bench_synth_residues(None, SEED, r * nprot, nprot, offs.data_ptr(), bg.ctypes.data, prd.ctypes.data,
+                                         PRD_RATE, X_RATE, codes.data_ptr())
+            torch.from_numpy(pb_tmp.array[:shard_res[r]]).copy_(codes[:shard_res[r]])
+            torch.cuda.synchronize()
+            pos = plaac_b200.pack_append(pb_tmp.array[:shard_res[r]], pb_words.array, pos)
+            del lens, offs, codes
+        prep_s = time.perf_counter() - t0
+        pb_tmp.close()
+        cap = ntot_prot // 8 + 1024
+        pb_hrec = plaac_b200.PinnedBuffer(cap * 160, np.uint8)
+        pb_hidx = plaac_b200.PinnedBuffer(cap, np.int32)
+        hits = plaac_b200.Hits(mode=plaac_b200.HITS_CORE, rank_flags=0, capacity=cap, records=pb_hrec.ptr, index=pb_hidx.ptr,
+                               count=0, n_core=0)
+        ms = plaac_b200.MultiScorer(devices=list(range(world)))
+        handles = (C.c_void_p * world)(*[s._h for s in ms.scorers])
+
+        def run():
+            rc = L.plaac_score_multi_packed(handles, world, pb_words.ptr, pb_len.ptr, ntot_prot, nres, None, None, C.byref(hits))
+            if rc != 0:
+                raise SystemExit("plaac_score_multi_packed failed: %d %s" % (rc, [L.plaac_last_error(s._h) for s in ms.scorers]))
+
+        for _ in range(2):
+            run()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run()
+        dt = time.perf_counter() - t0
+        n = int(hits.count)
+        rec = np.frombuffer(pb_hrec.array[:n * 160].tobytes(), dtype=plaac_b200.SUMMARY_DTYPE)
+        cs, ll, idx = rec["core_score"], rec["llr"], pb_hidx.array[:n].astype(np.int64)
+        ordered = bool(np.all((cs[:-1] > cs[1:]) | ((cs[:-1] == cs[1:]) & ((ll[:-1] > ll[1:]) | ((ll[:-1] == ll[1:]) & (idx[:-1] < idx[1:]))))))
+        out = {"value": nres * steps / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "steps": steps, "gpus": world,
+               "call": "plaac_score_multi_packed(ctxs[0..N), words, lengths, hits=PLAAC_HITS_CORE), one process",
+               "proteins": ntot_prot, "residues": nres,
+               "h2d_bytes_per_step": 4 * nwords + 4 * ntot_prot, "d2h_bytes_per_step": 164 * n,
+               "hits": {"n_core": int(hits.n_core), "returned": n, "order_verified": ordered,
+                        "complete": n == int(hits.n_core)},
+               "host_prep_s": prep_s,
+               "note": "rank 0 alone, every other rank idle at a host barrier; page-locked buffers; wall clock around the calls"}
+        ms.close()
+        for b in (pb_len, pb_words, pb_hrec, pb_hidx):
+            b.close()
+    dist.barrier(group=host_group)
+    return out
 
 
 def measure_per_residue(L, scorer, dev, hbm_peak):

@@ -168,6 +168,9 @@ int64_t plaac_packed_words(int64_t nres);
 /* codes (0..21, one byte each; larger bytes are packed as X and the call returns PLAAC_E_INVALID after packing
  * everything) -> words.  nthreads <= 0: all host threads.  Pure host code (no GPU, no ctx). */
 int plaac_pack_host(const uint8_t *codes, int64_t nres, uint32_t *words, int nthreads);
+/* The same for a batch that is built piece by piece: packs codes[0 .. nres) at residue positions [pos, pos + nres) of
+ * the batch.  The word that holds residue pos keeps its digits below pos % 7; pieces must be appended in order. */
+int plaac_pack_append_host(const uint8_t *codes, int64_t nres, uint32_t *words, int64_t pos, int nthreads);
 /* FASTA letters -> words in one pass: aatoint (plaac.java:1508-1534) fused with the packing. */
 int plaac_pack_chars_host(const char *chars, int64_t nres, uint32_t *words, int nthreads);
 /* words -> codes for residues [first, first + count) of the packed batch (the host needs residues again for the

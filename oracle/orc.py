@@ -99,6 +99,8 @@ def lib():
                                         C.POINTER(ResidueOut), C.c_int]
         L.orc_java_fmt.restype = C.c_int
         L.orc_java_fmt.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int]
+        L.orc_fi_min_margin.restype = C.c_double
+        L.orc_fi_min_margin.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
         L.orc_max_threads.restype = C.c_int
         L.orc_slidingaverage.restype = None
         L.orc_slidingaverage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -159,6 +161,15 @@ def score_batch(P: Params, codes: np.ndarray, offsets: np.ndarray, full_jar_work
     lib().orc_score_batch(C.byref(P), codes.ctypes.data, offsets.ctypes.data, nprot, out.ctypes.data,
                           int(full_jar_work), int(nthreads))
     return out
+
+
+def fi_min_margin(P: Params, codes: np.ndarray, offsets: np.ndarray, nthreads=1):
+    """min |fi| * taps over every FoldIndex value the run scan tests (test instrumentation) -> (margin, protein index)."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    at = C.c_int64(-1)
+    m = lib().orc_fi_min_margin(C.byref(P), codes.ctypes.data, offsets.ctypes.data, len(offsets) - 1, int(nthreads), C.byref(at))
+    return float(m), int(at.value)
 
 
 def residue_batch(P: Params, codes: np.ndarray, offsets: np.ndarray, nthreads=1) -> dict:

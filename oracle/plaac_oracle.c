@@ -663,6 +663,56 @@ void orc_residue_batch(const orc_params *P, const uint8_t *codes, const int64_t 
         orc_residue_protein(P, codes + offsets[i], (int)(offsets[i + 1] - offsets[i]), out, offsets[i]);
 }
 
+/* Test instrumentation (no reference counterpart): how close does any FoldIndex value that the run scan of
+ * plaac.java:5010-5059 looks at come to its threshold 0?  Returns min over proteins and scanned positions i of
+ * |fi[i]| * (taps in the window of i), the quantity whose sign the CUDA kernels test on running sums (DESIGN.md,
+ * "tie classes"); *at receives the protein index of the minimum. */
+double orc_fi_min_margin(const orc_params *P, const uint8_t *codes, const int64_t *offsets, int64_t nprot, int nthreads,
+                         int64_t *at)
+{
+    double best = INFINITY;
+    int64_t best_at = -1;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+    {
+        double mine = INFINITY;
+        int64_t mine_at = -1;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 64)
+#endif
+        for (int64_t p = 0; p < nprot; p++) {
+            const int n = (int)(offsets[p + 1] - offsets[p]);
+            if (n < 1) continue;
+            disorderreport d;
+            dr_compute(P, codes + offsets[p], n, &d);
+            int w = P->ww1 / 2;
+            if (w > n - 1) w = n - 1;
+            int halfw = (P->ww1 - 1) / 2;
+            if (halfw > n / 2) halfw = n / 2;
+            for (int i = halfw; i < n - halfw; i++) {
+                const int lo = i - w < 0 ? 0 : i - w, hi = i + w > n - 1 ? n - 1 : i + w;
+                const double m = fabs(d.fi[i]) * (double)(hi - lo + 1);
+                if (m < mine) {
+                    mine = m;
+                    mine_at = p;
+                }
+            }
+            dr_free(&d);
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        if (mine < best) {
+            best = mine;
+            best_at = mine_at;
+        }
+    }
+    if (at) *at = best_at;
+    return best;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

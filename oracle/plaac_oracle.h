@@ -117,6 +117,9 @@ void orc_residue_batch(const orc_params *P, const uint8_t *codes, const int64_t 
  * "Infinity"/"-Infinity"), used to print rows the way plaac.java:899-945 does. */
 int orc_java_fmt(char *buf, int buflen, double x, int decimals);
 
+/* test instrumentation: min over the FoldIndex values the run scan looks at of |fi| * window taps (see the .c file) */
+double orc_fi_min_margin(const orc_params *P, const uint8_t *codes, const int64_t *offsets, int64_t nprot, int nthreads,
+                         int64_t *at);
 int orc_max_threads(void);
 
 #ifdef __cplusplus

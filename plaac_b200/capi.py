@@ -139,6 +139,8 @@ def lib():
         L.plaac_packed_words.argtypes = [i64]
         L.plaac_pack_host.restype = C.c_int
         L.plaac_pack_host.argtypes = [vp, i64, vp, C.c_int]
+        L.plaac_pack_append_host.restype = C.c_int
+        L.plaac_pack_append_host.argtypes = [vp, i64, vp, i64, C.c_int]
         L.plaac_pack_chars_host.restype = C.c_int
         L.plaac_pack_chars_host.argtypes = [vp, i64, vp, C.c_int]
         L.plaac_unpack_host.restype = C.c_int
@@ -213,6 +215,17 @@ def pack_words(codes: np.ndarray, nthreads: int = 0, out: np.ndarray | None = No
     if rc != 0:
         raise PlaacError(rc, "plaac_pack_host: residue code > 21")
     return words
+
+
+def pack_append(codes: np.ndarray, words: np.ndarray, pos: int, nthreads: int = 0) -> int:
+    """plaac_pack_append_host: packs `codes` at residue positions [pos, pos + len) of the batch held in `words`; returns
+    the position after them."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    assert words.dtype == np.uint32 and len(words) >= lib().plaac_packed_words(pos + len(codes))
+    rc = lib().plaac_pack_append_host(codes.ctypes.data if len(codes) else None, len(codes), words.ctypes.data, pos, nthreads)
+    if rc != 0:
+        raise PlaacError(rc, "plaac_pack_append_host: residue code > 21")
+    return pos + len(codes)
 
 
 def pack_chars(text: bytes, nthreads: int = 0) -> np.ndarray:

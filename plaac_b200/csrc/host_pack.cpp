@@ -100,6 +100,35 @@ try {
     return PLAAC_E_NOMEM;
 }
 
+int plaac_pack_append_host(const uint8_t* codes, int64_t nres, uint32_t* words, int64_t pos, int nthreads)
+try {
+    if (nres < 0 || pos < 0 || (nres > 0 && (!codes || !words))) return PLAAC_E_INVALID;
+    int bad = 0;
+    int64_t done = 0;
+    const int k0 = (int)(pos % kPer);
+    if (k0 != 0 && nres > 0) {
+        // the first word already holds k0 digits of earlier residues: add ours above them
+        const int64_t w = pos / kPer;
+        uint32_t scale = 1;
+        for (int i = 0; i < k0; i++) scale *= 22u;
+        uint32_t v = words[w] % scale;  // (digits above k0 are rewritten)
+        for (int k = k0; k < kPer && done < nres; k++, done++) {
+            uint32_t c = codes[done];
+            if (c > 21u) c = 0, bad = 1;
+            v += c * scale;
+            scale *= 22u;
+        }
+        words[w] = v;
+    }
+    if (done < nres) {
+        const int rc = pack_threads(codes + done, nres - done, words + (pos + done) / kPer, nthreads, [](uint8_t c) -> uint32_t { return c; });
+        if (rc != PLAAC_OK) return rc;
+    }
+    return bad ? PLAAC_E_INVALID : PLAAC_OK;
+} catch (...) {
+    return PLAAC_E_NOMEM;
+}
+
 int plaac_unpack_host(const uint32_t* words, int64_t first, int64_t count, uint8_t* codes)
 {
     if (first < 0 || count < 0 || (count > 0 && (!words || !codes))) return PLAAC_E_INVALID;

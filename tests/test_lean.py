@@ -26,6 +26,20 @@ def test_pack_roundtrip_and_layout():
                 assert np.array_equal(plaac_b200.unpack_words(words, first, cnt), codes[first:first + cnt])
 
 
+def test_pack_append_builds_the_same_words_piece_by_piece():
+    rng = np.random.default_rng(6)
+    codes = rng.integers(0, 22, 100_003).astype(np.uint8)
+    want = plaac_b200.pack_words(codes)
+    words = np.full(len(want), 0xFFFFFFFF, dtype=np.uint32)  # (stale contents must not leak into the result)
+    words[0] = 0
+    pos = 0
+    cuts = [0, 1, 2, 9, 10, 24, 700, 701, 7000, 7013, 50_000, 100_003]
+    for a, b in zip(cuts, cuts[1:]):
+        pos = plaac_b200.pack_append(codes[a:b], words, pos)
+    assert pos == len(codes)
+    assert np.array_equal(words, want)
+
+
 def test_pack_threads_agree():
     rng = np.random.default_rng(4)
     codes = rng.integers(0, 22, 5_000_003).astype(np.uint8)
