@@ -670,10 +670,11 @@ def measure_per_residue(L, scorer, dev, hbm_peak):
         L.plaac_bench_synth_residues(None, 1001, 0, nprot, offsets.data_ptr(), bg.ctypes.data, prd.ctypes.data, PRD_RATE,
                                      X_RATE, codes.data_ptr())
         u8 = torch.empty(2 * ntotal, dtype=torch.uint8, device=dev)
-        f64 = torch.empty(10 * ntotal, dtype=torch.float64, device=dev)
+        stride = (ntotal + 3) & ~3   # track arrays at multiples of 32 bytes (the kernels then use 256-bit stores)
+        f64 = torch.empty(10 * stride, dtype=torch.float64, device=dev)
         ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + ntotal}
         for k, nm in enumerate(plaac_b200.RESIDUE_F64):
-            ptrs[nm] = f64.data_ptr() + 8 * k * ntotal
+            ptrs[nm] = f64.data_ptr() + 8 * k * stride
         torch.cuda.synchronize()
 
         def f():

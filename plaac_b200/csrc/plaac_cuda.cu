@@ -53,7 +53,7 @@ struct Slot {
     DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_extT, lg_tb, lg_vit;                             // long-sequence path
     unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues, or 3 x kLongBins bins
     DevBuf lg_bins;
-    cudaStream_t aux1 = nullptr, aux2 = nullptr;
+    cudaStream_t aux1 = nullptr, aux2 = nullptr, aux3 = nullptr;
     // staging for callers whose buffers are pageable (plaac_score): pinned copies of the chunk's codes and records
     void* h_stage_codes = nullptr;
     size_t h_stage_codes_cap = 0;
@@ -61,7 +61,7 @@ struct Slot {
     size_t h_stage_sum_cap = 0;
     plaac_summary* out_dst = nullptr;  // where the staged records of the chunk in flight go once it has finished
     size_t out_bytes = 0;
-    cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr, ev_j3 = nullptr;
     int64_t* h_total = nullptr;        // pinned
     int* h_err = nullptr;              // pinned
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
@@ -371,9 +371,11 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     CU(ctx, cudaEventCreate(&s.ev_d));
     CU(ctx, cudaStreamCreateWithFlags(&s.aux1, cudaStreamNonBlocking));
     CU(ctx, cudaStreamCreateWithFlags(&s.aux2, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamCreateWithFlags(&s.aux3, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_j1, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_j2, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_j3, cudaEventDisableTiming));
     int rc = ensure(ctx, s.errflag, sizeof(int));
     if (rc) return rc;
     CU(ctx, cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream));
@@ -398,9 +400,9 @@ void slot_free(Slot& s)
     s.h_stage_codes_cap = s.h_stage_sum_cap = 0;
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
-    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_fork, s.ev_j1, s.ev_j2})
+    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_fork, s.ev_j1, s.ev_j2, s.ev_j3})
         if (e) cudaEventDestroy(e);
-    for (cudaStream_t a : {s.aux1, s.aux2})
+    for (cudaStream_t a : {s.aux1, s.aux2, s.aux3})
         if (a) cudaStreamDestroy(a);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -720,8 +722,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             ta.nx = ctx->res_plan.nx;
             ta.per_x = ctx->res_plan.per_x;
             ta.per_s = ctx->res_plan.per_s;
-            rc = launch_residue_v2(ctx->res_plan, ra, ta, ctx->sm_count, st, s.aux1, s.aux2, s.ev_fork, s.ev_j1, s.ev_j2,
-                                   &ctx->stats.kernel_launches);
+            rc = launch_residue_v2(ctx->res_plan, ra, ta, ctx->sm_count, st, s.aux1, s.aux2, s.aux3, s.ev_fork, s.ev_j1, s.ev_j2,
+                                   s.ev_j3, &ctx->stats.kernel_launches);
         } else
             rc = launch_residue(ctx->ks, ctx->d_tabs, bv, *d_res, res_base, ctx->sm_count, st, &ctx->stats.kernel_launches);
         if (rc != PLAAC_OK) return fail(ctx, rc, "per-residue kernels failed to launch");
@@ -1589,22 +1591,24 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
         plaac_residue_out dres;
         if (per_res) {
             if ((rc = ensure(ctx, s.res_u8, (size_t)2 * (nres + 16)))) break;
-            if ((rc = ensure(ctx, s.res_f64, sizeof(double) * 10 * (size_t)(nres + 2)))) break;
+            // (track arrays at multiples of 32 bytes: k_res_tracks3 then writes them with 256-bit stores)
+            const size_t Np = ((size_t)nres + 3) & ~(size_t)3;
+            if ((rc = ensure(ctx, s.res_f64, sizeof(double) * 10 * (Np + 4)))) break;
             uint8_t* u = (uint8_t*)s.res_u8.p;
             double* d = (double*)s.res_f64.p;
             const size_t N = (size_t)nres;
             dres.vit = u;
             dres.map = u + N;
             dres.charge = d;
-            dres.hydro = d + N;
-            dres.fi = d + 2 * N;
-            dres.plaac = d + 3 * N;
-            dres.papa = d + 4 * N;
-            dres.fix2 = d + 5 * N;
-            dres.plaacx2 = d + 6 * N;
-            dres.papax2 = d + 7 * N;
-            dres.post_bg = d + 8 * N;
-            dres.post_prd = d + 9 * N;
+            dres.hydro = d + Np;
+            dres.fi = d + 2 * Np;
+            dres.plaac = d + 3 * Np;
+            dres.papa = d + 4 * Np;
+            dres.fix2 = d + 5 * Np;
+            dres.plaacx2 = d + 6 * Np;
+            dres.papax2 = d + 7 * Np;
+            dres.post_bg = d + 8 * Np;
+            dres.post_prd = d + 9 * Np;
         }
         const void* src_main = packed ? (const void*)(in.words + w0) : (const void*)(in.codes + first_off + pos);
         const size_t main_bytes = packed ? sizeof(uint32_t) * (size_t)nwords : (size_t)nres;

@@ -690,26 +690,29 @@ inline int residue_v2_setup(const ResidueV2Plan& P, int optin_bytes)
     return PLAAC_OK;
 }
 
-// Kernel order; aux streams (may be NULL) let the independent recurrences overlap:
-//   st:   vit -> tracks --\
+// Kernel order; aux streams (may be NULL) let the independent chains overlap:
+//   st:   vit ------------\
+//   aux3: tracks ---------+
 //   aux1: bwd ------------+--> lpseq -> post -> bits   (on st)
 //   aux2: fwd ------------/
+// (the tracks only read the residue codes: beside the Viterbi pass instead of behind it)
 // (Running the posterior chain on aux1 beside the tracks was measured slower: 6.2 vs 5.7 ms at 200 k proteins.)
 inline int launch_residue_v2(const ResidueV2Plan& P, const ResArgs& ra, const TrackArgs& ta, int sm_count, cudaStream_t st,
-                             cudaStream_t aux1, cudaStream_t aux2, cudaEvent_t ev_fork, cudaEvent_t ev_j1, cudaEvent_t ev_j2,
-                             int64_t* launches)
+                             cudaStream_t aux1, cudaStream_t aux2, cudaStream_t aux3, cudaEvent_t ev_fork, cudaEvent_t ev_j1,
+                             cudaEvent_t ev_j2, cudaEvent_t ev_j3, int64_t* launches)
 {
     const plaac_residue_out& out = ra.out;
     if (!out.post_bg || !out.post_prd || !out.charge || !out.hydro || !out.fi || !out.plaac || !out.papa || !out.fix2 ||
         !out.plaacx2 || !out.papax2)
         return PLAAC_E_INVALID;
     const int64_t nb = ra.bv.nbuckets;
-    const bool fork = aux1 && aux2;
-    cudaStream_t s1 = fork ? aux1 : st, s2 = fork ? aux2 : st;
+    const bool fork = aux1 && aux2 && aux3;
+    cudaStream_t s1 = fork ? aux1 : st, s2 = fork ? aux2 : st, s3 = fork ? aux3 : st;
     if (fork) {
         cudaEventRecord(ev_fork, st);
         cudaStreamWaitEvent(s1, ev_fork, 0);
         cudaStreamWaitEvent(s2, ev_fork, 0);
+        cudaStreamWaitEvent(s3, ev_fork, 0);
     }
     const unsigned g_vit = (unsigned)std::min<int64_t>((nb + kResThreads / 32 - 1) / (kResThreads / 32), (int64_t)sm_count * 8);
     const unsigned g_hmm = (unsigned)std::min<int64_t>((nb + kResHmmThreads / 32 - 1) / (kResHmmThreads / 32), (int64_t)sm_count * 2);
@@ -719,12 +722,14 @@ inline int launch_residue_v2(const ResidueV2Plan& P, const ResArgs& ra, const Tr
     k_res_bwd<<<g_hmm, kResHmmThreads, P.bwd_smem, s1>>>(ra);
     k_res_fwd<<<g_hmm, kResHmmThreads, P.fwd_smem, s2>>>(ra);
     k_res_vit<<<g_vit, kResThreads, 0, st>>>(ra);
-    k_res_tracks<<<g_trk, kTrackWarps * 32, P.trk_smem, st>>>(ta);
+    k_res_tracks<<<g_trk, kTrackWarps * 32, P.trk_smem, s3>>>(ta);
     if (fork) {
         cudaEventRecord(ev_j1, s1);
         cudaEventRecord(ev_j2, s2);
+        cudaEventRecord(ev_j3, s3);
         cudaStreamWaitEvent(st, ev_j1, 0);
         cudaStreamWaitEvent(st, ev_j2, 0);
+        cudaStreamWaitEvent(st, ev_j3, 0);
     }
     k_res_lpseq<<<(unsigned)((ra.bv.nprot + 255) / 256), 256, 0, st>>>(ra);
     k_res_post<<<g_post, kResPostThreads, 0, st>>>(ra);

@@ -33,7 +33,7 @@ P = orc.make_params()
 t0 = time.perf_counter()
 int_bad = {f: 0 for f in orc.INT_FIELDS}
 maxrel = {f: 0.0 for f in orc.DBL_FIELDS}
-bad_rows, cen_diff, cen_rejected = [], 0, 0
+bad_rows, cen_diff, tie_rows = [], 0, 0
 margin, margin_at = float("inf"), -1
 fi_int = ("fi_numaa", "fi_maxrun")
 for lo in range(0, nprot, chunk):
@@ -47,18 +47,22 @@ for lo in range(0, nprot, chunk):
     for f in orc.DBL_FIELDS:
         maxrel[f] = max(maxrel[f], parity.max_rel(got, ref, f))
     cen_diff += int((got["papa_center"] != ref["papa_center"]).sum())
-    bad = parity.compare_summaries(got, ref, orc.INT_FIELDS, orc.DBL_FIELDS)
+    # (documented exact-tie class of the PAPA centre, DESIGN.md section 3: accepted only if, in the oracle's own tracks,
+    # the other centre attains the maximum, passes the same FoldIndex gate and reports the oracle's values there)
+    bad, nties = parity.compare_with_tie_classes(P, cds, offs, got, ref, orc.INT_FIELDS, orc.DBL_FIELDS)
+    tie_rows += nties
     bad_rows += [f"[{lo}+] {b}" for b in bad[:10]]
     m, at = orc.fi_min_margin(P, cds, offs, nthreads=nthreads)
     if m < margin:
         margin, margin_at = m, lo + at
-    print(f"{hi}/{nprot} proteins, {time.perf_counter() - t0:.0f} s, mismatching rows so far {len(bad_rows)}", flush=True)
+    print(f"{hi}/{nprot} proteins, {time.perf_counter() - t0:.0f} s, mismatches outside the tie class so far {len(bad_rows)}, tie-class rows {tie_rows}", flush=True)
 dt = time.perf_counter() - t0
 res = {
     "proteins": nprot, "residues": ntotal, "oracle_threads": nthreads, "oracle_seconds": dt,
     "integer_mismatches_by_field": int_bad, "papa_center_differs": cen_diff,
     "max_relative_error_by_field": maxrel,
-    "rows_failing_tests_parity_rules": len(bad_rows), "first_failures": bad_rows[:10],
+    "papa_center_rows_in_documented_tie_class": tie_rows,
+    "mismatches_outside_tie_class": len(bad_rows), "first_failures": bad_rows[:10],
     "fi_threshold_margin": {"min_abs_fi_times_taps": margin, "protein": margin_at,
                             "note": "smallest |fi[i]| * (window taps) over every position the FoldIndex run scan "
                                     "(plaac.java:5010-5059) looks at, in the oracle's arithmetic; the CUDA kernels test the "
