@@ -213,7 +213,9 @@ int plaac_score_multi(plaac_ctx *const *ctxs, int nctx, const uint8_t *codes, co
                       plaac_summary *summaries, const plaac_residue_out *per_res);
 
 /* The transport-lean form of plaac_score_multi (see plaac_score_packed): shards are cut on the lengths, a shard may
- * start in the middle of a word; the shards' ranked lists are merged on the host into `hits`. */
+ * start in the middle of a word.  Compact output: every shard's candidate rows (its proteins with a CORE, or its top K)
+ * are pulled onto the first context's GPU over NVLink / PCIe peer copies, ranked there as one set and copied to `hits`
+ * once -- the only exchange between GPUs on the whole path. */
 int plaac_score_multi_packed(plaac_ctx *const *ctxs, int nctx, const uint32_t *words, const int32_t *lengths, int64_t nprot,
                              int64_t nres, plaac_summary *summaries, const plaac_residue_out *per_res, plaac_hits *hits);
 

@@ -91,4 +91,18 @@ k_hits_keys(const plaac_summary* __restrict__ rec, const int32_t* __restrict__ v
     keys[i] = rank_desc_key(field ? r.core_score : r.llr);
 }
 
+// plaac_score_multi_packed: indices of a shard's rows become indices of the whole batch
+__global__ void __launch_bounds__(256) k_hits_add_base(int32_t* __restrict__ idx, int64_t n, int32_t base)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] += base;
+}
+
+__global__ void __launch_bounds__(256)
+k_hits_gather_idx(const int32_t* __restrict__ idx, const int32_t* __restrict__ order, int64_t n, int32_t* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = idx[order[i]];
+}
+
 }  // namespace plaac

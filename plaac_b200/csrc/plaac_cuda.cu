@@ -82,6 +82,7 @@ struct plaac_ctx {
     DeviceTables* d_tabs = nullptr;
     Slot slot[kSlots];
     DevBuf all_summaries;      // records of a whole host-buffer call, kept on the device for the compact ranked output
+    DevBuf union_rec, union_idx, union_order, union_out_idx;  // plaac_score_multi_packed: the shards' hit rows merged on this GPU
     // pageable <-> device copies of the FASTA calls: two pinned staging buffers, filled / emptied by a multi-threaded memcpy
     void* stage_buf[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -1111,6 +1112,7 @@ void plaac_destroy(plaac_ctx* ctx)
     cudaSetDevice(ctx->device);
     for (int i = 0; i < kSlots; i++) slot_free(ctx->slot[i]);
     release(ctx->all_summaries);
+    for (DevBuf* b : {&ctx->union_rec, &ctx->union_idx, &ctx->union_order, &ctx->union_out_idx}) release(*b);
     for (int b = 0; b < 2; b++) {
         if (ctx->stage_buf[b]) cudaFreeHost(ctx->stage_buf[b]);
         if (ctx->stage_ev[b]) cudaEventDestroy(ctx->stage_ev[b]);
@@ -1373,7 +1375,9 @@ struct HostInput {
 };
 
 // Compact ranked output of a whole host-buffer call: the records of every chunk were kept in ctx->all_summaries.
-int finish_hits(plaac_ctx* ctx, int64_t nprot, plaac_hits* hits)
+// on_device: the rows stay on the GPU (slot 0: `summaries` holds the hits->count ranked records, `rk_order` their indices
+// in this call's batch) for plaac_score_multi_packed, which merges the shards' rows on one GPU.
+int finish_hits(plaac_ctx* ctx, int64_t nprot, plaac_hits* hits, bool on_device = false)
 {
     Slot& s = ctx->slot[0];
     cudaStream_t st = s.stream;
@@ -1425,13 +1429,14 @@ int finish_hits(plaac_ctx* ctx, int64_t nprot, plaac_hits* hits)
     }
     hits->count = count;
     if (count > 0) {
-        if (!hits->records && !hits->index) return fail(ctx, PLAAC_E_INVALID, "plaac_hits: no output array");
-        if (hits->records) {
+        if (!on_device && !hits->records && !hits->index) return fail(ctx, PLAAC_E_INVALID, "plaac_hits: no output array");
+        if (hits->records || on_device) {
             if ((rc = ensure(ctx, s.summaries, sizeof(plaac_summary) * (size_t)count))) return rc;
             if ((rc = plaac_gather_device(ctx, all, d_order, count, (plaac_summary*)s.summaries.p))) return rc;
-            CU(ctx, cudaMemcpyAsync(hits->records, s.summaries.p, sizeof(plaac_summary) * (size_t)count, cudaMemcpyDeviceToHost, st));
+            if (!on_device)
+                CU(ctx, cudaMemcpyAsync(hits->records, s.summaries.p, sizeof(plaac_summary) * (size_t)count, cudaMemcpyDeviceToHost, st));
         }
-        if (hits->index)
+        if (hits->index && !on_device)
             CU(ctx, cudaMemcpyAsync(hits->index, d_order, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, st));
     }
     CU(ctx, cudaStreamSynchronize(st));
@@ -1439,7 +1444,7 @@ int finish_hits(plaac_ctx* ctx, int64_t nprot, plaac_hits* hits)
 }
 
 int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary* summaries, const plaac_residue_out* per_res,
-               plaac_hits* hits)
+               plaac_hits* hits, bool hits_on_device = false)
 {
     if (nprot < 0) return fail(ctx, PLAAC_E_INVALID, "negative nprot");
     if (hits) {
@@ -1694,7 +1699,7 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
     if (hits && (rc == PLAAC_OK || (rc == PLAAC_E_INVALID && start >= nprot))) {
         // (invalid residue codes are reported after the batch, with every record computed: the compact output too)
         const std::string keep = ctx->err;
-        const int rch = finish_hits(ctx, nprot, hits);
+        const int rch = finish_hits(ctx, nprot, hits, hits_on_device);
         if (rch != PLAAC_OK)
             rc = rch;
         else
@@ -1828,24 +1833,6 @@ try {
     return api_caught((ctxs && nctx > 0 ? ctxs[0] : nullptr), "plaac_score_multi");
 }
 
-// Is row a of the web order before row b?  (COREscore desc, LLR desc, rows without a CORE last, then input order:
-// rank.cuh's keys compared on the host, for merging the shards' ranked lists.)
-static bool hit_before(const plaac_summary& a, int64_t ia, const plaac_summary& b, int64_t ib)
-{
-    auto key = [](double v) -> uint64_t {
-        if (v != v) return ~0ull;
-        uint64_t u;
-        memcpy(&u, &v, 8);
-        const uint64_t asc = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-        return ~asc;
-    };
-    const uint64_t ca = key(a.core_score), cb = key(b.core_score);
-    if (ca != cb) return ca < cb;
-    const uint64_t ka = key(a.llr), kb = key(b.llr);
-    if (ka != kb) return ka < kb;
-    return ia < ib;
-}
-
 int plaac_score_multi_packed(plaac_ctx* const* ctxs, int nctx, const uint32_t* words, const int32_t* lengths, int64_t nprot,
                              int64_t nres, plaac_summary* summaries, const plaac_residue_out* per_res, plaac_hits* hits)
 try {
@@ -1853,61 +1840,87 @@ try {
     for (int k = 0; k < nctx; k++)
         if (!ctxs[k]) return fail(nullptr, PLAAC_E_INVALID, "plaac_score_multi_packed: NULL ctx %d", k);
     if (nctx == 1) return plaac_score_packed(ctxs[0], words, lengths, nprot, nres, summaries, per_res, hits);
-    if (nprot < 0 || (nprot > 0 && !lengths)) return fail(ctxs[0], PLAAC_E_INVALID, "plaac_score_multi_packed: bad lengths/nprot");
+    plaac_ctx* c0 = ctxs[0];
+    if (nprot < 0 || (nprot > 0 && !lengths)) return fail(c0, PLAAC_E_INVALID, "plaac_score_multi_packed: bad lengths/nprot");
     if (hits) {
         hits->count = hits->n_core = 0;
-        if (hits->capacity < 0 || nprot > 0x7fffffff) return fail(ctxs[0], PLAAC_E_INVALID, "plaac_hits: bad capacity / too many proteins");
+        if (hits->mode != PLAAC_HITS_CORE && hits->mode != PLAAC_HITS_TOPK) return fail(c0, PLAAC_E_INVALID, "plaac_hits.mode must be PLAAC_HITS_CORE or PLAAC_HITS_TOPK");
+        if (hits->capacity < 0 || nprot > 0x7fffffff) return fail(c0, PLAAC_E_INVALID, "plaac_hits: bad capacity / too many proteins");
+        if (hits->rank_flags != 0) return fail(c0, PLAAC_E_INVALID, "plaac_hits.rank_flags is reserved and must be 0");
     }
-    if (nprot == 0) return nres == 0 ? PLAAC_OK : fail(ctxs[0], PLAAC_E_INVALID, "nres does not equal the sum of the lengths");
-    // shard bounds balanced on residues + 64 per protein (as plaac_shard_plan): one pass over the lengths
-    std::vector<int64_t> bounds((size_t)nctx + 1, nprot), rpos((size_t)nctx + 1, 0);
+    if (nprot == 0) return nres == 0 ? PLAAC_OK : fail(c0, PLAAC_E_INVALID, "nres does not equal the sum of the lengths");
+    // Shard bounds balanced on residues + 64 per protein (as plaac_shard_plan).  The prefix over the lengths is taken on
+    // several host threads: block sums first, then every block finds the bounds that fall into it.
+    std::vector<int64_t> bounds((size_t)nctx + 1, nprot), rpos((size_t)nctx + 1, nres);
     {
         constexpr int64_t kPerProtein = 64;
-        int64_t tot = 0;
-        for (int64_t i = 0; i < nprot; i++) {
-            if (lengths[i] < 0) return fail(ctxs[0], PLAAC_E_INVALID, "negative length at protein %lld", (long long)i);
-            tot += lengths[i];
+        const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(16, nprot / (1 << 20)));
+        const int64_t per = (nprot + nb - 1) / nb;
+        std::vector<int64_t> bsum((size_t)nb, 0);
+        std::vector<int> bneg((size_t)nb, 0);
+        auto block = [&](int b) {
+            const int64_t lo = std::min(nprot, b * per), hi = std::min(nprot, lo + per);
+            int64_t t = 0;
+            int neg = 0;
+            for (int64_t i = lo; i < hi; i++) {
+                neg |= lengths[i] < 0;
+                t += lengths[i];
+            }
+            bsum[(size_t)b] = t;
+            bneg[(size_t)b] = neg;
+        };
+        {
+            std::vector<std::thread> th;
+            for (int b = 1; b < nb; b++) th.emplace_back(block, b);
+            block(0);
+            for (auto& t : th) t.join();
         }
-        if (tot != nres) return fail(ctxs[0], PLAAC_E_INVALID, "the lengths add up to %lld residues, nres is %lld", (long long)tot, (long long)nres);
+        int64_t tot = 0;
+        for (int b = 0; b < nb; b++) {
+            if (bneg[(size_t)b]) return fail(c0, PLAAC_E_INVALID, "negative length in the batch");
+            tot += bsum[(size_t)b];
+        }
+        if (tot != nres) return fail(c0, PLAAC_E_INVALID, "the lengths add up to %lld residues, nres is %lld", (long long)tot, (long long)nres);
         const int64_t total = tot + kPerProtein * nprot;
         bounds[0] = 0;
+        rpos[0] = 0;
         int k = 1;
-        int64_t cost = 0, r = 0;
-        for (int64_t i = 0; i < nprot && k < nctx; i++) {
-            while (k < nctx && cost >= (int64_t)(((__int128)total * k) / nctx)) {
-                bounds[k] = i;
-                rpos[k] = r;
+        int64_t r = 0;  // residues before the current block
+        for (int b = 0; b < nb && k < nctx; b++) {
+            const int64_t lo = std::min(nprot, b * per), hi = std::min(nprot, lo + per);
+            const int64_t cost_end = (r + bsum[(size_t)b]) + kPerProtein * hi;
+            int64_t i = lo, rr = r;
+            // first i with cost(i) >= target_k, for every target that is reached inside this block
+            while (k < nctx && (int64_t)(((__int128)total * k) / nctx) <= cost_end) {
+                const int64_t target = (int64_t)(((__int128)total * k) / nctx);
+                while (i < hi && rr + kPerProtein * i < target) rr += lengths[i++];
+                if (i >= hi && rr + kPerProtein * i < target) break;  // reached in a later block
+                bounds[(size_t)k] = i;
+                rpos[(size_t)k] = rr;
                 k++;
             }
-            cost += lengths[i] + kPerProtein;
-            r += lengths[i];
+            r += bsum[(size_t)b];
         }
-        for (; k < nctx; k++) bounds[k] = nprot, rpos[k] = nres;
-        bounds[nctx] = nprot;
-        rpos[nctx] = nres;
+        bounds[(size_t)nctx] = nprot;
+        rpos[(size_t)nctx] = nres;
     }
     std::vector<int> rcs((size_t)nctx, PLAAC_OK);
     std::vector<plaac_hits> sh_hits((size_t)nctx);
-    std::vector<std::vector<plaac_summary>> sh_rec((size_t)nctx);
-    std::vector<std::vector<int32_t>> sh_idx((size_t)nctx);
     std::vector<std::thread> threads;
     for (int k = 0; k < nctx; k++) {
-        const int64_t lo = bounds[k], hi = bounds[k + 1];
+        const int64_t lo = bounds[(size_t)k], hi = bounds[(size_t)k + 1];
         if (hi <= lo) continue;
         if (hits) {
-            const int64_t cap = std::min<int64_t>(hits->capacity, hi - lo);
-            sh_rec[k].resize((size_t)cap);
-            sh_idx[k].resize((size_t)cap);
-            sh_hits[k] = *hits;
-            sh_hits[k].capacity = cap;
-            sh_hits[k].records = sh_rec[k].data();
-            sh_hits[k].index = sh_idx[k].data();
+            sh_hits[(size_t)k] = *hits;
+            sh_hits[(size_t)k].capacity = std::min<int64_t>(hits->capacity, hi - lo);
+            sh_hits[(size_t)k].records = nullptr;  // the shard's rows stay on its GPU (finish_hits, on_device)
+            sh_hits[(size_t)k].index = nullptr;
         }
-        auto shard = [=, &rcs, &sh_hits]() {
+        auto shard = [=, &rcs, &sh_hits, &rpos]() {
             plaac_residue_out shifted;
             const plaac_residue_out* pr = nullptr;
             if (per_res) {
-                const int64_t o = rpos[k];
+                const int64_t o = rpos[(size_t)k];
                 shifted = *per_res;
                 uint8_t** u8s[2] = {&shifted.vit, &shifted.map};
                 for (auto p : u8s)
@@ -1919,15 +1932,16 @@ try {
                 pr = &shifted;
             }
             HostInput in;
-            const int64_t w0 = rpos[k] / PLAAC_PACK_PER_WORD;
+            const int64_t w0 = rpos[(size_t)k] / PLAAC_PACK_PER_WORD;
             in.words = words + w0;
             in.lengths = lengths + lo;
-            in.nres = rpos[k + 1] - rpos[k];
-            in.pos0 = rpos[k] - w0 * PLAAC_PACK_PER_WORD;
+            in.nres = rpos[(size_t)k + 1] - rpos[(size_t)k];
+            in.pos0 = rpos[(size_t)k] - w0 * PLAAC_PACK_PER_WORD;
             try {
-                rcs[k] = score_host(ctxs[k], in, hi - lo, summaries ? summaries + lo : nullptr, pr, hits ? &sh_hits[k] : nullptr);
+                rcs[(size_t)k] = score_host(ctxs[k], in, hi - lo, summaries ? summaries + lo : nullptr, pr,
+                                            hits ? &sh_hits[(size_t)k] : nullptr, /*hits_on_device=*/true);
             } catch (...) {
-                rcs[k] = api_caught(ctxs[k], "plaac_score_multi_packed (shard)");
+                rcs[(size_t)k] = api_caught(ctxs[k], "plaac_score_multi_packed (shard)");
             }
         };
         try {
@@ -1938,31 +1952,69 @@ try {
     }
     for (auto& t : threads) t.join();
     for (int k = 0; k < nctx; k++)
-        if (rcs[k] != PLAAC_OK) return rcs[k];
+        if (rcs[(size_t)k] != PLAAC_OK && !(rcs[(size_t)k] == PLAAC_E_INVALID && hits)) return rcs[(size_t)k];
+    int rc_shards = PLAAC_OK;
+    for (int k = 0; k < nctx; k++)
+        if (rcs[(size_t)k] != PLAAC_OK) rc_shards = rcs[(size_t)k];  // (invalid residue codes: reported after the merge)
     if (hits) {
-        // k-way merge of the shards' ranked lists (each is the head of its shard's order, so the merged head is exact up
-        // to min over shards of what each returned: every shard returned min(capacity, its rows))
-        std::vector<int64_t> cur((size_t)nctx, 0);
-        int64_t out = 0;
-        for (int k = 0; k < nctx; k++) hits->n_core += bounds[k + 1] > bounds[k] ? sh_hits[k].n_core : 0;
-        while (out < hits->capacity) {
-            int best = -1;
-            for (int k = 0; k < nctx; k++) {
-                if (bounds[k + 1] <= bounds[k] || cur[k] >= sh_hits[k].count) continue;
-                if (best < 0 ||
-                    hit_before(sh_rec[k][(size_t)cur[k]], bounds[k] + sh_idx[k][(size_t)cur[k]], sh_rec[best][(size_t)cur[best]],
-                               bounds[best] + sh_idx[best][(size_t)cur[best]]))
-                    best = k;
+        // The one exchange step of the path: every shard's candidate rows (its proteins with a CORE, or its top K) are
+        // pulled onto the first GPU over NVLink (cudaMemcpyPeerAsync), ranked there as one set, and leave the box once.
+        int64_t total = 0;
+        for (int k = 0; k < nctx; k++)
+            if (bounds[(size_t)k + 1] > bounds[(size_t)k]) {
+                total += sh_hits[(size_t)k].count;
+                hits->n_core += sh_hits[(size_t)k].n_core;
             }
-            if (best < 0) break;
-            if (hits->records) hits->records[out] = sh_rec[best][(size_t)cur[best]];
-            if (hits->index) hits->index[out] = (int32_t)(bounds[best] + sh_idx[best][(size_t)cur[best]]);
-            cur[best]++;
-            out++;
+        if (total > 0) {
+            CU(c0, cudaSetDevice(c0->device));
+            Slot& s0 = c0->slot[0];
+            cudaStream_t st = s0.stream;
+            int rc;
+            if ((rc = ensure(c0, c0->union_rec, sizeof(plaac_summary) * (size_t)total))) return rc;
+            if ((rc = ensure(c0, c0->union_idx, sizeof(int32_t) * (size_t)total))) return rc;
+            if ((rc = ensure(c0, c0->union_order, sizeof(int32_t) * (size_t)total))) return rc;
+            if ((rc = ensure(c0, c0->union_out_idx, sizeof(int32_t) * (size_t)total))) return rc;
+            int64_t off = 0;
+            for (int k = 0; k < nctx; k++) {
+                const int64_t cnt = bounds[(size_t)k + 1] > bounds[(size_t)k] ? sh_hits[(size_t)k].count : 0;
+                if (cnt <= 0) continue;
+                const Slot& sk = ctxs[k]->slot[0];
+                CU(c0, cudaMemcpyPeerAsync((plaac_summary*)c0->union_rec.p + off, c0->device, sk.summaries.p, ctxs[k]->device,
+                                           sizeof(plaac_summary) * (size_t)cnt, st));
+                CU(c0, cudaMemcpyPeerAsync((int32_t*)c0->union_idx.p + off, c0->device, sk.rk_order.p, ctxs[k]->device,
+                                           sizeof(int32_t) * (size_t)cnt, st));
+                k_hits_add_base<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((int32_t*)c0->union_idx.p + off, cnt,
+                                                                              (int32_t)bounds[(size_t)k]);
+                c0->stats.kernel_launches += 1;
+                off += cnt;
+            }
+            int64_t ncore_u = 0;
+            if ((rc = plaac_rank_device(c0, (const plaac_summary*)c0->union_rec.p, total, 0, (int32_t*)c0->union_order.p, &ncore_u)))
+                return rc;
+            const int64_t want = hits->mode == PLAAC_HITS_CORE ? ncore_u : total;
+            const int64_t count = std::min<int64_t>(hits->capacity, want);
+            hits->count = count;
+            if (count > 0) {
+                if (!hits->records && !hits->index) return fail(c0, PLAAC_E_INVALID, "plaac_hits: no output array");
+                if (hits->records) {
+                    if ((rc = ensure(c0, s0.summaries, sizeof(plaac_summary) * (size_t)count))) return rc;
+                    if ((rc = plaac_gather_device(c0, (const plaac_summary*)c0->union_rec.p, (const int32_t*)c0->union_order.p, count,
+                                                  (plaac_summary*)s0.summaries.p)))
+                        return rc;
+                    if ((rc = d2h_any(c0, hits->records, s0.summaries.p, sizeof(plaac_summary) * (size_t)count, st))) return rc;
+                }
+                if (hits->index) {
+                    k_hits_gather_idx<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
+                        (const int32_t*)c0->union_idx.p, (const int32_t*)c0->union_order.p, count, (int32_t*)c0->union_out_idx.p);
+                    c0->stats.kernel_launches += 1;
+                    if ((rc = d2h_any(c0, hits->index, c0->union_out_idx.p, sizeof(int32_t) * (size_t)count, st))) return rc;
+                }
+            }
+            CU(c0, cudaStreamSynchronize(st));
+            CU(c0, cudaGetLastError());
         }
-        hits->count = out;
     }
-    return PLAAC_OK;
+    return rc_shards;
 } catch (...) {
     return api_caught((ctxs && nctx > 0 ? ctxs[0] : nullptr), "plaac_score_multi_packed");
 }
