@@ -262,6 +262,15 @@ __device__ __forceinline__ uint32_t bytes_in_set(uint32_t w, uint32_t set)
     return r;
 }
 
+// 0x80 in every byte of w (all bytes < 0x80) whose value lies in [lo, hi]: two carries instead of a zero-byte test per
+// member (k_pack is bound by the integer ALU pipe: ncu round 1, math_pipe_throttle 3.6 per issue)
+__device__ __forceinline__ uint32_t bytes_in_range(uint32_t w, uint32_t lo, uint32_t hi)
+{
+    const uint32_t ge_lo = w + (0x80u - lo) * 0x01010101u;       // bit 7 set: byte >= lo   (byte + 0x80 - lo < 0x100)
+    const uint32_t gt_hi = w + (0x7fu - hi) * 0x01010101u;       // bit 7 set: byte > hi
+    return ge_lo & ~gt_hi & 0x80808080u;
+}
+
 // Ext byte layout: bits 4:0 residue code (22 = pad), bit 5 PAPA proline mask, bits 7:6 charge class.
 // One warp per bucket.  Lane l streams protein order[32b+l]: aligned 16-byte loads two blocks ahead, a
 // two-level word barrel shifter + funnel shifts for the byte realignment, SWAR sanitising / padding / PAPA
@@ -280,6 +289,9 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
     // up to two codes per charge class are matched with straight-line SWAR compares (PLAAC has D,E / K,R);
     // 0xffffffff never matches a sanitised byte
     const bool small_sets = __popc(charge_plus) <= 2 && __popc(charge_minus) <= 2;
+    // a set of consecutive codes (PLAAC: D, E = 3, 4 are +1) is one range test
+    const bool plus_run = charge_plus != 0 && ((charge_plus >> (__ffs((int)charge_plus) - 1)) & ((charge_plus >> (__ffs((int)charge_plus) - 1)) + 1u)) == 0u;
+    const uint32_t plus_lo = charge_plus ? (uint32_t)__ffs((int)charge_plus) - 1u : 0u, plus_hi = charge_plus ? 31u - (uint32_t)__clz((int)charge_plus) : 0u;
     uint32_t cp0 = 0xffffffffu, cp1 = 0xffffffffu, cm0 = 0xffffffffu, cm1 = 0xffffffffu;
     if (charge_plus) cp0 = ((uint32_t)__ffs((int)charge_plus) - 1u) * 0x01010101u;
     if (charge_plus & (charge_plus - 1u)) cp1 = (31u - (uint32_t)__clz((int)charge_plus)) * 0x01010101u;
@@ -337,7 +349,7 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
                 w = (w & vmask) | (kPadW & ~vmask);
                 uint32_t ext = w;
                 if (adjust_prolines) {
-                    const uint32_t eq = bytes_eq(w, 13u);
+                    const uint32_t eq = bytes_in_range(w, 13u, 13u);
                     const uint32_t prev1 = __funnelshift_l(carry, eq, 8);   // proline one position earlier
                     const uint32_t prev2 = __funnelshift_l(carry, eq, 16);  // two positions earlier
                     carry = eq;
@@ -346,7 +358,7 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
                 // charge class in bits 7:6 of every byte: 01 = +1, 11 = -1 (so (int8)byte >> 6 is the charge)
                 uint32_t pl, mi;
                 if (small_sets) {
-                    pl = bytes_zero(w ^ cp0) | bytes_zero(w ^ cp1);
+                    pl = plus_run ? bytes_in_range(w, plus_lo, plus_hi) : (bytes_zero(w ^ cp0) | bytes_zero(w ^ cp1));
                     mi = bytes_zero(w ^ cm0) | bytes_zero(w ^ cm1);
                 } else {
                     pl = bytes_in_set(w, charge_plus);

@@ -36,6 +36,7 @@ print(json.dumps({"kernel_ms": k, "total_ms": t, "residues": ntotal, "sha": h[:1
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 variants = [
+    ("default", {}),
     ("v3_opt1", {"PLAAC_V3_OPT": "1"}),
     ("v3_opt1_mix", {"PLAAC_V3_OPT": "1", "PLAAC_V3_MIX": "1"}),
     ("v3_onlyA", {"PLAAC_V3_OPT": "1", "PLAAC_V3_MIX": "256"}),
