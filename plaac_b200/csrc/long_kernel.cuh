@@ -75,6 +75,7 @@ struct LongArgs {
     KScalars ks;
     const DeviceTables* tabs;
     plaac_summary* out;
+    int out_by_slot;  // 1: the record of list[i] goes to out[i] (per-residue calls without records: out is scratch)
     uint8_t* ext;   // ext code per residue (same byte layout as the bucketed stream)
     uint8_t* extT;  // the same, chunk-major: [position in chunk][chunk], so the 32 chunk lanes of a warp read 32
                     // consecutive bytes per step (one sector) instead of 32 different lines.  Used from cm_min
@@ -130,7 +131,8 @@ struct LongShared {
 __global__ void __launch_bounds__(256)
 k_long_select(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_min, int c, int mw,
               int32_t* __restrict__ list, int64_t* __restrict__ scratch_off,
-              unsigned long long* __restrict__ counters /* [0] count, [1] scratch cursor */)
+              unsigned long long* __restrict__ counters /* [0] count, [1] scratch cursor, [2] count of >= big_min residues */,
+              int64_t big_min)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nprot) return;
@@ -140,6 +142,7 @@ k_long_select(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_m
     const unsigned long long need = (unsigned long long)long_scratch_need(len, c, mw);
     list[slot] = (int32_t)i;
     scratch_off[slot] = (int64_t)atomicAdd(&counters[1], need);
+    if (len >= big_min) atomicAdd(&counters[2], 1ull);
 }
 
 // barrier of the chunk warps only: the single-lane walks on the other warps take longer and join at the end
@@ -961,7 +964,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         }
         long_combined_wait();
         if (lane == 0) {
-            g.out[prot].hmm_all = sm.lmarg - sm.sum0;
+            g.out[g.out_by_slot ? (int32_t)blockIdx.x : prot].hmm_all = sm.lmarg - sm.sum0;
             if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
         }
         return;
@@ -970,7 +973,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
     LONG_STAMP(6);
 
     if (tid != 0) return;
-    plaac_summary* r = g.out + prot;
+    plaac_summary* r = g.out + (g.out_by_slot ? (int32_t)blockIdx.x : prot);
     r->prot_len = n;
     r->mw_score = sm.mw_best;
     r->mw_start = sm.mw_stop - mw + 1;

@@ -24,6 +24,7 @@
 #include "summary_kernel_v2.cuh"
 #include "summary_kernel_v3.cuh"
 #include "long_kernel.cuh"
+#include "long_residue.cuh"
 #include "lean.cuh"
 #include "generic_windows.cuh"
 
@@ -51,9 +52,10 @@ struct Slot {
     DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
     DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
     DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_extT, lg_tb, lg_vit;                             // long-sequence path
+    DevBuf lg_rec, lp_s0, lp_s1, lp_bnd, lp_lpseq;  // ... in per-residue mode (long_residue.cuh)
     unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues, or 3 x kLongBins bins
     DevBuf lg_bins;
-    cudaStream_t aux1 = nullptr, aux2 = nullptr, aux3 = nullptr;
+    cudaStream_t aux1 = nullptr, aux2 = nullptr, aux3 = nullptr, aux4 = nullptr, aux5 = nullptr;
     // staging for callers whose buffers are pageable (plaac_score): pinned copies of the chunk's codes and records
     void* h_stage_codes = nullptr;
     size_t h_stage_codes_cap = 0;
@@ -61,7 +63,7 @@ struct Slot {
     size_t h_stage_sum_cap = 0;
     plaac_summary* out_dst = nullptr;  // where the staged records of the chunk in flight go once it has finished
     size_t out_bytes = 0;
-    cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr, ev_j3 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_j1 = nullptr, ev_j2 = nullptr, ev_j3 = nullptr, ev_j4 = nullptr, ev_j5 = nullptr;
     int64_t* h_total = nullptr;        // pinned
     int* h_err = nullptr;              // pinned
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
@@ -373,10 +375,14 @@ int slot_init(plaac_ctx* ctx, Slot& s)
     CU(ctx, cudaStreamCreateWithFlags(&s.aux1, cudaStreamNonBlocking));
     CU(ctx, cudaStreamCreateWithFlags(&s.aux2, cudaStreamNonBlocking));
     CU(ctx, cudaStreamCreateWithFlags(&s.aux3, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamCreateWithFlags(&s.aux4, cudaStreamNonBlocking));
+    CU(ctx, cudaStreamCreateWithFlags(&s.aux5, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_j1, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_j2, cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&s.ev_j3, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_j4, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_j5, cudaEventDisableTiming));
     int rc = ensure(ctx, s.errflag, sizeof(int));
     if (rc) return rc;
     CU(ctx, cudaMemsetAsync(s.errflag.p, 0, sizeof(int), s.stream));
@@ -392,7 +398,7 @@ void slot_free(Slot& s)
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
-                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins})
+                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins, &s.lg_rec, &s.lp_s0, &s.lp_s1, &s.lp_bnd, &s.lp_lpseq})
         release(*b);
     if (s.h_long) cudaFreeHost(s.h_long);
     if (s.h_stage_codes) cudaFreeHost(s.h_stage_codes);
@@ -401,9 +407,9 @@ void slot_free(Slot& s)
     s.h_stage_codes_cap = s.h_stage_sum_cap = 0;
     if (s.h_total) cudaFreeHost(s.h_total);
     if (s.h_err) cudaFreeHost(s.h_err);
-    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_fork, s.ev_j1, s.ev_j2, s.ev_j3})
+    for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_fork, s.ev_j1, s.ev_j2, s.ev_j3, s.ev_j4, s.ev_j5})
         if (e) cudaEventDestroy(e);
-    for (cudaStream_t a : {s.aux1, s.aux2, s.aux3})
+    for (cudaStream_t a : {s.aux1, s.aux2, s.aux3, s.aux4, s.aux5})
         if (a) cudaStreamDestroy(a);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -434,16 +440,24 @@ int64_t effective_long_min(const plaac_ctx* ctx)
     return std::max<int64_t>(std::max<int64_t>(ctx->long_min, 1024), 4 * maxoff);
 }
 
+// Per-residue mode has a long-sequence path only beside the throughput kernels of residue_kernel_v2.cuh, and not when the
+// window tracks come from generic_windows.cuh's protein-major kernels anyway (they need no help with long proteins, but
+// the bookkeeping below assumes k_res_tracks).
+bool long_res_ok(const plaac_ctx* ctx)
+{
+    return ctx->res_plan.ok && ctx->v2_nwr > 0 && ctx->variant != 1 && !getenv("PLAAC_NO_LONG_RES");
+}
+
 // Automatic threshold (long_min == -1).  The long-sequence path is a LATENCY device: one CTA per protein is far less
 // efficient per residue than the bucketed kernel, so a protein goes there only if its sequential walk (~170 ns per
 // residue in a lane of the bucketed kernel) would be a visible part of the batch's time, and only as many proteins
 // as fit one wave of CTAs.  bins: k_long_levels' layout (or the host walk's).  Returns the threshold (0 = none) and
 // the exact count / scratch size / longest remaining protein for it.
 struct LongChoice {
-    int64_t thr = 0, nlong = 0, scratch = 0;
+    int64_t thr = 0, nlong = 0, scratch = 0, nbig = 0;  // nbig: of those, proteins of >= kLpBigMin residues
     int64_t lmax_rest = 0, n_hist_rest = 0;  // among proteins >= 1024 that stay on the bucketed path
 };
-LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long* bins, int64_t ntotal)
+LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long* bins, int64_t ntotal, bool per_res = false)
 {
     LongChoice c;
     const int64_t maxoff = std::max<int64_t>(std::max(4 * ctx->ks.w + 2, ctx->ks.core_len), ctx->ks.mw_window);
@@ -452,8 +466,10 @@ LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long*
     int best = -1;
     for (int b = kLongBins - 1; b >= 0; b--) {  // suffix sums: proteins with len >= long_edge(b)
         if (long_edge(b) < lb) break;
-        if (cnt + (int64_t)bins[b] > ctx->sm_count) break;
+        // (per-residue mode runs two CTAs per long protein side by side: k_long_score and k_long_post)
+        if (cnt + (int64_t)bins[b] > (per_res ? ctx->sm_count / 2 : ctx->sm_count)) break;
         cnt += (int64_t)bins[b];
+        if (long_edge(b) >= kLpBigMin) c.nbig += (int64_t)bins[b];
         scr += (int64_t)bins[kLongBins + b];
         best = b;
     }
@@ -461,7 +477,8 @@ LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long*
         c.thr = long_edge(best);
         c.nlong = cnt;
         c.scratch = scr;
-    }
+    } else
+        c.nbig = 0;
     for (int b = 0; b < (c.thr ? best : kLongBins); b++) {
         if (!bins[b]) continue;
         c.lmax_rest = std::max<int64_t>(c.lmax_rest, (int64_t)bins[2 * kLongBins + b]);
@@ -495,7 +512,7 @@ int launch_scan(plaac_ctx* ctx, Slot& s, const int32_t* in, int64_t* out, int64_
 int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_offsets, int64_t off_base,
               int64_t nprot, int64_t ntotal, plaac_summary* d_summaries, const plaac_residue_out* d_res,
               int64_t res_base, int64_t slots_bound = -1, int64_t nlong_known = -1, int64_t long_scratch_known = -1,
-              int64_t long_thr_known = -1)
+              int64_t long_thr_known = -1, int64_t nbig_known = -1)
 {
     if (nprot == 0) return PLAAC_OK;
     if (nprot > 0x7fffffff) return fail(ctx, PLAAC_E_INVALID, "more than 2^31-1 proteins in one device batch");
@@ -503,10 +520,12 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     const int64_t nbuckets = (nprot + 31) / 32;
     int rc;
     const bool use_v2 = ctx->variant >= 2 || (ctx->variant == 0 && ctx->v2_nwr > 0);  // v2 or v3: the role-split kernels
-    // Long-sequence path: summary mode of the throughput kernel only.
+    // Long-sequence path: the throughput kernels only (summary mode: long_kernel.cuh; per-residue mode: long_residue.cuh
+    // beside it, for the bucketed per-residue kernels of residue_kernel_v2.cuh).
     CU(ctx, cudaEventRecord(s.ev_a, st));
+    const bool long_ok = use_v2 && (d_res ? long_res_ok(ctx) : d_summaries != nullptr);
     int64_t long_min = long_thr_known >= 0 ? long_thr_known : effective_long_min(ctx);
-    if (d_summaries && !d_res && use_v2 && ctx->long_min < 0 && long_thr_known < 0 && ntotal >= 1024) {
+    if (long_ok && ctx->long_min < 0 && long_thr_known < 0 && ntotal >= 1024) {
         // automatic threshold with device-resident offsets: bin the lengths, let the host choose
         if ((rc = ensure(ctx, s.lg_bins, 3 * kLongBins * sizeof(unsigned long long)))) return rc;
         CU(ctx, cudaMemsetAsync(s.lg_bins.p, 0, 3 * kLongBins * sizeof(unsigned long long), st));
@@ -515,29 +534,33 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         ctx->stats.kernel_launches += 1;
         CU(ctx, cudaMemcpyAsync(s.h_long, s.lg_bins.p, 3 * kLongBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(ctx, cudaStreamSynchronize(st));
-        const LongChoice lc = choose_long_threshold(ctx, s.h_long, ntotal);
+        const LongChoice lc = choose_long_threshold(ctx, s.h_long, ntotal, d_res != nullptr);
         long_min = lc.thr;
         nlong_known = lc.nlong;
         long_scratch_known = lc.scratch;
+        nbig_known = lc.nbig;
     }
-    const bool use_long = d_summaries && !d_res && use_v2 && long_min > 0 && ntotal >= long_min && nlong_known != 0;
+    const bool use_long = long_ok && long_min > 0 && ntotal >= long_min && nlong_known != 0;
     const int64_t lm = use_long ? long_min : INT64_MAX;
-    int64_t nlong = 0, long_scratch = 0;
+    int64_t nlong = 0, long_scratch = 0, nbig = -1;
     if (use_long) {
         const int64_t cap = ntotal / long_min + 1;
         if ((rc = ensure(ctx, s.lg_list, sizeof(int32_t) * (size_t)cap))) return rc;
         if ((rc = ensure(ctx, s.lg_off, sizeof(int64_t) * (size_t)cap))) return rc;
-        if ((rc = ensure(ctx, s.lg_cnt, 32 + 16 * 8))) return rc;  // [0] count, [1] scratch cursor, [2] redone chunks (cumulative)
-        CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 16, st));
+        // [0] count, [1] scratch cursor, [2] count of >= kLpBigMin residues, [3] redone chunks (cumulative)
+        if ((rc = ensure(ctx, s.lg_cnt, 32 + 16 * 8))) return rc;
+        CU(ctx, cudaMemsetAsync(s.lg_cnt.p, 0, 24, st));
         k_long_select<<<(unsigned)((nprot + 255) / 256), 256, 0, st>>>(d_offsets, nprot, long_min, ctx->ks.core_len,
                                                                       ctx->ks.mw_window, (int32_t*)s.lg_list.p,
-                                                                      (int64_t*)s.lg_off.p, (unsigned long long*)s.lg_cnt.p);
+                                                                      (int64_t*)s.lg_off.p, (unsigned long long*)s.lg_cnt.p,
+                                                                      (int64_t)kLpBigMin);
         ctx->stats.kernel_launches += 1;
         if (nlong_known >= 0) {
             nlong = nlong_known;
             long_scratch = long_scratch_known;
+            nbig = nbig_known;
         } else {
-            CU(ctx, cudaMemcpyAsync(s.h_long, s.lg_cnt.p, 16, cudaMemcpyDeviceToHost, st));  // read after the sync below
+            CU(ctx, cudaMemcpyAsync(s.h_long, s.lg_cnt.p, 24, cudaMemcpyDeviceToHost, st));  // read after the sync below
         }
     }
     if ((rc = ensure(ctx, s.hist, sizeof(int32_t) * (kHistBins + 1)))) return rc;
@@ -567,11 +590,13 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         if (use_long && nlong_known < 0) {
             nlong = (int64_t)s.h_long[0];
             long_scratch = (int64_t)s.h_long[1];
+            nbig = (int64_t)s.h_long[2];
         }
     } else if (use_long && nlong_known < 0) {
         CU(ctx, cudaStreamSynchronize(st));
         nlong = (int64_t)s.h_long[0];
         long_scratch = (int64_t)s.h_long[1];
+        nbig = (int64_t)s.h_long[2];
     }
     if ((rc = ensure(ctx, s.stream_buf, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint4)))) return rc;
     if ((rc = ensure(ctx, s.tbw, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint32_t)))) return rc;
@@ -604,45 +629,103 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     }
     CU(ctx, cudaEventRecord(s.ev_b, st));
     bool long_launched = false;
-    if (d_summaries && use_v2) {
-        if (use_long && nlong > 0) {
-            if ((rc = ensure(ctx, s.lg_ext, (size_t)long_scratch + 256))) return rc;
-            if ((rc = ensure(ctx, s.lg_extT, (size_t)long_scratch + 256))) return rc;
-            if ((rc = ensure(ctx, s.lg_tb, (size_t)long_scratch + 256))) return rc;
-            if ((rc = ensure(ctx, s.lg_vit, (size_t)long_scratch / 8 + 256))) return rc;
-            LongArgs la;
-            la.codes = d_codes;
-            la.offsets = d_offsets;
-            la.off_base = off_base;
-            la.list = (const int32_t*)s.lg_list.p;
-            la.scratch_off = (const int64_t*)s.lg_off.p;
-            la.ks = ctx->ks;
-            la.tabs = ctx->d_tabs;
-            la.out = d_summaries;
-            la.ext = (uint8_t*)s.lg_ext.p;
-            la.extT = (uint8_t*)s.lg_extT.p;
-            la.cm_min = getenv("PLAAC_LONG_CM_MIN") ? atoi(getenv("PLAAC_LONG_CM_MIN")) : kLongChunkMajorMin;
-            la.tb = (uint8_t*)s.lg_tb.p;
-            la.vit = (uint32_t*)s.lg_vit.p;
-            la.errflag = (int*)s.errflag.p;
-            la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 16);
-            la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
-            // PLAAC_LONG_TIES (testing): "1" treats every binade as a tie binade (everything redone sequentially), "0"
-            // ignores the masks (shows what they are for)
-            const char* ties_env = getenv("PLAAC_LONG_TIES");
-            for (int i = 0; i < 4; i++)
-                la.tie_mask[i] = !ties_env ? ctx->long_tie[i] : (ties_env[0] == '0' ? 0ull : ~0ull >> 1);
-            la.warm = std::max(1, std::abs(ctx->long_warm));
-            la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
-            // on its own stream, launched first: its CTAs (one per long protein) take SMs while the persistent CTAs of
-            // the bucketed kernel start on the others and pick up the rest of the queue as SMs free up
-            CU(ctx, cudaEventRecord(s.ev_fork, st));
-            CU(ctx, cudaStreamWaitEvent(s.aux1, s.ev_fork, 0));
-            k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), s.aux1>>>(la);
-            long_launched = true;
-            ctx->stats.kernel_launches += 1;
-            ctx->stats.long_proteins += nlong;
+    // k_long_score on its own stream, launched first: its CTAs (one per long protein) take SMs while the persistent CTAs
+    // of the bucketed kernel start on the others and pick up the rest of the queue as SMs free up.  In per-residue mode it
+    // also supplies the Viterbi bits of the long proteins, and the posterior kernel runs beside it on a stream of its own.
+    cudaStream_t long_st = d_res ? s.aux4 : s.aux1;
+    if (use_long && nlong > 0) {
+        if ((rc = ensure(ctx, s.lg_ext, (size_t)long_scratch + 256))) return rc;
+        if ((rc = ensure(ctx, s.lg_extT, (size_t)long_scratch + 256))) return rc;
+        if ((rc = ensure(ctx, s.lg_tb, (size_t)long_scratch + 256))) return rc;
+        if ((rc = ensure(ctx, s.lg_vit, (size_t)long_scratch / 8 + 256))) return rc;
+        LongArgs la;
+        la.codes = d_codes;
+        la.offsets = d_offsets;
+        la.off_base = off_base;
+        la.list = (const int32_t*)s.lg_list.p;
+        la.scratch_off = (const int64_t*)s.lg_off.p;
+        la.ks = ctx->ks;
+        la.tabs = ctx->d_tabs;
+        la.out = d_summaries;
+        la.out_by_slot = 0;
+        if (!d_summaries) {
+            // per-residue call without records: the kernel still writes one, into scratch
+            if ((rc = ensure(ctx, s.lg_rec, sizeof(plaac_summary) * (size_t)nlong))) return rc;
+            la.out = (plaac_summary*)s.lg_rec.p;
+            la.out_by_slot = 1;
         }
+        la.ext = (uint8_t*)s.lg_ext.p;
+        la.extT = (uint8_t*)s.lg_extT.p;
+        la.cm_min = getenv("PLAAC_LONG_CM_MIN") ? atoi(getenv("PLAAC_LONG_CM_MIN")) : kLongChunkMajorMin;
+        la.tb = (uint8_t*)s.lg_tb.p;
+        la.vit = (uint32_t*)s.lg_vit.p;
+        la.errflag = (int*)s.errflag.p;
+        la.redone = (unsigned long long*)((char*)s.lg_cnt.p + 24);
+        la.dbg_clocks = getenv("PLAAC_LONG_CLOCKS") ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
+        // PLAAC_LONG_TIES (testing): "1" treats every binade as a tie binade (everything redone sequentially), "0"
+        // ignores the masks (shows what they are for)
+        const char* ties_env = getenv("PLAAC_LONG_TIES");
+        for (int i = 0; i < 4; i++)
+            la.tie_mask[i] = !ties_env ? ctx->long_tie[i] : (ties_env[0] == '0' ? 0ull : ~0ull >> 1);
+        la.warm = std::max(1, std::abs(ctx->long_warm));
+        la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
+        CU(ctx, cudaEventRecord(s.ev_fork, st));
+        CU(ctx, cudaStreamWaitEvent(long_st, s.ev_fork, 0));
+        k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), long_st>>>(la);
+        long_launched = true;
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.long_proteins += nlong;
+        if (d_res) {
+            if (d_res->vit) {
+                k_long_vit_bytes<<<dim3(8, (unsigned)nlong), 256, 0, long_st>>>(d_offsets, res_base, la.list, la.scratch_off, la.vit, d_res->vit);
+                ctx->stats.kernel_launches += 1;
+            }
+            // posteriors + MAP parse of the long proteins: one cluster per protein, two size classes
+            if ((rc = ensure(ctx, s.lp_s0, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
+            if ((rc = ensure(ctx, s.lp_s1, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
+            if ((rc = ensure(ctx, s.lp_bnd, sizeof(double) * (size_t)kLpBndStride * (size_t)nlong))) return rc;
+            if ((rc = ensure(ctx, s.lp_lpseq, sizeof(double) * (size_t)nlong))) return rc;
+            LongPostArgs pa;
+            pa.codes = d_codes;
+            pa.offsets = d_offsets;
+            pa.off_base = off_base;
+            pa.res_base = res_base;
+            pa.list = la.list;
+            pa.scratch_off = la.scratch_off;
+            pa.ks = ctx->ks;
+            pa.tabs = ctx->d_tabs;
+            pa.out = *d_res;
+            pa.S0 = (double*)s.lp_s0.p;
+            pa.S1 = (double*)s.lp_s1.p;
+            pa.bnd = (double*)s.lp_bnd.p;
+            pa.lpseq = (double*)s.lp_lpseq.p;
+            pa.warm = std::max(1, std::abs(ctx->long_warm));
+            pa.big_min = getenv("PLAAC_LP_BIG_MIN") ? atoll(getenv("PLAAC_LP_BIG_MIN")) : (int64_t)kLpBigMin;
+            pa.redone = la.redone;
+            CU(ctx, cudaStreamWaitEvent(s.aux5, s.ev_fork, 0));
+            if (pa.big_min != kLpBigMin) nbig = -1;  // (testing: the class counts are those of the default boundary)
+            for (int cls = 0; cls < 2; cls++) {
+                const int64_t ncls = nbig < 0 ? nlong : (cls ? nbig : nlong - nbig);
+                if (ncls == 0) continue;
+                pa.cluster = cls ? kLpBigCluster : 1;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(nlong * pa.cluster));
+                cfg.blockDim = dim3(kLpThreads);
+                cfg.dynamicSmemBytes = sizeof(LpShared);
+                cfg.stream = s.aux5;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)pa.cluster;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                CU(ctx, cudaLaunchKernelEx(&cfg, k_long_post, pa));
+                ctx->stats.kernel_launches += 1;
+            }
+        }
+    }
+    if (d_summaries && use_v2) {
         V2Args g;
         g.bv = bv;
         g.ks = ctx->ks;
@@ -677,7 +760,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             k_core_search<<<ctx->sm_count * 4, 128, 0, st>>>(bv, ctx->ks, ctx->d_tabs, d_summaries, g.core_list, g.core_count);
         ctx->stats.kernel_launches += 2;
         ctx->stats.score_launches += 1;
-        if (long_launched) {
+        if (long_launched && !d_res) {
             CU(ctx, cudaEventRecord(s.ev_j1, s.aux1));
             CU(ctx, cudaStreamWaitEvent(st, s.ev_j1, 0));
         }
@@ -723,11 +806,28 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             ta.nx = ctx->res_plan.nx;
             ta.per_x = ctx->res_plan.per_x;
             ta.per_s = ctx->res_plan.per_s;
+            ta.long_min = lm;
+            ta.long_list = nullptr;
+            if (long_launched) {
+                // the eight tracks of the long proteins: the grid's warps share a protein's tiles (they only read the
+                // residue codes; on the stream of the other tracks launch, ahead of it)
+                TrackArgs tl = ta;
+                tl.long_list = (const int32_t*)s.lg_list.p;
+                CU(ctx, cudaStreamWaitEvent(s.aux3, s.ev_fork, 0));
+                k_res_tracks<<<dim3(16, (unsigned)nlong), kTrackWarps * 32, ctx->res_plan.trk_smem, s.aux3>>>(tl);
+                ctx->stats.kernel_launches += 1;
+            }
             rc = launch_residue_v2(ctx->res_plan, ra, ta, ctx->sm_count, st, s.aux1, s.aux2, s.aux3, s.ev_fork, s.ev_j1, s.ev_j2,
                                    s.ev_j3, &ctx->stats.kernel_launches);
         } else
             rc = launch_residue(ctx->ks, ctx->d_tabs, bv, *d_res, res_base, ctx->sm_count, st, &ctx->stats.kernel_launches);
         if (rc != PLAAC_OK) return fail(ctx, rc, "per-residue kernels failed to launch");
+        if (long_launched) {
+            CU(ctx, cudaEventRecord(s.ev_j4, s.aux4));
+            CU(ctx, cudaEventRecord(s.ev_j5, s.aux5));
+            CU(ctx, cudaStreamWaitEvent(st, s.ev_j4, 0));
+            CU(ctx, cudaStreamWaitEvent(st, s.ev_j5, 0));
+        }
     }
     if (ctx->generic_windows) {
         // everything that depends on the windows, tap by tap in the jar's order (generic_windows.cuh): into the caller's
@@ -1063,6 +1163,7 @@ try {
     {
         const int optin = (int)prop.sharedMemPerBlockOptin;
         const std::pair<const void*, size_t> fns[] = {{(const void*)k_long_score, sizeof(LongShared)},
+                                                      {(const void*)k_long_post, sizeof(LpShared)},
                                                       {(const void*)k_score_summary, ctx->smem_bytes},
                                                       {(const void*)k_score_summary_v2, ctx->v2_smem_bytes},
                                                       {(const void*)k_len_hist, kHistSmemBytes},
@@ -1204,7 +1305,7 @@ try {
     for (int i = 0; i < kSlots; i++) {
         unsigned long long v = 0;
         if (ctx->slot[i].lg_cnt.p && cudaSetDevice(ctx->device) == cudaSuccess &&
-            cudaMemcpy(&v, (char*)ctx->slot[i].lg_cnt.p + 16, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess)
+            cudaMemcpy(&v, (char*)ctx->slot[i].lg_cnt.p + 24, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess)
             ctx->stats.long_redone_chunks += (int64_t)v;
     }
     if (getenv("PLAAC_LONG_CLOCKS") && ctx->slot[0].lg_cnt.p) {
@@ -1510,9 +1611,10 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
         const int64_t remaining = total_res - (pos - pos0);
         const int64_t max_res = std::min(max_res_full, std::max(min_res, std::min(ramp, remaining / 2)));
         ramp = std::min(max_res_full, ramp * 2);
-        int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0, nres = 0;
-        int64_t long_min = per_res ? 0 : effective_long_min(ctx);
-        const bool long_auto = !per_res && ctx->long_min < 0 && ctx->v2_nwr > 0 && ctx->variant != 1;
+        int64_t lmax = 0, nlong = 0, nlp = 0, lp_scratch = 0, nres = 0, nbigp = 0;
+        const bool long_allowed = !per_res || long_res_ok(ctx);
+        int64_t long_min = long_allowed ? effective_long_min(ctx) : 0;
+        const bool long_auto = long_allowed && ctx->long_min < 0 && ctx->v2_nwr > 0 && ctx->variant != 1;
         unsigned long long bins[3 * kLongBins];
         if (long_auto) memset(bins, 0, sizeof(bins));
         while (end < nprot && end - start < max_prot) {
@@ -1536,6 +1638,7 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
             } else if (long_min > 0 && len >= long_min) {
                 // scored by the long-sequence path; the bucketed stream sees an empty protein
                 nlp++;
+                nbigp += len >= kLpBigMin;
                 lp_scratch += long_scratch_need(len, ctx->ks.core_len, ctx->ks.mw_window);
             } else {
                 lmax = std::max(lmax, len);
@@ -1550,11 +1653,12 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
             break;
         }
         const int64_t np = end - start;
-        int64_t long_thr = per_res ? 0 : (long_auto ? 0 : long_min);
+        int64_t long_thr = long_auto ? 0 : long_min;
         if (long_auto) {
-            const LongChoice lc = choose_long_threshold(ctx, bins, nres);
+            const LongChoice lc = choose_long_threshold(ctx, bins, nres, per_res != nullptr);
             long_thr = lc.thr;
             nlp = lc.nlong;
+            nbigp = lc.nbig;
             lp_scratch = lc.scratch;
             lmax = std::max(lmax, lc.lmax_rest);
             nlong += lc.n_hist_rest;
@@ -1643,7 +1747,7 @@ int score_host(plaac_ctx* ctx, const HostInput& in, int64_t nprot, plaac_summary
             CUB(cudaMemcpyAsync(s.offsets.p, in.offsets + start, sizeof(int64_t) * (np + 1), cudaMemcpyHostToDevice, s.stream));
         }
         rc = run_batch(ctx, s, d_codes, (const int64_t*)s.offsets.p, off_base, np, nres, want_rec ? d_sum : nullptr,
-                       per_res ? &dres : nullptr, off_base, slots_bound, nlp, lp_scratch, long_thr);
+                       per_res ? &dres : nullptr, off_base, slots_bound, nlp, lp_scratch, long_thr, nbigp);
         if (rc) break;
         if (summaries && hits) {
             CUB(cudaMemcpyAsync(stage_sum ? (plaac_summary*)s.h_stage_sum : summaries + start, d_sum, sizeof(plaac_summary) * np,

@@ -86,7 +86,7 @@ __device__ __forceinline__ LaneView lane_view(const BatchView& bv, int64_t b, in
     if (rank < bv.nprot) {
         v.prot = bv.order[rank];
         const int64_t o = bv.offsets[v.prot];
-        v.n = (int)(bv.offsets[v.prot + 1] - o);
+        v.n = (int)eff_len(bv.offsets[v.prot + 1] - o, bv.long_min);  // long proteins: long_residue.cuh
         v.base = o - res_base;
     }
     v.cb = bv.chunk_base[b];
@@ -271,6 +271,10 @@ __global__ void __launch_bounds__(256) k_res_lpseq(ResArgs g)
 {
     const int64_t rank = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (rank >= g.bv.nprot) return;
+    {
+        const int32_t prot = g.bv.order[rank];
+        if (eff_len(g.bv.offsets[prot + 1] - g.bv.offsets[prot], g.bv.long_min) == 0) return;  // no slot to read
+    }
     const size_t at = (size_t)g.bv.chunk_base[rank >> 5] * 512 + (size_t)(rank & 31);
     g.lpseq[rank] = lse_lut_g(g.A0[at] + g.B0[at], g.A1[at] + g.B1[at], g.tabs->lut, g.ks.ln2);
 }
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kResPostThreads) k_res_post(ResArgs g)
         if (rank < g.bv.nprot) {
             const int32_t prot = g.bv.order[rank];
             const int64_t o = g.bv.offsets[prot];
-            n = (int)(g.bv.offsets[prot + 1] - o);
+            n = (int)eff_len(g.bv.offsets[prot + 1] - o, g.bv.long_min);
             base = o - g.res_base;
             lpseq = g.lpseq[rank];
         }
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(kResThreads) k_res_bits(ResArgs g)
             if (rank >= g.bv.nprot) break;
             const int32_t prot = g.bv.order[rank];
             const int64_t o = g.bv.offsets[prot];
-            const int n = (int)(g.bv.offsets[prot + 1] - o);
+            const int n = (int)eff_len(g.bv.offsets[prot + 1] - o, g.bv.long_min);
             const int64_t base = o - g.res_base;
             const uint32_t* vw = g.bv.tbw + cb * 32 + q;
             const uint32_t* mw = g.mapw + cb * 32 + q;
@@ -457,6 +461,10 @@ struct TrackArgs {
     plaac_residue_out out;
     int nx;                   // kTrackTile + 4w
     int per_x, per_s;         // elements per lane of the two scans (odd: conflict-free)
+    // Long proteins (>= long_min residues) are skipped by the protein-per-warp launch and handled by a second launch
+    // with long_list set: blockIdx.y picks the protein, the warps of the grid's x dimension share its tiles.
+    int64_t long_min;
+    const int32_t* long_list;
 };
 
 __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
@@ -487,12 +495,18 @@ __global__ void __launch_bounds__(kTrackWarps * 32) k_res_tracks(TrackArgs g)
     int* Sc = Xc;
 
     const int64_t warps = (int64_t)gridDim.x * kTrackWarps;
-    for (int64_t p = (int64_t)blockIdx.x * kTrackWarps + wid; p < g.nprot; p += warps) {
+    const bool by_tile = g.long_list != nullptr;
+    for (int64_t it = (int64_t)blockIdx.x * kTrackWarps + wid; it < (by_tile ? warps : g.nprot); it += warps) {
+        const int64_t p = by_tile ? (int64_t)g.long_list[blockIdx.y] : it;
         const int64_t o = g.offsets[p];
         const int n = (int)(g.offsets[p + 1] - o);
+        if (!by_tile && n >= g.long_min) continue;
         const uint8_t* src = g.codes + (o - g.off_base);
         const int64_t ob = o - g.res_base;
-        for (int t0 = 0; t0 < n; t0 += kTrackTile) {
+        const int t_first = by_tile ? (int)it * kTrackTile : 0;
+        const int64_t t_step = by_tile ? warps * kTrackTile : kTrackTile;
+        for (int64_t t0l = t_first; t0l < n; t0l += t_step) {
+            const int t0 = (int)t0l;
             const int u_lo = t0 - 2 * w;  // residue of X*[0]
             // the last tile of a protein is shorter: nothing beyond residue n-1 has to be staged or scanned (prefix
             // sums stay constant there; reads clamp to the last element)

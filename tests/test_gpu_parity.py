@@ -449,6 +449,78 @@ def test_per_residue_long_and_other_params():
     _check_residue(got, ref, "long per-residue")
 
 
+def _residue_equal_bits(a, b, what):
+    for k in orc.RESIDUE_U8:
+        assert (a[k] == b[k]).all(), (what, k, int((a[k] != b[k]).sum()))
+    for k in orc.RESIDUE_F64:
+        same = (a[k] == b[k]) | (np.isnan(a[k]) & np.isnan(b[k]))
+        assert same.all(), (what, k, int((~same).sum()), a[k][~same][:3], b[k][~same][:3])
+
+
+def test_per_residue_long_path_is_the_sequential_walk_bit_for_bit(monkeypatch):
+    """Long proteins in per-residue mode (long_residue.cuh: one thread-block cluster per protein, binade-frame forward
+    and backward recurrences with an exact carry over the chunk boundaries) against (i) the oracle and (ii) the bucketed
+    kernels' single-lane walk of the same proteins: the same bits in every column, in both cluster size classes, with
+    several warm-up lengths (3 residues: most chunks are redone sequentially), mixed with short proteins, with and
+    without records in the same call, through the host API and the device-resident one."""
+    rng = np.random.default_rng(77)
+    lc, lo = synth.long_proteins(seed=1009, lengths=(1300, 9000, 35000, 2049, 100000))
+    sc_, so = synth.proteome(300, seed=5, median=300.0)
+    codes = np.concatenate([sc_[:so[150]], lc, sc_[so[150]:]])
+    lens = np.concatenate([np.diff(so)[:150], np.diff(lo), np.diff(so)[150:]])
+    offs = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    P = orc.make_params()
+    ref = orc.residue_batch(P, codes, offs, nthreads=NT)
+    ref_s = orc.score_batch(P, codes, offs, nthreads=NT)
+
+    monkeypatch.setenv("PLAAC_NO_LONG_RES", "1")
+    sc = plaac_b200.Scorer()
+    sc.set_long_path(1024)
+    _, walk = sc.score(codes, offs, per_residue=True)
+    assert sc.stats().long_proteins == 0
+    monkeypatch.delenv("PLAAC_NO_LONG_RES")
+    _check_residue(walk, ref, "sequential walk")
+
+    for warm, big_min in ((256, None), (3, None), (64, "1024"), (256, "200000")):
+        if big_min:
+            monkeypatch.setenv("PLAAC_LP_BIG_MIN", big_min)
+        sc.set_long_path(1024, warm)
+        n0 = sc.stats().long_proteins
+        summ, got = sc.score(codes, offs, per_residue=True)
+        assert sc.stats().long_proteins - n0 == int((lens >= 1024).sum())
+        _check_residue(got, ref, f"long per-residue warm={warm} big_min={big_min}")
+        _residue_equal_bits(got, walk, f"long path vs walk warm={warm} big_min={big_min}")
+        _check(summ, ref_s, "records beside the long per-residue path", P, codes, offs, max_ties=2)
+        if big_min:
+            monkeypatch.delenv("PLAAC_LP_BIG_MIN")
+    # automatic threshold; per-residue arrays only (no records), device-resident
+    sc.set_long_path(-1)
+    n0 = sc.stats().long_proteins
+    _, got = sc.score(codes, offs, per_residue=True)
+    assert sc.stats().long_proteins > n0
+    _residue_equal_bits(got, walk, "automatic threshold")
+    import torch
+    dev = torch.device("cuda", 0)
+    dc = torch.from_numpy(np.concatenate([codes, np.zeros(64, np.uint8)])).to(dev)
+    do = torch.from_numpy(offs).to(dev)
+    ntot = int(offs[-1])
+    u8 = torch.zeros(2 * ntot, dtype=torch.uint8, device=dev)
+    f64 = torch.zeros(10 * ntot, dtype=torch.float64, device=dev)
+    ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + ntot}
+    for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+        ptrs[nm] = f64.data_ptr() + 8 * k * ntot
+    for thr in (1024, -1):
+        sc.set_long_path(thr)
+        sc.score_device(dc.data_ptr(), do.data_ptr(), len(lens), ntot, 0, residue_ptrs=ptrs, sync=True)
+        h8, hf = u8.cpu().numpy(), f64.cpu().numpy()
+        dev_got = {"vit": h8[:ntot], "map": h8[ntot:]}
+        for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+            dev_got[nm] = hf[k * ntot:(k + 1) * ntot]
+        _residue_equal_bits(dev_got, walk, f"device-resident, threshold {thr}")
+    sc.close()
+
+
 @pytest.mark.parametrize("kw", [dict(core_len=100, ww1=21, ww2=21), dict(core_len=7, ww1=5, ww2=5),
                                 dict(core_len=30, ww1=40, ww2=40, adjust_prolines=False),
                                 dict(alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS), dict(core_len=250, ww1=61, ww2=61),
