@@ -648,12 +648,6 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         la.tabs = ctx->d_tabs;
         la.out = d_summaries;
         la.out_by_slot = 0;
-        if (!d_summaries) {
-            // per-residue call without records: the kernel still writes one, into scratch
-            if ((rc = ensure(ctx, s.lg_rec, sizeof(plaac_summary) * (size_t)nlong))) return rc;
-            la.out = (plaac_summary*)s.lg_rec.p;
-            la.out_by_slot = 1;
-        }
         la.ext = (uint8_t*)s.lg_ext.p;
         la.extT = (uint8_t*)s.lg_extT.p;
         la.cm_min = getenv("PLAAC_LONG_CM_MIN") ? atoi(getenv("PLAAC_LONG_CM_MIN")) : kLongChunkMajorMin;
@@ -671,12 +665,16 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         la.force_seq_forward = ctx->long_warm < 0 ? 1 : 0;
         CU(ctx, cudaEventRecord(s.ev_fork, st));
         CU(ctx, cudaStreamWaitEvent(long_st, s.ev_fork, 0));
-        k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), long_st>>>(la);
+        // (a per-residue call without records gets its Viterbi parse from k_long_post instead)
+        const bool run_score = d_summaries != nullptr;
+        if (run_score) {
+            k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), long_st>>>(la);
+            ctx->stats.kernel_launches += 1;
+        }
         long_launched = true;
-        ctx->stats.kernel_launches += 1;
         ctx->stats.long_proteins += nlong;
         if (d_res) {
-            if (d_res->vit) {
+            if (d_res->vit && run_score) {
                 k_long_vit_bytes<<<dim3(8, (unsigned)nlong), 256, 0, long_st>>>(d_offsets, res_base, la.list, la.scratch_off, la.vit, d_res->vit);
                 ctx->stats.kernel_launches += 1;
             }
@@ -700,8 +698,13 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             pa.bnd = (double*)s.lp_bnd.p;
             pa.lpseq = (double*)s.lp_lpseq.p;
             pa.warm = std::max(1, std::abs(ctx->long_warm));
+            pa.warm2 = getenv("PLAAC_LP_WARM2") ? atoi(getenv("PLAAC_LP_WARM2")) : 64;
             pa.big_min = getenv("PLAAC_LP_BIG_MIN") ? atoll(getenv("PLAAC_LP_BIG_MIN")) : (int64_t)kLpBigMin;
             pa.redone = la.redone;
+            pa.want_vit = (!run_score && d_res->vit) ? 1 : 0;
+            pa.tb = la.tb;
+            pa.vit_tie_mask = la.tie_mask[0];
+            pa.dbg_clocks = (getenv("PLAAC_LONG_CLOCKS") && !run_score) ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
             CU(ctx, cudaStreamWaitEvent(s.aux5, s.ev_fork, 0));
             if (pa.big_min != kLpBigMin) nbig = -1;  // (testing: the class counts are those of the default boundary)
             for (int cls = 0; cls < 2; cls++) {
@@ -1312,7 +1315,7 @@ try {
         long long ck[16];
         if (cudaMemcpy(ck, (char*)ctx->slot[0].lg_cnt.p + 32, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
             std::fprintf(stderr, "long-path clocks (cycles since kernel start):");
-            for (int i = 1; i <= 13; i++) std::fprintf(stderr, " %lld", ck[i] ? ck[i] - ck[0] : 0LL);
+            for (int i = 1; i <= 13; i++) std::fprintf(stderr, " %lld", ck[i] ? (i >= 8 && getenv("PLAAC_LONG_CLOCKS")[0] == '2' ? ck[i] : ck[i] - ck[0]) : 0LL);
             std::fprintf(stderr, "\n");
         }
     }

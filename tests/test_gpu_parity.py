@@ -482,24 +482,6 @@ def test_per_residue_long_path_is_the_sequential_walk_bit_for_bit(monkeypatch):
     monkeypatch.delenv("PLAAC_NO_LONG_RES")
     _check_residue(walk, ref, "sequential walk")
 
-    for warm, big_min in ((256, None), (3, None), (64, "1024"), (256, "200000")):
-        if big_min:
-            monkeypatch.setenv("PLAAC_LP_BIG_MIN", big_min)
-        sc.set_long_path(1024, warm)
-        n0 = sc.stats().long_proteins
-        summ, got = sc.score(codes, offs, per_residue=True)
-        assert sc.stats().long_proteins - n0 == int((lens >= 1024).sum())
-        _check_residue(got, ref, f"long per-residue warm={warm} big_min={big_min}")
-        _residue_equal_bits(got, walk, f"long path vs walk warm={warm} big_min={big_min}")
-        _check(summ, ref_s, "records beside the long per-residue path", P, codes, offs, max_ties=2)
-        if big_min:
-            monkeypatch.delenv("PLAAC_LP_BIG_MIN")
-    # automatic threshold; per-residue arrays only (no records), device-resident
-    sc.set_long_path(-1)
-    n0 = sc.stats().long_proteins
-    _, got = sc.score(codes, offs, per_residue=True)
-    assert sc.stats().long_proteins > n0
-    _residue_equal_bits(got, walk, "automatic threshold")
     import torch
     dev = torch.device("cuda", 0)
     dc = torch.from_numpy(np.concatenate([codes, np.zeros(64, np.uint8)])).to(dev)
@@ -510,14 +492,43 @@ def test_per_residue_long_path_is_the_sequential_walk_bit_for_bit(monkeypatch):
     ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + ntot}
     for k, nm in enumerate(plaac_b200.RESIDUE_F64):
         ptrs[nm] = f64.data_ptr() + 8 * k * ntot
-    for thr in (1024, -1):
-        sc.set_long_path(thr)
+
+    def device_call(what):
+        # per-residue arrays only (no records): the Viterbi parse of the long proteins then comes from k_long_post
+        u8.zero_()
+        f64.zero_()
         sc.score_device(dc.data_ptr(), do.data_ptr(), len(lens), ntot, 0, residue_ptrs=ptrs, sync=True)
         h8, hf = u8.cpu().numpy(), f64.cpu().numpy()
         dev_got = {"vit": h8[:ntot], "map": h8[ntot:]}
         for k, nm in enumerate(plaac_b200.RESIDUE_F64):
             dev_got[nm] = hf[k * ntot:(k + 1) * ntot]
-        _residue_equal_bits(dev_got, walk, f"device-resident, threshold {thr}")
+        _residue_equal_bits(dev_got, walk, "device-resident, no records: " + what)
+
+    for warm, big_min, ties in ((256, None, None), (3, None, None), (64, "1024", None), (256, "200000", None), (256, None, "1")):
+        if big_min:
+            monkeypatch.setenv("PLAAC_LP_BIG_MIN", big_min)
+        if ties:
+            monkeypatch.setenv("PLAAC_LONG_TIES", ties)   # every binade a tie binade: every Viterbi chunk redone sequentially
+        what = f"warm={warm} big_min={big_min} ties={ties}"
+        sc.set_long_path(1024, warm)
+        n0 = sc.stats().long_proteins
+        summ, got = sc.score(codes, offs, per_residue=True)
+        assert sc.stats().long_proteins - n0 == int((lens >= 1024).sum())
+        _check_residue(got, ref, "long per-residue " + what)
+        _residue_equal_bits(got, walk, "long path vs walk " + what)
+        _check(summ, ref_s, "records beside the long per-residue path", P, codes, offs, max_ties=2)
+        device_call(what)
+        if big_min:
+            monkeypatch.delenv("PLAAC_LP_BIG_MIN")
+        if ties:
+            monkeypatch.delenv("PLAAC_LONG_TIES")
+    # automatic threshold
+    sc.set_long_path(-1, 256)
+    n0 = sc.stats().long_proteins
+    _, got = sc.score(codes, offs, per_residue=True)
+    assert sc.stats().long_proteins > n0
+    _residue_equal_bits(got, walk, "automatic threshold")
+    device_call("automatic threshold")
     sc.close()
 
 
