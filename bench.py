@@ -680,19 +680,32 @@ def measure_per_residue(L, scorer, dev, hbm_peak):
         def f():
             scorer.score_device(codes.data_ptr(), offsets.data_ptr(), nprot, ntotal, 0, residue_ptrs=ptrs, sync=True)
 
-        for _ in range(3):
-            f()
-        ms = []
-        for _ in range(5):
-            f()
-            ms.append(scorer.stats().last_total_ms)
-        t = sum(ms) / len(ms) * 1e-3
+        def timed():
+            for _ in range(3):
+                f()
+            ms = []
+            for _ in range(5):
+                f()
+                ms.append(scorer.stats().last_total_ms)
+            return sum(ms) / len(ms) * 1e-3
+
+        # long proteins through the per-residue long-sequence path (automatic threshold per batch), and, for contrast,
+        # every protein walked by one lane of the bucketed kernels (the round-1 behaviour)
+        scorer.set_long_path(-1)
+        n0 = scorer.stats().long_proteins
+        t = timed()
+        nlong = (scorer.stats().long_proteins - n0) // 8
+        scorer.set_long_path(0)
+        t_walk = timed()
+        scorer.set_long_path(8192)
         out[tag] = {"proteins": nprot, "residues": ntotal, "ms": t * 1e3, "residues_per_s": ntotal / t,
-                    "hbm_out_gbs": 82.0 * ntotal / t / 1e9, "frac_of_hbm_write_roofline": 83.0 * ntotal / t / 1e9 / hbm_peak}
+                    "hbm_out_gbs": 82.0 * ntotal / t / 1e9, "frac_of_hbm_write_roofline": 83.0 * ntotal / t / 1e9 / hbm_peak,
+                    "long_path_proteins": int(nlong), "ms_without_long_path": t_walk * 1e3}
         del u8, f64, codes, offsets, lens
     out["note"] = ("device-resident, CUDA-event time of the whole per-residue pipeline inside the library; 83 algorithmic "
-                   "bytes/residue (1 in + 82 out) against the measured HBM peak; the 6k set is latency-bound by the "
-                   "sequential forward/backward chains of its longest proteins")
+                   "bytes/residue (1 in + 82 out) against the measured HBM peak; automatic long-path threshold "
+                   "(plaac_set_long_path(-1)): the longest proteins of the batch go to one thread-block cluster each "
+                   "(long_residue.cuh), the rest is latency-bound by the sequential chains of the longest bucket")
     return out
 
 
@@ -727,9 +740,28 @@ def measure_extras(scorer, dev, summaries, nprot):
             res[tag] = sum(ms) / len(ms)
         scorer.set_long_path(8192)
         res["residues_per_s_long_path"] = n / (res["long_path_ms"] * 1e-3)
+        # the same protein in per-residue mode (82 B/residue out, no records): cluster path vs single-lane walk
+        import plaac_b200
+        u8 = torch.empty(2 * n, dtype=torch.uint8, device=dev)
+        f64 = torch.empty(10 * n, dtype=torch.float64, device=dev)
+        ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + n}
+        for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+            ptrs[nm] = f64.data_ptr() + 8 * k * n
+        d_codes_p = torch.from_numpy(np.concatenate([s, np.zeros(64, np.uint8)])).to(dev)
+        for tag, min_len in (("per_residue_long_path_ms", 8192), ("per_residue_single_lane_ms", 0)):
+            scorer.set_long_path(min_len)
+            ms = []
+            for it in range(5):
+                scorer.score_device(d_codes_p.data_ptr(), d_offs.data_ptr(), 1, n, 0, residue_ptrs=ptrs, sync=True)
+                if it:
+                    ms.append(scorer.stats().last_total_ms)
+            res[tag] = sum(ms) / len(ms)
+        scorer.set_long_path(8192)
+        del u8, f64, d_codes_p
         out["long_sequences"]["n%d" % n] = res
     out["long_sequences"]["note"] = ("whole device pipeline of one call (CUDA events inside the library), a single "
-                                     "protein on the GPU; both paths give the same 160-byte record bit for bit")
+                                     "protein on the GPU; both paths give the same 160-byte record bit for bit, and the same per-residue "
+                                     "arrays bit for bit (per_residue_*: posteriors, MAP and Viterbi parse, eight tracks)")
     out["fasta_ingest"] = measure_ingest(scorer, dev)
     order = torch.empty(nprot, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
