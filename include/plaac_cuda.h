@@ -288,7 +288,7 @@ void plaac_encode_host(const char *chars, int64_t n, uint8_t *codes);
 /* Tuning/testing knob for plaac_score(): upper bounds of one device chunk (0 = keep default). */
 int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
 
-/* Long-sequence path (BASELINE config 5; summary mode): proteins of at least min_len residues are scored by one CTA
+/* Long-sequence path (BASELINE config 5).  Summary mode: proteins of at least min_len residues are scored by one CTA
  * each, cut into <= 384 chunks (csrc/long_kernel.cuh): a warp-shuffle scan of 2x2 max-plus chunk matrices and
  * warm-started LUT forward chunks fix the absolute magnitudes, then both recurrences are re-run chunk-parallel in the
  * jar's own binade, where every rounding commutes with the chunk's shift, so the combined HMMall / HMMvit / Viterbi
@@ -301,7 +301,12 @@ int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
  * host synchronisation per device-resident call.  min_len = 0: path off.  warm: forward warm-up length, 0 keeps the
  * current value (default 256); a negative value redoes every forward chunk sequentially (testing).  Both paths give the
  * same bytes in every column (the recurrences by the binade-frame argument, the window columns because their sums are
- * exact on a 2^-41 grid), so records do not depend on the setting, the batching or the sharding. */
+ * exact on a 2^-41 grid), so records do not depend on the setting, the batching or the sharding.
+ * Per-residue mode (plotsomefastas :610-647 on long proteins): the same threshold sends a protein to one thread-block
+ * cluster (csrc/long_residue.cuh: 1 CTA below 32768 residues, 8 above; forward, backward and Viterbi recurrences
+ * chunk-parallel in the jar's binade with an exact carry over the chunk boundaries, relayed between the CTAs through
+ * distributed shared memory), and the per-residue arrays are byte for byte those of the single-lane walk; the automatic
+ * threshold then admits half as many proteins (two CTAs per long protein run side by side). */
 int plaac_set_long_path(plaac_ctx *ctx, int64_t min_len, int warm);
 
 /* Kernel selection for testing: 0 = automatic (default), 1 = the reference-order anchor kernel (one fused
