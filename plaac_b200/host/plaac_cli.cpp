@@ -7,7 +7,8 @@
 // Extra options (all start with "--" so they cannot collide with the jar's single-letter flags):
 //   --gpus N        shard every batch over the first N GPUs (plaac_score_multi)
 //   --device D      GPU index when --gpus is 1 (default 0)
-//   --batch-mb M    residues per scoring batch in MiB (default 256)
+//   --batch-mb M    residues per scoring batch in MiB (default 256; the file-to-table fast path cuts 64 MiB pieces unless
+//                   the table is ranked)
 //   --compat-F      keep the jar's -F bug (plaac.java:388 reads the -B file name)
 //   --rank          print the rows of every scoring batch in the web front end's order (COREscore desc, LLR desc, no-CORE
 //                   rows last; web/lib/server.rb:222-229), computed on the GPU (plaac_rank); --rank-core prints only the
@@ -394,6 +395,7 @@ struct Options {
     bool printheaders = false, printparameters = true, adjustprolines = true;
     int gpus = 1, device = 0;
     int64_t batch_res = (int64_t)256 << 20;
+    bool batch_set = false;  // --batch-mb given
     bool compat_F = false;
     bool gpu_ingest = false, host_reader = false;
     bool rank = false, rank_core_only = false;
@@ -757,7 +759,11 @@ std::vector<size_t> cut_pieces(const char* text, size_t size, size_t piece)
 template <class Sink>
 int score_fasta_gpu(const Options& o, Scorers& S, const MappedFile& F, bool count_only, double* bg_total, Sink sink)
 {
-    const std::vector<size_t> cuts = cut_pieces(F.data, F.size, (size_t)std::max<int64_t>(o.batch_res, 1 << 20));
+    // Piece size: --batch-mb if given; else 64 MiB of text, which pipelines better than one 256 MiB piece after another
+    // (measured, 1.5 GB file: 0.95 s instead of 1.25 s after the driver's start-up); a ranked table keeps the larger
+    // default, because a file that fits one piece is ranked as a whole.
+    const int64_t piece = (o.batch_set || o.rank) ? o.batch_res : std::min<int64_t>(o.batch_res, (int64_t)64 << 20);
+    const std::vector<size_t> cuts = cut_pieces(F.data, F.size, (size_t)std::max<int64_t>(piece, 1 << 20));
     const size_t npieces = cuts.size() - 1;
     const int G = (int)S.ctx.size();
     const int nthreads = std::max(1, host_threads() / std::max(1, std::min<int>(G, (int)npieces)));
@@ -907,7 +913,7 @@ int main(int argc, char** argv)
         else if (a == "--device")
             o.device = std::atoi(val("--device"));
         else if (a == "--batch-mb")
-            o.batch_res = (int64_t)std::atoll(val("--batch-mb")) << 20;
+            o.batch_res = (int64_t)std::atoll(val("--batch-mb")) << 20, o.batch_set = true;
         else if (a == "--compat-F")
             o.compat_F = true;
         else if (a == "--rank")
