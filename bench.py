@@ -361,7 +361,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "bound": "fp64", "kernel": "k_score_summary_v2 (+ k_core_search_jump, same event bracket)",
+        "bound": "fp64", "kernel": "k_score_summary_v3 (+ k_core_search_jump, same event bracket)",
         "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "TFLOP/s",
         "frac": achieved_ops / peak_ops, "traffic": traffic,
         "note": "fp64 pipe binds (SURVEY 8d): achieved = 67 algorithmic fp64 ops/residue x residues per launch / "
