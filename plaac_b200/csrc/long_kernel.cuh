@@ -148,7 +148,10 @@ k_long_select(const int64_t* __restrict__ offsets, int64_t nprot, int64_t long_m
 // barrier of the chunk warps only: the single-lane walks on the other warps take longer and join at the end
 __device__ __forceinline__ void long_chunk_bar()
 {
-    asm volatile("bar.sync 1, %0;" ::"n"(kLongChunkWarps * 32) : "memory");
+    // (barrier.sync without .aligned: the compiler may place the statement on both sides of a branch a warp has diverged
+    // on -- compute-sanitizer's synccheck found warps arriving divergent at the aligned form; __syncwarp first)
+    __syncwarp();
+    asm volatile("barrier.sync 1, %0;" ::"n"(kLongChunkWarps * 32) : "memory");
 }
 
 // The exact forward combine (the longest single-lane walk: it redoes the binade-crossing chunks sequentially, ~300 cycles per
@@ -158,16 +161,19 @@ __device__ __forceinline__ void long_chunk_bar()
 constexpr int kLongFwdWarp = kLongChunkWarps;
 __device__ __forceinline__ void long_pass2_bar()
 {
-    asm volatile("bar.sync 2, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
+    __syncwarp();
+    asm volatile("barrier.sync 2, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
 }
 __device__ __forceinline__ void long_combined_arrive()
 {
     __threadfence_block();
-    asm volatile("bar.arrive 3, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
+    __syncwarp();
+    asm volatile("barrier.arrive 3, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
 }
 __device__ __forceinline__ void long_combined_wait()
 {
-    asm volatile("bar.sync 3, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
+    __syncwarp();
+    asm volatile("barrier.sync 3, %0;" ::"n"((kLongChunkWarps + 1) * 32) : "memory");
 }
 
 // Automatic threshold: length bins from 1024 up (256-residue steps to 16384, then powers of two); the host picks the

@@ -273,7 +273,10 @@ __global__ void __launch_bounds__(256) k_res_lpseq(ResArgs g)
     if (rank >= g.bv.nprot) return;
     {
         const int32_t prot = g.bv.order[rank];
-        if (eff_len(g.bv.offsets[prot + 1] - g.bv.offsets[prot], g.bv.long_min) == 0) return;  // no slot to read
+        if (eff_len(g.bv.offsets[prot + 1] - g.bv.offsets[prot], g.bv.long_min) == 0) {  // no slot to read
+            g.lpseq[rank] = 0.0;
+            return;
+        }
     }
     const size_t at = (size_t)g.bv.chunk_base[rank >> 5] * 512 + (size_t)(rank & 31);
     g.lpseq[rank] = lse_lut_g(g.A0[at] + g.B0[at], g.A1[at] + g.B1[at], g.tabs->lut, g.ks.ln2);
