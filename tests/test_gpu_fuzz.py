@@ -91,17 +91,40 @@ def test_random_case_against_oracle(seed):
 
 @pytest.mark.parametrize("seed", range(N_RESIDUE))
 def test_random_case_per_residue_against_oracle(seed):
+    """Per-residue mode with random parameters; the long proteins of the case (1.1 k - 13 k residues) stay in, so the
+    random long-path threshold sends them through k_long_post (long_residue.cuh) under random HMM tables, window sizes
+    and backgrounds -- with records (Viterbi bits from k_long_score) or, device-resident, without (Viterbi parse inside
+    k_long_post)."""
     kw, seqs, api = _random_case(100 + seed)
-    seqs = [s for s in seqs if len(s) <= 3000][:300]
+    seqs = [s for s in seqs if len(s) <= 3000 or len(s) >= 1100][:300]
+    seqs = [s for s in seqs if len(s) <= 3000][:260] + [s for s in seqs if len(s) > 3000]
     codes, offs = plaac_b200.pack(seqs)
     P = orc.make_params(**kw)
-    ref = orc.residue_batch(P, codes, offs)
+    ref = orc.residue_batch(P, codes, offs, nthreads=NT)
     sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
-    if api["chunk"]:
-        sc.set_chunk(api["chunk"], 300)
-    _, got = sc.score(codes, offs, per_residue=True)
+    sc.set_long_path(api["long_min"])
+    if api["device"]:
+        import torch
+
+        ntot = int(offs[-1])
+        d_codes = torch.from_numpy(np.concatenate([codes, np.zeros(64, np.uint8)])).cuda()
+        d_offs = torch.from_numpy(offs).cuda()
+        u8 = torch.zeros(2 * ntot, dtype=torch.uint8, device="cuda")
+        f64 = torch.zeros(10 * ntot, dtype=torch.float64, device="cuda")
+        ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + ntot}
+        for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+            ptrs[nm] = f64.data_ptr() + 8 * k * ntot
+        sc.score_device(d_codes.data_ptr(), d_offs.data_ptr(), len(seqs), ntot, 0, residue_ptrs=ptrs, sync=True)
+        h8, hf = u8.cpu().numpy(), f64.cpu().numpy()
+        got = {"vit": h8[:ntot], "map": h8[ntot:]}
+        for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+            got[nm] = hf[k * ntot:(k + 1) * ntot]
+    else:
+        if api["chunk"]:
+            sc.set_chunk(api["chunk"], 300)
+        _, got = sc.score(codes, offs, per_residue=True)
     sc.close()
-    assert (got["vit"] == ref["vit"]).all() and (got["map"] == ref["map"]).all(), seed
+    assert (got["vit"] == ref["vit"]).all() and (got["map"] == ref["map"]).all(), (seed, kw, api)
     for f in orc.RESIDUE_F64:
         assert (np.isnan(got[f]) == np.isnan(ref[f])).all(), (seed, f)
-        assert parity.close(got[f], ref[f], parity.SCALE[f]).all(), (seed, f)
+        assert parity.close(got[f], ref[f], parity.SCALE[f]).all(), (seed, f, kw, api)
