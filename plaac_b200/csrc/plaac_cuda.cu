@@ -457,7 +457,7 @@ struct LongChoice {
     int64_t thr = 0, nlong = 0, scratch = 0, nbig = 0;  // nbig: of those, proteins of >= kLpBigMin residues
     int64_t lmax_rest = 0, n_hist_rest = 0;  // among proteins >= 1024 that stay on the bucketed path
 };
-LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long* bins, int64_t ntotal, bool per_res = false)
+LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long* bins, int64_t ntotal, bool two_ctas = false)
 {
     LongChoice c;
     const int64_t maxoff = std::max<int64_t>(std::max(4 * ctx->ks.w + 2, ctx->ks.core_len), ctx->ks.mw_window);
@@ -466,8 +466,9 @@ LongChoice choose_long_threshold(const plaac_ctx* ctx, const unsigned long long*
     int best = -1;
     for (int b = kLongBins - 1; b >= 0; b--) {  // suffix sums: proteins with len >= long_edge(b)
         if (long_edge(b) < lb) break;
-        // (per-residue mode runs two CTAs per long protein side by side: k_long_score and k_long_post)
-        if (cnt + (int64_t)bins[b] > (per_res ? ctx->sm_count / 2 : ctx->sm_count)) break;
+        // (per-residue mode: k_long_post takes a whole SM per protein (190 KB of shared memory) and the bucketed kernels need
+        // SMs beside it -- with records k_long_score runs too; measured on a yeast-sized set: 46 long proteins 0.75 ms, 146: 0.78)
+        if (cnt + (int64_t)bins[b] > (two_ctas ? ctx->sm_count / 2 : ctx->sm_count)) break;
         cnt += (int64_t)bins[b];
         if (long_edge(b) >= kLpBigMin) c.nbig += (int64_t)bins[b];
         scr += (int64_t)bins[kLongBins + b];
