@@ -59,6 +59,7 @@ struct LongPostArgs {
     uint8_t* tb;                 // 4 traceback bits per residue, indexed scratch_off + t
     unsigned long long vit_tie_mask;  // binades in which a Viterbi constant is an exact rounding tie (plaac_create)
     long long* dbg_clocks;       // optional: phase time stamps of the first CTA (PLAAC_LONG_CLOCKS)
+    int* errflag;                // invalid residue codes (> 21) are scored as X and reported, as by k_pack
 };
 
 struct LpShared {
@@ -774,12 +775,15 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
         const int64_t ob = o - g.res_base;
         const int per = (n + X - 1) / X;
         const int t_lo = rank * per, t_hi = min(n, t_lo + per);
+        bool bad = false;
         for (int t = t_lo + tid; t < t_hi; t += kLpThreads) {
+            bad |= src[t] > 21;
             const double p0 = exp(S0[t] - lpseq), p1 = exp(S1[t] - lpseq);
             g.out.post_bg[ob + t] = p0;
             g.out.post_prd[ob + t] = p1;
             if (g.out.map) g.out.map[ob + t] = p1 > p0 ? 1 : 0;
         }
+        if (bad && g.errflag) atomicOr(g.errflag, 1);
     }
     LP_STAMP(7);
 }

@@ -705,6 +705,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             pa.want_vit = (!run_score && d_res->vit) ? 1 : 0;
             pa.tb = la.tb;
             pa.vit_tie_mask = la.tie_mask[0];
+            pa.errflag = la.errflag;
             pa.dbg_clocks = (getenv("PLAAC_LONG_CLOCKS") && !run_score) ? (long long*)((char*)s.lg_cnt.p + 32) : nullptr;
             CU(ctx, cudaStreamWaitEvent(s.aux5, s.ev_fork, 0));
             if (pa.big_min != kLpBigMin) nbig = -1;  // (testing: the class counts are those of the default boundary)

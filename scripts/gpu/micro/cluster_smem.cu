@@ -11,7 +11,7 @@ struct Sh {
     int peer;
 };
 
-__global__ void k(long long* out, int n, int use_map)
+__global__ void k(long long* out, int n, int use_map, int fence_first)
 {
     extern __shared__ __align__(16) unsigned char raw[];
     Sh& sm = *reinterpret_cast<Sh*>(raw);
@@ -24,6 +24,12 @@ __global__ void k(long long* out, int n, int use_map)
     }
     cluster.sync();
     if (threadIdx.x == 0) {
+        if (fence_first == 1) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        if (fence_first == 2) {  // a volatile poll of a flag in own shared memory written by the neighbour, then the fence
+            while (*reinterpret_cast<volatile int*>(&sm.peer) < 0) {
+            }
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        }
         // (a) compiler-addressed accesses
         int p = 0;
         double acc = 0;
@@ -55,8 +61,9 @@ int main()
     long long* d;
     cudaMalloc(&d, 8 * 4 * 8);
     const int n = 20000;
-    for (int use_map = 0; use_map < 2; use_map++)
-        for (int X : {1, 2, 8}) {
+    for (int fence_first = 0; fence_first < 3; fence_first++)
+    for (int use_map = 1; use_map < 2; use_map++)
+        for (int X : {1, 8}) {
             cudaMemset(d, 0, 8 * 4 * 8);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(X);
@@ -67,13 +74,13 @@ int main()
             at[0].val.clusterDim.x = X, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, k, d, n, use_map);
+            cudaLaunchKernelEx(&cfg, k, d, n, use_map, fence_first);
             cudaDeviceSynchronize();
             long long h[32];
             cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
             for (int r = 0; r < X; r++)
-                printf("map %d cluster %d rank %d: compiler-addressed %.1f cycles/iteration, explicit ld.shared %.1f cycles/load, cvta base 0x%llx (%s)\n",
-                       use_map, X, r, (double)h[r * 4] / n, (double)h[r * 4 + 1] / n, h[r * 4 + 2], cudaGetErrorString(cudaGetLastError()));
+                printf("fence %d map %d cluster %d rank %d: compiler-addressed %.1f cycles/iteration, explicit ld.shared %.1f cycles/load, cvta base 0x%llx (%s)\n",
+                       fence_first, use_map, X, r, (double)h[r * 4] / n, (double)h[r * 4 + 1] / n, h[r * 4 + 2], cudaGetErrorString(cudaGetLastError()));
         }
     return 0;
 }

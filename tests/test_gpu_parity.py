@@ -282,6 +282,29 @@ def test_invalid_inputs_are_reported(scorer):
     # the ctx still works afterwards
     got = scorer.score(np.array([1, 2, 3], np.uint8), np.array([0, 3], np.int64))
     assert got["prot_len"][0] == 3
+    # an invalid code inside a LONG protein in per-residue mode without records (only k_long_post sees its residues):
+    # scored as X, reported after the batch
+    import torch
+    rng = np.random.default_rng(3)
+    seq = rng.integers(1, 21, size=3000).astype(np.uint8)
+    seq[1234] = 77
+    sc = plaac_b200.Scorer()
+    sc.set_long_path(1024)
+    dc = torch.from_numpy(np.concatenate([seq, np.zeros(64, np.uint8)])).cuda()
+    do = torch.tensor([0, 3000], dtype=torch.int64, device="cuda")
+    u8 = torch.zeros(2 * 3000, dtype=torch.uint8, device="cuda")
+    f64 = torch.zeros(10 * 3000, dtype=torch.float64, device="cuda")
+    ptrs = {"vit": u8.data_ptr(), "map": u8.data_ptr() + 3000}
+    for k, nm in enumerate(plaac_b200.RESIDUE_F64):
+        ptrs[nm] = f64.data_ptr() + 8 * k * 3000
+    with pytest.raises(plaac_b200.PlaacError) as e:
+        sc.score_device(dc.data_ptr(), do.data_ptr(), 1, 3000, 0, residue_ptrs=ptrs, sync=True)
+    assert e.value.code == -1
+    seq[1234] = 0
+    ref = orc.residue_batch(orc.make_params(), seq, np.array([0, 3000], np.int64))
+    assert (u8.cpu().numpy()[3000:] == ref["map"]).all()
+    assert np.abs(f64.cpu().numpy()[9 * 3000:] - ref["post_prd"]).max() < 1e-9
+    sc.close()
 
 
 def test_pinned_host_buffers(scorer):
