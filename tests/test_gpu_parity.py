@@ -447,11 +447,16 @@ def test_per_residue_windows_with_different_half_widths(kw):
     codes, offs = synth.proteome(700, seed=31, median=180.0)
     e, eo = synth.edge_cases()
     codes, offs = np.concatenate([codes, e]), np.concatenate([offs, eo[1:] + offs[-1]])
+    # ... and two long proteins: with the threshold below they take the long-sequence paths (records: k_long_score,
+    # posteriors / MAP: k_long_post) while every window column still comes from the tap-by-tap kernels
+    lc, lo = synth.long_proteins(seed=4, lengths=(2500, 6000))
+    codes, offs = np.concatenate([codes, lc]), np.concatenate([offs, lo[1:] + offs[-1]])
     P = orc.make_params(**kw)
     ref_s = orc.score_batch(P, codes, offs, nthreads=NT)
     ref_r = orc.residue_batch(P, codes, offs)
     sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
     sc.set_chunk(40000, 300)
+    sc.set_long_path(2048)
     got_s, got_r = sc.score(codes, offs, per_residue=True)
     sc.close()
     _check(got_s, ref_s, f"summary beside per-residue {kw}", P, codes, offs, max_ties=6)
