@@ -21,6 +21,18 @@ def load():
     return _cache
 
 
+_cache_long = None
+
+
+def load_long_residue():
+    """tests/golden/jar_vectors_long_residue.json.gz: `-p all` on the 4 500- and 9 000-residue proteins of long_fasta."""
+    global _cache_long
+    if _cache_long is None:
+        with gzip.open(os.path.join(HERE, "golden", "jar_vectors_long_residue.json.gz"), "rb") as f:
+            _cache_long = json.loads(f.read().decode())
+    return _cache_long
+
+
 def val(v):
     if isinstance(v, str):
         if v == "NaN":
@@ -87,6 +99,8 @@ def scenario(which):
         text, kw, rows = J["edge_fasta"], dict(alpha=0.5), J["edge_summary"]
     elif which == "long_summary":
         text, kw, rows = J["long_fasta"], {}, J["long_summary"]
+    elif which == "long_residue":
+        text, kw, rows = J["long_fasta"], {}, load_long_residue()["long_residue"]
     elif which == "prions_residue":
         text, kw, rows = J["prions_fasta"], {}, J["prions_residue"]
     elif which == "edge_residue":

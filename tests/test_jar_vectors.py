@@ -44,7 +44,7 @@ def test_oracle_summary_is_bit_identical_to_the_jar(which):
         assert row["PAPAaa"] == sub(r["papa_center"] - hw, r["papa_center"] + hw), name
 
 
-@pytest.mark.parametrize("which", ["prions_residue", "edge_residue", "edge_alt_residue"])
+@pytest.mark.parametrize("which", ["prions_residue", "edge_residue", "edge_alt_residue", "long_residue"])
 def test_oracle_per_residue_is_bit_identical_to_the_jar(which):
     enc, kw, prots = jarvec.scenario(which)
     P = orc.make_params(**kw)
@@ -118,14 +118,24 @@ def test_cuda_summary_against_the_jar(which):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["prions_residue", "edge_residue", "edge_alt_residue"])
-def test_cuda_per_residue_against_the_jar(which):
+@pytest.mark.parametrize("which", ["prions_residue", "edge_residue", "edge_alt_residue", "long_residue", "long_residue_cluster"])
+def test_cuda_per_residue_against_the_jar(which, monkeypatch):
+    """long_residue: the 4 500- and 9 000-residue proteins through the per-residue long-sequence path (k_long_post; one
+    CTA per protein, and with `_cluster` a cluster of eight) against the jar's own per-residue table."""
     import plaac_b200
 
+    cluster = which.endswith("_cluster")
+    which = which.replace("_cluster", "")
     enc, kw, prots = jarvec.scenario(which)
     codes, offs = plaac_b200.pack([c for _, c in enc])
     sc = plaac_b200.Scorer(plaac_b200.default_params(**kw))
+    if which == "long_residue":
+        if cluster:
+            monkeypatch.setenv("PLAAC_LP_BIG_MIN", "1024")
+        sc.set_long_path(1024)
     _, res = sc.score(codes, offs, per_residue=True)
+    if which == "long_residue":
+        assert sc.stats().long_proteins == 2
     sc.close()
     for i, ((name, aa), pr) in enumerate(zip(enc, prots)):
         lo, hi = int(offs[i]), int(offs[i + 1])
