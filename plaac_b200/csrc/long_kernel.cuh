@@ -76,6 +76,11 @@ struct LongArgs {
     const DeviceTables* tabs;
     plaac_summary* out;
     int out_by_slot;  // 1: the record of list[i] goes to out[i] (per-residue calls without records: out is scratch)
+    // hmm_ext = 1: the Viterbi parse and both HMM scores come from k_long_post (long_residue.cuh: one thread-block cluster
+    // per protein); this kernel then computes only the plain sums, the window columns and the MW / LLR searches, leaves
+    // sum0 (hmm0's log-emission sum) in sum0_out[i] and k_long_final completes the record
+    int hmm_ext;
+    double* sum0_out;
     uint8_t* ext;   // ext code per residue (same byte layout as the bucketed stream)
     uint8_t* extT;  // the same, chunk-major: [position in chunk][chunk], so the 32 chunk lanes of a warp read 32
                     // consecutive bytes per step (one sector) instead of 32 different lines.  Used from cm_min
@@ -351,7 +356,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                     a0 = ks.li0 + le.x;
                     a1 = ks.li1 + le.y;
                     b1 = -INFINITY;
-                    tbk[0] = 0;
+                    if (!g.hmm_ext) tbk[0] = 0;
                     t0 = 1;
                 } else {
                     a0 = 0.0;
@@ -380,6 +385,10 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                     }
                 };
                 if (k == 0) stats(0, xt(0));
+                if (g.hmm_ext) {
+#pragma unroll 4
+                    for (int t = t0; t < ce; t++) stats(t, xt(t));
+                } else {
 #pragma unroll 4
                 for (int t = t0; t < ce; t++) {
                     const uint32_t e = xt(t);
@@ -394,6 +403,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                     if (k == 0) tbk[(size_t)(t - cs) * sR] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
                     stats(t, e);
                 }
+                }
                 sm.M[0][k] = a0;
                 sm.M[1][k] = a1;
                 sm.M[2][k] = b0;
@@ -406,7 +416,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                 sm.m_stop[k] = mstop;
             }
             // ---- forward LUT recurrence from `warm` residues before the chunk (first chunk: the true chain)
-            {
+            if (!g.hmm_ext) {
                 const int ts = (k == 0) ? 0 : max(0, cs - warm);
                 const int tmid = ce - warm;  // where the next chunk's warm-up starts
                 const double2 le0 = sm.le[xt(ts) & 31];
@@ -505,7 +515,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         long_chunk_bar();
         LONG_STAMP(1);
         // ================= combine 1: approximate absolute values (they only fix the binade of pass 2) =================
-        if (wid == 0) {
+        if (wid == 0 && !g.hmm_ext) {
             // Scan of the 2x2 max-plus chunk matrices: S_k = S_0 (x) M_1 (x) ... (x) M_k, 32 chunks per round with the
             // running product of all earlier rounds as carry (Kogge-Stone over warp shuffles).
             double c0 = sm.M[0][0], c1 = sm.M[1][0];
@@ -541,7 +551,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                 c0 = __shfl_sync(0xffffffffu, s0, 31);
                 c1 = __shfl_sync(0xffffffffu, s1, 31);
             }
-        } else if (wid == 1) {
+        } else if (wid == 1 && !g.hmm_ext) {
             // prefix sums of the forward increments (warp-shuffle scan with carry): a0 at cs-1 and at the warm-up start
             double carry = 0.0;
             for (int base = 0; base < K; base += 32) {
@@ -577,7 +587,40 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         // jar's sequential values up to an EXACT shift: Viterbi transfer entries and forward increments become exact
         // multiples of the ulp and their ordered combination is the jar's number bit for bit.  Chunks in which the
         // magnitude crosses a power of two (about one per binade) are redone sequentially from the exact values.
-        if (live && k >= 1) {
+        if (live && k >= 1 && g.hmm_ext) {
+            // (the HMM columns come from k_long_post: only the psum[] LLR search and the two plain sums, in their own frames)
+            double lagsum = 0;
+            for (int t = cs - c; t < cs; t++) lagsum += sm.llr[xt(t) & 31];
+            double lag = sm.q_abs[0][k] - lagsum;
+            double lead = lag;
+            for (int t = cs - c; t < cs; t++) lead = lead + sm.llr[xt(t) & 31];
+            const double lead0 = lead;
+            double best = -INFINITY, mid = lead;
+            int stop = -1;
+            const double x10 = sm.q_abs[1][k], x20 = sm.q_abs[2][k];
+            double x1 = x10, x2 = x20;
+#pragma unroll 4
+            for (int t = cs; t < ce; t++) {
+                const uint32_t e = xt(t);
+                lead = lead + sm.llr[e & 31];
+                lag = lag + sm.llr[xt(t - c) & 31];
+                const double d = lead - lag;  // exact, and the jar's number
+                if (d > best) {
+                    best = d;
+                    stop = t;
+                }
+                if (t == ce - c - 1) mid = lead;
+                x1 = x1 + sm.le[e & 31].x;
+                x2 = x2 + sm.hyd[e & 63];
+            }
+            sm.q_inc[0][k] = lead - lead0;
+            sm.q_mid[k] = mid - lead0;
+            sm.q_best[k] = best;
+            sm.q_stop[k] = stop;
+            sm.q_inc[1][k] = x1 - x10;
+            sm.q_inc[2][k] = x2 - x20;
+        }
+        if (live && k >= 1 && !g.hmm_ext) {
             {
                 const double lo = fmin(fabs(sm.Sa[0][k - 1]), fabs(sm.Sa[1][k - 1])) - 64.0;
                 const double hi = fmax(fabs(sm.Sa[0][k]), fabs(sm.Sa[1][k])) + 64.0;
@@ -733,7 +776,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         long_pass2_bar();
         LONG_STAMP(3);
         // ================= combine 2: exact, in chunk order =================
-        if (wid == 0 && lane == 0) {
+        if (wid == 0 && lane == 0 && !g.hmm_ext) {
             double S0 = sm.M[0][0], S1 = sm.M[1][0];
             sm.choice[0] = 0;
             for (int kk = 1; kk < K; kk++) {
@@ -893,7 +936,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         long_combined_arrive();
         LONG_STAMP(4);
         // ---- traceback of every chunk in parallel (:3110-3113) + run statistics for longestrun (:1787-1804)
-        if (live) {
+        if (live && !g.hmm_ext) {
             int v = sm.endstate[k];
             const int sh = 2 * sm.variant[k];
             int cur = 0, suf = 0, inmax = 0;
@@ -926,7 +969,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         long_chunk_bar();
     } else if (wid == kLongFwdWarp) {
         long_pass2_bar();
-        if (lane == 0) {
+        if (lane == 0 && !g.hmm_ext) {
             // forward: the chunk's trajectory is the jar's iff it enters the chunk with the bits of d the previous
             // chunk left with; then its increment is added exactly.  Otherwise the chunk is redone from the exact values.
             double A0 = sm.f_inc[0], dex = sm.f_dexit[0];
@@ -969,7 +1012,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             LONG_STAMP_LANE(11);
         }
         long_combined_wait();
-        if (lane == 0) {
+        if (lane == 0 && !g.hmm_ext) {
             g.out[g.out_by_slot ? (int32_t)blockIdx.x : prot].hmm_all = sm.lmarg - sm.sum0;
             if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
         }
@@ -987,7 +1030,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
     r->llr = sm.llr_best;
     r->llr_start = sm.llr_stop - c + 1;
     r->llr_end = sm.llr_stop;
-    r->hmm_vit = sm.lvit - sm.sum0;
+    if (!g.hmm_ext) r->hmm_vit = sm.lvit - sm.sum0;
     const double mh = (1.0 * sm.sh) / (double)n;
     const double mc = (1.0 * (double)sm.csum) / (double)n;
     r->fi_meanhydro = mh;
@@ -1019,6 +1062,11 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
     } else {
         r->papa_combo = -INFINITY;
         r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = nan("");
+    }
+    if (g.hmm_ext) {
+        // Viterbi run statistics, CORE search and the two HMM scores: k_long_final, from k_long_post's parse
+        g.sum0_out[blockIdx.x] = sm.sum0;
+        return;
     }
     // longestrun
     int open = 0, mx = 0;
@@ -1120,6 +1168,153 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
         long_score_body<true>(g);
     else
         long_score_body<false>(g);
+}
+
+// The Viterbi-dependent columns of a long protein whose HMM columns come from k_long_post (LongArgs::hmm_ext): Viterbi
+// bytes -> bit words, longestrun (:1787-1804), the -1e6-masked CORE search with PrD expansion and PRDscore (:816-873)
+// exactly as at the end of k_long_score.  It needs nothing from k_long_score (residue codes straight from the input), so
+// it runs behind k_long_post while k_long_score is still at work; k_long_fix then writes the two HMM scores.
+constexpr int kLongFinalThreads = 256;
+__global__ void __launch_bounds__(kLongFinalThreads)
+k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
+{
+    __shared__ double llr_s[kTabN];
+    __shared__ int s_all[kLongFinalThreads], s_pre[kLongFinalThreads], s_suf[kLongFinalThreads], s_max[kLongFinalThreads];
+    const int tid = threadIdx.x;
+    const int32_t prot = g.list[blockIdx.x];
+    const int64_t so = g.scratch_off[blockIdx.x];
+    const int n = (int)(g.offsets[prot + 1] - g.offsets[prot]);
+    const uint8_t* __restrict__ src = g.codes + (g.offsets[prot] - g.off_base);
+    const uint8_t* __restrict__ vb = vbytes_all + so;
+    uint32_t* __restrict__ vit = g.vit + (so >> 5);
+    const KScalars& ks = g.ks;
+    const int c = ks.core_len;
+    if (tid < kTabN) llr_s[tid] = g.tabs->llr[tid];
+    // ---- bytes -> bit words; per-thread run statistics of a contiguous range of words
+    const int nwords = (n + 31) >> 5;
+    const int per = (nwords + kLongFinalThreads - 1) / kLongFinalThreads;
+    {
+        const int w_lo = tid * per, w_hi = min(nwords, w_lo + per);
+        int cur = 0, pre = 0, inmax = 0;
+        bool closed = false;
+        for (int j = w_lo; j < w_hi; j++) {
+            uint32_t word = 0;
+            const int t_hi = min(n, 32 * j + 32);
+            for (int t = 32 * j; t < t_hi; t++) {
+                const uint32_t v = vb[t] & 1u;
+                word |= v << (t & 31);
+                if (v)
+                    cur++;
+                else {
+                    if (!closed) {
+                        pre = cur;
+                        closed = true;
+                    } else
+                        inmax = max(inmax, cur);
+                    cur = 0;
+                }
+            }
+            vit[j] = word;
+        }
+        s_all[tid] = closed ? 0 : 1;      // the range is one run of ones (or empty)
+        s_pre[tid] = closed ? pre : cur;  // ones at its start
+        s_suf[tid] = cur;                 // ones at its end
+        s_max[tid] = inmax;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    plaac_summary* r = g.out + (g.out_by_slot ? (int32_t)blockIdx.x : prot);
+    auto code = [&](int p) -> uint32_t {
+        const uint32_t cd = src[p];
+        return cd > 21u ? 0u : cd;
+    };
+    int open = 0, mx = 0;
+    for (int k = 0; k < kLongFinalThreads; k++) {
+        if (s_all[k])
+            open += s_pre[k];
+        else {
+            mx = max(mx, max(open + s_pre[k], s_max[k]));
+            open = s_suf[k];
+        }
+    }
+    mx = max(mx, open);
+    r->vit_maxrun = mx;
+    r->core_start = -1;
+    r->core_end = -2;
+    r->prd_start = -1;
+    r->prd_end = -2;
+    r->core_score = nan("");
+    r->prd_score = 0.0;
+    if (mx < c) return;
+    const double big_neg = ks.big_neg;
+    const bool can_jump = big_neg < 0 && big_neg == floor(big_neg) && big_neg >= -4194304.0;
+    double ps = 0.0, lag = 0.0, best = -INFINITY, runsum = 0.0, prd_sc = 0.0;
+    int bstop = -1, run = 0, last = 0, run_start = 0, prd_s = -1, prd_e = -2;
+    bool hit = false;
+    for (int j = 0; j < nwords; j++) {
+        uint32_t bits = vit[j];
+        while (bits) {
+            const int i = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int p = 32 * j + i;
+            if (p != last) {
+                if (hit) {
+                    prd_s = run_start;
+                    prd_e = last - 1;
+                    prd_sc = runsum;
+                    hit = false;
+                }
+                if (can_jump)
+                    ps = masked_jump(ps, p - last, big_neg);
+                else
+                    for (int q = last; q < p; q++) ps = ps + big_neg;
+                run = 0;
+            }
+            if (run == 0) {
+                lag = ps;
+                run_start = p;
+                runsum = 0.0;
+            }
+            const double x = llr_s[code(p)];
+            ps = ps + x;
+            runsum = runsum + x;
+            if (run >= c - 1) {
+                const double d = ps - lag;
+                if (d > best) {
+                    best = d;
+                    bstop = p;
+                    hit = true;
+                }
+                lag = lag + llr_s[code(p - c + 1)];
+            }
+            run++;
+            last = p + 1;
+        }
+    }
+    if (hit) {
+        prd_s = run_start;
+        prd_e = last - 1;
+        prd_sc = runsum;
+    }
+    if (best > big_neg / 2) {
+        r->core_start = bstop - c + 1;
+        r->core_end = bstop;
+        r->core_score = best;
+        r->prd_start = prd_s;
+        r->prd_end = prd_e;
+        r->prd_score = prd_sc;
+    }
+}
+
+// HMMall = lmarginalprob - sum0, HMMvit = lviterbiprob - sum0 (:790-800) once k_long_post (scores) and k_long_score (sum0) are done
+__global__ void __launch_bounds__(128) k_long_fix(LongArgs g, const double* __restrict__ hmm_out, int nlong)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlong) return;
+    plaac_summary* r = g.out + (g.out_by_slot ? i : g.list[i]);
+    const double sum0 = g.sum0_out[i];
+    r->hmm_all = hmm_out[2 * i] - sum0;
+    r->hmm_vit = hmm_out[2 * i + 1] - sum0;
 }
 
 }  // namespace plaac

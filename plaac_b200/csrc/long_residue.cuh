@@ -56,6 +56,9 @@ struct LongPostArgs {
     // Viterbi parse (viterbidecodel :3077-3121) for calls without records, where k_long_score does not run: chunk
     // transfer matrices, a max-plus scan for the binades, two exact frames per chunk, exact combine, parallel traceback
     int want_vit;
+    int want_post;               // 0: records only (summary mode): forward + Viterbi, no backward pass, no per-residue arrays
+    double* hmm_out;             // per listed protein {lmarginalprob, lviterbiprob} (:3369-3375, :3102-3108) for k_long_final
+    uint8_t* vbytes;             // Viterbi parse, one byte per residue at scratch_off + t, when out.vit is NULL
     uint8_t* tb;                 // 4 traceback bits per residue, indexed scratch_off + t
     unsigned long long vit_tie_mask;  // binades in which a Viterbi constant is an exact rounding tie (plaac_create)
     long long* dbg_clocks;       // optional: phase time stamps of the first CTA (PLAAC_LONG_CLOCKS)
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
     unsigned char* __restrict__ gC = reinterpret_cast<unsigned char*>(gA + 4 * kLpBndRow);  // per chunk: choice | cross << 2; [K]: vlast
     uint8_t* __restrict__ tb = g.tb + so;
     const bool vit = g.want_vit != 0;
+    const bool post = g.want_post != 0;
 
     // geometry: C residues per chunk, K chunks over the cluster's lanes, warm-up of m whole chunks
     const int lanes = X * kLpThreads;
@@ -264,7 +268,10 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                 sm.g_ea0[0][1][tid] = a0, sm.g_den[0][1][tid] = a1;
             }
         }
-        {
+        if (!post) {
+            sm.inc[1][tid] = 0.0;
+            sm.mode[1][tid] = 1;
+        } else {
             double b0 = ks.lf0, b1 = ks.lf1, e0 = 0.0, e1 = 0.0;
             if (bi2 == bi) bw_x = b0, bw_d = b1 - b0;
 #pragma unroll 4
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
             }
         }
         // ---- backward
-        if (bi != n - 1) {
+        if (post && bi != n - 1) {
             if (lp_cross(gB[kg + 1], gB[kg])) {
                 sm.mode[1][tid] = 1;
             } else {
@@ -558,10 +565,12 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                 *reinterpret_cast<volatile double*>(&o->vcarry[1]) = Sx1;
                 lp_signal(&o->flag[2]);
             } else {
-                gC[K] = (unsigned char)((Sx1 + ks.lf1 > Sx0 + ks.lf0) ? 1 : 0);  // :3102-3108
+                const double e0v = Sx0 + ks.lf0, e1v = Sx1 + ks.lf1;  // :3102-3108
+                gC[K] = (unsigned char)(e1v > e0v ? 1 : 0);
+                if (g.hmm_out) g.hmm_out[2 * pslot + 1] = e1v > e0v ? e1v : e0v;
             }
         }
-        const int dir = (tid == 0) ? 0 : (tid == 32 ? 1 : -1);
+        const int dir = (tid == 0) ? 0 : ((tid == 32 && post) ? 1 : -1);
         if (dir >= 0 && rank < R) {
             const bool first = dir == 0 ? rank == 0 : rank == R - 1;
             if (!first) lp_wait(&sm.flag[dir]);
@@ -647,6 +656,8 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                 *reinterpret_cast<volatile double*>(&o->carry[dir][1]) = x1;
                 *reinterpret_cast<volatile int*>(&o->carry_acc[dir]) = acc ? 1 : 0;
                 lp_signal(&o->flag[dir]);
+            } else if (dir == 0 && g.hmm_out) {
+                g.hmm_out[2 * pslot] = lse_lut2<false>(x0 + ks.lf0, x1 + ks.lf1, lut);  // lmarginalprob :3369-3375
             }
         }
         __syncthreads();  // (the other lanes sleep here; the waiting walkers of other CTAs poll their flags with back-off)
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
 
     LP_STAMP(5);
     // ================= pass 3: every chunk from its exact boundary state =================
-    if (live) {
+    if (live && post) {
         {
             double b0, b1;
             int t = ce - 1;
@@ -743,10 +754,10 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
             }
         }
         __syncthreads();
-        if (live && g.out.vit) {
+        if (live && (g.out.vit || g.vbytes)) {
             // :3110-3113 for every chunk in parallel; frame A if the chunk is entered in state 0, B if in state 1 (redone
             // chunks and the first one hold the exact bits as frame A)
-            uint8_t* dst = g.out.vit + (o - g.res_base);
+            uint8_t* dst = g.out.vit ? g.out.vit + (o - g.res_base) : g.vbytes + so;
             int v = sm.vend[tid];
             const unsigned cb = sm.vall[kg];
             const int sh = (cb & 4u) || kg == 0 ? 0 : 2 * (int)((cb >> v) & 1u);
@@ -770,7 +781,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
 
     LP_STAMP(6);
     // ================= pass 4: posteriors and MAP bytes, coalesced =================
-    {
+    if (post) {
         const double lpseq = g.lpseq[pslot];
         const int64_t ob = o - g.res_base;
         const int per = (n + X - 1) / X;

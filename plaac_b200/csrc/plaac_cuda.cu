@@ -53,6 +53,7 @@ struct Slot {
     DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
     DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_extT, lg_tb, lg_vit;                             // long-sequence path
     DevBuf lg_rec, lp_s0, lp_s1, lp_bnd, lp_lpseq;  // ... in per-residue mode (long_residue.cuh)
+    DevBuf lg_hmm, lg_sum0, lg_vb;                  // ... records with the HMM columns from k_long_post (k_long_final)
     unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues, or 3 x kLongBins bins
     DevBuf lg_bins;
     cudaStream_t aux1 = nullptr, aux2 = nullptr, aux3 = nullptr, aux4 = nullptr, aux5 = nullptr;
@@ -398,7 +399,7 @@ void slot_free(Slot& s)
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
-                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins, &s.lg_rec, &s.lp_s0, &s.lp_s1, &s.lp_bnd, &s.lp_lpseq})
+                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins, &s.lg_rec, &s.lp_s0, &s.lp_s1, &s.lp_bnd, &s.lp_lpseq, &s.lg_hmm, &s.lg_sum0, &s.lg_vb})
         release(*b);
     if (s.h_long) cudaFreeHost(s.h_long);
     if (s.h_stage_codes) cudaFreeHost(s.h_stage_codes);
@@ -668,22 +669,39 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         CU(ctx, cudaStreamWaitEvent(long_st, s.ev_fork, 0));
         // (a per-residue call without records gets its Viterbi parse from k_long_post instead)
         const bool run_score = d_summaries != nullptr;
+        // Records without per-residue arrays: the HMM columns (Viterbi parse, lviterbiprob, lmarginalprob) come from
+        // k_long_post's thread-block cluster, k_long_score computes the rest beside it on its own SM and k_long_final
+        // completes the record.  PLAAC_LONG_HYBRID=0: k_long_score alone (one CTA per protein, the round-1 path).
+        const bool hybrid = run_score && !d_res && !(getenv("PLAAC_LONG_HYBRID") && getenv("PLAAC_LONG_HYBRID")[0] == '0');
+        if (hybrid) {
+            if ((rc = ensure(ctx, s.lg_hmm, sizeof(double) * 2 * (size_t)nlong))) return rc;
+            if ((rc = ensure(ctx, s.lg_sum0, sizeof(double) * (size_t)nlong))) return rc;
+            if ((rc = ensure(ctx, s.lg_vb, (size_t)long_scratch + 256))) return rc;
+            la.hmm_ext = 1;
+            la.sum0_out = (double*)s.lg_sum0.p;
+        } else {
+            la.hmm_ext = 0;
+            la.sum0_out = nullptr;
+        }
         if (run_score) {
             k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), long_st>>>(la);
             ctx->stats.kernel_launches += 1;
         }
         long_launched = true;
         ctx->stats.long_proteins += nlong;
-        if (d_res) {
-            if (d_res->vit && run_score) {
+        if (d_res || hybrid) {
+            if (d_res && d_res->vit && run_score) {
                 k_long_vit_bytes<<<dim3(8, (unsigned)nlong), 256, 0, long_st>>>(d_offsets, res_base, la.list, la.scratch_off, la.vit, d_res->vit);
                 ctx->stats.kernel_launches += 1;
             }
-            // posteriors + MAP parse of the long proteins: one cluster per protein, two size classes
-            if ((rc = ensure(ctx, s.lp_s0, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
-            if ((rc = ensure(ctx, s.lp_s1, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
+            // one cluster per long protein, two size classes: posteriors + MAP parse (+ Viterbi parse), or, for records,
+            // the forward score and the Viterbi parse
+            if (d_res) {
+                if ((rc = ensure(ctx, s.lp_s0, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
+                if ((rc = ensure(ctx, s.lp_s1, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
+                if ((rc = ensure(ctx, s.lp_lpseq, sizeof(double) * (size_t)nlong))) return rc;
+            }
             if ((rc = ensure(ctx, s.lp_bnd, sizeof(double) * (size_t)kLpBndStride * (size_t)nlong))) return rc;
-            if ((rc = ensure(ctx, s.lp_lpseq, sizeof(double) * (size_t)nlong))) return rc;
             LongPostArgs pa;
             pa.codes = d_codes;
             pa.offsets = d_offsets;
@@ -693,16 +711,22 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             pa.scratch_off = la.scratch_off;
             pa.ks = ctx->ks;
             pa.tabs = ctx->d_tabs;
-            pa.out = *d_res;
-            pa.S0 = (double*)s.lp_s0.p;
-            pa.S1 = (double*)s.lp_s1.p;
+            if (d_res)
+                pa.out = *d_res;
+            else
+                memset(&pa.out, 0, sizeof(pa.out));
+            pa.S0 = d_res ? (double*)s.lp_s0.p : nullptr;
+            pa.S1 = d_res ? (double*)s.lp_s1.p : nullptr;
             pa.bnd = (double*)s.lp_bnd.p;
-            pa.lpseq = (double*)s.lp_lpseq.p;
+            pa.lpseq = d_res ? (double*)s.lp_lpseq.p : nullptr;
             pa.warm = std::max(1, std::abs(ctx->long_warm));
             pa.warm2 = getenv("PLAAC_LP_WARM2") ? atoi(getenv("PLAAC_LP_WARM2")) : 64;
             pa.big_min = getenv("PLAAC_LP_BIG_MIN") ? atoll(getenv("PLAAC_LP_BIG_MIN")) : (int64_t)kLpBigMin;
             pa.redone = la.redone;
-            pa.want_vit = (!run_score && d_res->vit) ? 1 : 0;
+            pa.want_post = d_res ? 1 : 0;
+            pa.want_vit = hybrid ? 1 : ((!run_score && d_res->vit) ? 1 : 0);
+            pa.hmm_out = hybrid ? (double*)s.lg_hmm.p : nullptr;
+            pa.vbytes = hybrid ? (uint8_t*)s.lg_vb.p : nullptr;
             pa.tb = la.tb;
             pa.vit_tie_mask = la.tie_mask[0];
             pa.errflag = la.errflag;
@@ -727,6 +751,15 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
                 cfg.numAttrs = 1;
                 CU(ctx, cudaLaunchKernelEx(&cfg, k_long_post, pa));
                 ctx->stats.kernel_launches += 1;
+            }
+            if (hybrid) {
+                // the Viterbi-dependent columns right behind the cluster kernel, beside k_long_score; the two HMM scores
+                // when both are done
+                k_long_final<<<(unsigned)nlong, kLongFinalThreads, 0, s.aux5>>>(la, (const uint8_t*)s.lg_vb.p);
+                CU(ctx, cudaEventRecord(s.ev_j5, s.aux5));
+                CU(ctx, cudaStreamWaitEvent(long_st, s.ev_j5, 0));
+                k_long_fix<<<(unsigned)((nlong + 127) / 128), 128, 0, long_st>>>(la, (const double*)s.lg_hmm.p, (int)nlong);
+                ctx->stats.kernel_launches += 2;
             }
         }
     }
