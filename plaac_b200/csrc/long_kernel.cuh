@@ -1180,6 +1180,7 @@ k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
 {
     __shared__ double llr_s[kTabN];
     __shared__ int s_all[kLongFinalThreads], s_pre[kLongFinalThreads], s_suf[kLongFinalThreads], s_max[kLongFinalThreads];
+    __shared__ unsigned char s_any[kLongFinalThreads];  // the thread's range of words holds a Viterbi-1 residue
     const int tid = threadIdx.x;
     const int32_t prot = g.list[blockIdx.x];
     const int64_t so = g.scratch_off[blockIdx.x];
@@ -1197,6 +1198,7 @@ k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
         const int w_lo = tid * per, w_hi = min(nwords, w_lo + per);
         int cur = 0, pre = 0, inmax = 0;
         bool closed = false;
+        uint32_t any = 0;
         for (int j = w_lo; j < w_hi; j++) {
             uint32_t word = 0;
             const int t_hi = min(n, 32 * j + 32);
@@ -1215,7 +1217,9 @@ k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
                 }
             }
             vit[j] = word;
+            any |= word;
         }
+        s_any[tid] = any ? 1 : 0;
         s_all[tid] = closed ? 0 : 1;      // the range is one run of ones (or empty)
         s_pre[tid] = closed ? pre : cur;  // ones at its start
         s_suf[tid] = cur;                 // ones at its end
@@ -1252,6 +1256,10 @@ k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
     int bstop = -1, run = 0, last = 0, run_start = 0, prd_s = -1, prd_e = -2;
     bool hit = false;
     for (int j = 0; j < nwords; j++) {
+        if (j % per == 0 && !s_any[j / per]) {  // a range without a Viterbi-1 residue is one masked stretch
+            j += per - 1;
+            continue;
+        }
         uint32_t bits = vit[j];
         while (bits) {
             const int i = __ffs((int)bits) - 1;
