@@ -1176,7 +1176,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) k_long_score(LongArgs g)
 // it runs behind k_long_post while k_long_score is still at work; k_long_fix then writes the two HMM scores.
 constexpr int kLongFinalThreads = 256;
 __global__ void __launch_bounds__(kLongFinalThreads)
-k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
+k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all, const uint8_t* __restrict__ vit_out, int64_t res_base)
 {
     __shared__ double llr_s[kTabN];
     __shared__ int s_all[kLongFinalThreads], s_pre[kLongFinalThreads], s_suf[kLongFinalThreads], s_max[kLongFinalThreads];
@@ -1186,7 +1186,8 @@ k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all)
     const int64_t so = g.scratch_off[blockIdx.x];
     const int n = (int)(g.offsets[prot + 1] - g.offsets[prot]);
     const uint8_t* __restrict__ src = g.codes + (g.offsets[prot] - g.off_base);
-    const uint8_t* __restrict__ vb = vbytes_all + so;
+    // the parse lies in the caller's per-residue array if there is one, else in scratch
+    const uint8_t* __restrict__ vb = vit_out ? vit_out + (g.offsets[prot] - res_base) : vbytes_all + so;
     uint32_t* __restrict__ vit = g.vit + (so >> 5);
     const KScalars& ks = g.ks;
     const int c = ks.core_len;

@@ -669,10 +669,10 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         CU(ctx, cudaStreamWaitEvent(long_st, s.ev_fork, 0));
         // (a per-residue call without records gets its Viterbi parse from k_long_post instead)
         const bool run_score = d_summaries != nullptr;
-        // Records without per-residue arrays: the HMM columns (Viterbi parse, lviterbiprob, lmarginalprob) come from
+        // Records: the HMM columns (Viterbi parse, lviterbiprob, lmarginalprob) come from
         // k_long_post's thread-block cluster, k_long_score computes the rest beside it on its own SM and k_long_final
         // completes the record.  PLAAC_LONG_HYBRID=0: k_long_score alone (one CTA per protein, the round-1 path).
-        const bool hybrid = run_score && !d_res && !(getenv("PLAAC_LONG_HYBRID") && getenv("PLAAC_LONG_HYBRID")[0] == '0');
+        const bool hybrid = run_score && !(getenv("PLAAC_LONG_HYBRID") && getenv("PLAAC_LONG_HYBRID")[0] == '0');
         if (hybrid) {
             if ((rc = ensure(ctx, s.lg_hmm, sizeof(double) * 2 * (size_t)nlong))) return rc;
             if ((rc = ensure(ctx, s.lg_sum0, sizeof(double) * (size_t)nlong))) return rc;
@@ -690,7 +690,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         long_launched = true;
         ctx->stats.long_proteins += nlong;
         if (d_res || hybrid) {
-            if (d_res && d_res->vit && run_score) {
+            if (d_res && d_res->vit && run_score && !hybrid) {
                 k_long_vit_bytes<<<dim3(8, (unsigned)nlong), 256, 0, long_st>>>(d_offsets, res_base, la.list, la.scratch_off, la.vit, d_res->vit);
                 ctx->stats.kernel_launches += 1;
             }
@@ -726,7 +726,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             pa.want_post = d_res ? 1 : 0;
             pa.want_vit = hybrid ? 1 : ((!run_score && d_res->vit) ? 1 : 0);
             pa.hmm_out = hybrid ? (double*)s.lg_hmm.p : nullptr;
-            pa.vbytes = hybrid ? (uint8_t*)s.lg_vb.p : nullptr;
+            pa.vbytes = (hybrid && !(d_res && d_res->vit)) ? (uint8_t*)s.lg_vb.p : nullptr;
             pa.tb = la.tb;
             pa.vit_tie_mask = la.tie_mask[0];
             pa.errflag = la.errflag;
@@ -755,7 +755,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             if (hybrid) {
                 // the Viterbi-dependent columns right behind the cluster kernel, beside k_long_score; the two HMM scores
                 // when both are done
-                k_long_final<<<(unsigned)nlong, kLongFinalThreads, 0, s.aux5>>>(la, (const uint8_t*)s.lg_vb.p);
+                k_long_final<<<(unsigned)nlong, kLongFinalThreads, 0, s.aux5>>>(la, (const uint8_t*)s.lg_vb.p, (d_res && d_res->vit) ? d_res->vit : nullptr, res_base);
                 CU(ctx, cudaEventRecord(s.ev_j5, s.aux5));
                 CU(ctx, cudaStreamWaitEvent(long_st, s.ev_j5, 0));
                 k_long_fix<<<(unsigned)((nlong + 127) / 128), 128, 0, long_st>>>(la, (const double*)s.lg_hmm.p, (int)nlong);
