@@ -302,6 +302,8 @@ int plaac_set_chunk(plaac_ctx *ctx, int64_t max_residues, int64_t max_proteins);
  * current value (default 256); a negative value redoes every forward chunk sequentially (testing).  Both paths give the
  * same bytes in every column (the recurrences by the binade-frame argument, the window columns because their sums are
  * exact on a 2^-41 grid), so records do not depend on the setting, the batching or the sharding.
+ * Since round 2 the HMM columns of such a record (forward score, Viterbi parse and score) come from the cluster kernel
+ * below, run beside the CTA that computes the other columns; the bytes are the same.
  * Per-residue mode (plotsomefastas :610-647 on long proteins): the same threshold sends a protein to one thread-block
  * cluster (csrc/long_residue.cuh: 1 CTA below 32768 residues, 8 above; forward, backward and Viterbi recurrences
  * chunk-parallel in the jar's binade with an exact carry over the chunk boundaries, relayed between the CTAs through
