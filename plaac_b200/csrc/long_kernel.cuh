@@ -75,7 +75,6 @@ struct LongArgs {
     KScalars ks;
     const DeviceTables* tabs;
     plaac_summary* out;
-    int out_by_slot;  // 1: the record of list[i] goes to out[i] (per-residue calls without records: out is scratch)
     // hmm_ext = 1: the Viterbi parse and both HMM scores come from k_long_post (long_residue.cuh: one thread-block cluster
     // per protein); this kernel then computes only the plain sums, the window columns and the MW / LLR searches, leaves
     // sum0 (hmm0's log-emission sum) in sum0_out[i] and k_long_final completes the record
@@ -1013,7 +1012,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         }
         long_combined_wait();
         if (lane == 0 && !g.hmm_ext) {
-            g.out[g.out_by_slot ? (int32_t)blockIdx.x : prot].hmm_all = sm.lmarg - sm.sum0;
+            g.out[prot].hmm_all = sm.lmarg - sm.sum0;
             if (g.redone && sm.fwd_redone) atomicAdd(g.redone, (unsigned long long)sm.fwd_redone);
         }
         return;
@@ -1022,7 +1021,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
     LONG_STAMP(6);
 
     if (tid != 0) return;
-    plaac_summary* r = g.out + (g.out_by_slot ? (int32_t)blockIdx.x : prot);
+    plaac_summary* r = g.out + prot;
     r->prot_len = n;
     r->mw_score = sm.mw_best;
     r->mw_start = sm.mw_stop - mw + 1;
@@ -1228,7 +1227,7 @@ k_long_final(LongArgs g, const uint8_t* __restrict__ vbytes_all, const uint8_t* 
     }
     __syncthreads();
     if (tid != 0) return;
-    plaac_summary* r = g.out + (g.out_by_slot ? (int32_t)blockIdx.x : prot);
+    plaac_summary* r = g.out + prot;
     auto code = [&](int p) -> uint32_t {
         const uint32_t cd = src[p];
         return cd > 21u ? 0u : cd;
@@ -1320,7 +1319,7 @@ __global__ void __launch_bounds__(128) k_long_fix(LongArgs g, const double* __re
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlong) return;
-    plaac_summary* r = g.out + (g.out_by_slot ? i : g.list[i]);
+    plaac_summary* r = g.out + g.list[i];
     const double sum0 = g.sum0_out[i];
     r->hmm_all = hmm_out[2 * i] - sum0;
     r->hmm_vit = hmm_out[2 * i + 1] - sum0;

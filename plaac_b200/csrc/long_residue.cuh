@@ -1,19 +1,26 @@
-// Long-sequence path, per-residue mode (plotsomefastas :610-647 on titin-length proteins): the posterior columns and the
-// MAP parse of proteins the bucketed kernels would walk in a single lane (posteriorl :3349-3411, mapdecodel :4032-4045).
+// Long-sequence path on a thread-block cluster: the per-residue arrays of proteins the bucketed kernels would walk in a
+// single lane (plotsomefastas :610-647 on titin-length proteins: posteriorl :3349-3411, mapdecodel :4032-4045,
+// viterbidecodel :3077-3121) and, in records-only mode, the HMM columns of their summary record (forward score, Viterbi
+// parse and score; the other columns: long_kernel.cuh).
 //
 // ONE THREAD-BLOCK CLUSTER per long protein (1 or 8 CTAs x 512 lanes), one lane per chunk of >= 32 residues.  Forward and
-// backward LUT recurrences both get the binade-frame treatment of long_kernel.cuh (pass 1: chunk-local frame after a
-// warm-up, prefix / suffix sums of the chunk increments; pass 2: two frames one ulp apart in the jar's own binade), then
+// backward LUT recurrences both get the binade-frame treatment of long_kernel.cuh, the Viterbi recurrence its max-plus
+// transfer matrices:
 //
-//   carry    one lane per direction walks the chunks in order and accepts the frame that enters the chunk an even number of
+//   pass 1   chunk-local frame: forward / backward after a 256-residue warm-up, the chunk's 2x2 max-plus matrix; prefix /
+//            suffix sums and a Kogge-Stone matrix scan over warp shuffles give approximate absolute values at every chunk
+//            boundary (they only decide binades); the CTA totals cross the cluster through DISTRIBUTED SHARED MEMORY
+//   pass 2   the jar's own binade: two frames one ulp apart from pass 1's d (64-residue warm-up), two exact Viterbi frames
+//   carry    one lane per chain walks the chunks in order and accepts the frame that enters the chunk an even number of
 //            ulps from the exact value with exactly the bits of d = x1 - x0 the previous chunk left with (else it redoes the
-//            chunk sequentially: binade crossings, |x| < 1024, uncoalesced warm-ups).  The exact state at every chunk
-//            boundary is kept.  Across the CTAs of the cluster the walk is a relay: the CTA's walker hands its exact state to
-//            the next CTA through DISTRIBUTED SHARED MEMORY (forward: rank r -> r+1, backward: r -> r-1), one cluster
-//            barrier per stage; the approximate prefix sums of pass 1 get their cross-CTA carry the same way.
+//            chunk sequentially: binade crossings, |x| < 1024, uncoalesced warm-ups); chunks known beforehand to be linked
+//            cost one addition.  The exact state at every chunk boundary is kept.  Across the CTAs the walk is a relay:
+//            the walker writes its exact state into the next CTA's shared memory (DSMEM), fences at cluster scope and sets
+//            a flag the next walker polls with back-off (forward and Viterbi: rank r -> r+1, backward: r -> r-1)
 //   pass 3   every lane re-runs its chunk from the EXACT boundary state: backward first (b into scratch), then forward,
-//            which leaves a + b per state in scratch.  These are the jar's a[][] and b[][] bit for bit.
-//   pass 4   all threads, coalesced: pp = exp((a + b) - lpseq) (:3401-3405), MAP byte = pp1 > pp0.
+//            which leaves a + b per state in scratch -- the jar's a[][] and b[][] bit for bit; Viterbi chunks are traced
+//            back in parallel from the end states (a warp-parallel suffix composition of the chunks' choice maps)
+//   pass 4   all threads, coalesced: pp = exp((a + b) - lpseq) (:3401-3405), MAP byte = pp1 > pp0
 //
 // Small chunks make the sequential part cheap: a binade crossing costs its 2-3 chunks of 32-200 residues instead of a
 // 288-residue chunk, and chunks whose warm-up reaches the protein's start (end) run the true chain and are exact as they are.

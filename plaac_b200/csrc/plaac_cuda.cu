@@ -52,7 +52,7 @@ struct Slot {
     DevBuf ing_text, ing_codes, ing_offsets, ing_npos, ing_nlen, ing_flags, ing_hist;  // staging for the host-buffer ingest
     DevBuf rk_keys[2], rk_vals[2], rk_hist, rk_offs, rk_order;                         // ranking scratch
     DevBuf lg_list, lg_off, lg_cnt, lg_ext, lg_extT, lg_tb, lg_vit;                             // long-sequence path
-    DevBuf lg_rec, lp_s0, lp_s1, lp_bnd, lp_lpseq;  // ... in per-residue mode (long_residue.cuh)
+    DevBuf lp_s0, lp_s1, lp_bnd, lp_lpseq;          // ... in per-residue mode (long_residue.cuh)
     DevBuf lg_hmm, lg_sum0, lg_vb;                  // ... records with the HMM columns from k_long_post (k_long_final)
     unsigned long long* h_long = nullptr;  // pinned: [0] long proteins, [1] scratch residues, or 3 x kLongBins bins
     DevBuf lg_bins;
@@ -399,7 +399,7 @@ void slot_free(Slot& s)
                       &s.res_b1, &s.res_a0, &s.res_a1, &s.res_mapw, &s.res_lpseq, &s.ing_agg, &s.ing_cnt, &s.ing_base,
                       &s.ing_misc, &s.ing_text, &s.ing_codes, &s.ing_offsets, &s.ing_npos, &s.ing_nlen, &s.ing_flags,
                       &s.ing_hist, &s.rk_keys[0], &s.rk_keys[1], &s.rk_vals[0], &s.rk_vals[1], &s.rk_hist, &s.rk_offs,
-                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins, &s.lg_rec, &s.lp_s0, &s.lp_s1, &s.lp_bnd, &s.lp_lpseq, &s.lg_hmm, &s.lg_sum0, &s.lg_vb})
+                      &s.rk_order, &s.lg_list, &s.lg_off, &s.lg_cnt, &s.lg_ext, &s.lg_extT, &s.lg_tb, &s.lg_vit, &s.lg_bins, &s.lp_s0, &s.lp_s1, &s.lp_bnd, &s.lp_lpseq, &s.lg_hmm, &s.lg_sum0, &s.lg_vb})
         release(*b);
     if (s.h_long) cudaFreeHost(s.h_long);
     if (s.h_stage_codes) cudaFreeHost(s.h_stage_codes);
@@ -649,7 +649,6 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         la.ks = ctx->ks;
         la.tabs = ctx->d_tabs;
         la.out = d_summaries;
-        la.out_by_slot = 0;
         la.ext = (uint8_t*)s.lg_ext.p;
         la.extT = (uint8_t*)s.lg_extT.p;
         la.cm_min = getenv("PLAAC_LONG_CM_MIN") ? atoi(getenv("PLAAC_LONG_CM_MIN")) : kLongChunkMajorMin;
