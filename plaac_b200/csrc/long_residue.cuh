@@ -38,8 +38,10 @@ constexpr int kLpThreads = 512;   // chunk lanes per CTA
 constexpr int kLpMinChunk = 32;
 constexpr int kLpBigCluster = 8;  // CTAs per protein of at least kLpBigMin residues
 constexpr int kLpBigMin = 32768;  // (an edge of k_long_levels' length bins: the host counts the classes from them)
-constexpr int kLpBndRow = kLpBigCluster * kLpThreads + 8;
-constexpr int kLpBndStride = 5 * kLpBndRow;  // doubles of boundary scratch per listed protein: gA, gB, gV0, gV1, bytes
+// Boundary scratch: five planes (gA, gB, gV0, gV1, bytes) of bnd_plane doubles; a protein's row starts at scratch_off / 32
+// in every plane and has (n + 128) / 32 >= K + 2 entries (K <= n / 32 + 1 chunks), so the scratch is 1.25 bytes per long residue
+// however many long proteins there are.
+constexpr int kLpBndPlanes = 5;
 
 struct LongPostArgs {
     const uint8_t* codes;
@@ -53,7 +55,8 @@ struct LongPostArgs {
     plaac_residue_out out;
     double* S0;                  // scratch planes, indexed scratch_off + t: b0 then a0 + b0
     double* S1;
-    double* bnd;                 // per listed protein kLpBndStride doubles: approximate a0 / b0 at the chunk boundaries
+    double* bnd;                 // kLpBndPlanes planes of bnd_plane doubles: approximate a0 / b0 / Viterbi scores at the chunk boundaries
+    int64_t bnd_plane;
     double* lpseq;               // per listed protein
     int warm;                    // warm-up residues of pass 1 (rounded up to whole chunks): d coalesces from a generic start
     int warm2;                   // ... of pass 2, which starts from pass 1's d (within a few ulps of the jar's)
@@ -203,11 +206,11 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
     const int64_t so = g.scratch_off[pslot];
     double* __restrict__ S0 = g.S0 + so;
     double* __restrict__ S1 = g.S1 + so;
-    double* __restrict__ gA = g.bnd + (size_t)pslot * kLpBndStride;  // gA[j]: approximate a0 at residue j*C - 1 (j = 1..K)
-    double* __restrict__ gB = gA + kLpBndRow;                        // gB[j]: approximate b0 at residue j*C     (j = 0..K-1)
-    double* __restrict__ gV0 = gA + 2 * kLpBndRow;                   // gV*[k]: approximate Viterbi scores at chunk k's last residue
-    double* __restrict__ gV1 = gA + 3 * kLpBndRow;
-    unsigned char* __restrict__ gC = reinterpret_cast<unsigned char*>(gA + 4 * kLpBndRow);  // per chunk: choice | cross << 2; [K]: vlast
+    double* __restrict__ gA = g.bnd + (so >> 5);                     // gA[j]: approximate a0 at residue j*C - 1 (j = 1..K)
+    double* __restrict__ gB = gA + g.bnd_plane;                      // gB[j]: approximate b0 at residue j*C     (j = 0..K-1)
+    double* __restrict__ gV0 = gA + 2 * g.bnd_plane;                 // gV*[k]: approximate Viterbi scores at chunk k's last residue
+    double* __restrict__ gV1 = gA + 3 * g.bnd_plane;
+    unsigned char* __restrict__ gC = reinterpret_cast<unsigned char*>(gA + 4 * g.bnd_plane);  // per chunk: choice | cross << 2; [K]: vlast
     uint8_t* __restrict__ tb = g.tb + so;
     const bool vit = g.want_vit != 0;
     const bool post = g.want_post != 0;

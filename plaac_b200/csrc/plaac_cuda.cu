@@ -703,7 +703,8 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
                 if ((rc = ensure(ctx, s.lp_s1, sizeof(double) * ((size_t)long_scratch + 256)))) return rc;
                 if ((rc = ensure(ctx, s.lp_lpseq, sizeof(double) * (size_t)nlong))) return rc;
             }
-            if ((rc = ensure(ctx, s.lp_bnd, sizeof(double) * (size_t)kLpBndStride * (size_t)nlong))) return rc;
+            const int64_t bnd_plane = long_scratch / 32 + 64;
+            if ((rc = ensure(ctx, s.lp_bnd, sizeof(double) * (size_t)kLpBndPlanes * (size_t)bnd_plane))) return rc;
             LongPostArgs pa;
             pa.codes = d_codes;
             pa.offsets = d_offsets;
@@ -720,6 +721,7 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             pa.S0 = d_res ? (double*)s.lp_s0.p : nullptr;
             pa.S1 = d_res ? (double*)s.lp_s1.p : nullptr;
             pa.bnd = (double*)s.lp_bnd.p;
+            pa.bnd_plane = bnd_plane;
             pa.lpseq = d_res ? (double*)s.lp_lpseq.p : nullptr;
             pa.warm = std::max(1, std::abs(ctx->long_warm));
             pa.warm2 = getenv("PLAAC_LP_WARM2") ? atoi(getenv("PLAAC_LP_WARM2")) : 64;

@@ -560,6 +560,34 @@ def test_per_residue_long_path_is_the_sequential_walk_bit_for_bit(monkeypatch):
     sc.close()
 
 
+def test_many_proteins_on_the_long_paths():
+    """A threshold far below what the path is meant for: 500 proteins of 1 030 - 1 400 residues each get their own CTAs
+    (scratch proportional to the residues, not to the number of proteins); records and per-residue arrays against the oracle."""
+    rng = np.random.default_rng(99)
+    lens = rng.integers(1030, 1400, size=500)
+    bgp, prdp = synth.BG_SCER / synth.BG_SCER.sum(), synth.PRD_28 / synth.PRD_28.sum()
+    seqs = []
+    for i, n in enumerate(lens):
+        s = rng.choice(22, size=int(n), p=bgp).astype(np.uint8)
+        if i % 3 == 0:
+            st = int(rng.integers(0, n - 200))
+            s[st:st + 150] = rng.choice(22, size=150, p=prdp)
+        seqs.append(s)
+    codes, offs = plaac_b200.pack(seqs)
+    P = orc.make_params()
+    ref_s = orc.score_batch(P, codes, offs, nthreads=NT)
+    ref_r = orc.residue_batch(P, codes, offs, nthreads=NT)
+    sc = plaac_b200.Scorer()
+    sc.set_long_path(1024)
+    got_s = sc.score(codes, offs)
+    assert sc.stats().long_proteins == 500
+    _check(got_s, ref_s, "500 proteins on the long path, records", P, codes, offs, max_ties=3)
+    got_s2, got_r = sc.score(codes, offs, per_residue=True)
+    sc.close()
+    assert got_s2.tobytes() == got_s.tobytes()
+    _check_residue(got_r, ref_r, "500 proteins on the long path, per-residue")
+
+
 @pytest.mark.parametrize("kw", [dict(core_len=100, ww1=21, ww2=21), dict(core_len=7, ww1=5, ww2=5),
                                 dict(core_len=30, ww1=40, ww2=40, adjust_prolines=False),
                                 dict(alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS), dict(core_len=250, ww1=61, ww2=61),
