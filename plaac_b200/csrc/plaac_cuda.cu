@@ -693,8 +693,11 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
         ctx->stats.long_proteins += nlong;
         if (d_res || hybrid) {
             if (d_res && d_res->vit && run_score && !hybrid) {
-                k_long_vit_bytes<<<dim3(8, (unsigned)nlong), 256, 0, long_st>>>(d_offsets, res_base, la.list, la.scratch_off, la.vit, d_res->vit);
-                ctx->stats.kernel_launches += 1;
+                for (int64_t off = 0; off < nlong; off += 65535) {
+                    k_long_vit_bytes<<<dim3(8, (unsigned)std::min<int64_t>(65535, nlong - off)), 256, 0, long_st>>>(
+                        d_offsets, res_base, la.list + off, la.scratch_off + off, la.vit, d_res->vit);
+                    ctx->stats.kernel_launches += 1;
+                }
             }
             // one cluster per long protein, two size classes: posteriors + MAP parse (+ Viterbi parse), or, for records,
             // the forward score and the Viterbi parse
@@ -856,8 +859,11 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
                 TrackArgs tl = ta;
                 tl.long_list = (const int32_t*)s.lg_list.p;
                 CU(ctx, cudaStreamWaitEvent(s.aux3, s.ev_fork, 0));
-                k_res_tracks<<<dim3(16, (unsigned)nlong), kTrackWarps * 32, ctx->res_plan.trk_smem, s.aux3>>>(tl);
-                ctx->stats.kernel_launches += 1;
+                for (int64_t off = 0; off < nlong; off += 65535) {  // (gridDim.y is limited to 65535)
+                    tl.long_list = (const int32_t*)s.lg_list.p + off;
+                    k_res_tracks<<<dim3(16, (unsigned)std::min<int64_t>(65535, nlong - off)), kTrackWarps * 32, ctx->res_plan.trk_smem, s.aux3>>>(tl);
+                    ctx->stats.kernel_launches += 1;
+                }
             }
             rc = launch_residue_v2(ctx->res_plan, ra, ta, ctx->sm_count, st, s.aux1, s.aux2, s.aux3, s.ev_fork, s.ev_j1, s.ev_j2,
                                    s.ev_j3, &ctx->stats.kernel_launches);
