@@ -80,6 +80,9 @@ struct LongArgs {
     // sum0 (hmm0's log-emission sum) in sum0_out[i] and k_long_final completes the record
     int hmm_ext;
     double* sum0_out;
+    // split = 1 (with hmm_ext): two CTAs per protein, blockIdx.y = 0: sums, MW and LLR searches; 1: the window columns
+    // (FoldIndex runs, PAPA centre and its values) from an ext copy of its own (extT's space, protein-major)
+    int split;
     uint8_t* ext;   // ext code per residue (same byte layout as the bucketed stream)
     uint8_t* extT;  // the same, chunk-major: [position in chunk][chunk], so the 32 chunk lanes of a warp read 32
                     // consecutive bytes per step (one sector) instead of 32 different lines.  Used from cm_min
@@ -251,7 +254,10 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
     const int64_t so = g.scratch_off[blockIdx.x];
     const int n = (int)(g.offsets[prot + 1] - g.offsets[prot]);
     const uint8_t* src = g.codes + (g.offsets[prot] - g.off_base);
-    uint8_t* __restrict__ ext = g.ext + so;
+    // part 0 / 1 of a split protein (see LongArgs::split); do_main: everything but the window columns, do_win: those
+    const int part = g.split ? (int)blockIdx.y : 0;
+    const bool do_main = !g.split || part == 0, do_win = !g.split || part == 1;
+    uint8_t* __restrict__ ext = (g.split && part == 1 ? g.extT : g.ext) + so;
     uint8_t* __restrict__ extT = g.extT + so;
     uint8_t* __restrict__ tbT = g.tb + so;
     uint32_t* __restrict__ vit = g.vit + (so >> 5);
@@ -347,7 +353,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         // ================= pass 1: chunk-local frame =================
         if (live) {
             // ---- Viterbi: the chunk's 2x2 max-plus transfer matrix (first chunk: the true chain, with its traceback)
-            {
+            if (do_main) {
                 double a0, a1, b0 = -INFINITY, b1 = 0.0;
                 int t0 = cs;
                 if (k == 0) {
@@ -436,7 +442,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                 if (k == 0) sm.f_dexit[0] = a1 - a0;
             }
             // ---- sliding windows: FoldIndex runs and the PAPA centre over the positions this chunk owns
-            {
+            if (do_win) {
                 const int off1 = 2 * w + 1, off2 = 4 * w + 2;
                 const int full = 2 * w + 1, Wfull = full * full;
                 const int t_start = max(0, cs - 2 * w);
@@ -586,7 +592,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
         // jar's sequential values up to an EXACT shift: Viterbi transfer entries and forward increments become exact
         // multiples of the ulp and their ordered combination is the jar's number bit for bit.  Chunks in which the
         // magnitude crosses a power of two (about one per binade) are redone sequentially from the exact values.
-        if (live && k >= 1 && g.hmm_ext) {
+        if (live && k >= 1 && g.hmm_ext && do_main) {
             // (the HMM columns come from k_long_post: only the psum[] LLR search and the two plain sums, in their own frames)
             double lagsum = 0;
             for (int t = cs - c; t < cs; t++) lagsum += sm.llr[xt(t) & 31];
@@ -728,7 +734,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
                 }
             }
         }
-        if (live) {
+        if (live && do_main) {
             // ---- the three sequential sums in their own binade (same argument, no state besides the sum itself)
             // crossing test over every value the running sum takes in the region (for the LLR search the lagged sum
             // starts c residues before the chunk, i.e. inside the previous chunk)
@@ -823,7 +829,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             sm.endstate[0] = (unsigned char)e;
             sm.variant[0] = 0;
             LONG_STAMP_LANE(9);
-        } else if (wid == 3 && lane == 0) {
+        } else if (wid == 3 && lane == 0 && do_main) {
             // LLR window search: chunk maxima in order (first strict maximum), crossing chunks redone from exact values
             double P = sm.q_inc[0][0], Pl = sm.q_mid[0];
             double best = sm.q_best[0];
@@ -863,7 +869,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             sm.llr_best = best;
             sm.llr_stop = stop;
             LONG_STAMP_LANE(10);
-        } else if (wid == 4 && lane < 2) {
+        } else if (wid == 4 && lane < 2 && do_main) {
             // hmm0's emission sum (lane 0) and the hydropathy sum (lane 1)
             const int q = 1 + lane;
             double x = sm.q_inc[q][0];
@@ -883,7 +889,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             else
                 sm.sh = x;
             LONG_STAMP_LANE(12 + lane);
-        } else if (wid == 5 && lane == 0) {
+        } else if (wid == 5 && lane == 0 && do_main) {
             int best = sm.m_best[0], stop = sm.m_stop[0], cq = sm.c_sum[0];
             for (int kk = 1; kk < K; kk++) {
                 if (sm.m_best[kk] > best) {
@@ -895,7 +901,7 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
             sm.mw_best = best;
             sm.mw_stop = stop;
             sm.csum = cq;
-        } else if (wid == 2 && lane == 0) {
+        } else if (wid == 2 && lane == 0 && do_win) {
         // FoldIndex runs (:5010-5059) and PAPA centre (:4941-4948) merged in chunk order
         int open = 0, num = 0, mx = 0;
         int pcen = -1;
@@ -1022,49 +1028,53 @@ __device__ __forceinline__ void long_score_body(const LongArgs& g)
 
     if (tid != 0) return;
     plaac_summary* r = g.out + prot;
-    r->prot_len = n;
-    r->mw_score = sm.mw_best;
-    r->mw_start = sm.mw_stop - mw + 1;
-    r->mw_end = sm.mw_stop;
-    r->llr = sm.llr_best;
-    r->llr_start = sm.llr_stop - c + 1;
-    r->llr_end = sm.llr_stop;
-    if (!g.hmm_ext) r->hmm_vit = sm.lvit - sm.sum0;
-    const double mh = (1.0 * sm.sh) / (double)n;
-    const double mc = (1.0 * (double)sm.csum) / (double)n;
-    r->fi_meanhydro = mh;
-    r->fi_meancharge = mc;
-    r->fi_meancombo = (ks.cc2 + ks.cc1 * fabs(mc)) + ks.cc0 * mh;
-    r->fi_numaa = sm.fi_numaa;
-    r->fi_maxrun = sm.fi_maxrun;
-    const int pcen = sm.pcen;
-    r->papa_center = pcen;
-    if (pcen >= 0) {
-        const double prop = sm.pTb / sm.pWb;
-        r->papa_combo = prop;
-        r->papa_prop = prop;
-        r->papa_fi = sm.pVfi / sm.pWb;
-        const int full = 2 * w + 1;
-        const int q0 = max(pcen - 2 * w, 0), q1 = min(pcen + 2 * w, n - 1);
-        double sc = 0.0, den = 0.0, t2 = 0.0;
-        for (int q = q0; q <= q1; q++) {
-            const double x = sm.llr[ext[q] & 63];
-            const int dist = abs(q - pcen);
-            if (dist <= w) {
-                den = den + 1.0;
-                sc = sc + 1.0 * x;
+    if (do_main) {
+        r->prot_len = n;
+        r->mw_score = sm.mw_best;
+        r->mw_start = sm.mw_stop - mw + 1;
+        r->mw_end = sm.mw_stop;
+        r->llr = sm.llr_best;
+        r->llr_start = sm.llr_stop - c + 1;
+        r->llr_end = sm.llr_stop;
+        if (!g.hmm_ext) r->hmm_vit = sm.lvit - sm.sum0;
+        const double mh = (1.0 * sm.sh) / (double)n;
+        const double mc = (1.0 * (double)sm.csum) / (double)n;
+        r->fi_meanhydro = mh;
+        r->fi_meancharge = mc;
+        r->fi_meancombo = (ks.cc2 + ks.cc1 * fabs(mc)) + ks.cc0 * mh;
+    }
+    if (do_win) {
+        r->fi_numaa = sm.fi_numaa;
+        r->fi_maxrun = sm.fi_maxrun;
+        const int pcen = sm.pcen;
+        r->papa_center = pcen;
+        if (pcen >= 0) {
+            const double prop = sm.pTb / sm.pWb;
+            r->papa_combo = prop;
+            r->papa_prop = prop;
+            r->papa_fi = sm.pVfi / sm.pWb;
+            const int full = 2 * w + 1;
+            const int q0 = max(pcen - 2 * w, 0), q1 = min(pcen + 2 * w, n - 1);
+            double sc = 0.0, den = 0.0, t2 = 0.0;
+            for (int q = q0; q <= q1; q++) {
+                const double x = sm.llr[ext[q] & 63];
+                const int dist = abs(q - pcen);
+                if (dist <= w) {
+                    den = den + 1.0;
+                    sc = sc + 1.0 * x;
+                }
+                t2 = t2 + x * (double)(full - dist);
             }
-            t2 = t2 + x * (double)(full - dist);
+            r->papa_llr = sc / den;
+            r->papa_llr2 = t2 / sm.pWb;
+        } else {
+            r->papa_combo = -INFINITY;
+            r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = nan("");
         }
-        r->papa_llr = sc / den;
-        r->papa_llr2 = t2 / sm.pWb;
-    } else {
-        r->papa_combo = -INFINITY;
-        r->papa_prop = r->papa_fi = r->papa_llr = r->papa_llr2 = nan("");
     }
     if (g.hmm_ext) {
         // Viterbi run statistics, CORE search and the two HMM scores: k_long_final, from k_long_post's parse
-        g.sum0_out[blockIdx.x] = sm.sum0;
+        if (do_main) g.sum0_out[blockIdx.x] = sm.sum0;
         return;
     }
     // longestrun

@@ -681,12 +681,15 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
             // (without the Viterbi and forward loops the protein-major copy is the faster one at every length: 100 k residues
             // 0.785 -> 0.755 ms)
             if (!getenv("PLAAC_LONG_CM_MIN")) la.cm_min = 0x7fffffff;
+            // the window columns on a second CTA (it needs the protein-major layout: its ext copy lives in extT's space)
+            la.split = (la.cm_min == 0x7fffffff && !(getenv("PLAAC_LONG_SPLIT") && getenv("PLAAC_LONG_SPLIT")[0] == '0')) ? 1 : 0;
         } else {
             la.hmm_ext = 0;
             la.sum0_out = nullptr;
+            la.split = 0;
         }
         if (run_score) {
-            k_long_score<<<(unsigned)nlong, kLongThreads, sizeof(LongShared), long_st>>>(la);
+            k_long_score<<<dim3((unsigned)nlong, la.split ? 2u : 1u), kLongThreads, sizeof(LongShared), long_st>>>(la);
             ctx->stats.kernel_launches += 1;
         }
         long_launched = true;
