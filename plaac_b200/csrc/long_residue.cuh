@@ -96,7 +96,6 @@ struct LpShared {
     double vM[4][kLpThreads], vtot[4], vcarry[2];
     unsigned char vcross[kLpThreads], vchoice[kLpThreads], vend[kLpThreads];
     double vE0, vE1;                    // exact scores at the first chunk's last residue
-    double vR[kLpThreads];              // the frame's entry score R of the chunk
     unsigned char vall[kLpBigCluster * kLpThreads + 8];  // the cluster's choice bytes, staged for the end-state walk
     int redone;
     int flag[3];                        // relay: the neighbour's state has arrived ([0] forward, [1] backward, [2] Viterbi)
@@ -465,7 +464,6 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
             const bool cross = !(lo >= 1024.0) || (__double2hiint(lo) >> 20) != (__double2hiint(hi) >> 20) ||
                                ((g.vit_tie_mask >> (((__double2hiint(lo) >> 20) & 0x7ff) - 1023)) & 1ull);
             sm.vcross[tid] = cross ? 1 : 0;
-            sm.vR[tid] = p0;
             if (!cross) {
                 const double R = p0;
                 double a0 = R, a1 = -INFINITY, b0 = -INFINITY, b1 = R;
@@ -481,7 +479,8 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                     b1 = (pB1 ? vB11 : vB01) + le.y;
                     tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
                 }
-                sm.vM[0][tid] = a0, sm.vM[1][tid] = a1, sm.vM[2][tid] = b0, sm.vM[3][tid] = b1;
+                // relative to the entry score: exact differences (one binade), so the walker's S + (M - R) is its (S - R) + M
+                sm.vM[0][tid] = a0 - R, sm.vM[1][tid] = a1 - R, sm.vM[2][tid] = b0 - R, sm.vM[3][tid] = b1 - R;
             }
         } else if (vit) {
             sm.vcross[tid] = 0;  // first chunk: the true chain of pass 1 (vE0, vE1)
@@ -519,17 +518,17 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
             const int k_lo = rank * kLpThreads, k_hi = min(K, k_lo + kLpThreads);
             double Sx0 = *reinterpret_cast<volatile double*>(&sm.vcarry[0]), Sx1 = *reinterpret_cast<volatile double*>(&sm.vcarry[1]);
             const long long tw0 = clock64();
-            const uint32_t aR = sbase + LP_OFF(vR), aM = sbase + LP_OFF(vM), aX = sbase + LP_OFF(vcross), aCh = sbase + LP_OFF(vchoice);
+            const uint32_t aM = sbase + LP_OFF(vM), aX = sbase + LP_OFF(vcross), aCh = sbase + LP_OFF(vchoice);
             constexpr uint32_t kRow = kLpThreads * 8;
-            double nR = lp_lds(aR), n0 = lp_lds(aM), n1 = lp_lds(aM + kRow), n2 = lp_lds(aM + 2 * kRow), n3 = lp_lds(aM + 3 * kRow);
+            double n0 = lp_lds(aM), n1 = lp_lds(aM + kRow), n2 = lp_lds(aM + 2 * kRow), n3 = lp_lds(aM + 3 * kRow);
             uint32_t ncr = lp_lds_u8(aX);
             for (int k = k_lo; k < k_hi; k++) {
                 const int l = k - k_lo;
-                const double Rk = nR, M0 = n0, M1 = n1, M2 = n2, M3 = n3;
+                const double M0 = n0, M1 = n1, M2 = n2, M3 = n3;
                 const uint32_t cr = ncr;
                 if (k + 1 < k_hi) {
                     const uint32_t o8 = (uint32_t)(l + 1) * 8u;
-                    nR = lp_lds(aR + o8), n0 = lp_lds(aM + o8), n1 = lp_lds(aM + kRow + o8), n2 = lp_lds(aM + 2 * kRow + o8);
+                    n0 = lp_lds(aM + o8), n1 = lp_lds(aM + kRow + o8), n2 = lp_lds(aM + 2 * kRow + o8);
                     n3 = lp_lds(aM + 3 * kRow + o8);
                     ncr = lp_lds_u8(aX + (uint32_t)(l + 1));
                 }
@@ -554,9 +553,8 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                     }
                     lp_sts_u8(aCh + (uint32_t)l, (uint32_t)(f0 | (f1 << 1)));
                 } else {
-                    const double d0 = Sx0 - Rk, d1 = Sx1 - Rk;  // exact shifts
-                    const double x00 = d0 + M0, x10 = d1 + M2;
-                    const double x01 = d0 + M1, x11 = d1 + M3;
+                    const double x00 = Sx0 + M0, x10 = Sx1 + M2;  // exact: M holds the chunk's transfer entries relative to R
+                    const double x01 = Sx0 + M1, x11 = Sx1 + M3;
                     const int ch0 = x10 > x00 ? 1 : 0, ch1 = x11 > x01 ? 1 : 0;
                     Sx0 = ch0 ? x10 : x00;
                     Sx1 = ch1 ? x11 : x01;
