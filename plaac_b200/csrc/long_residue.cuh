@@ -92,8 +92,10 @@ struct LpShared {
     double tot[2];                      // pass 1: this CTA's total increment per direction
     double carry[2][2];                 // relay: exact state handed over by the neighbour CTA
     int carry_acc[2];                   // ... and whether its last chunk was accepted with its frames
-    // Viterbi: chunk transfer matrix [0] 0->0, [1] 0->1, [2] 1->0, [3] 1->1 (pass 1: chunk-local, then its scan; pass 2: exact frame)
-    double vM[4][kLpThreads], vtot[4], vcarry[2];
+    // Viterbi: chunk transfer matrix [.][0] 0->0, [1] 0->1, [2] 1->0, [3] 1->1 (pass 1: chunk-local, then its scan; pass 2: exact
+    // frame, relative to its entry score)
+    alignas(16) double vMi[kLpThreads][4];
+    double vtot[4], vcarry[2];  // (interleaved: the walker loads a chunk's four entries with two 128-bit loads)
     unsigned char vcross[kLpThreads], vchoice[kLpThreads], vend[kLpThreads];
     double vE0, vE1;                    // exact scores at the first chunk's last residue
     unsigned char vall[kLpBigCluster * kLpThreads + 8];  // the cluster's choice bytes, staged for the end-state walk
@@ -320,13 +322,13 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                 b1 = fmax(vB01, vB11) + le.y;
                 if (kg == 0) tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1));
             }
-            sm.vM[0][tid] = a0, sm.vM[1][tid] = a1, sm.vM[2][tid] = b0, sm.vM[3][tid] = b1;
+            sm.vMi[tid][0] = a0, sm.vMi[tid][1] = a1, sm.vMi[tid][2] = b0, sm.vMi[tid][3] = b1;
             if (kg == 0) sm.vE0 = a0, sm.vE1 = a1;
         }
     } else {
         sm.inc[0][tid] = 0.0;
         sm.inc[1][tid] = 0.0;
-        sm.vM[0][tid] = 0.0, sm.vM[1][tid] = -INFINITY, sm.vM[2][tid] = -INFINITY, sm.vM[3][tid] = 0.0;  // identity
+        sm.vMi[tid][0] = 0.0, sm.vMi[tid][1] = -INFINITY, sm.vMi[tid][2] = -INFINITY, sm.vMi[tid][3] = 0.0;  // identity
     }
     __syncthreads();
     if (vit && wid == 2) {
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
         LpMP c = {0.0, -INFINITY, -INFINITY, 0.0};
         for (int r = 0; r < kLpThreads / 32; r++) {
             const int idx = r * 32 + lane;
-            LpMP p = {sm.vM[0][idx], sm.vM[1][idx], sm.vM[2][idx], sm.vM[3][idx]};
+            LpMP p = {sm.vMi[idx][0], sm.vMi[idx][1], sm.vMi[idx][2], sm.vMi[idx][3]};
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 LpMP q;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                 if (lane >= d) p = lp_mp_mul(q, p);
             }
             p = lp_mp_mul(c, p);
-            sm.vM[0][idx] = p.m00, sm.vM[1][idx] = p.m01, sm.vM[2][idx] = p.m10, sm.vM[3][idx] = p.m11;
+            sm.vMi[idx][0] = p.m00, sm.vMi[idx][1] = p.m01, sm.vMi[idx][2] = p.m10, sm.vMi[idx][3] = p.m11;
             c.m00 = __shfl_sync(0xffffffffu, p.m00, 31), c.m01 = __shfl_sync(0xffffffffu, p.m01, 31);
             c.m10 = __shfl_sync(0xffffffffu, p.m10, 31), c.m11 = __shfl_sync(0xffffffffu, p.m11, 31);
         }
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                 cin = lp_mp_mul(cin, m);
             }
             if (live) {
-                gV0[kg] = fmax(cin.m00 + sm.vM[0][tid], cin.m01 + sm.vM[2][tid]);
-                gV1[kg] = fmax(cin.m00 + sm.vM[1][tid], cin.m01 + sm.vM[3][tid]);
+                gV0[kg] = fmax(cin.m00 + sm.vMi[tid][0], cin.m01 + sm.vMi[tid][2]);
+                gV1[kg] = fmax(cin.m00 + sm.vMi[tid][1], cin.m01 + sm.vMi[tid][3]);
             }
         }
     }
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
                     tb[t] = (uint8_t)((int)pA0 | ((int)pA1 << 1) | ((int)pB0 << 2) | ((int)pB1 << 3));
                 }
                 // relative to the entry score: exact differences (one binade), so the walker's S + (M - R) is its (S - R) + M
-                sm.vM[0][tid] = a0 - R, sm.vM[1][tid] = a1 - R, sm.vM[2][tid] = b0 - R, sm.vM[3][tid] = b1 - R;
+                sm.vMi[tid][0] = a0 - R, sm.vMi[tid][1] = a1 - R, sm.vMi[tid][2] = b0 - R, sm.vMi[tid][3] = b1 - R;
             }
         } else if (vit) {
             sm.vcross[tid] = 0;  // first chunk: the true chain of pass 1 (vE0, vE1)
@@ -518,24 +520,27 @@ __global__ void __launch_bounds__(kLpThreads, 1) k_long_post(LongPostArgs g)
             const int k_lo = rank * kLpThreads, k_hi = min(K, k_lo + kLpThreads);
             double Sx0 = *reinterpret_cast<volatile double*>(&sm.vcarry[0]), Sx1 = *reinterpret_cast<volatile double*>(&sm.vcarry[1]);
             const long long tw0 = clock64();
-            const uint32_t aM = sbase + LP_OFF(vM), aX = sbase + LP_OFF(vcross), aCh = sbase + LP_OFF(vchoice);
-            constexpr uint32_t kRow = kLpThreads * 8;
-            double n0 = lp_lds(aM), n1 = lp_lds(aM + kRow), n2 = lp_lds(aM + 2 * kRow), n3 = lp_lds(aM + 3 * kRow);
-            uint32_t ncr = lp_lds_u8(aX);
-            for (int k = k_lo; k < k_hi; k++) {
+            const uint32_t aM = sbase + LP_OFF(vMi), aX = sbase + LP_OFF(vcross), aCh = sbase + LP_OFF(vchoice);
+            int k = k_lo;
+            if (k == 0) {  // the first chunk is the true chain of pass 1
+                Sx0 = sm.vE0, Sx1 = sm.vE1;
+                lp_sts_u8(aCh, 0u);
+                k = 1;
+            }
+            double2 nA = make_double2(0.0, 0.0), nB = nA;
+            uint32_t ncr = 0;
+            if (k < k_hi) {
+                nA = lds_v2f64(aM + (uint32_t)(k - k_lo) * 32u), nB = lds_v2f64(aM + (uint32_t)(k - k_lo) * 32u + 16u);
+                ncr = lp_lds_u8(aX + (uint32_t)(k - k_lo));
+            }
+            for (; k < k_hi; k++) {
                 const int l = k - k_lo;
-                const double M0 = n0, M1 = n1, M2 = n2, M3 = n3;
+                const double M0 = nA.x, M1 = nA.y, M2 = nB.x, M3 = nB.y;
                 const uint32_t cr = ncr;
                 if (k + 1 < k_hi) {
-                    const uint32_t o8 = (uint32_t)(l + 1) * 8u;
-                    n0 = lp_lds(aM + o8), n1 = lp_lds(aM + kRow + o8), n2 = lp_lds(aM + 2 * kRow + o8);
-                    n3 = lp_lds(aM + 3 * kRow + o8);
+                    const uint32_t o32 = (uint32_t)(l + 1) * 32u;
+                    nA = lds_v2f64(aM + o32), nB = lds_v2f64(aM + o32 + 16u);
                     ncr = lp_lds_u8(aX + (uint32_t)(l + 1));
-                }
-                if (k == 0) {
-                    Sx0 = sm.vE0, Sx1 = sm.vE1;
-                    lp_sts_u8(aCh, 0u);
-                    continue;
                 }
                 if (cr) {
                     const int s = k * C, e = min(n, s + C);
