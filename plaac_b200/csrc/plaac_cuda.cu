@@ -604,11 +604,22 @@ int run_batch(plaac_ctx* ctx, Slot& s, const uint8_t* d_codes, const int64_t* d_
     if ((rc = ensure(ctx, s.tbw, (size_t)std::max<int64_t>(slots, 1) * 32 * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(ctx, s.slot_bucket, (size_t)std::max<int64_t>(slots, 1) * sizeof(int32_t)))) return rc;
 
-    const int pack_blocks = (int)std::min<int64_t>((nbuckets + 7) / 8, (int64_t)ctx->sm_count * 8);
-    k_pack<<<pack_blocks, 256, 0, st>>>(d_codes, d_offsets, off_base, (const int32_t*)s.order.p,
-                                        (const int64_t*)s.chunk_base.p, nprot, nbuckets, lm, ctx->ks.adjust_prolines,
-                                        ctx->ks.charge_plus, ctx->ks.charge_minus, (uint4*)s.stream_buf.p,
-                                        (int32_t*)s.slot_bucket.p, (int*)s.errflag.p);
+    // one block per 8 buckets, no grid-stride: buckets come in descending length, so handing them out as blocks retire is
+    // longest-first list scheduling.  A resident grid with a stride gave the warps that own the first (longest) buckets
+    // twice the average work (measured at 4 M proteins, time outside the scoring kernel: 1.28 ms with 5 CTAs per SM,
+    // 1.17 with 8, 1.03 with 32).  PLAAC_PACK_CTAS caps the grid at that many blocks per SM.
+    static const int pack_ctas_env = [] { const char* e = getenv("PLAAC_PACK_CTAS"); return e ? atoi(e) : 0; }();
+    int64_t pack_blocks64 = (nbuckets + 7) / 8;
+    if (pack_ctas_env > 0) pack_blocks64 = std::min<int64_t>(pack_blocks64, (int64_t)ctx->sm_count * pack_ctas_env);
+    const unsigned pack_blocks = (unsigned)std::min<int64_t>(pack_blocks64, 0x7fffffff);
+    {
+        auto pack = k_pack<false, false>;
+        if (pack_is_std(ctx->ks.charge_plus, ctx->ks.charge_minus)) pack = ctx->ks.adjust_prolines ? k_pack<true, true> : k_pack<true, false>;
+        pack<<<pack_blocks, 256, 0, st>>>(d_codes, d_offsets, off_base, (const int32_t*)s.order.p,
+                                          (const int64_t*)s.chunk_base.p, nprot, nbuckets, lm, ctx->ks.adjust_prolines,
+                                          ctx->ks.charge_plus, ctx->ks.charge_minus, (uint4*)s.stream_buf.p,
+                                          (int32_t*)s.slot_bucket.p, (int*)s.errflag.p);
+    }
     ctx->stats.kernel_launches += 1;
 
     BatchView bv;

@@ -262,8 +262,19 @@ __device__ __forceinline__ uint32_t bytes_in_set(uint32_t w, uint32_t set)
     return r;
 }
 
+// Zero-byte tests for words whose bytes are all < 0x80 (sanitised codes xor a code pattern < 0x80): byte + 0x7f carries
+// into bit 7 exactly when the byte is not zero and never into the next byte.  The "matches nothing" pattern is 0x7f7f7f7f.
+__device__ __forceinline__ uint32_t bytes_eq7(uint32_t w, uint32_t pat)
+{
+    return ~((w ^ pat) + 0x7f7f7f7fu) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t bytes_eq7_2(uint32_t w, uint32_t pat0, uint32_t pat1)
+{
+    return ~(((w ^ pat0) + 0x7f7f7f7fu) & ((w ^ pat1) + 0x7f7f7f7fu)) & 0x80808080u;
+}
+
 // 0x80 in every byte of w (all bytes < 0x80) whose value lies in [lo, hi]: two carries instead of a zero-byte test per
-// member (k_pack is bound by the integer ALU pipe: ncu round 1, math_pipe_throttle 3.6 per issue)
+// member (the ALU pipe is k_pack's busiest: 57 % in the round-2 capture)
 __device__ __forceinline__ uint32_t bytes_in_range(uint32_t w, uint32_t lo, uint32_t hi)
 {
     const uint32_t ge_lo = w + (0x80u - lo) * 0x01010101u;       // bit 7 set: byte >= lo   (byte + 0x80 - lo < 0x100)
@@ -271,11 +282,25 @@ __device__ __forceinline__ uint32_t bytes_in_range(uint32_t w, uint32_t lo, uint
     return ge_lo & ~gt_hi & 0x80808080u;
 }
 
+inline bool pack_is_std(uint32_t charge_plus, uint32_t charge_minus)
+{
+    if (charge_plus == 0 || __builtin_popcount(charge_plus) > 2 || __builtin_popcount(charge_minus) > 2) return false;
+    const uint32_t run = charge_plus >> __builtin_ctz(charge_plus);
+    return (run & (run + 1u)) == 0u;
+}
+
 // Ext byte layout: bits 4:0 residue code (22 = pad), bit 5 PAPA proline mask, bits 7:6 charge class.
 // One warp per bucket.  Lane l streams protein order[32b+l]: aligned 16-byte loads two blocks ahead, a
 // two-level word barrel shifter + funnel shifts for the byte realignment, SWAR sanitising / padding / PAPA
 // proline flags / charge classes, one coalesced 512-byte store per slot.
-__global__ void __launch_bounds__(256)
+// Where the time goes (ncu round 2, profiles/r02_pack_summary.txt): 74 % of the warp stalls wait for the lane's own
+// 16-byte load (each lane walks its own protein, so a warp's load touches 32 lines; the L1 holds them for 25 % hits, and
+// loads that skip the L1 are 30 % slower), the ALU pipe is 57 % busy.  A third block in flight and 128-byte L2 prefetch
+// sizes changed nothing.
+// kStd: both charge sets have at most two members and the +1 set is a run of consecutive codes (PLAAC's D, E), kPro: the
+// PAPA proline rule is on -- the warp-uniform tests of the general kernel decided once by the host (pack_is_std).
+template <bool kStd, bool kPro>
+__global__ void __launch_bounds__(256, 5)
 k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
        int64_t off_base, const int32_t* __restrict__ order, const int64_t* __restrict__ chunk_base, int64_t nprot,
        int64_t nbuckets, int64_t long_min, int adjust_prolines, uint32_t charge_plus, uint32_t charge_minus,
@@ -287,12 +312,12 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
     constexpr uint32_t kPadW = 0x01010101u * kPad;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     // up to two codes per charge class are matched with straight-line SWAR compares (PLAAC has D,E / K,R);
-    // 0xffffffff never matches a sanitised byte
-    const bool small_sets = __popc(charge_plus) <= 2 && __popc(charge_minus) <= 2;
+    // 0x7f7f7f7f never matches a sanitised byte
+    const bool small_sets = kStd || (__popc(charge_plus) <= 2 && __popc(charge_minus) <= 2);
     // a set of consecutive codes (PLAAC: D, E = 3, 4 are +1) is one range test
-    const bool plus_run = charge_plus != 0 && ((charge_plus >> (__ffs((int)charge_plus) - 1)) & ((charge_plus >> (__ffs((int)charge_plus) - 1)) + 1u)) == 0u;
+    const bool plus_run = kStd || (charge_plus != 0 && ((charge_plus >> (__ffs((int)charge_plus) - 1)) & ((charge_plus >> (__ffs((int)charge_plus) - 1)) + 1u)) == 0u);
     const uint32_t plus_lo = charge_plus ? (uint32_t)__ffs((int)charge_plus) - 1u : 0u, plus_hi = charge_plus ? 31u - (uint32_t)__clz((int)charge_plus) : 0u;
-    uint32_t cp0 = 0xffffffffu, cp1 = 0xffffffffu, cm0 = 0xffffffffu, cm1 = 0xffffffffu;
+    uint32_t cp0 = 0x7f7f7f7fu, cp1 = 0x7f7f7f7fu, cm0 = 0x7f7f7f7fu, cm1 = 0x7f7f7f7fu;
     if (charge_plus) cp0 = ((uint32_t)__ffs((int)charge_plus) - 1u) * 0x01010101u;
     if (charge_plus & (charge_plus - 1u)) cp1 = (31u - (uint32_t)__clz((int)charge_plus)) * 0x01010101u;
     if (charge_minus) cm0 = ((uint32_t)__ffs((int)charge_minus) - 1u) * 0x01010101u;
@@ -332,24 +357,11 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
             uint32_t o[4] = {__funnelshift_r(W0, W1, s1), __funnelshift_r(W1, W2, s1), __funnelshift_r(W2, W3, s1),
                              __funnelshift_r(W3, W4, s1)};
             const int64_t rem = n - (int64_t)j * kChunk;  // valid bytes from this slot on
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t w = o[q];
-                uint32_t vmask = 0xffffffffu;
-                if (rem < 16) {
-                    const int64_t rq = rem - 4 * q;
-                    vmask = rq >= 4 ? 0xffffffffu : (rq <= 0 ? 0u : ((1u << (8 * (int)rq)) - 1u));
-                }
-                // sanitise: bytes > 21 are invalid input -> X (0), flagged
-                const uint32_t bad = ((w & 0x80808080u) | (((w & 0x7f7f7f7fu) + 0x6a6a6a6au) & 0x80808080u)) & vmask;
-                if (bad) {
-                    bad_any = 1;
-                    w &= ~((bad >> 7) * 0xffu);
-                }
-                w = (w & vmask) | (kPadW & ~vmask);
+            // flags of one sanitised word (all bytes <= 22): PAPA proline mask and charge class
+            auto classify = [&](uint32_t w) -> uint32_t {
                 uint32_t ext = w;
-                if (adjust_prolines) {
-                    const uint32_t eq = bytes_in_range(w, 13u, 13u);
+                if (kPro || (!kStd && adjust_prolines)) {
+                    const uint32_t eq = bytes_eq7(w, 13u * 0x01010101u);
                     const uint32_t prev1 = __funnelshift_l(carry, eq, 8);   // proline one position earlier
                     const uint32_t prev2 = __funnelshift_l(carry, eq, 16);  // two positions earlier
                     carry = eq;
@@ -358,14 +370,42 @@ k_pack(const uint8_t* __restrict__ codes, const int64_t* __restrict__ offsets,
                 // charge class in bits 7:6 of every byte: 01 = +1, 11 = -1 (so (int8)byte >> 6 is the charge)
                 uint32_t pl, mi;
                 if (small_sets) {
-                    pl = plus_run ? bytes_in_range(w, plus_lo, plus_hi) : (bytes_zero(w ^ cp0) | bytes_zero(w ^ cp1));
-                    mi = bytes_zero(w ^ cm0) | bytes_zero(w ^ cm1);
+                    pl = plus_run ? bytes_in_range(w, plus_lo, plus_hi) : bytes_eq7_2(w, cp0, cp1);
+                    mi = bytes_eq7_2(w, cm0, cm1);
                 } else {
                     pl = bytes_in_set(w, charge_plus);
                     mi = bytes_in_set(w, charge_minus);
                 }
-                ext |= (pl >> 1) | mi | (mi >> 1);
-                o[q] = ext;
+                return ext | (pl >> 1) | mi | (mi >> 1);
+            };
+            if (rem >= 16) {
+                // a full slot (all but the last one or two of a protein): no padding, and one validity test for the
+                // four words -- bit 7 of (byte | (low 7 bits + 0x6a)) is set exactly for bytes > 21
+                const uint32_t t0 = o[0] | ((o[0] & 0x7f7f7f7fu) + 0x6a6a6a6au), t1 = o[1] | ((o[1] & 0x7f7f7f7fu) + 0x6a6a6a6au);
+                const uint32_t t2 = o[2] | ((o[2] & 0x7f7f7f7fu) + 0x6a6a6a6au), t3 = o[3] | ((o[3] & 0x7f7f7f7fu) + 0x6a6a6a6au);
+                if ((t0 | t1 | t2 | t3) & 0x80808080u) {  // invalid input -> X (0), flagged
+                    bad_any = 1;
+                    o[0] &= ~(((t0 & 0x80808080u) >> 7) * 0xffu);
+                    o[1] &= ~(((t1 & 0x80808080u) >> 7) * 0xffu);
+                    o[2] &= ~(((t2 & 0x80808080u) >> 7) * 0xffu);
+                    o[3] &= ~(((t3 & 0x80808080u) >> 7) * 0xffu);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) o[q] = classify(o[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t w = o[q];
+                    const int64_t rq = rem - 4 * q;
+                    const uint32_t vmask = rq >= 4 ? 0xffffffffu : (rq <= 0 ? 0u : ((1u << (8 * (int)rq)) - 1u));
+                    // sanitise: bytes > 21 are invalid input -> X (0), flagged
+                    const uint32_t bad = ((w & 0x80808080u) | (((w & 0x7f7f7f7fu) + 0x6a6a6a6au) & 0x80808080u)) & vmask;
+                    if (bad) {
+                        bad_any = 1;
+                        w &= ~((bad >> 7) * 0xffu);
+                    }
+                    o[q] = classify((w & vmask) | (kPadW & ~vmask));
+                }
             }
             __stcs(dst + (size_t)j * 32, make_uint4(o[0], o[1], o[2], o[3]));  // streaming: keep L2 for the reads
             A = B;

@@ -467,6 +467,30 @@ def test_per_residue_windows_with_different_half_widths(kw):
         assert ((a == b) | (np.isnan(a) & np.isnan(b))).all(), k
 
 
+@pytest.mark.parametrize("plus,minus", [((3, 4, 7), (9, 15, 2)), ((3, 20), (9,)), ((), (15,)), ((4, 5), (3,))])
+def test_other_charge_classes(plus, minus):
+    """aacharge tables other than PLAAC's (:37-60): k_pack's general class tests (sets of any size, a +1 set that is
+    not a run of consecutive codes, an empty set) against the oracle, records and per-residue tracks."""
+    codes, offs = synth.proteome(600, seed=77, median=150.0)
+    e, eo = synth.edge_cases()
+    codes, offs = np.concatenate([codes, e]), np.concatenate([offs, eo[1:] + offs[-1]])
+    P = orc.make_params()
+    gp = plaac_b200.default_params()
+    for i in range(len(P.charge)):
+        c = 1.0 if i in plus else (-1.0 if i in minus else 0.0)
+        P.charge[i] = c
+        gp.charge[i] = c
+    ref_s = orc.score_batch(P, codes, offs, nthreads=NT)
+    ref_r = orc.residue_batch(P, codes, offs)
+    sc = plaac_b200.Scorer(gp)
+    got_s, got_r = sc.score(codes, offs, per_residue=True)
+    only_s = sc.score(codes, offs)
+    sc.close()
+    _check(got_s, ref_s, f"charge classes +{plus} -{minus}", P, codes, offs, max_ties=6)
+    _check(only_s, ref_s, f"charge classes +{plus} -{minus} (records only)", P, codes, offs, max_ties=6)
+    _check_residue(got_r, ref_r, f"charge classes +{plus} -{minus}")
+
+
 def test_per_residue_long_and_other_params():
     codes, offs = synth.long_proteins(lengths=(35000,))
     kw = dict(core_len=30, ww1=21, ww2=21, alpha=0.5, bg_counts=synth.BG_HUMAN_COUNTS)
