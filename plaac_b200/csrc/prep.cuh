@@ -293,10 +293,10 @@ inline bool pack_is_std(uint32_t charge_plus, uint32_t charge_minus)
 // One warp per bucket.  Lane l streams protein order[32b+l]: aligned 16-byte loads two blocks ahead, a
 // two-level word barrel shifter + funnel shifts for the byte realignment, SWAR sanitising / padding / PAPA
 // proline flags / charge classes, one coalesced 512-byte store per slot.
-// Where the time goes (ncu round 2, profiles/r02_pack_summary.txt): 74 % of the warp stalls wait for the lane's own
-// 16-byte load (each lane walks its own protein, so a warp's load touches 32 lines; the L1 holds them for 25 % hits, and
-// loads that skip the L1 are 30 % slower), the ALU pipe is 57 % busy.  A third block in flight and 128-byte L2 prefetch
-// sizes changed nothing.
+// Where the time goes (ncu round 2, profiles/r02_pack_summary.txt): the warps wait for their own 16-byte loads (each lane
+// walks its own protein, so a warp's load touches 32 lines; the L1 keeps them for 26 % hits and loads that skip it are
+// 30 % slower) with the ALU pipe 61 % busy and DRAM at 52 %.  Measured without effect: a third block in flight, 128-byte L2
+// prefetch sizes, 128 / 384 / 512 threads per block (40 / 36 / 32 resident warps).
 // kStd: both charge sets have at most two members and the +1 set is a run of consecutive codes (PLAAC's D, E), kPro: the
 // PAPA proline rule is on -- the warp-uniform tests of the general kernel decided once by the host (pack_is_std).
 template <bool kStd, bool kPro>

@@ -6,7 +6,7 @@ src = open(spec.origin).read().split("variants = [")[0]
 ns = {}
 exec(compile(src, spec.origin, "exec"), ns)
 res = {}
-for name, env in [("default", {}), ("ld1", {"PLAAC_PACK_LD": "1"}), ("ld2", {"PLAAC_PACK_LD": "2"}), ("ld3", {"PLAAC_PACK_LD": "3"})]:
+for name, env in [("default", {}), ("ctas8", {"PLAAC_PACK_CTAS": "8"}), ("ctas5", {"PLAAC_PACK_CTAS": "5"})]:
     if len(sys.argv) > 1 and name not in sys.argv[1:]:
         continue
     r = ns["run"](env)
